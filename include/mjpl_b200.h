@@ -1,0 +1,130 @@
+/*
+ * mjpl_b200.h -- C ABI of the B200 configuration-validity engine.
+ *
+ * This is the drop-in boundary for mjpl's validity hot path.  The reference has no FFI of its
+ * own (it is pure Python calling the `mujoco` wheel), so each entry point below cites the
+ * reference interface it replaces (paths relative to the reference checkout) and
+ * INTEGRATION.md shows the ctypes stub a maintainer would add to mjpl.
+ *
+ * Conventions: plain C, every call returns 0 on success or a non-zero status with a message in
+ * mjb_last_error() (thread local).  Device pointers are caller-owned; launches are
+ * stream-ordered on `stream` (a cudaStream_t passed as void*) with no hidden synchronisation
+ * unless stated.  A handle is bound to the CUDA device that was current at mjb_model_create
+ * and, like the reference's CollisionConstraint (which owns one mutable MjData,
+ * src/mjpl/constraint/collision_constraint.py:23), it is NOT re-entrant: one call at a time
+ * per handle (its scratch buffers are per handle).  There is no CPU fallback: every compute
+ * entry point fails with MJB_ERR_CUDA when no device is usable.
+ */
+#ifndef MJPL_B200_H
+#define MJPL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MJB_OK 0
+#define MJB_ERR_ARG 1     /* bad argument (ValueError on the Python side) */
+#define MJB_ERR_MODEL 2   /* model uses something outside the supported subset */
+#define MJB_ERR_CUDA 3    /* CUDA runtime failure / no device */
+
+/* flags of the check entry points */
+#define MJB_CHECK_LIMITS 1u     /* JointLimitConstraint.valid_config  (joint_limit_constraint.py:19-20) */
+#define MJB_CHECK_COLLISION 2u  /* CollisionConstraint.valid_config   (collision_constraint.py:26-30)  */
+#define MJB_NO_OBB_CULL 4u      /* debugging: skip the OBB mid-phase (results must not change) */
+#define MJB_NO_FP64_RECHECK 8u  /* debugging: leave uncertain rows marked 2 instead of re-evaluating */
+
+/*
+ * Constant tables taken from the MuJoCo model, under MjModel's own field names so that a real
+ * mujoco.MjModel can be passed through field by field.  Everything is copied at
+ * mjb_model_create; the caller may free its arrays afterwards.
+ * Replaces: the MjModel argument of CollisionConstraint.__init__ / JointLimitConstraint.__init__
+ * (collision_constraint.py:10-24, joint_limit_constraint.py:10-17) and the body-name ->
+ * sorted-id allow-list built by CollisionRuleset.__init__ (collision_constraint.py:42-64).
+ */
+typedef struct mjb_model_desc {
+  int32_t nq, nbody, njnt, ngeom, nmesh, nmeshvert, nexclude, nallowed;
+  int32_t disable_contact, disable_filterparent;   /* opt.disableflags bits */
+  const int32_t *body_parentid, *body_weldid, *body_jntadr, *body_jntnum;
+  const double *body_pos, *body_quat;               /* (nbody,3) (nbody,4 wxyz) */
+  const int32_t *jnt_type, *jnt_qposadr, *jnt_bodyid, *jnt_limited;
+  const double *jnt_pos, *jnt_axis, *jnt_range, *qpos0;
+  const int32_t *geom_type, *geom_bodyid, *geom_contype, *geom_conaffinity, *geom_dataid;
+  const double *geom_size, *geom_pos, *geom_quat, *geom_margin, *geom_gap;
+  const int32_t *mesh_vertadr, *mesh_vertnum;       /* convex-hull vertices only */
+  const double *mesh_vert;                          /* (nmeshvert,3) */
+  const int64_t *exclude_signature;                 /* (b1<<16)+b2 per <exclude> */
+  const int32_t *allowed_body_pairs;                /* (nallowed,2) body ids */
+} mjb_model_desc;
+
+typedef struct mjb_model mjb_model;
+
+typedef struct mjb_stats {
+  int64_t rows;            /* configurations submitted since the last reset */
+  int64_t narrow_items;    /* (row, pair) items that reached the narrow phase */
+  int64_t uncertain_rows;  /* rows re-evaluated by the fp64 kernel */
+  int64_t queue_overflow;  /* rows sent to the fp64 kernel because a tile queue filled up */
+  int64_t launches;        /* kernels launched by this handle */
+} mjb_stats;
+
+const char *mjb_last_error(void);
+int mjb_device_count(void);
+
+/* Build device tables on the current CUDA device. */
+int mjb_model_create(const mjb_model_desc *desc, mjb_model **out);
+void mjb_model_destroy(mjb_model *m);
+
+/* Static geom-pair list after MuJoCo's filters minus allowed body pairs (introspection). */
+int32_t mjb_model_npair(const mjb_model *m);
+int mjb_model_pairs(const mjb_model *m, int32_t *geom1, int32_t *geom2);
+
+/*
+ * valid[i] = 1 iff row i passes the selected checks, else 0.
+ * Replaces, for a whole block of rows: obeys_constraints(q, [JointLimitConstraint,
+ * CollisionConstraint]) (src/mjpl/constraint/utils.py:6-19), i.e. per row
+ * JointLimitConstraint.valid_config and data.qpos=q; mj_kinematics; mj_collision;
+ * CollisionRuleset.obeys_ruleset(data.contact.geom) (collision_constraint.py:27-30).
+ * d_q: (n, nq) fp32, row stride ldq elements; d_valid: (n,) bytes.
+ */
+int mjb_check_configs(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, uint8_t *d_valid,
+                      uint32_t flags, void *stream);
+
+/* Same, host buffers: H2D copy, kernels, D2H copy, stream synchronised before returning.
+ * This is what a Python caller holding numpy arrays uses (the end-to-end path). */
+int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n, uint8_t *h_valid,
+                           uint32_t flags);
+
+/* mj_kinematics for a block of rows (call site collision_constraint.py:28):
+ * d_xpos (n,nbody,3), d_xquat (n,nbody,4 wxyz), fp32.  Parity/debug entry point. */
+int mjb_fk(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, float *d_xpos, float *d_xquat,
+           void *stream);
+
+/*
+ * Edge validation: _valid_collision_interval(start, end, step, constraint)
+ * (src/mjpl/planning/utils.py:188-216) for ne edges at once.  Interior waypoints
+ * q0 + k*step*(q1-q0)/|q1-q0|, k = 1..K, K = ceil(|q1-q0|/step)-1, are generated on the device;
+ * d_valid[e] = 1 iff all of them pass `flags` (the reference checks collisions only);
+ * d_first_bad[e] (optional) = smallest failing k-1, or -1.
+ */
+int mjb_check_edges(mjb_model *m, const float *d_q0, const float *d_q1, int64_t ne, int32_t ldq,
+                    float step, uint8_t *d_valid, int32_t *d_first_bad, uint32_t flags,
+                    void *stream);
+
+/*
+ * Validity sweep with rows generated on the device: row r (global index row0+i), joint j is
+ * lo_j + u*(hi_j-lo_j) with u a counter-based hash of (seed, r, j) -- no host->device traffic.
+ * mjb_sweep_rows writes the same rows out (n,nq) so a host checker can see them.
+ */
+int mjb_check_sweep(mjb_model *m, uint64_t seed, int64_t row0, int64_t n, uint8_t *d_valid,
+                    uint32_t flags, void *stream);
+int mjb_sweep_rows(mjb_model *m, uint64_t seed, int64_t row0, int64_t n, float *d_q, void *stream);
+
+int mjb_get_stats(mjb_model *m, mjb_stats *out);   /* synchronises the handle's last stream */
+int mjb_reset_stats(mjb_model *m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

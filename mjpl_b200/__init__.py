@@ -1,0 +1,47 @@
+"""mjpl_b200: B200-native configuration-validity engine behind mjpl's Constraint API.
+
+Drop-in surface (same names as the reference's ``mjpl`` package for the validity path):
+``CollisionConstraint``, ``JointLimitConstraint``, ``obeys_constraints``, ``apply_constraints``,
+``RRT``, ``smooth_path``, ``path_length``, ``random_config``, ``all_joints``, ``qpos_idx``,
+``qvel_idx`` -- plus the batched entry points ``obeys_constraints_batch``,
+``Constraint.valid_configs``, ``CollisionConstraint.valid_edges`` and ``BatchedRRT``.
+"""
+
+from . import mjcf, models
+from .constraint import (
+    CollisionConstraint,
+    CollisionRuleset,
+    Constraint,
+    JointLimitConstraint,
+    apply_constraints,
+    obeys_constraints,
+    obeys_constraints_batch,
+)
+from .engine import EngineUnavailable, ValidityEngine, get_engine
+from .model import Model
+from .planning import RRT, BatchedRRT, path_length, smooth_path
+from .utils import all_joints, qpos_idx, qvel_idx, random_config
+
+__all__ = (
+    "BatchedRRT",
+    "CollisionConstraint",
+    "CollisionRuleset",
+    "Constraint",
+    "EngineUnavailable",
+    "JointLimitConstraint",
+    "Model",
+    "RRT",
+    "ValidityEngine",
+    "all_joints",
+    "apply_constraints",
+    "get_engine",
+    "mjcf",
+    "models",
+    "obeys_constraints",
+    "obeys_constraints_batch",
+    "path_length",
+    "qpos_idx",
+    "qvel_idx",
+    "random_config",
+    "smooth_path",
+)

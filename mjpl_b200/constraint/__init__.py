@@ -1,0 +1,14 @@
+from .collision_constraint import CollisionConstraint, CollisionRuleset
+from .constraint_interface import Constraint
+from .joint_limit_constraint import JointLimitConstraint
+from .utils import apply_constraints, obeys_constraints, obeys_constraints_batch
+
+__all__ = (
+    "Constraint",
+    "CollisionConstraint",
+    "CollisionRuleset",
+    "JointLimitConstraint",
+    "apply_constraints",
+    "obeys_constraints",
+    "obeys_constraints_batch",
+)

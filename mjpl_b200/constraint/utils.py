@@ -1,0 +1,76 @@
+"""Constraint dispatch: the reference's two helpers plus their batched twins.
+
+Reference: ``src/mjpl/constraint/utils.py:6-43``.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .. import engine as _engine
+from .collision_constraint import CollisionConstraint
+from .constraint_interface import Constraint
+from .joint_limit_constraint import JointLimitConstraint
+
+
+def obeys_constraints(q: np.ndarray, constraints: list[Constraint]) -> bool:
+    """True if ``q`` obeys each constraint (short-circuit AND, reference :6-19)."""
+    for c in constraints:
+        if not c.valid_config(q):
+            return False
+    return True
+
+
+def apply_constraints(q_old: np.ndarray, q: np.ndarray, constraints: list[Constraint]) -> np.ndarray | None:
+    """Apply constraints in order, then re-validate the result (reference :22-43)."""
+    q_constrained = q
+    for c in constraints:
+        q_constrained = c.apply(q_old, q_constrained)
+        if q_constrained is None:
+            return None
+    return q_constrained if obeys_constraints(q_constrained, constraints) else None
+
+
+def _fusable(constraints):
+    """[JointLimitConstraint, CollisionConstraint] on one model -> (engine, flags) for a single
+    fused kernel launch (limits + FK + collision), else None."""
+    if not constraints:
+        return None
+    flags, eng = 0, None
+    for c in constraints:
+        if type(c) is JointLimitConstraint:
+            flags |= _engine.CHECK_LIMITS
+            model = c.model
+        elif type(c) is CollisionConstraint:
+            if flags & _engine.CHECK_COLLISION:
+                return None
+            flags |= _engine.CHECK_COLLISION
+            eng = c.engine
+            model = c.model
+        else:
+            return None
+        if eng is not None and model is not eng.model:
+            return None
+    if eng is None:
+        eng = constraints[0].engine
+    if any(c.model is not eng.model for c in constraints):
+        return None
+    return eng, flags
+
+
+def obeys_constraints_batch(Q, constraints: list[Constraint]):
+    """Batched :func:`obeys_constraints`: ``(n,nq) -> (n,) bool`` (numpy in -> numpy out,
+    tensor in -> tensor out).  Non-projecting built-in constraints on one model are fused into
+    one kernel launch; anything else is AND-ed constraint by constraint."""
+    fused = _fusable(constraints)
+    if fused is not None:
+        eng, flags = fused
+        return eng.valid_configs(Q, flags)
+    out = None
+    for c in constraints:
+        v = c.valid_configs(Q)
+        out = v if out is None else (out & v)
+    if out is None:
+        n = len(Q)
+        return np.ones(n, dtype=bool)
+    return out

@@ -1,0 +1,401 @@
+// mjpl_b200.cu -- C-ABI entry points (include/mjpl_b200.h) and launch logic.
+//
+// No CPU fallback: every compute entry point needs a CUDA device and fails with
+// MJB_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cub/device/device_scan.cuh>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mjpl_b200.h"
+#include "vk_build.h"
+#include "vk_core.cuh"
+#include "vk_kernels.cuh"
+
+using namespace vk;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CU(call)                                                                                 \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return fail(MJB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));            \
+  } while (0)
+
+struct mjb_model {
+  vkb::HostModel H;
+  int device = 0;
+  int num_sms = 0;
+  int tile = 0;         // rows per tile (= threads per CTA)
+  int ctas_per_sm = 1;
+  int grid = 0;
+  size_t smem_bytes = 0;
+  KArgs kargs;          // constant part pre-filled
+  RArgs rargs;
+  FArgs fargs;
+  // device tables
+  Shape<float> *d_shapes32 = nullptr; Vtx<float> *d_verts32 = nullptr; Pair *d_pairs = nullptr;
+  Shape<double> *d_shapes64 = nullptr; Vtx<double> *d_verts64 = nullptr; FkTables<double> *d_fk64 = nullptr;
+  double *d_rsum64 = nullptr, *d_bsum64 = nullptr;
+  int *d_body_slot = nullptr; float *d_static_pose = nullptr;
+  // scratch
+  float *d_pose = nullptr;
+  unsigned long long *d_counters = nullptr;
+  long long *d_recheck = nullptr; size_t recheck_cap = 0;
+  long long *d_edge_count = nullptr, *d_edge_prefix = nullptr; int *d_first_bad = nullptr; size_t edge_cap = 0;
+  void *d_cub = nullptr; size_t cub_bytes = 0;
+  float *d_stage_q = nullptr; uint8_t *d_stage_v = nullptr; size_t stage_rows = 0;
+  float *h_pin_q = nullptr; uint8_t *h_pin_v = nullptr; size_t pin_rows = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t last_stream = nullptr;
+  long long rows_total = 0, launches = 0;
+};
+
+extern "C" const char *mjb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mjb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+template <typename T> static int upload(T **dst, const std::vector<T> &src) {
+  size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+  CU(cudaMalloc((void **)dst, align_up(bytes, 256)));
+  if (!src.empty()) CU(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return MJB_OK;
+}
+
+// rows resident per SM with TILE rows per CTA, or -1 if the tables do not fit
+template <int TILE> static int try_tile(const vkb::HostModel &H, int max_smem_optin, int *ctas, size_t *smem) {
+  SmemLayout L = smem_layout<TILE>((int)H.verts.size(), (int)H.shapes.size(), (int)H.pairs.size(), H.nmoving_shapes, H.nq);
+  if ((int)L.total > max_smem_optin) return -1;
+  if (cudaFuncSetAttribute(validity_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, validity_kernel<TILE>, TILE, L.total) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    return -1;
+  }
+  *ctas = occ;
+  *smem = L.total;
+  return occ * TILE;
+}
+
+extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
+  if (!desc || !out) return fail(MJB_ERR_ARG, "null argument");
+  *out = nullptr;
+  mjb_model *m = new mjb_model();
+  if (!vkb::build_host_model(desc, m->H)) {
+    std::string e = m->H.err;
+    delete m;
+    return fail(MJB_ERR_MODEL, e);
+  }
+  auto bail = [&](int rc) { mjb_model_destroy(m); return rc; };
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+    cudaGetLastError();
+    delete m;
+    return fail(MJB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  }
+  cudaError_t ce = cudaGetDevice(&m->device);
+  if (ce != cudaSuccess) { delete m; return fail(MJB_ERR_CUDA, cudaGetErrorString(ce)); }
+  cudaDeviceProp prop;
+  ce = cudaGetDeviceProperties(&prop, m->device);
+  if (ce != cudaSuccess) { delete m; return fail(MJB_ERR_CUDA, cudaGetErrorString(ce)); }
+  m->num_sms = prop.multiProcessorCount;
+  const auto &H = m->H;
+
+  // device tables (fp32 fast path + fp64 re-evaluation path)
+  std::vector<Shape<float>> s32; std::vector<Vtx<float>> v32;
+  for (auto &s : H.shapes) s32.push_back(vkb::convert_shape<float>(s));
+  for (auto &v : H.verts) { Vtx<float> f; f.x = (float)v.x; f.y = (float)v.y; f.z = (float)v.z; f.w = 0; v32.push_back(f); }
+  int rc;
+  if ((rc = upload(&m->d_shapes32, s32))) return bail(rc);
+  if ((rc = upload(&m->d_verts32, v32))) return bail(rc);
+  if ((rc = upload(&m->d_pairs, H.pairs))) return bail(rc);
+  if ((rc = upload(&m->d_shapes64, H.shapes))) return bail(rc);
+  if ((rc = upload(&m->d_verts64, H.verts))) return bail(rc);
+  if ((rc = upload(&m->d_rsum64, H.pair_rsum64))) return bail(rc);
+  if ((rc = upload(&m->d_bsum64, H.pair_bsum64))) return bail(rc);
+  std::vector<FkTables<double>> fk1(1, H.fk);
+  if ((rc = upload(&m->d_fk64, fk1))) return bail(rc);
+  std::vector<float> sp(7 * (size_t)H.nbody);
+  for (int b = 0; b < H.nbody; b++) {
+    const auto &P = H.static_pose[b];
+    float v[7] = {(float)P.p.x, (float)P.p.y, (float)P.p.z, (float)P.q.w, (float)P.q.x, (float)P.q.y, (float)P.q.z};
+    if (H.body_slot[b] >= 0) { v[0] = v[1] = v[2] = 0; v[3] = 1; v[4] = v[5] = v[6] = 0; }
+    memcpy(&sp[7 * b], v, sizeof v);
+  }
+  if ((rc = upload(&m->d_static_pose, sp))) return bail(rc);
+  if ((rc = upload(&m->d_body_slot, H.body_slot))) return bail(rc);
+
+  // kernel configuration: the tile (rows per CTA) that keeps most rows resident per SM
+  int optin = 0;
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, m->device);
+  int best = -1, r, ctas = 0;
+  size_t smem = 0;
+  const char *force = getenv("MJB_TILE");  // tuning knob: force the rows-per-CTA choice
+  const int forced = force ? atoi(force) : 0;
+  if ((!forced || forced == 512) && (r = try_tile<512>(H, optin, &ctas, &smem)) > best) { best = r; m->tile = 512; m->ctas_per_sm = ctas; m->smem_bytes = smem; }
+  if ((!forced || forced == 256) && (r = try_tile<256>(H, optin, &ctas, &smem)) > best) { best = r; m->tile = 256; m->ctas_per_sm = ctas; m->smem_bytes = smem; }
+  if ((!forced || forced == 128) && (r = try_tile<128>(H, optin, &ctas, &smem)) > best) { best = r; m->tile = 128; m->ctas_per_sm = ctas; m->smem_bytes = smem; }
+  if (best < 0) return bail(fail(MJB_ERR_MODEL, "model tables do not fit in shared memory"));
+  m->grid = m->num_sms * m->ctas_per_sm;
+
+  CU(cudaMalloc((void **)&m->d_pose, (size_t)m->grid * std::max(H.nslot, 1) * 7 * m->tile * sizeof(float)));
+  CU(cudaMalloc((void **)&m->d_counters, C_NCOUNTERS * sizeof(unsigned long long)));
+  CU(cudaMemset(m->d_counters, 0, C_NCOUNTERS * sizeof(unsigned long long)));
+  CU(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+
+  // constant kernel arguments
+  KArgs &k = m->kargs;
+  memset(&k, 0, sizeof k);
+  k.fk = vkb::convert_fk<float>(H.fk);
+  for (int j = 0; j < H.njnt; j++) { k.jnt_lo[j] = H.jnt_lo[j]; k.jnt_hi[j] = H.jnt_hi[j]; }
+  for (int s = 0; s < H.nslot; s++) { k.slot_shape_adr[s] = H.slot_shape_adr[s]; k.slot_shape_num[s] = H.slot_shape_num[s]; }
+  k.shapes = m->d_shapes32; k.verts = m->d_verts32; k.pairs = m->d_pairs;
+  k.nshape = (int)H.shapes.size(); k.nmoving = H.nmoving_shapes; k.nvert = (int)H.verts.size();
+  k.npair = (int)H.pairs.size(); k.nslot = H.nslot;
+  k.pose_scratch = m->d_pose; k.counters = m->d_counters;
+  RArgs &ra = m->rargs;
+  memset(&ra, 0, sizeof ra);
+  ra.fk = m->d_fk64; ra.shapes = m->d_shapes64; ra.verts = m->d_verts64; ra.pairs = m->d_pairs;
+  ra.pair_rsum = m->d_rsum64; ra.pair_bsum = m->d_bsum64; ra.npair = k.npair; ra.nslot = H.nslot;
+  ra.counters = m->d_counters;
+  FArgs &fa = m->fargs;
+  memset(&fa, 0, sizeof fa);
+  fa.fk = k.fk; fa.nbody_all = H.nbody; fa.body_slot = m->d_body_slot; fa.static_pose = m->d_static_pose;
+  *out = m;
+  return MJB_OK;
+}
+
+extern "C" void mjb_model_destroy(mjb_model *m) {
+  if (!m) return;
+  cudaFree(m->d_shapes32); cudaFree(m->d_verts32); cudaFree(m->d_pairs); cudaFree(m->d_shapes64);
+  cudaFree(m->d_verts64); cudaFree(m->d_fk64); cudaFree(m->d_rsum64); cudaFree(m->d_bsum64);
+  cudaFree(m->d_body_slot); cudaFree(m->d_static_pose); cudaFree(m->d_pose); cudaFree(m->d_counters);
+  cudaFree(m->d_recheck); cudaFree(m->d_edge_count); cudaFree(m->d_edge_prefix); cudaFree(m->d_first_bad);
+  cudaFree(m->d_cub); cudaFree(m->d_stage_q); cudaFree(m->d_stage_v);
+  if (m->h_pin_q) cudaFreeHost(m->h_pin_q);
+  if (m->h_pin_v) cudaFreeHost(m->h_pin_v);
+  if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  cudaGetLastError();
+  delete m;
+}
+
+extern "C" int32_t mjb_model_npair(const mjb_model *m) { return m ? (int32_t)m->H.pairs.size() : 0; }
+extern "C" int mjb_model_pairs(const mjb_model *m, int32_t *g1, int32_t *g2) {
+  if (!m || !g1 || !g2) return fail(MJB_ERR_ARG, "null argument");
+  for (size_t i = 0; i < m->H.pairs.size(); i++) { g1[i] = m->H.pair_g1[i]; g2[i] = m->H.pair_g2[i]; }
+  return MJB_OK;
+}
+
+static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st) {
+  if (rows <= m->recheck_cap) return MJB_OK;
+  if (m->d_recheck) { CU(cudaStreamSynchronize(st)); CU(cudaFree(m->d_recheck)); m->d_recheck = nullptr; }
+  size_t cap = std::max<size_t>(rows, 1 << 20);
+  CU(cudaMalloc((void **)&m->d_recheck, cap * sizeof(long long)));
+  m->recheck_cap = cap;
+  return MJB_OK;
+}
+
+static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
+  CU(cudaMemsetAsync(m->d_counters, 0, C_PER_LAUNCH * sizeof(unsigned long long), st));
+  k.recheck_rows = m->d_recheck;
+  r.recheck_rows = m->d_recheck;
+  switch (m->tile) {
+    case 512: validity_kernel<512><<<m->grid, 512, m->smem_bytes, st>>>(k); break;
+    case 256: validity_kernel<256><<<m->grid, 256, m->smem_bytes, st>>>(k); break;
+    default: validity_kernel<128><<<m->grid, 128, m->smem_bytes, st>>>(k); break;
+  }
+  CU(cudaGetLastError());
+  m->launches++;
+  if ((k.flags & F_COLLISION) && !(k.flags & F_NO_RECHECK)) {
+    recheck_kernel<<<m->num_sms * 2, 64, 0, st>>>(r);
+    CU(cudaGetLastError());
+    m->launches++;
+  }
+  m->last_stream = st;
+  return MJB_OK;
+}
+
+static int check_common(mjb_model *m, uint32_t flags) {
+  if (!m) return fail(MJB_ERR_ARG, "null model");
+  if (!(flags & (MJB_CHECK_LIMITS | MJB_CHECK_COLLISION))) return fail(MJB_ERR_ARG, "flags select no check");
+  int dev = -1;
+  CU(cudaGetDevice(&dev));
+  if (dev != m->device) CU(cudaSetDevice(m->device));
+  return MJB_OK;
+}
+
+extern "C" int mjb_check_configs(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, uint8_t *d_valid,
+                                 uint32_t flags, void *stream) {
+  int rc = check_common(m, flags);
+  if (rc) return rc;
+  if (n < 0 || ldq < m->H.nq) return fail(MJB_ERR_ARG, "bad n / ldq");
+  if (n == 0) return MJB_OK;
+  if (!d_q || !d_valid) return fail(MJB_ERR_ARG, "null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_recheck(m, (size_t)n, st))) return rc;
+  KArgs k = m->kargs;
+  k.mode = MODE_DENSE; k.q = d_q; k.ldq = ldq; k.n = n; k.valid = d_valid; k.flags = flags;
+  RArgs r = m->rargs;
+  r.mode = MODE_DENSE; r.q = d_q; r.ldq = ldq; r.valid = d_valid;
+  m->rows_total += n;
+  return launch_validity(m, k, r, st);
+}
+
+extern "C" int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n, uint8_t *h_valid, uint32_t flags) {
+  int rc = check_common(m, flags);
+  if (rc) return rc;
+  if (n < 0) return fail(MJB_ERR_ARG, "bad n");
+  if (n == 0) return MJB_OK;
+  if (!h_q || !h_valid) return fail(MJB_ERR_ARG, "null host pointer");
+  const int nq = m->H.nq;
+  cudaStream_t st = m->own_stream;
+  if ((size_t)n > m->stage_rows) {
+    CU(cudaStreamSynchronize(st));
+    cudaFree(m->d_stage_q); cudaFree(m->d_stage_v);
+    m->d_stage_q = nullptr; m->d_stage_v = nullptr;
+    size_t cap = std::max<size_t>((size_t)n, 4096);
+    CU(cudaMalloc((void **)&m->d_stage_q, cap * nq * sizeof(float)));
+    CU(cudaMalloc((void **)&m->d_stage_v, cap));
+    m->stage_rows = cap;
+  }
+  CU(cudaMemcpyAsync(m->d_stage_q, h_q, (size_t)n * nq * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = mjb_check_configs(m, m->d_stage_q, n, nq, m->d_stage_v, flags, st);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h_valid, m->d_stage_v, (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return MJB_OK;
+}
+
+extern "C" int mjb_fk(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, float *d_xpos, float *d_xquat, void *stream) {
+  int rc = check_common(m, MJB_CHECK_COLLISION);
+  if (rc) return rc;
+  if (n < 0 || ldq < m->H.nq) return fail(MJB_ERR_ARG, "bad n / ldq");
+  if (n == 0) return MJB_OK;
+  if (!d_q || !d_xpos || !d_xquat) return fail(MJB_ERR_ARG, "null device pointer");
+  FArgs f = m->fargs;
+  f.q = d_q; f.ldq = ldq; f.n = n; f.xpos = d_xpos; f.xquat = d_xquat;
+  cudaStream_t st = (cudaStream_t)stream;
+  fk_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(f);
+  CU(cudaGetLastError());
+  m->launches++;
+  m->last_stream = st;
+  return MJB_OK;
+}
+
+extern "C" int mjb_check_edges(mjb_model *m, const float *d_q0, const float *d_q1, int64_t ne, int32_t ldq, float step,
+                               uint8_t *d_valid, int32_t *d_first_bad, uint32_t flags, void *stream) {
+  int rc = check_common(m, flags);
+  if (rc) return rc;
+  // reference: raise ValueError("`step_dist` must be > 0") (src/mjpl/planning/utils.py:203-204)
+  if (!(step > 0.0f)) return fail(MJB_ERR_ARG, "`step_dist` must be > 0");
+  if (ne < 0 || ldq < m->H.nq) return fail(MJB_ERR_ARG, "bad ne / ldq");
+  if (ne == 0) return MJB_OK;
+  if (!d_q0 || !d_q1 || !d_valid) return fail(MJB_ERR_ARG, "null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((size_t)ne + 1 > m->edge_cap) {
+    CU(cudaStreamSynchronize(st));
+    cudaFree(m->d_edge_count); cudaFree(m->d_edge_prefix); cudaFree(m->d_first_bad); cudaFree(m->d_cub);
+    m->d_edge_count = m->d_edge_prefix = nullptr; m->d_first_bad = nullptr; m->d_cub = nullptr;
+    size_t cap = std::max<size_t>((size_t)ne + 1, 1 << 16);
+    CU(cudaMalloc((void **)&m->d_edge_count, cap * sizeof(long long)));
+    CU(cudaMalloc((void **)&m->d_edge_prefix, cap * sizeof(long long)));
+    CU(cudaMalloc((void **)&m->d_first_bad, cap * sizeof(int)));
+    size_t tb = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, m->d_edge_count, m->d_edge_prefix, (int)cap, st));
+    CU(cudaMalloc(&m->d_cub, tb + 256));
+    m->cub_bytes = tb + 256;
+    m->edge_cap = cap;
+  }
+  const int nq = m->H.nq;
+  edge_count_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(d_q0, d_q1, ne, nq, ldq, step, m->d_edge_count, m->d_first_bad);
+  CU(cudaGetLastError());
+  CU(cudaMemsetAsync(m->d_edge_count + ne, 0, sizeof(long long), st));
+  size_t tb = m->cub_bytes;
+  CU(cub::DeviceScan::ExclusiveSum(m->d_cub, tb, m->d_edge_count, m->d_edge_prefix, (int)(ne + 1), st));
+  // size the fp64 work list for the worst case (every waypoint uncertain): one small D2H read
+  // of the waypoint total -- this entry point synchronises `stream` once here.
+  long long total = 0;
+  CU(cudaMemcpyAsync(&total, m->d_edge_prefix + ne, sizeof total, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if ((rc = ensure_recheck(m, (size_t)std::max<long long>(total, 1), st))) return rc;
+  m->rows_total += total;
+  KArgs k = m->kargs;
+  k.mode = MODE_EDGES; k.q0 = d_q0; k.q1 = d_q1; k.ldq = ldq; k.edge_prefix = m->d_edge_prefix; k.nedge = ne;
+  k.step = step; k.first_bad = m->d_first_bad; k.flags = flags; k.n = 0;
+  RArgs r = m->rargs;
+  r.mode = MODE_EDGES; r.q0 = d_q0; r.q1 = d_q1; r.ldq = ldq; r.edge_prefix = m->d_edge_prefix; r.nedge = ne;
+  r.step = step; r.first_bad = m->d_first_bad;
+  m->launches += 2;
+  if ((rc = launch_validity(m, k, r, st))) return rc;
+  edge_finalize_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(ne, m->d_first_bad, d_valid, d_first_bad);
+  CU(cudaGetLastError());
+  m->launches++;
+  return MJB_OK;
+}
+
+extern "C" int mjb_check_sweep(mjb_model *m, uint64_t seed, int64_t row0, int64_t n, uint8_t *d_valid, uint32_t flags, void *stream) {
+  int rc = check_common(m, flags);
+  if (rc) return rc;
+  if (n < 0 || row0 < 0) return fail(MJB_ERR_ARG, "bad n / row0");
+  if (n == 0) return MJB_OK;
+  if (!d_valid) return fail(MJB_ERR_ARG, "null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = ensure_recheck(m, (size_t)n, st))) return rc;
+  KArgs k = m->kargs;
+  k.mode = MODE_SWEEP; k.seed = seed; k.row0 = row0; k.n = n; k.valid = d_valid; k.flags = flags; k.ldq = m->H.nq;
+  RArgs r = m->rargs;
+  r.mode = MODE_SWEEP; r.seed = seed; r.row0 = row0; r.valid = d_valid;
+  m->rows_total += n;
+  return launch_validity(m, k, r, st);
+}
+
+extern "C" int mjb_sweep_rows(mjb_model *m, uint64_t seed, int64_t row0, int64_t n, float *d_q, void *stream) {
+  int rc = check_common(m, MJB_CHECK_COLLISION);
+  if (rc) return rc;
+  if (n < 0 || row0 < 0) return fail(MJB_ERR_ARG, "bad n / row0");
+  if (n == 0) return MJB_OK;
+  if (!d_q) return fail(MJB_ERR_ARG, "null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long total = n * m->H.nq;
+  sweep_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->kargs.fk, seed, row0, n, d_q);
+  CU(cudaGetLastError());
+  m->launches++;
+  m->last_stream = st;
+  return MJB_OK;
+}
+
+extern "C" int mjb_get_stats(mjb_model *m, mjb_stats *out) {
+  if (!m || !out) return fail(MJB_ERR_ARG, "null argument");
+  CU(cudaSetDevice(m->device));
+  CU(cudaDeviceSynchronize());
+  unsigned long long c[C_NCOUNTERS];
+  CU(cudaMemcpy(c, m->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+  out->rows = m->rows_total;
+  out->narrow_items = (int64_t)c[C_ITEMS];
+  out->uncertain_rows = (int64_t)c[C_UNCERTAIN];
+  out->queue_overflow = (int64_t)c[C_OVERFLOW];
+  out->launches = m->launches;
+  return MJB_OK;
+}
+
+extern "C" int mjb_reset_stats(mjb_model *m) {
+  if (!m) return fail(MJB_ERR_ARG, "null argument");
+  CU(cudaSetDevice(m->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemset(m->d_counters, 0, C_NCOUNTERS * sizeof(unsigned long long)));
+  m->rows_total = 0;
+  m->launches = 0;
+  return MJB_OK;
+}

@@ -1,0 +1,423 @@
+// vk_build.h -- host-side (C++) construction of the device tables from MjModel-named arrays.
+//
+// Restates MuJoCo's static collision filtering (engine_collision_driver.c: filterBodyPair,
+// mj_contactFilter) and mjpl's allow-list rule (reference:
+// src/mjpl/constraint/collision_constraint.py:42-64, 83-95 -- deleting allowed body pairs up
+// front is equivalent to ignoring their contacts afterwards), then lowers every colliding geom
+// to a sphere-swept vertex set / cylinder / plane in its body frame.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mjpl_b200.h"
+#include "vk_core.cuh"
+
+namespace vkb {
+
+using namespace vk;
+
+enum { G_PLANE = 0, G_HFIELD = 1, G_SPHERE = 2, G_CAPSULE = 3, G_ELLIPSOID = 4, G_CYLINDER = 5, G_BOX = 6, G_MESH = 7 };
+enum { J_FREE = 0, J_BALL = 1, J_SLIDE = 2, J_HINGE = 3 };
+
+struct HostModel {
+  int nq = 0, nbody = 0, njnt = 0, ngeom = 0, nslot = 0;
+  FkTables<double> fk;                  // indexed by SLOT (moving bodies only)
+  std::vector<int> slot_body;           // slot -> body id
+  std::vector<int> body_slot;           // body -> slot or -1
+  std::vector<Pose<double>> static_pose;  // world pose of world-fixed bodies (by body id)
+  std::vector<double> jnt_lo, jnt_hi;   // fp64 limits (reference compares in fp64)
+  std::vector<Shape<double>> shapes;    // moving shapes first (sorted by slot), then static
+  int nmoving_shapes = 0;
+  std::vector<int> slot_shape_adr, slot_shape_num;
+  std::vector<Vtx<double>> verts;
+  std::vector<Pair> pairs;              // processing order
+  std::vector<int> pair_g1, pair_g2;    // MuJoCo geom ids, same order as `pairs`
+  std::vector<double> pair_rsum64, pair_bsum64;  // fp64 copies of Pair::rsum / bsum
+  std::string err;
+};
+
+inline Q4<double> qd(const double *q) { Q4<double> r; r.w = q[0]; r.x = q[1]; r.y = q[2]; r.z = q[3]; return r; }
+inline V3<double> vd(const double *v) { return mk<double>(v[0], v[1], v[2]); }
+
+// symmetric 3x3 eigen decomposition (cyclic Jacobi); columns of V are eigenvectors
+inline void jacobi3(double A[3][3], double V[3][3]) {
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) V[i][j] = i == j;
+  for (int sweep = 0; sweep < 32; sweep++) {
+    double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off < 1e-18) break;
+    for (int p = 0; p < 2; p++)
+      for (int q = p + 1; q < 3; q++) {
+        if (fabs(A[p][q]) < 1e-300) continue;
+        double th = (A[q][q] - A[p][p]) / (2 * A[p][q]);
+        double t = (th >= 0 ? 1 : -1) / (fabs(th) + sqrt(th * th + 1));
+        double c = 1 / sqrt(t * t + 1), s = t * c;
+        for (int k = 0; k < 3; k++) {
+          double akp = A[k][p], akq = A[k][q];
+          A[k][p] = c * akp - s * akq; A[k][q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < 3; k++) {
+          double apk = A[p][k], aqk = A[q][k];
+          A[p][k] = c * apk - s * aqk; A[q][k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < 3; k++) {
+          double vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = c * vkp - s * vkq; V[k][q] = s * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+inline void orthobasis_from_z(V3<double> z, double R[9]) {
+  V3<double> a = fabs(z.x) < 0.9 ? mk<double>(1, 0, 0) : mk<double>(0, 1, 0);
+  V3<double> x = cross(a, z);
+  double n = sqrt(dot(x, x));
+  x = x * (1.0 / n);
+  V3<double> y = cross(z, x);
+  R[0] = x.x; R[1] = y.x; R[2] = z.x;
+  R[3] = x.y; R[4] = y.y; R[5] = z.y;
+  R[6] = x.z; R[7] = y.z; R[8] = z.z;
+}
+
+// bounding sphere + OBB of a sphere-swept vertex set
+inline void fit_bounds(Shape<double> &s, const std::vector<Vtx<double>> &verts) {
+  const int n = s.nvert;
+  const Vtx<double> *v = verts.data() + s.vadr;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < n; i++) {
+    const double p[3] = {v[i].x, v[i].y, v[i].z};
+    for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); }
+  }
+  // bounding sphere: start at the AABB centre, then a few Ritter-style shrink steps
+  double c[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+  auto radius_at = [&](const double *cc) {
+    double r = 0;
+    for (int i = 0; i < n; i++) {
+      double dx = v[i].x - cc[0], dy = v[i].y - cc[1], dz = v[i].z - cc[2];
+      r = std::max(r, sqrt(dx * dx + dy * dy + dz * dz));
+    }
+    return r;
+  };
+  double r = radius_at(c);
+  for (int it = 0; it < 200 && n > 1; it++) {  // move towards the farthest point while it helps
+    int far = 0; double fr = -1;
+    for (int i = 0; i < n; i++) {
+      double dx = v[i].x - c[0], dy = v[i].y - c[1], dz = v[i].z - c[2];
+      double d = dx * dx + dy * dy + dz * dz;
+      if (d > fr) { fr = d; far = i; }
+    }
+    double step = 0.05 / (1 + it * 0.1);
+    double c2[3] = {c[0] + step * (v[far].x - c[0]), c[1] + step * (v[far].y - c[1]), c[2] + step * (v[far].z - c[2])};
+    double r2 = radius_at(c2);
+    if (r2 < r) { r = r2; memcpy(c, c2, sizeof c); }
+  }
+  s.bc[0] = c[0]; s.bc[1] = c[1]; s.bc[2] = c[2];
+  s.brad = r + s.radius;
+  // OBB
+  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  if (n == 2) {
+    V3<double> d = mk<double>(v[1].x - v[0].x, v[1].y - v[0].y, v[1].z - v[0].z);
+    double len = sqrt(dot(d, d));
+    if (len > 1e-12) orthobasis_from_z(d * (1.0 / len), R);
+  } else if (n >= 4) {
+    double m[3] = {0, 0, 0};
+    for (int i = 0; i < n; i++) { m[0] += v[i].x; m[1] += v[i].y; m[2] += v[i].z; }
+    for (int k = 0; k < 3; k++) m[k] /= n;
+    double C[3][3] = {{0}}, V[3][3];
+    for (int i = 0; i < n; i++) {
+      double d[3] = {v[i].x - m[0], v[i].y - m[1], v[i].z - m[2]};
+      for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) C[a][b] += d[a] * d[b];
+    }
+    jacobi3(C, V);
+    // make it a proper rotation
+    V3<double> x = mk<double>(V[0][0], V[1][0], V[2][0]), y = mk<double>(V[0][1], V[1][1], V[2][1]);
+    double nx = sqrt(dot(x, x)); x = x * (1.0 / nx);
+    y = y - x * dot(x, y);
+    double ny = sqrt(dot(y, y));
+    if (ny > 1e-9) {
+      y = y * (1.0 / ny);
+      V3<double> z = cross(x, y);
+      R[0] = x.x; R[1] = y.x; R[2] = z.x; R[3] = x.y; R[4] = y.y; R[5] = z.y; R[6] = x.z; R[7] = y.z; R[8] = z.z;
+    }
+  }
+  // try both the PCA frame and the body-axis frame, keep the smaller volume
+  double bestvol = 1e300;
+  for (int cand = 0; cand < 2; cand++) {
+    double Rc[9];
+    if (cand == 0) memcpy(Rc, R, sizeof Rc);
+    else { double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; memcpy(Rc, I, sizeof Rc); }
+    double l[3] = {1e300, 1e300, 1e300}, h[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < 3; k++) {
+        double pr = Rc[k] * v[i].x + Rc[3 + k] * v[i].y + Rc[6 + k] * v[i].z;  // column k
+        l[k] = std::min(l[k], pr); h[k] = std::max(h[k], pr);
+      }
+    double half[3], cen[3];
+    for (int k = 0; k < 3; k++) { half[k] = 0.5 * (h[k] - l[k]) + s.radius; cen[k] = 0.5 * (h[k] + l[k]); }
+    double vol = (half[0] + 1e-4) * (half[1] + 1e-4) * (half[2] + 1e-4);
+    if (vol < bestvol) {
+      bestvol = vol;
+      for (int k = 0; k < 9; k++) s.orot[k] = Rc[k];
+      for (int k = 0; k < 3; k++) s.ohalf[k] = half[k];
+      for (int k = 0; k < 3; k++) s.oc[k] = Rc[3 * k] * cen[0] + Rc[3 * k + 1] * cen[1] + Rc[3 * k + 2] * cen[2];
+    }
+  }
+}
+
+inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
+  H.nq = d->nq; H.nbody = d->nbody; H.njnt = d->njnt; H.ngeom = d->ngeom;
+  if (d->nbody < 1 || d->nbody > 4096 || d->njnt < 0 || d->ngeom < 0) { H.err = "bad model sizes"; return false; }
+  if (d->njnt > MAX_JNT) { H.err = "too many joints (max 32)"; return false; }
+  int nq_expected = 0;
+  for (int j = 0; j < d->njnt; j++) {
+    if (d->jnt_type[j] != J_HINGE && d->jnt_type[j] != J_SLIDE) {
+      // mjpl itself only plans for hinge/slide joints (reference README.md:19-20)
+      H.err = "only hinge and slide joints are supported (joint " + std::to_string(j) + ")";
+      return false;
+    }
+    nq_expected++;
+  }
+  if (nq_expected != d->nq) { H.err = "nq does not match the joint list"; return false; }
+
+  // ---- moving bodies get pose slots; world-fixed bodies get constant world poses ------------
+  H.body_slot.assign(d->nbody, -1);
+  H.static_pose.resize(d->nbody);
+  Pose<double> ident; ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  H.static_pose[0] = ident;
+  memset(&H.fk, 0, sizeof H.fk);
+  H.fk.nq = d->nq; H.fk.njnt = d->njnt;
+  for (int b = 1; b < d->nbody; b++) {
+    int p = d->body_parentid[b];
+    if (p < 0 || p >= b) { H.err = "bodies must be ordered parent-first"; return false; }
+    bool moving = d->body_weldid[b] != 0;
+    Pose<double> local; local.p = vd(d->body_pos + 3 * b); local.q = qnormalize(qd(d->body_quat + 4 * b));
+    if (!moving) {
+      if (d->body_jntnum[b] != 0) { H.err = "inconsistent body_weldid"; return false; }
+      const Pose<double> &P = H.static_pose[p];
+      H.static_pose[b].p = P.p + qrot(P.q, local.p);
+      H.static_pose[b].q = qnormalize(qmul(P.q, local.q));
+      continue;
+    }
+    int s = H.nslot++;
+    if (s >= MAX_BODY) { H.err = "too many moving bodies (max 32)"; return false; }
+    H.body_slot[b] = s;
+    H.slot_body.push_back(b);
+    int ps = H.body_slot[p];
+    H.fk.body_parent[s] = ps;
+    if (ps < 0) {  // fold the fixed parent's world pose into this body's local offset
+      const Pose<double> &P = H.static_pose[p];
+      Pose<double> f; f.p = P.p + qrot(P.q, local.p); f.q = qnormalize(qmul(P.q, local.q));
+      local = f;
+    }
+    H.fk.body_pos[s][0] = local.p.x; H.fk.body_pos[s][1] = local.p.y; H.fk.body_pos[s][2] = local.p.z;
+    H.fk.body_quat[s][0] = local.q.w; H.fk.body_quat[s][1] = local.q.x; H.fk.body_quat[s][2] = local.q.y; H.fk.body_quat[s][3] = local.q.z;
+    H.fk.body_jntadr[s] = d->body_jntadr[b] < 0 ? 0 : d->body_jntadr[b];
+    H.fk.body_jntnum[s] = d->body_jntnum[b];
+    H.fk.body_slot[s] = b;
+  }
+  H.fk.nbody = H.nslot;
+  H.jnt_lo.resize(d->njnt); H.jnt_hi.resize(d->njnt);
+  for (int j = 0; j < d->njnt; j++) {
+    H.fk.jnt_type[j] = d->jnt_type[j];
+    H.fk.jnt_qadr[j] = d->jnt_qposadr[j];
+    for (int k = 0; k < 3; k++) { H.fk.jnt_pos[j][k] = d->jnt_pos[3 * j + k]; H.fk.jnt_axis[j][k] = d->jnt_axis[3 * j + k]; }
+    H.fk.jnt_lo[j] = H.jnt_lo[j] = d->jnt_range[2 * j];
+    H.fk.jnt_hi[j] = H.jnt_hi[j] = d->jnt_range[2 * j + 1];
+  }
+  for (int a = 0; a < d->nq; a++) H.fk.qpos0[a] = d->qpos0[a];
+
+  // ---- static pair list (MuJoCo filters, then mjpl's allow-list) -------------------------------
+  struct RawPair { int g1, g2; };
+  std::vector<RawPair> raw;
+  auto allowed = [&](int b1, int b2) {
+    int lo = std::min(b1, b2), hi = std::max(b1, b2);
+    for (int k = 0; k < d->nallowed; k++) {
+      int a = d->allowed_body_pairs[2 * k], b = d->allowed_body_pairs[2 * k + 1];
+      if (std::min(a, b) == lo && std::max(a, b) == hi) return true;
+    }
+    return false;
+  };
+  if (!d->disable_contact)
+    for (int g1 = 0; g1 < d->ngeom; g1++)
+      for (int g2 = g1 + 1; g2 < d->ngeom; g2++) {
+        int b1 = d->geom_bodyid[g1], b2 = d->geom_bodyid[g2];
+        int w1 = d->body_weldid[b1], w2 = d->body_weldid[b2];
+        if (w1 == w2) continue;                       // same weld body
+        int wp1 = d->body_weldid[d->body_parentid[w1]], wp2 = d->body_weldid[d->body_parentid[w2]];
+        if (!d->disable_filterparent && w1 != 0 && w2 != 0 && (w1 == wp2 || w2 == wp1)) continue;
+        int64_t sig = ((int64_t)std::min(b1, b2) << 16) + std::max(b1, b2);
+        bool ex = false;
+        for (int k = 0; k < d->nexclude; k++) ex |= d->exclude_signature[k] == sig;
+        if (ex) continue;
+        if (!((d->geom_contype[g1] & d->geom_conaffinity[g2]) || (d->geom_contype[g2] & d->geom_conaffinity[g1]))) continue;
+        if (allowed(b1, b2)) continue;
+        int t1 = d->geom_type[g1], t2 = d->geom_type[g2];
+        if (t1 == G_PLANE && t2 == G_PLANE) continue;  // MuJoCo has no plane-plane collider
+        if (t1 == G_HFIELD || t2 == G_HFIELD) { H.err = "height fields are not supported"; return false; }
+        if (t1 == G_ELLIPSOID || t2 == G_ELLIPSOID) { H.err = "ellipsoid geoms are not supported"; return false; }
+        raw.push_back({g1, g2});
+      }
+
+  // ---- shapes ----------------------------------------------------------------------------------
+  std::vector<int> geom_shape(d->ngeom, -1);
+  std::vector<Shape<double>> tmp;
+  std::vector<int> tmp_slot;
+  auto make_shape = [&](int g) -> bool {
+    if (geom_shape[g] >= 0) return true;
+    Shape<double> s; memset(&s, 0, sizeof s);
+    s.geom = g;
+    int b = d->geom_bodyid[g];
+    s.slot = H.body_slot[b];
+    Pose<double> T; T.p = vd(d->geom_pos + 3 * g); T.q = qnormalize(qd(d->geom_quat + 4 * g));
+    if (s.slot < 0) {  // world-fixed: express in the world frame once and for all
+      const Pose<double> &P = H.static_pose[b];
+      Pose<double> W; W.p = P.p + qrot(P.q, T.p); W.q = qnormalize(qmul(P.q, T.q));
+      T = W;
+    }
+    M3<double> R = q2mat(T.q);
+    const double *sz = d->geom_size + 3 * g;
+    auto push = [&](double x, double y, double z) {
+      V3<double> w = T.p + mul(R, mk<double>(x, y, z));
+      Vtx<double> v; v.x = w.x; v.y = w.y; v.z = w.z; v.w = 0;
+      H.verts.push_back(v);
+    };
+    s.vadr = (int)H.verts.size();
+    switch (d->geom_type[g]) {
+      case G_PLANE:
+        s.kind = SK_PLANE;
+        if (s.slot >= 0) { H.err = "plane geoms must be attached to a world-fixed body"; return false; }
+        s.c[0] = T.p.x; s.c[1] = T.p.y; s.c[2] = T.p.z;
+        s.ax[0] = R.m[2]; s.ax[1] = R.m[5]; s.ax[2] = R.m[8];
+        break;
+      case G_SPHERE: s.kind = SK_VERTS; s.radius = sz[0]; push(0, 0, 0); break;
+      case G_CAPSULE: s.kind = SK_VERTS; s.radius = sz[0]; push(0, 0, -sz[1]); push(0, 0, sz[1]); break;
+      case G_BOX:
+        s.kind = SK_VERTS;
+        for (int i = 0; i < 8; i++) push((i & 1 ? 1 : -1) * sz[0], (i & 2 ? 1 : -1) * sz[1], (i & 4 ? 1 : -1) * sz[2]);
+        break;
+      case G_CYLINDER: {
+        s.kind = SK_CYL; s.radius = sz[0]; s.halflen = sz[1];
+        s.c[0] = T.p.x; s.c[1] = T.p.y; s.c[2] = T.p.z;
+        s.ax[0] = R.m[2]; s.ax[1] = R.m[5]; s.ax[2] = R.m[8];
+        s.bc[0] = s.c[0]; s.bc[1] = s.c[1]; s.bc[2] = s.c[2];
+        s.brad = sqrt(sz[0] * sz[0] + sz[1] * sz[1]);
+        s.oc[0] = s.c[0]; s.oc[1] = s.c[1]; s.oc[2] = s.c[2];
+        orthobasis_from_z(mk<double>(s.ax[0], s.ax[1], s.ax[2]), s.orot);
+        s.ohalf[0] = s.ohalf[1] = sz[0]; s.ohalf[2] = sz[1];
+        break;
+      }
+      case G_MESH: {
+        s.kind = SK_VERTS;
+        int id = d->geom_dataid[g];
+        if (id < 0 || id >= d->nmesh || d->mesh_vertnum[id] < 1) { H.err = "mesh geom without hull vertices"; return false; }
+        const double *mv = d->mesh_vert + 3 * d->mesh_vertadr[id];
+        for (int i = 0; i < d->mesh_vertnum[id]; i++) push(mv[3 * i], mv[3 * i + 1], mv[3 * i + 2]);
+        break;
+      }
+      default: H.err = "unsupported geom type"; return false;
+    }
+    s.nvert = (int)H.verts.size() - s.vadr;
+    if (s.kind == SK_VERTS) fit_bounds(s, H.verts);
+    geom_shape[g] = (int)tmp.size();
+    tmp.push_back(s);
+    tmp_slot.push_back(s.slot);
+    return true;
+  };
+  for (auto &rp : raw) { if (!make_shape(rp.g1) || !make_shape(rp.g2)) return false; }
+
+  // order shapes: moving ones by slot, then static ones
+  std::vector<int> order(tmp.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    int sa = tmp_slot[a] < 0 ? 1 << 20 : tmp_slot[a], sb = tmp_slot[b] < 0 ? 1 << 20 : tmp_slot[b];
+    return sa < sb;
+  });
+  std::vector<int> newidx(tmp.size());
+  H.slot_shape_adr.assign(std::max(H.nslot, 1), 0);
+  H.slot_shape_num.assign(std::max(H.nslot, 1), 0);
+  for (size_t i = 0; i < order.size(); i++) {
+    newidx[order[i]] = (int)i;
+    const Shape<double> &s = tmp[order[i]];
+    H.shapes.push_back(s);
+    if (s.slot >= 0) {
+      if (H.slot_shape_num[s.slot] == 0) H.slot_shape_adr[s.slot] = (int)i;
+      H.slot_shape_num[s.slot]++;
+      H.nmoving_shapes++;
+    }
+  }
+  if (H.shapes.size() > 4096) { H.err = "too many collision geoms"; return false; }
+
+  // ---- pairs in processing order --------------------------------------------------------------------
+  struct Tmp { Pair p; int g1, g2; long key; double rsum, bsum; };
+  std::vector<Tmp> tp;
+  for (auto &rp : raw) {
+    int a = newidx[geom_shape[rp.g1]], b = newidx[geom_shape[rp.g2]];
+    const Shape<double> *A = &H.shapes[a], *B = &H.shapes[b];
+    double margin = std::max(d->geom_margin[rp.g1], d->geom_margin[rp.g2]);
+    // plane first; otherwise the shape with more vertices is A (its frame hosts the GJK)
+    if (B->kind == SK_PLANE || (A->kind != SK_PLANE && B->nvert > A->nvert)) { std::swap(a, b); std::swap(A, B); }
+    Tmp t; memset(&t, 0, sizeof t);
+    t.g1 = rp.g1; t.g2 = rp.g2;
+    t.p.sa = (uint16_t)a; t.p.sb = (uint16_t)b;
+    if (A->kind == SK_PLANE) {
+      t.p.kind = PK_PLANE;
+      t.rsum = (B->kind == SK_VERTS ? B->radius : 0.0) + margin;
+      t.bsum = B->brad + margin;
+      t.key = 0;
+    } else {
+      bool seg = A->kind == SK_VERTS && B->kind == SK_VERTS && A->nvert <= 2 && B->nvert <= 2;
+      t.p.kind = seg ? PK_SEGSEG : PK_GJK;
+      double ra = A->kind == SK_VERTS ? A->radius : 0.0, rb = B->kind == SK_VERTS ? B->radius : 0.0;
+      t.rsum = ra + rb + margin;
+      t.bsum = A->brad + B->brad + margin;
+      int cost = (A->kind == SK_CYL ? 16 : A->nvert) + (B->kind == SK_CYL ? 16 : B->nvert);
+      t.p.flags = (!seg && cost >= 12) ? 1 : 0;
+      t.key = seg ? 1 : 1000 + cost;
+    }
+    t.p.rsum = (float)t.rsum;
+    t.p.bsum = (float)t.bsum;
+    tp.push_back(t);
+  }
+  std::stable_sort(tp.begin(), tp.end(), [](const Tmp &x, const Tmp &y) {
+    if (x.key != y.key) return x.key < y.key;
+    if (x.p.sa != y.p.sa) return x.p.sa < y.p.sa;
+    return x.p.sb < y.p.sb;
+  });
+  for (auto &t : tp) {
+    H.pairs.push_back(t.p); H.pair_g1.push_back(t.g1); H.pair_g2.push_back(t.g2);
+    H.pair_rsum64.push_back(t.rsum); H.pair_bsum64.push_back(t.bsum);
+  }
+  if (H.pairs.size() > 60000) { H.err = "too many geom pairs"; return false; }
+  return true;
+}
+
+template <typename T> inline FkTables<T> convert_fk(const FkTables<double> &s) {
+  FkTables<T> o; memset(&o, 0, sizeof o);
+  o.nq = s.nq; o.nbody = s.nbody; o.njnt = s.njnt;
+  for (int i = 0; i < MAX_BODY; i++) {
+    o.body_parent[i] = s.body_parent[i]; o.body_jntadr[i] = s.body_jntadr[i];
+    o.body_jntnum[i] = s.body_jntnum[i]; o.body_slot[i] = s.body_slot[i];
+    for (int k = 0; k < 3; k++) o.body_pos[i][k] = (T)s.body_pos[i][k];
+    for (int k = 0; k < 4; k++) o.body_quat[i][k] = (T)s.body_quat[i][k];
+  }
+  for (int j = 0; j < MAX_JNT; j++) {
+    o.jnt_type[j] = s.jnt_type[j]; o.jnt_qadr[j] = s.jnt_qadr[j];
+    for (int k = 0; k < 3; k++) { o.jnt_pos[j][k] = (T)s.jnt_pos[j][k]; o.jnt_axis[j][k] = (T)s.jnt_axis[j][k]; }
+    o.jnt_lo[j] = (T)s.jnt_lo[j]; o.jnt_hi[j] = (T)s.jnt_hi[j]; o.qpos0[j] = (T)s.qpos0[j];
+  }
+  return o;
+}
+
+template <typename T> inline Shape<T> convert_shape(const Shape<double> &s) {
+  Shape<T> o; memset(&o, 0, sizeof o);
+  o.kind = s.kind; o.slot = s.slot; o.vadr = s.vadr; o.nvert = s.nvert; o.geom = s.geom;
+  o.radius = (T)s.radius; o.halflen = (T)s.halflen; o.brad = (T)s.brad;
+  for (int k = 0; k < 3; k++) { o.c[k] = (T)s.c[k]; o.ax[k] = (T)s.ax[k]; o.bc[k] = (T)s.bc[k]; o.oc[k] = (T)s.oc[k]; o.ohalf[k] = (T)s.ohalf[k]; }
+  for (int k = 0; k < 9; k++) o.orot[k] = (T)s.orot[k];
+  return o;
+}
+
+}  // namespace vkb

@@ -1,0 +1,579 @@
+// vk_core.cuh -- geometric core of the validity kernels (host+device, templated on scalar).
+//
+// float  instance: the sm_100a fast path (vk_kernels.cu).
+// double instance: the on-device re-evaluation of rows the fast path could not certify.
+//
+// What it restates (MuJoCo 3.x semantics; reference call sites
+// src/mjpl/constraint/collision_constraint.py:27-30):
+//   * mj_kinematics for hinge / slide / fixed bodies                      -> fk_body()
+//   * the boolean "closed convex sets at signed distance <= margin" that every MuJoCo
+//     narrow-phase routine reduces to when it decides whether to emit a contact
+//     (mjc_Convex / mjc_BoxBox / mjc_CapsuleBox / ... / mjc_PlaneConvex)   -> gjk_classify(),
+//     segseg_classify(), plane tests in the kernels.
+//
+// Design: every convex collision geom is a "sphere-swept vertex set" in its BODY frame
+// (mesh = hull vertices, box = 8 corners, capsule = 2 end points + radius, sphere = 1 point
+// + radius), or a cylinder.  One GJK loop serves them all; it returns a three-way verdict
+// with certified bounds so that the fp32 path never guesses:
+//   SEP  : a separating direction proves   distance >  R + tol
+//   PEN  : a witness point / enclosed origin proves distance <  R - tol
+//   UNC  : neither (|distance - R| <~ tol, or no convergence) -> re-evaluated in fp64
+// The simplex solver is the signed-volume formulation (barycentric cofactors) rather than
+// Voronoi-region tests; the CPU oracle deliberately uses the other one.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define VK_HD __host__ __device__ __forceinline__
+#define VK_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define VK_HD inline
+#define VK_HD_NOINLINE
+#endif
+
+namespace vk {
+
+enum Verdict : int { V_SEP = 0, V_PEN = 1, V_UNC = 2 };
+enum ShapeKind : int { SK_VERTS = 0, SK_CYL = 1, SK_PLANE = 2 };
+enum PairKind : int { PK_PLANE = 0, PK_SEGSEG = 1, PK_GJK = 2, PK_BOXBOX = 3 };
+enum JointKind : int { JK_SLIDE = 2, JK_HINGE = 3 };
+
+constexpr int MAX_BODY = 32;
+constexpr int MAX_JNT = 32;
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+  static constexpr float tol = 4e-6f;        // certification slack (FK + GJK rounding)
+  static constexpr float conv_rel = 1e-6f;   // GJK relative convergence on |v|^2 - v.w
+  static constexpr float tiny = 1e-30f;
+  static constexpr int maxit = 24;
+};
+template <> struct Num<double> {
+  static constexpr double tol = 0.0;
+  static constexpr double conv_rel = 1e-12;
+  static constexpr double tiny = 1e-280;
+  static constexpr int maxit = 64;
+};
+
+template <typename T> struct V3 { T x, y, z; };
+template <typename T> struct Q4 { T w, x, y, z; };
+template <typename T> struct M3 { T m[9]; };  // row-major
+template <typename T> struct Pose { V3<T> p; Q4<T> q; };
+
+template <typename T> VK_HD V3<T> mk(T x, T y, T z) { V3<T> r; r.x = x; r.y = y; r.z = z; return r; }
+template <typename T> VK_HD V3<T> operator+(V3<T> a, V3<T> b) { return mk<T>(a.x + b.x, a.y + b.y, a.z + b.z); }
+template <typename T> VK_HD V3<T> operator-(V3<T> a, V3<T> b) { return mk<T>(a.x - b.x, a.y - b.y, a.z - b.z); }
+template <typename T> VK_HD V3<T> operator-(V3<T> a) { return mk<T>(-a.x, -a.y, -a.z); }
+template <typename T> VK_HD V3<T> operator*(V3<T> a, T s) { return mk<T>(a.x * s, a.y * s, a.z * s); }
+template <typename T> VK_HD T dot(V3<T> a, V3<T> b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+template <typename T> VK_HD V3<T> cross(V3<T> a, V3<T> b) {
+  return mk<T>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+template <typename T> VK_HD T det3(V3<T> a, V3<T> b, V3<T> c) { return dot(a, cross(b, c)); }
+
+VK_HD float vk_sqrt(float x) { return sqrtf(x); }
+VK_HD double vk_sqrt(double x) { return sqrt(x); }
+VK_HD float vk_abs(float x) { return fabsf(x); }
+VK_HD double vk_abs(double x) { return fabs(x); }
+VK_HD float vk_min(float a, float b) { return fminf(a, b); }
+VK_HD double vk_min(double a, double b) { return fmin(a, b); }
+VK_HD float vk_max(float a, float b) { return fmaxf(a, b); }
+VK_HD double vk_max(double a, double b) { return fmax(a, b); }
+VK_HD void vk_sincos(float x, float *s, float *c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, s, c);
+#else
+  *s = sinf(x); *c = cosf(x);
+#endif
+}
+VK_HD void vk_sincos(double x, double *s, double *c) {
+#if defined(__CUDA_ARCH__)
+  sincos(x, s, c);
+#else
+  *s = sin(x); *c = cos(x);
+#endif
+}
+
+// Hamilton product (w,x,y,z) -- mju_mulQuat
+template <typename T> VK_HD Q4<T> qmul(Q4<T> a, Q4<T> b) {
+  Q4<T> r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+  r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+  return r;
+}
+template <typename T> VK_HD Q4<T> qconj(Q4<T> a) { Q4<T> r; r.w = a.w; r.x = -a.x; r.y = -a.y; r.z = -a.z; return r; }
+// rotate v by unit quaternion q:  v + 2w(u x v) + 2 u x (u x v)
+template <typename T> VK_HD V3<T> qrot(Q4<T> q, V3<T> v) {
+  V3<T> u = mk<T>(q.x, q.y, q.z);
+  V3<T> t = cross(u, v) * T(2);
+  return v + t * q.w + cross(u, t);
+}
+template <typename T> VK_HD Q4<T> qnormalize(Q4<T> q) {
+  T n = vk_sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  T inv = T(1) / n;
+  Q4<T> r; r.w = q.w * inv; r.x = q.x * inv; r.y = q.y * inv; r.z = q.z * inv;
+  return r;
+}
+template <typename T> VK_HD M3<T> q2mat(Q4<T> q) {
+  M3<T> r;
+  T q00 = q.w * q.w, q11 = q.x * q.x, q22 = q.y * q.y, q33 = q.z * q.z;
+  T q01 = q.w * q.x, q02 = q.w * q.y, q03 = q.w * q.z, q12 = q.x * q.y, q13 = q.x * q.z, q23 = q.y * q.z;
+  r.m[0] = q00 + q11 - q22 - q33; r.m[4] = q00 - q11 + q22 - q33; r.m[8] = q00 - q11 - q22 + q33;
+  r.m[1] = 2 * (q12 - q03); r.m[2] = 2 * (q13 + q02);
+  r.m[3] = 2 * (q12 + q03); r.m[5] = 2 * (q23 - q01);
+  r.m[6] = 2 * (q13 - q02); r.m[7] = 2 * (q23 + q01);
+  return r;
+}
+template <typename T> VK_HD V3<T> mul(const M3<T> &m, V3<T> v) {
+  return mk<T>(m.m[0] * v.x + m.m[1] * v.y + m.m[2] * v.z, m.m[3] * v.x + m.m[4] * v.y + m.m[5] * v.z,
+               m.m[6] * v.x + m.m[7] * v.y + m.m[8] * v.z);
+}
+template <typename T> VK_HD V3<T> mulT(const M3<T> &m, V3<T> v) {
+  return mk<T>(m.m[0] * v.x + m.m[3] * v.y + m.m[6] * v.z, m.m[1] * v.x + m.m[4] * v.y + m.m[7] * v.z,
+               m.m[2] * v.x + m.m[5] * v.y + m.m[8] * v.z);
+}
+
+// ------------------------------------------------------------------------------ model tables
+// Kinematic tree (passed to the fp32 kernel as a __grid_constant__ parameter: constant bank).
+template <typename T> struct FkTables {
+  int nq, nbody, njnt, pad;
+  int body_parent[MAX_BODY];
+  int body_jntadr[MAX_BODY];
+  int body_jntnum[MAX_BODY];
+  int body_slot[MAX_BODY];     // pose slot of a moving body, -1 for world-fixed bodies
+  T body_pos[MAX_BODY][3];
+  T body_quat[MAX_BODY][4];
+  int jnt_type[MAX_JNT];
+  int jnt_qadr[MAX_JNT];
+  T jnt_pos[MAX_JNT][3];
+  T jnt_axis[MAX_JNT][3];
+  T jnt_lo[MAX_JNT], jnt_hi[MAX_JNT], qpos0[MAX_JNT];
+};
+
+// One collision geom, expressed in the frame of its body (world-fixed geoms: body = -1 and the
+// data is already in the world frame).
+template <typename T> struct Shape {
+  int kind;        // ShapeKind
+  int slot;        // pose slot of the carrying body, -1 = world frame (static)
+  int vadr, nvert; // SK_VERTS: range in the vertex table
+  T radius;        // swept radius (sphere / capsule) or cylinder radius
+  T halflen;       // cylinder half length
+  T c[3];          // SK_CYL: centre; SK_PLANE: a point of the plane
+  T ax[3];         // SK_CYL: axis (unit); SK_PLANE: normal (unit)
+  T bc[3];         // bounding-sphere centre
+  T brad;          // bounding-sphere radius (includes swept radius)
+  T oc[3];         // OBB centre
+  T orot[9];       // OBB axes = columns, row-major 3x3
+  T ohalf[3];      // OBB half extents (include swept radius)
+  int geom;        // MuJoCo geom id
+  int pad;
+};
+
+struct Pair {
+  uint16_t sa, sb;  // shape indices (sa: plane if any; else the one with more vertices first)
+  uint16_t kind;    // PairKind
+  uint16_t flags;   // bit0: OBB mid-phase is worthwhile
+  float rsum;       // swept radii + margin: contact iff core distance <= rsum
+  float bsum;       // bounding radii sum + margin
+};
+
+// ------------------------------------------------------------------------------ forward kinematics
+// One body of mj_kinematics (engine_core_smooth.c), SURVEY.md A.1: parent pose -> body pose.
+template <typename T, typename TQ>
+VK_HD Pose<T> fk_body(const FkTables<T> &tb, int i, const Pose<T> &parent, const TQ *q) {
+  Pose<T> o;
+  V3<T> bp = mk<T>(tb.body_pos[i][0], tb.body_pos[i][1], tb.body_pos[i][2]);
+  Q4<T> bq; bq.w = tb.body_quat[i][0]; bq.x = tb.body_quat[i][1]; bq.y = tb.body_quat[i][2]; bq.z = tb.body_quat[i][3];
+  o.p = parent.p + qrot(parent.q, bp);
+  o.q = qmul(parent.q, bq);
+  const int ja = tb.body_jntadr[i], jn = tb.body_jntnum[i];
+  for (int k = 0; k < jn; k++) {
+    const int j = ja + k;
+    const int a = tb.jnt_qadr[j];
+    V3<T> jp = mk<T>(tb.jnt_pos[j][0], tb.jnt_pos[j][1], tb.jnt_pos[j][2]);
+    V3<T> jax = mk<T>(tb.jnt_axis[j][0], tb.jnt_axis[j][1], tb.jnt_axis[j][2]);
+    T dq = T(q[a]) - tb.qpos0[a];
+    if (tb.jnt_type[j] == JK_SLIDE) {
+      o.p = o.p + qrot(o.q, jax) * dq;
+    } else {
+      V3<T> anchor = o.p + qrot(o.q, jp);
+      T s, c;
+      vk_sincos(dq * T(0.5), &s, &c);
+      Q4<T> ql; ql.w = c; ql.x = jax.x * s; ql.y = jax.y * s; ql.z = jax.z * s;
+      o.q = qmul(o.q, ql);
+      o.p = anchor - qrot(o.q, jp);
+    }
+  }
+  o.q = qnormalize(o.q);
+  return o;
+}
+
+// ------------------------------------------------------------------------------ simplex solver
+// Closest point of conv{P0..P(n-1)} to the origin as barycentric weights (signed volumes).
+template <typename T> struct Simplex {
+  V3<T> p0, p1, p2, p3;
+  int n;
+};
+
+template <typename T> VK_HD void solve1(V3<T> a, V3<T> b, T &la, T &lb) {
+  V3<T> t = b - a;
+  T tt = dot(t, t);
+  T s = tt > T(0) ? -dot(a, t) / tt : T(0);
+  s = s < T(0) ? T(0) : (s > T(1) ? T(1) : s);
+  la = T(1) - s;
+  lb = s;
+}
+
+template <typename T> VK_HD T comb2(V3<T> a, V3<T> b, T la, T lb) {
+  V3<T> v = a * la + b * lb;
+  return dot(v, v);
+}
+
+template <typename T> VK_HD void solve2(V3<T> a, V3<T> b, V3<T> c, T &la, T &lb, T &lc) {
+  V3<T> n = cross(b - a, c - a);
+  T nn = dot(n, n);
+  bool inside = false;
+  T ca = T(0), cb = T(0), cc = T(0);
+  if (nn > Num<T>::tiny) {
+    V3<T> p = n * (dot(a, n) / nn);  // origin projected on the plane
+    ca = dot(n, cross(b - p, c - p));
+    cb = dot(n, cross(c - p, a - p));
+    cc = dot(n, cross(a - p, b - p));
+    inside = (ca >= T(0)) && (cb >= T(0)) && (cc >= T(0));
+  }
+  if (inside) {
+    T s = T(1) / (ca + cb + cc);
+    la = ca * s; lb = cb * s; lc = cc * s;
+    return;
+  }
+  // best of the edges whose opposite signed area is negative (all three if degenerate)
+  T best = T(-1);
+  la = T(1); lb = T(0); lc = T(0);
+  const bool deg = !(nn > Num<T>::tiny);
+  if (deg || ca < T(0)) {  // edge bc
+    T x, y; solve1(b, c, x, y);
+    T d = comb2(b, c, x, y);
+    best = d; la = T(0); lb = x; lc = y;
+  }
+  if (deg || cb < T(0)) {  // edge ca
+    T x, y; solve1(c, a, x, y);
+    T d = comb2(c, a, x, y);
+    if (best < T(0) || d < best) { best = d; la = y; lb = T(0); lc = x; }
+  }
+  if (deg || cc < T(0)) {  // edge ab
+    T x, y; solve1(a, b, x, y);
+    T d = comb2(a, b, x, y);
+    if (best < T(0) || d < best) { best = d; la = x; lb = y; lc = T(0); }
+  }
+}
+
+template <typename T> VK_HD T comb3(V3<T> a, V3<T> b, V3<T> c, T la, T lb, T lc) {
+  V3<T> v = a * la + b * lb + c * lc;
+  return dot(v, v);
+}
+
+// returns true when the origin is inside the tetrahedron (weights then all > 0)
+template <typename T>
+VK_HD bool solve3(V3<T> a, V3<T> b, V3<T> c, V3<T> d, T &la, T &lb, T &lc, T &ld) {
+  T Ca = -det3(b, c, d), Cb = det3(a, c, d), Cc = -det3(a, b, d), Cd = det3(a, b, c);
+  T dm = Ca + Cb + Cc + Cd;
+  // scale for the degeneracy test: product of edge lengths ~ volume scale
+  T sc = vk_abs(Ca) + vk_abs(Cb) + vk_abs(Cc) + vk_abs(Cd);
+  const bool deg = !(vk_abs(dm) > T(1e-6) * sc) || !(sc > Num<T>::tiny);
+  if (dm < T(0)) { Ca = -Ca; Cb = -Cb; Cc = -Cc; Cd = -Cd; dm = -dm; }
+  if (!deg && Ca > T(0) && Cb > T(0) && Cc > T(0) && Cd > T(0)) {
+    T s = T(1) / dm;
+    la = Ca * s; lb = Cb * s; lc = Cc * s; ld = Cd * s;
+    return true;
+  }
+  T best = T(-1);
+  la = T(1); lb = lc = ld = T(0);
+  if (deg || Ca <= T(0)) {  // face bcd
+    T x, y, z; solve2(b, c, d, x, y, z);
+    best = comb3(b, c, d, x, y, z); la = T(0); lb = x; lc = y; ld = z;
+  }
+  if (deg || Cb <= T(0)) {  // face acd
+    T x, y, z; solve2(a, c, d, x, y, z);
+    T e = comb3(a, c, d, x, y, z);
+    if (best < T(0) || e < best) { best = e; la = x; lb = T(0); lc = y; ld = z; }
+  }
+  if (deg || Cc <= T(0)) {  // face abd
+    T x, y, z; solve2(a, b, d, x, y, z);
+    T e = comb3(a, b, d, x, y, z);
+    if (best < T(0) || e < best) { best = e; la = x; lb = y; lc = T(0); ld = z; }
+  }
+  if (deg || Cd <= T(0)) {  // face abc
+    T x, y, z; solve2(a, b, c, x, y, z);
+    T e = comb3(a, b, c, x, y, z);
+    if (best < T(0) || e < best) { best = e; la = x; lb = y; lc = z; ld = T(0); }
+  }
+  return false;
+}
+
+// distance from the origin to the plane through (a,b,c); 0 for a degenerate triangle
+template <typename T> VK_HD T plane_dist(V3<T> a, V3<T> b, V3<T> c) {
+  V3<T> n = cross(b - a, c - a);
+  T nn = dot(n, n);
+  return nn > Num<T>::tiny ? vk_abs(dot(a, n)) / vk_sqrt(nn) : T(0);
+}
+
+template <typename T> VK_HD void cswap(bool p, V3<T> &a, V3<T> &b) {
+  V3<T> ta = a, tb = b;
+  a.x = p ? tb.x : ta.x; a.y = p ? tb.y : ta.y; a.z = p ? tb.z : ta.z;
+  b.x = p ? ta.x : tb.x; b.y = p ? ta.y : tb.y; b.z = p ? ta.z : tb.z;
+}
+template <typename T> VK_HD void cswap(bool p, T &a, T &b) { T ta = a, tb = b; a = p ? tb : ta; b = p ? ta : tb; }
+
+// ------------------------------------------------------------------------------ support functions
+// Vertex tables are stored as 4 scalars per vertex (x,y,z,0).
+template <typename T> struct Vtx { T x, y, z, w; };
+
+template <typename T>
+VK_HD V3<T> support_verts(const Vtx<T> *__restrict__ v, int n, V3<T> d) {
+  T best = v[0].x * d.x + v[0].y * d.y + v[0].z * d.z;
+  V3<T> bp = mk<T>(v[0].x, v[0].y, v[0].z);
+  for (int i = 1; i < n; i++) {
+    Vtx<T> p = v[i];
+    T s = p.x * d.x + p.y * d.y + p.z * d.z;
+    bool g = s > best;
+    best = g ? s : best;
+    bp.x = g ? p.x : bp.x; bp.y = g ? p.y : bp.y; bp.z = g ? p.z : bp.z;
+  }
+  return bp;
+}
+
+template <typename T> VK_HD V3<T> support_cyl(const Shape<T> &s, V3<T> d) {
+  V3<T> ax = mk<T>(s.ax[0], s.ax[1], s.ax[2]);
+  V3<T> c = mk<T>(s.c[0], s.c[1], s.c[2]);
+  T da = dot(d, ax);
+  V3<T> rd = d - ax * da;  // radial part
+  T rn = vk_sqrt(dot(rd, rd));
+  V3<T> p = c + ax * (da >= T(0) ? s.halflen : -s.halflen);
+  if (rn > Num<T>::tiny) p = p + rd * (s.radius / rn);
+  return p;
+}
+
+template <typename T>
+VK_HD V3<T> support_shape(const Shape<T> &s, const Vtx<T> *__restrict__ verts, V3<T> d) {
+  if (s.kind == SK_CYL) return support_cyl(s, d);
+  return support_verts(verts + s.vadr, s.nvert, d);
+}
+
+// swept radius of a shape (0 for cylinders, whose `radius` is part of the core)
+template <typename T> VK_HD T swept_radius(const Shape<T> &s) { return s.kind == SK_VERTS ? s.radius : T(0); }
+
+// relative pose of B in A's frame
+template <typename T> struct Rel { M3<T> R; V3<T> t; };
+template <typename T> VK_HD Rel<T> relative_pose(const Pose<T> &A, const Pose<T> &B) {
+  Rel<T> r;
+  Q4<T> ai = qconj(A.q);
+  r.R = q2mat(qmul(ai, B.q));
+  r.t = qrot(ai, B.p - A.p);
+  return r;
+}
+
+// ------------------------------------------------------------------------------ GJK three-way classifier
+// A in its own frame, B through `rel`.  R = swept radii + margin.  `iters` (optional) counts
+// support evaluations.
+template <typename T>
+VK_HD int gjk_classify(const Shape<T> &A, const Shape<T> &B, const Vtx<T> *__restrict__ verts,
+                       const Rel<T> &rel, T R, int *iters) {
+  const T tol = Num<T>::tol;
+  V3<T> cA = mk<T>(A.bc[0], A.bc[1], A.bc[2]);
+  V3<T> cB = mul(rel.R, mk<T>(B.bc[0], B.bc[1], B.bc[2])) + rel.t;
+  V3<T> v = cA - cB;
+  if (!(dot(v, v) > Num<T>::tiny)) v = mk<T>(T(1), T(0), T(0));
+  V3<T> p0 = v, p1 = v, p2 = v, p3 = v;
+  int n = 0;
+  int verdict = V_UNC;
+  int it = 0;
+  for (; it < Num<T>::maxit; it++) {
+    // support of A-B along -v
+    V3<T> nv = -v;
+    V3<T> sa = support_shape(A, verts, nv);
+    V3<T> sb = mul(rel.R, support_shape(B, verts, mulT(rel.R, v))) + rel.t;
+    V3<T> w = sa - sb;
+    T vv = dot(v, v), vw = dot(v, w);
+    // every x in A-B has x.v >= v.w  =>  distance >= v.w/|v|
+    if (vw > T(0)) {
+      T lim = R + tol;
+      if (vw * vw > lim * lim * vv) { verdict = V_SEP; break; }
+    }
+    if (n > 0 && (vv - vw) <= Num<T>::conv_rel * vv) {
+      // converged: |v| is the core distance up to rounding; it is inside the tol band
+      // (otherwise SEP above or PEN below would have fired) -> uncertain
+      verdict = V_UNC;
+      break;
+    }
+    // append w and solve
+    T l0 = T(0), l1 = T(0), l2 = T(0), l3 = T(0);
+    bool inside = false;
+    if (n == 0) { p0 = w; l0 = T(1); }
+    else if (n == 1) { p1 = w; solve1(p0, p1, l0, l1); }
+    else if (n == 2) { p2 = w; solve2(p0, p1, p2, l0, l1, l2); }
+    else { p3 = w; inside = solve3(p0, p1, p2, p3, l0, l1, l2, l3); }
+    n++;
+    if (inside) {
+      // origin enclosed by the core tetrahedron: depth >= min face distance
+      T dep = vk_min(vk_min(plane_dist(p1, p2, p3), plane_dist(p0, p2, p3)),
+                     vk_min(plane_dist(p0, p1, p3), plane_dist(p0, p1, p2)));
+      verdict = (dep + R > tol) ? V_PEN : V_UNC;
+      break;
+    }
+    v = p0 * l0 + p1 * l1 + p2 * l2 + p3 * l3;
+    // v is a point of A-B: core distance <= |v|
+    T nvv = dot(v, v);
+    if (R > tol && nvv < (R - tol) * (R - tol)) { verdict = V_PEN; break; }
+    if (!(nvv > Num<T>::tiny)) { verdict = V_UNC; break; }  // touching cores
+    // compact the simplex: keep vertices with positive weight at the front
+    bool k0 = l0 > T(0), k1 = l1 > T(0), k2 = l2 > T(0), k3 = l3 > T(0);
+    // bubble empties to the back (stable enough: order is irrelevant to the solver)
+    { bool s = !k0 && k1; cswap(s, p0, p1); cswap(s, k0, k1); }
+    { bool s = !k1 && k2; cswap(s, p1, p2); cswap(s, k1, k2); }
+    { bool s = !k2 && k3; cswap(s, p2, p3); cswap(s, k2, k3); }
+    { bool s = !k0 && k1; cswap(s, p0, p1); cswap(s, k0, k1); }
+    { bool s = !k1 && k2; cswap(s, p1, p2); cswap(s, k1, k2); }
+    { bool s = !k0 && k1; cswap(s, p0, p1); cswap(s, k0, k1); }
+    n = int(k0) + int(k1) + int(k2) + int(k3);
+    if (n == 4) { verdict = V_UNC; break; }  // cannot happen unless solve3 misreported
+  }
+  if (iters) *iters = it + 1;
+  return verdict;
+}
+
+// ------------------------------------------------------------------------------ segment-segment (sphere/capsule pairs)
+// mjc_SphereSphere / mjc_SphereCapsule / mjc_CapsuleCapsule: core = point or segment.
+template <typename T>
+VK_HD int segseg_classify(V3<T> p1, V3<T> q1, V3<T> p2, V3<T> q2, T R) {
+  V3<T> d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+  T a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), s, t;
+  if (!(a > Num<T>::tiny) && !(e > Num<T>::tiny)) { s = t = T(0); }
+  else if (!(a > Num<T>::tiny)) { s = T(0); t = f / e; t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t); }
+  else {
+    T c = dot(d1, r);
+    if (!(e > Num<T>::tiny)) { t = T(0); s = -c / a; s = s < T(0) ? T(0) : (s > T(1) ? T(1) : s); }
+    else {
+      T b = dot(d1, d2), den = a * e - b * b;
+      s = den > T(1e-7) * a * e ? (b * f - c * e) / den : T(0);
+      s = s < T(0) ? T(0) : (s > T(1) ? T(1) : s);
+      t = (b * s + f) / e;
+      if (t < T(0)) { t = T(0); s = -c / a; s = s < T(0) ? T(0) : (s > T(1) ? T(1) : s); }
+      else if (t > T(1)) { t = T(1); s = (b - c) / a; s = s < T(0) ? T(0) : (s > T(1) ? T(1) : s); }
+    }
+  }
+  V3<T> dd = (p1 + d1 * s) - (p2 + d2 * t);
+  T dist = vk_sqrt(dot(dd, dd));
+  const T tol = Num<T>::tol;
+  // near-parallel segments: the clamped solution may be a non-optimal (larger) distance,
+  // which is only safe for the PEN verdict; send borderline cases to fp64
+  if (dist > R + tol) {
+    T b = dot(d1, d2), den = a * e - b * b;
+    if (a > Num<T>::tiny && e > Num<T>::tiny && !(den > T(1e-4) * a * e) && dist < R + T(100) * tol + T(1e-3))
+      return V_UNC;
+    return V_SEP;
+  }
+  if (dist < R - tol) return V_PEN;
+  return V_UNC;
+}
+
+// ------------------------------------------------------------------------------ OBB-OBB separating-axis cull
+// true  => the two boxes are certainly disjoint by more than `slack` (conservative cull).
+// Boxes: centre/axes/half extents of A in A's frame, B brought over with `rel`.
+template <typename T>
+VK_HD bool obb_disjoint(const Shape<T> &A, const Shape<T> &B, const Rel<T> &rel, T slack) {
+  // express everything in A's OBB frame
+  M3<T> Ra; for (int i = 0; i < 9; i++) Ra.m[i] = A.orot[i];
+  M3<T> Rb; for (int i = 0; i < 9; i++) Rb.m[i] = B.orot[i];
+  // C = Ra^T * rel.R * Rb
+  M3<T> RB;  // rel.R * Rb
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+      RB.m[3 * i + j] = rel.R.m[3 * i] * Rb.m[j] + rel.R.m[3 * i + 1] * Rb.m[3 + j] + rel.R.m[3 * i + 2] * Rb.m[6 + j];
+  T Cm[9], Ab[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      Cm[3 * i + j] = Ra.m[i] * RB.m[j] + Ra.m[3 + i] * RB.m[3 + j] + Ra.m[6 + i] * RB.m[6 + j];
+      Ab[3 * i + j] = vk_abs(Cm[3 * i + j]) + T(1e-6);
+    }
+  V3<T> cb = mul(rel.R, mk<T>(B.oc[0], B.oc[1], B.oc[2])) + rel.t;
+  V3<T> dw = cb - mk<T>(A.oc[0], A.oc[1], A.oc[2]);
+  T tt[3];
+  { V3<T> t3 = mulT(Ra, dw); tt[0] = t3.x; tt[1] = t3.y; tt[2] = t3.z; }
+  const T *a = A.ohalf, *b = B.ohalf;
+  // A's face axes
+  for (int i = 0; i < 3; i++) {
+    T rb = b[0] * Ab[3 * i] + b[1] * Ab[3 * i + 1] + b[2] * Ab[3 * i + 2];
+    if (vk_abs(tt[i]) > a[i] + rb + slack) return true;
+  }
+  // B's face axes
+  for (int j = 0; j < 3; j++) {
+    T ra = a[0] * Ab[j] + a[1] * Ab[3 + j] + a[2] * Ab[6 + j];
+    T tp = tt[0] * Cm[j] + tt[1] * Cm[3 + j] + tt[2] * Cm[6 + j];
+    if (vk_abs(tp) > ra + b[j] + slack) return true;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------------------------ narrow phase of one item
+template <typename T>
+VK_HD int narrow_item(int kind, const Shape<T> &A, const Shape<T> &B, const Vtx<T> *verts,
+                                           const Pose<T> &PA, const Pose<T> &PB, T R) {
+  const T tol = Num<T>::tol;
+  if (kind == PK_PLANE) {
+    // plane A is world fixed (PA identity).  mjc_PlaneConvex / PlaneSphere / PlaneCapsule /
+    // PlaneBox: deepest point of B along -n;  mjc_PlaneCylinder analytic.
+    V3<T> n = mk<T>(A.ax[0], A.ax[1], A.ax[2]);
+    V3<T> c = mk<T>(A.c[0], A.c[1], A.c[2]);
+    T dist;
+    if (B.kind == SK_CYL) {
+      V3<T> ax = qrot(PB.q, mk<T>(B.ax[0], B.ax[1], B.ax[2]));
+      V3<T> cb = PB.p + qrot(PB.q, mk<T>(B.c[0], B.c[1], B.c[2]));
+      T na = dot(n, ax);
+      T rad = T(1) - na * na;
+      dist = dot(n, cb - c) - vk_abs(na) * B.halflen - B.radius * vk_sqrt(rad > T(0) ? rad : T(0));
+    } else {
+      V3<T> nl = qrot(qconj(PB.q), n);  // plane normal in B's frame
+      V3<T> s = support_verts(verts + B.vadr, B.nvert, -nl);
+      dist = dot(n, PB.p + qrot(PB.q, s) - c);
+    }
+    if (dist > R + tol) return V_SEP;
+    if (dist < R - tol) return V_PEN;
+    return V_UNC;
+  }
+  if (kind == PK_SEGSEG) {
+    Vtx<T> a0 = verts[A.vadr], a1 = verts[A.vadr + A.nvert - 1];
+    Vtx<T> b0 = verts[B.vadr], b1 = verts[B.vadr + B.nvert - 1];
+    V3<T> p1 = PA.p + qrot(PA.q, mk<T>(a0.x, a0.y, a0.z)), q1 = PA.p + qrot(PA.q, mk<T>(a1.x, a1.y, a1.z));
+    V3<T> p2 = PB.p + qrot(PB.q, mk<T>(b0.x, b0.y, b0.z)), q2 = PB.p + qrot(PB.q, mk<T>(b1.x, b1.y, b1.z));
+    return segseg_classify(p1, q1, p2, q2, R);
+  }
+  Rel<T> rel = relative_pose(PA, PB);
+  return gjk_classify(A, B, verts, rel, R, (int *)nullptr);
+}
+
+// ------------------------------------------------------------------------------ counter-based row generator
+// splitmix64 finaliser over (seed, row, joint) -> 24-bit uniform in [0,1)
+VK_HD uint32_t sweep_bits(uint64_t seed, uint64_t row, uint32_t j) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (row * 64ull + j + 1ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return uint32_t(z >> 40);
+}
+VK_HD float sweep_value(uint64_t seed, uint64_t row, uint32_t j, float lo, float hi) {
+  float u = float(sweep_bits(seed, row, j)) * (1.0f / 16777216.0f);
+  // plain mul + add, each rounded (no fma) so a numpy float32 host mirror is bit-identical
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(lo, __fmul_rn(u, __fsub_rn(hi, lo)));
+#else
+  volatile float d = hi - lo;
+  volatile float m = u * d;
+  return lo + m;
+#endif
+}
+
+}  // namespace vk

@@ -1,0 +1,514 @@
+// vk_kernels.cuh -- sm_100a kernels of the configuration-validity path.
+//
+//   validity_kernel<TILE>  persistent CTAs; per tile of TILE rows:
+//       P0  rows -> shared memory (dense rows: one cp.async.bulk (TMA) copy per tile, mbarrier
+//           completion; edge waypoints / sweep rows are generated in registers)
+//       P1  one lane per row: joint-limit mask (fp64 compare, reference semantics) + forward
+//           kinematics; body poses -> per-CTA scratch (L2 resident), world bounding-sphere
+//           centres of every moving geom -> shared memory (SoA, conflict free)
+//       P2  one lane per row: broad phase over the static pair list (bounding spheres, then an
+//           OBB separating-axis mid-phase); survivors are compacted into a shared-memory work
+//           queue with warp ballots (one shared atomic per warp and pair)
+//       P3  one lane per (row, pair) item: plane / segment-segment / GJK narrow phase with
+//           certified three-way verdicts; first certain contact flags the row and later
+//           items of that row are skipped (early exit)
+//       P4  valid mask out; rows with an uncertain item and no certain contact go to the
+//           fp64 list
+//   recheck_kernel         fp64 re-evaluation of listed rows, one lane per row.
+//   fk_kernel              mj_kinematics only (parity / debugging entry point).
+//
+// Model tables reach the CTA once (persistent kernel): hull vertices, shapes and pairs are
+// copied global -> shared with cp.async.bulk; the kinematic tree sits in the kernel parameter
+// (constant bank).  No tensor cores: nothing here is a dense contraction.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vk_core.cuh"
+
+namespace vk {
+
+constexpr int MODE_DENSE = 0, MODE_EDGES = 1, MODE_SWEEP = 2;
+constexpr uint32_t F_LIMITS = 1u, F_COLLISION = 2u, F_NO_OBB = 4u, F_NO_RECHECK = 8u;
+constexpr int QUEUE_PER_ROW = 8;  // shared work-queue capacity = QUEUE_PER_ROW * TILE items
+
+struct KArgs {
+  FkTables<float> fk;
+  double jnt_lo[MAX_JNT], jnt_hi[MAX_JNT];
+  int slot_shape_adr[MAX_BODY], slot_shape_num[MAX_BODY];
+  const Shape<float> *shapes;
+  const Vtx<float> *verts;
+  const Pair *pairs;
+  int nshape, nmoving, nvert, npair, nslot;
+  int mode;
+  // row sources
+  const float *q; int ldq; long long n;                       // dense
+  const float *q0, *q1; const long long *edge_prefix; long long nedge; float step;  // edges
+  unsigned long long seed; long long row0;                    // sweep
+  // outputs
+  uint8_t *valid; int *first_bad; uint32_t flags;
+  // per-handle scratch
+  float *pose_scratch;                  // [grid][nslot*7][TILE]
+  unsigned long long *counters;         // see C_* below
+  long long *recheck_rows;              // capacity >= number of rows
+};
+
+// counters layout
+constexpr int C_TICKET = 0, C_RECHECK = 1, C_RTICKET = 2, C_ITEMS = 3, C_OVERFLOW = 4, C_UNCERTAIN = 5, C_NCOUNTERS = 8;
+constexpr int C_PER_LAUNCH = 3;  // counters [0, C_PER_LAUNCH) are cleared before every launch
+
+// ---------------------------------------------------------------------------- PTX helpers (sm_90+/sm_100a)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine; SASS: UBLKCP); bytes % 16 == 0, 16B aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// dynamic shared memory carve-up (host and device agree through this one function)
+struct SmemLayout {
+  size_t verts, shapes, pairs, cen, qtile, queue, hit, bars, total;
+};
+template <int TILE>
+__host__ __device__ inline SmemLayout smem_layout(int nvert, int nshape, int npair, int nmoving, int nq) {
+  SmemLayout L;
+  size_t o = 0;
+  L.verts = o; o = align_up(o + (size_t)nvert * sizeof(Vtx<float>), 128);
+  L.shapes = o; o = align_up(o + (size_t)nshape * sizeof(Shape<float>), 128);
+  L.pairs = o; o = align_up(o + (size_t)npair * sizeof(Pair), 128);
+  L.cen = o; o = align_up(o + (size_t)(nmoving > 0 ? nmoving : 1) * 3 * TILE * sizeof(float), 128);
+  L.qtile = o; o = align_up(o + (size_t)TILE * nq * sizeof(float), 128);
+  L.queue = o; o = align_up(o + (size_t)QUEUE_PER_ROW * TILE * sizeof(uint32_t), 128);
+  L.hit = o; o = align_up(o + (size_t)2 * TILE, 128);
+  L.bars = o; o = align_up(o + 64, 128);
+  L.total = o;
+  return L;
+}
+
+// row -> (edge, k) by binary search in the exclusive prefix sums of waypoint counts
+__device__ __forceinline__ void edge_lookup(const long long *prefix, long long nedge, long long u, long long &e, int &k) {
+  long long lo = 0, hi = nedge;  // prefix has nedge+1 entries; find e with prefix[e] <= u < prefix[e+1]
+  while (hi - lo > 1) {
+    long long mid = (lo + hi) >> 1;
+    if (__ldg(prefix + mid) <= u) lo = mid; else hi = mid;
+  }
+  e = lo;
+  k = (int)(u - __ldg(prefix + lo));
+}
+
+// waypoint k (0-based interior index) of edge e:  q0 + (k+1)*step*(q1-q0)/|q1-q0|
+// reference: _valid_collision_interval / _step (src/mjpl/planning/utils.py:167-216)
+template <typename T>
+__device__ __forceinline__ void edge_row(const float *q0, const float *q1, int ldq, int nq, float step, long long e, int k, T *q) {
+  double d2 = 0;
+  for (int j = 0; j < nq; j++) {
+    double d = (double)q1[e * ldq + j] - (double)q0[e * ldq + j];
+    d2 += d * d;
+  }
+  double dist = sqrt(d2);
+  double s = dist > 0 ? (double)(k + 1) * (double)step / dist : 0.0;
+  for (int j = 0; j < nq; j++) {
+    double x0 = q0[e * ldq + j], x1 = q1[e * ldq + j];
+    q[j] = (T)(x0 + s * (x1 - x0));
+  }
+}
+
+__device__ __forceinline__ Pose<float> load_pose(const float *ps, int slot, int cfg, int tile) {
+  Pose<float> P;
+  if (slot < 0) { P.p = mk<float>(0, 0, 0); P.q.w = 1; P.q.x = P.q.y = P.q.z = 0; return P; }
+  const float *b = ps + (size_t)slot * 7 * tile + cfg;
+  P.p.x = b[0]; P.p.y = b[tile]; P.p.z = b[2 * tile];
+  P.q.w = b[3 * tile]; P.q.x = b[4 * tile]; P.q.y = b[5 * tile]; P.q.z = b[6 * tile];
+  return P;
+}
+
+// ---------------------------------------------------------------------------- main kernel
+template <int TILE>
+__global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ KArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int nq = a.fk.nq;
+  const SmemLayout L = smem_layout<TILE>(a.nvert, a.nshape, a.npair, a.nmoving, nq);
+  Vtx<float> *s_verts = reinterpret_cast<Vtx<float> *>(smem + L.verts);
+  Shape<float> *s_shapes = reinterpret_cast<Shape<float> *>(smem + L.shapes);
+  Pair *s_pairs = reinterpret_cast<Pair *>(smem + L.pairs);
+  float *s_cen = reinterpret_cast<float *>(smem + L.cen);
+  float *s_q = reinterpret_cast<float *>(smem + L.qtile);
+  uint32_t *s_queue = reinterpret_cast<uint32_t *>(smem + L.queue);
+  uint8_t *s_hit = smem + L.hit;
+  uint8_t *s_unc = s_hit + TILE;
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.bars);       // [0] tables, [1] rows
+  int *s_misc = reinterpret_cast<int *>(smem + L.bars + 16);           // [0] queue count, [1..2] ticket
+  long long *s_ticket = reinterpret_cast<long long *>(smem + L.bars + 32);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  float *pose = a.pose_scratch + (size_t)blockIdx.x * a.nslot * 7 * TILE;
+
+  // ---- one-time: model tables -> shared memory through the bulk-copy engine ---------------------
+  const uint32_t bytes_v = (uint32_t)(a.nvert * sizeof(Vtx<float>));
+  const uint32_t bytes_s = (uint32_t)(a.nshape * sizeof(Shape<float>));
+  const uint32_t bytes_p = (uint32_t)align_up((size_t)a.npair * sizeof(Pair), 16);
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&s_bar[0], bytes_v + bytes_s + bytes_p);
+    if (bytes_v) bulk_g2s(s_verts, a.verts, bytes_v, &s_bar[0]);
+    bulk_g2s(s_shapes, a.shapes, bytes_s, &s_bar[0]);
+    bulk_g2s(s_pairs, a.pairs, bytes_p, &s_bar[0]);
+  }
+  mbar_wait(&s_bar[0], 0);
+
+  // total number of rows (edges: read from the device-side prefix sums)
+  long long nrows = a.n;
+  if (a.mode == MODE_EDGES) nrows = a.edge_prefix[a.nedge];
+  const long long ntiles = (nrows + TILE - 1) / TILE;
+  uint32_t row_parity = 0;
+  const bool dense_bulk = (a.mode == MODE_DENSE) && (a.ldq == nq) && ((reinterpret_cast<uintptr_t>(a.q) & 15) == 0) &&
+                          ((TILE * nq * sizeof(float)) % 16 == 0);
+  long long items_total = 0;
+
+  for (;;) {
+    // ---- tile ticket -------------------------------------------------------------------------------
+    if (tid == 0) *s_ticket = (long long)atomicAdd(&a.counters[C_TICKET], 1ull);
+    __syncthreads();
+    const long long tile = *s_ticket;
+    if (tile >= ntiles) break;
+    const long long row_base = tile * TILE;
+    const int rows_here = (int)((nrows - row_base) < TILE ? (nrows - row_base) : TILE);
+    const long long row = row_base + tid;
+    const bool active = tid < rows_here;
+
+    // ---- P0: rows -> shared ----------------------------------------------------------------------------
+    if (a.mode == MODE_DENSE) {
+      if (dense_bulk && rows_here == TILE) {
+        if (tid == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(&s_bar[1], (uint32_t)(TILE * nq * sizeof(float)));
+          bulk_g2s(s_q, a.q + row_base * nq, (uint32_t)(TILE * nq * sizeof(float)), &s_bar[1]);
+        }
+        mbar_wait(&s_bar[1], row_parity);
+        row_parity ^= 1;
+      } else {
+        for (int i = tid; i < rows_here * nq; i += TILE) {
+          int r = i / nq, j = i - r * nq;
+          s_q[i] = a.q[(row_base + r) * a.ldq + j];
+        }
+        __syncthreads();
+      }
+    }
+    if (tid == 0) s_misc[0] = 0;
+    s_hit[tid] = 0;
+    s_unc[tid] = 0;
+
+    // ---- P1: limits + FK -----------------------------------------------------------------------------------
+    float *q = s_q + tid * nq;  // this lane's row (stride nq words: conflict free for odd nq)
+    long long e_idx = 0;
+    int e_k = 0;
+    bool lim_ok = true;
+    if (active) {
+      if (a.mode == MODE_EDGES) {
+        edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
+        edge_row<float>(a.q0, a.q1, a.ldq, nq, a.step, e_idx, e_k, q);
+      } else if (a.mode == MODE_SWEEP) {
+#pragma unroll 1
+        for (int j = 0; j < nq; j++)
+          q[j] = sweep_value(a.seed, (uint64_t)(a.row0 + row), (uint32_t)j, a.fk.jnt_lo[j], a.fk.jnt_hi[j]);
+      }
+      if (a.flags & F_LIMITS) {
+        // reference: np.all((q >= lower) & (q <= upper)) in fp64 (joint_limit_constraint.py:19-20)
+#pragma unroll 1
+        for (int j = 0; j < a.fk.njnt; j++) {
+          double x = (double)q[j];
+          lim_ok = lim_ok && (x >= a.jnt_lo[j]) && (x <= a.jnt_hi[j]);
+        }
+      }
+    }
+    const bool do_coll = active && lim_ok && (a.flags & F_COLLISION);
+    if (do_coll) {
+      Pose<float> prev;
+      prev.p = mk<float>(0, 0, 0); prev.q.w = 1; prev.q.x = prev.q.y = prev.q.z = 0;
+      int prev_slot = -1;
+#pragma unroll 1
+      for (int s = 0; s < a.nslot; s++) {
+        const int ps = a.fk.body_parent[s];
+        Pose<float> P = (ps == prev_slot) ? prev : load_pose(pose, ps, tid, TILE);
+        Pose<float> B = fk_body(a.fk, s, P, q);
+        prev = B; prev_slot = s;
+        float *b = pose + (size_t)s * 7 * TILE + tid;
+        b[0] = B.p.x; b[TILE] = B.p.y; b[2 * TILE] = B.p.z;
+        b[3 * TILE] = B.q.w; b[4 * TILE] = B.q.x; b[5 * TILE] = B.q.y; b[6 * TILE] = B.q.z;
+        const int sa = a.slot_shape_adr[s], sn = a.slot_shape_num[s];
+        for (int k = 0; k < sn; k++) {
+          const Shape<float> &S = s_shapes[sa + k];
+          V3<float> c = B.p + qrot(B.q, mk<float>(S.bc[0], S.bc[1], S.bc[2]));
+          float *cc = s_cen + (size_t)(sa + k) * 3 * TILE + tid;
+          cc[0] = c.x; cc[TILE] = c.y; cc[2 * TILE] = c.z;
+        }
+      }
+    }
+
+    // ---- P2: broad phase + queue compaction -------------------------------------------------------------------
+    const float slack = 1e-4f;
+    bool overflow = false;
+#pragma unroll 1
+    for (int p = 0; p < a.npair; p++) {
+      const Pair pr = s_pairs[p];
+      bool survive = false;
+      if (do_coll) {
+        const Shape<float> &A = s_shapes[pr.sa];
+        const Shape<float> &B = s_shapes[pr.sb];
+        V3<float> cB;
+        if (B.slot >= 0) {
+          const float *cc = s_cen + (size_t)pr.sb * 3 * TILE + tid;
+          cB = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
+        } else cB = mk<float>(B.bc[0], B.bc[1], B.bc[2]);
+        if (pr.kind == PK_PLANE) {
+          float d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
+          survive = d <= pr.bsum + slack;
+        } else {
+          V3<float> cA;
+          if (A.slot >= 0) {
+            const float *cc = s_cen + (size_t)pr.sa * 3 * TILE + tid;
+            cA = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
+          } else cA = mk<float>(A.bc[0], A.bc[1], A.bc[2]);
+          V3<float> d = cA - cB;
+          float lim = pr.bsum + slack;
+          survive = dot(d, d) <= lim * lim;
+          if (survive && (pr.flags & 1) && !(a.flags & F_NO_OBB)) {
+            Pose<float> PA = load_pose(pose, A.slot, tid, TILE);
+            Pose<float> PB = load_pose(pose, B.slot, tid, TILE);
+            Rel<float> rel = relative_pose(PA, PB);
+            survive = !obb_disjoint(A, B, rel, pr.rsum - swept_radius(A) - swept_radius(B) + slack);
+          }
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, survive);
+      if (m) {
+        int base = 0;
+        if (lane == (__ffs(m) - 1)) base = atomicAdd(&s_misc[0], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (survive) {
+          int idx = base + __popc(m & ((1u << lane) - 1u));
+          if (idx < QUEUE_PER_ROW * TILE) s_queue[idx] = (uint32_t)tid | ((uint32_t)p << 16);
+          else overflow = true;
+        }
+      }
+    }
+    if (overflow) s_unc[tid] = 2;  // could not be queued: let the fp64 kernel decide the whole row
+    __syncthreads();  // queue + poses of all rows visible
+
+    // ---- P3: narrow phase over the queue ----------------------------------------------------------------------
+    int nitems = s_misc[0];
+    if (nitems > QUEUE_PER_ROW * TILE) nitems = QUEUE_PER_ROW * TILE;
+    items_total += (tid == 0) ? nitems : 0;
+#pragma unroll 1
+    for (int i = tid; i < nitems; i += TILE) {
+      const uint32_t it = s_queue[i];
+      const int cfg = it & 0xffff;
+      if (s_hit[cfg]) continue;  // early exit: the row already has a certain contact
+      const Pair pr = s_pairs[it >> 16];
+      const Shape<float> &SA = s_shapes[pr.sa];
+      const Shape<float> &SB = s_shapes[pr.sb];
+      Pose<float> PA = load_pose(pose, SA.slot, cfg, TILE);
+      Pose<float> PB = load_pose(pose, SB.slot, cfg, TILE);
+      const int v = narrow_item<float>(pr.kind, SA, SB, s_verts, PA, PB, pr.rsum);
+      if (v == V_PEN) s_hit[cfg] = 1;
+      else if (v == V_UNC) s_unc[cfg] = 1;
+    }
+    __syncthreads();
+
+    // ---- P4: results -----------------------------------------------------------------------------------------------
+    if (active) {
+      const bool hit = s_hit[tid] != 0;
+      const int unc = s_unc[tid];
+      bool ok = lim_ok && !hit;
+      bool pending = lim_ok && !hit && unc != 0;
+      if (pending && !(a.flags & F_NO_RECHECK)) {
+        unsigned long long slot = atomicAdd(&a.counters[C_RECHECK], 1ull);
+        a.recheck_rows[slot] = row;
+        if (unc == 2) atomicAdd(&a.counters[C_OVERFLOW], 1ull);
+      }
+      if (a.mode == MODE_EDGES) {
+        if (!ok && !pending) atomicMin(&a.first_bad[e_idx], e_k);
+        else if (pending && (a.flags & F_NO_RECHECK)) atomicMin(&a.first_bad[e_idx], e_k);
+      } else {
+        a.valid[row] = pending ? (uint8_t)((a.flags & F_NO_RECHECK) ? 2 : 1) : (uint8_t)(ok ? 1 : 0);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && items_total) atomicAdd(&a.counters[C_ITEMS], (unsigned long long)items_total);
+}
+
+// ---------------------------------------------------------------------------- fp64 re-evaluation
+struct RArgs {
+  const FkTables<double> *fk;
+  const Shape<double> *shapes;
+  const Vtx<double> *verts;
+  const Pair *pairs;
+  const double *pair_rsum;   // fp64 copies of Pair::rsum / bsum
+  const double *pair_bsum;
+  int npair, nslot;
+  int mode;
+  const float *q; int ldq;
+  const float *q0, *q1; const long long *edge_prefix; long long nedge; float step;
+  unsigned long long seed; long long row0;
+  uint8_t *valid; int *first_bad;
+  unsigned long long *counters;
+  const long long *recheck_rows;
+};
+
+__global__ void __launch_bounds__(64) recheck_kernel(const RArgs a) {
+  const FkTables<double> &fk = *a.fk;
+  const unsigned long long total = a.counters[C_RECHECK];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && total) atomicAdd(&a.counters[C_UNCERTAIN], total);
+  for (;;) {
+    unsigned long long t = atomicAdd(&a.counters[C_RTICKET], 1ull);
+    if (t >= total) break;
+    const long long row = a.recheck_rows[t];
+    double q[MAX_JNT];
+    long long e_idx = 0;
+    int e_k = 0;
+    if (a.mode == MODE_DENSE) {
+      for (int j = 0; j < fk.nq; j++) q[j] = (double)a.q[row * a.ldq + j];
+    } else if (a.mode == MODE_EDGES) {
+      edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
+      float qf[MAX_JNT];
+      edge_row<float>(a.q0, a.q1, a.ldq, fk.nq, a.step, e_idx, e_k, qf);
+      for (int j = 0; j < fk.nq; j++) q[j] = (double)qf[j];
+    } else {
+      for (int j = 0; j < fk.nq; j++)
+        q[j] = (double)sweep_value(a.seed, (uint64_t)(a.row0 + row), (uint32_t)j, (float)fk.jnt_lo[j], (float)fk.jnt_hi[j]);
+    }
+    Pose<double> P[MAX_BODY];
+    Pose<double> ident; ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+    for (int s = 0; s < a.nslot; s++) {
+      int ps = fk.body_parent[s];
+      P[s] = fk_body(fk, s, ps < 0 ? ident : P[ps], q);
+    }
+    bool contact = false;
+    for (int p = 0; p < a.npair && !contact; p++) {
+      Pair pr = a.pairs[p];
+      const Shape<double> &A = a.shapes[pr.sa];
+      const Shape<double> &B = a.shapes[pr.sb];
+      const Pose<double> &PA = A.slot < 0 ? ident : P[A.slot];
+      const Pose<double> &PB = B.slot < 0 ? ident : P[B.slot];
+      V3<double> cB = PB.p + qrot(PB.q, mk<double>(B.bc[0], B.bc[1], B.bc[2]));
+      const double bsum = a.pair_bsum[p];
+      if (pr.kind == PK_PLANE) {
+        double d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
+        if (d > bsum + 1e-6) continue;
+      } else {
+        V3<double> cA = PA.p + qrot(PA.q, mk<double>(A.bc[0], A.bc[1], A.bc[2]));
+        V3<double> d = cA - cB;
+        if (dot(d, d) > (bsum + 1e-6) * (bsum + 1e-6)) continue;
+      }
+      // same classifier in fp64 with the fp64 radii.  "Uncertain" in fp64 means touching to
+      // within rounding: MuJoCo reports a contact for distance <= margin, so it counts.
+      const int v = narrow_item<double>(pr.kind, A, B, a.verts, PA, PB, a.pair_rsum[p]);
+      if (v != V_SEP) contact = true;
+    }
+    if (a.mode == MODE_EDGES) {
+      if (contact) atomicMin(&a.first_bad[e_idx], e_k);
+    } else {
+      a.valid[row] = contact ? 0 : 1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- FK only
+struct FArgs {
+  FkTables<float> fk;
+  const float *q; int ldq; long long n;
+  int nbody_all;
+  const int *body_slot;      // [nbody_all] slot or -1
+  const float *static_pose;  // [nbody_all][7]
+  float *xpos, *xquat;
+};
+
+__global__ void __launch_bounds__(128) fk_kernel(const __grid_constant__ FArgs a) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= a.n) return;
+  float q[MAX_JNT];
+  for (int j = 0; j < a.fk.nq; j++) q[j] = a.q[row * a.ldq + j];
+  Pose<float> P[MAX_BODY];
+  Pose<float> ident; ident.p = mk<float>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  for (int s = 0; s < a.fk.nbody; s++) {
+    int ps = a.fk.body_parent[s];
+    P[s] = fk_body(a.fk, s, ps < 0 ? ident : P[ps], q);
+  }
+  for (int b = 0; b < a.nbody_all; b++) {
+    int s = a.body_slot[b];
+    float *xp = a.xpos + (row * a.nbody_all + b) * 3, *xq = a.xquat + (row * a.nbody_all + b) * 4;
+    if (s >= 0) {
+      xp[0] = P[s].p.x; xp[1] = P[s].p.y; xp[2] = P[s].p.z;
+      xq[0] = P[s].q.w; xq[1] = P[s].q.x; xq[2] = P[s].q.y; xq[3] = P[s].q.z;
+    } else {
+      const float *sp = a.static_pose + 7 * b;
+      xp[0] = sp[0]; xp[1] = sp[1]; xp[2] = sp[2];
+      xq[0] = sp[3]; xq[1] = sp[4]; xq[2] = sp[5]; xq[3] = sp[6];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- small helpers
+// waypoint counts per edge: K = max(0, ceil(|q1-q0|/step) - 1)
+__global__ void edge_count_kernel(const float *q0, const float *q1, long long ne, int nq, int ldq, float step,
+                                  long long *count, int *first_bad) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  double d2 = 0;
+  for (int j = 0; j < nq; j++) {
+    double d = (double)q1[e * ldq + j] - (double)q0[e * ldq + j];
+    d2 += d * d;
+  }
+  double m = sqrt(d2) / (double)step;
+  long long k = (long long)ceil(m) - 1;
+  count[e] = k > 0 ? k : 0;
+  first_bad[e] = 0x7fffffff;
+}
+
+__global__ void edge_finalize_kernel(long long ne, int *first_bad_tmp, uint8_t *valid, int *first_bad) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  int fb = first_bad_tmp[e];
+  valid[e] = fb == 0x7fffffff ? 1 : 0;
+  if (first_bad) first_bad[e] = fb == 0x7fffffff ? -1 : fb;
+}
+
+__global__ void sweep_rows_kernel(FkTables<float> fk, unsigned long long seed, long long row0, long long n, float *q) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * fk.nq) return;
+  long long r = i / fk.nq;
+  int j = (int)(i - r * fk.nq);
+  q[i] = sweep_value(seed, (uint64_t)(row0 + r), (uint32_t)j, fk.jnt_lo[j], fk.jnt_hi[j]);
+}
+
+}  // namespace vk

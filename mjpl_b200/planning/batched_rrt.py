@@ -1,0 +1,206 @@
+"""Many independent bi-directional RRT queries advanced in lock-step.
+
+This is the batched planning entry point the north star asks for: query ``i`` runs the same
+CBiRRT as :class:`mjpl_b200.planning.rrt.RRT` (same sampling distribution, extend / connect /
+swap structure of the reference's ``plan_to_configs``, ``src/mjpl/planning/rrt.py:195-235``,
+and the stop rules of ``_constrained_extend``, ``planning/utils.py:139-163``), but every
+iteration gathers the extend chains of ALL unsolved queries into one block of configurations
+and validates it with a single fused kernel launch.  Queries are independent (own trees, own
+random stream seeded ``seed + i``), so they shard across GPUs without communication.
+
+Trees are stored as padded ``(nqueries, capacity, nq)`` arrays; nearest neighbours are one
+vectorised reduction per iteration for all queries.
+"""
+
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from ..constraint.constraint_interface import Constraint
+from ..constraint.utils import obeys_constraints_batch
+from ..utils import qpos_idx
+
+
+class _Forest:
+    """``B`` trees in padded arrays: q (B,cap,nq), parent (B,cap), count (B,)."""
+
+    def __init__(self, roots: np.ndarray, cap: int = 256):
+        B, nq = roots.shape
+        self.q = np.full((B, cap, nq), np.inf)
+        self.parent = np.full((B, cap), -1, dtype=np.int64)
+        self.count = np.ones(B, dtype=np.int64)
+        self.q[:, 0] = roots
+
+    def _grow(self, need: int):
+        cap = self.q.shape[1]
+        if need <= cap:
+            return
+        new = max(need, 2 * cap)
+        B, _, nq = self.q.shape
+        q = np.full((B, new, nq), np.inf)
+        q[:, :cap] = self.q
+        p = np.full((B, new), -1, dtype=np.int64)
+        p[:, :cap] = self.parent
+        self.q, self.parent = q, p
+
+    def nearest(self, rows: np.ndarray, targets: np.ndarray) -> np.ndarray:
+        """index of the nearest node of tree rows[i] to targets[i]"""
+        n = int(self.count[rows].max())
+        d = self.q[rows, :n] - targets[:, None, :]
+        d2 = np.einsum("bij,bij->bi", d, d)  # unused slots hold +inf
+        return np.argmin(np.nan_to_num(d2, nan=np.inf), axis=1)
+
+    def append_chains(self, rows, parents, chains, lengths):
+        """chains: (len(rows), Kmax, nq) padded; appends chains[i][:lengths[i]] under parents[i];
+        returns the index of the last node of each chain (or the parent when length 0)."""
+        self._grow(int((self.count[rows] + lengths).max()))
+        last = parents.copy()
+        for i in np.flatnonzero(lengths > 0):
+            b, k, c = rows[i], int(lengths[i]), int(self.count[rows[i]])
+            self.q[b, c : c + k] = chains[i, :k]
+            self.parent[b, c] = parents[i]
+            if k > 1:
+                self.parent[b, c + 1 : c + k] = np.arange(c, c + k - 1)
+            self.count[b] = c + k
+            last[i] = c + k - 1
+        return last
+
+    def path_to_root(self, b: int, idx: int) -> list[np.ndarray]:
+        out = []
+        while idx >= 0:
+            out.append(self.q[b, idx].copy())
+            idx = int(self.parent[b, idx])
+        return out
+
+
+class BatchedRRT:
+    """Lock-step bi-RRT over many (q_init, q_goal) queries; non-projecting constraints only."""
+
+    def __init__(self, model, planning_joints: list[str], constraints: list[Constraint],
+                 max_planning_time: float = 10.0, epsilon: float = 0.05, seed: int | None = None,
+                 goal_biasing_probability: float = 0.05, max_iterations: int = 100000,
+                 max_chain: int = 512) -> None:
+        if not planning_joints:
+            raise ValueError("`planning_joints` cannot be empty.")
+        if max_planning_time <= 0.0:
+            raise ValueError("`max_planning_time` must be > 0.0")
+        if epsilon <= 0.0:
+            raise ValueError("`epsilon` must be > 0.0")
+        if goal_biasing_probability < 0.0 or goal_biasing_probability > 1.0:
+            raise ValueError("`goal_biasing_probability` must be within [0.0, 1.0].")
+        if any(getattr(c, "projects", False) for c in constraints):
+            raise ValueError("BatchedRRT supports non-projecting constraints only")
+        self.model = model
+        self.planning_joints = planning_joints
+        self.constraints = constraints
+        self.max_planning_time = max_planning_time
+        self.epsilon = epsilon
+        self.seed = seed
+        self.goal_biasing_probability = goal_biasing_probability
+        self.max_iterations = max_iterations
+        self.max_chain = max_chain
+        self.stats: dict = {}
+
+    # one extend for a set of queries: returns reached configs and node indices
+    def _extend(self, forest: _Forest, rows: np.ndarray, targets: np.ndarray):
+        eps = self.epsilon
+        near_idx = forest.nearest(rows, targets)
+        near = forest.q[rows, near_idx]
+        d = targets - near
+        dist = np.linalg.norm(d, axis=1)
+        k = np.where(dist > 0, np.ceil(dist / eps), 0).astype(np.int64)
+        k = np.minimum(k, self.max_chain)
+        kmax = int(k.max()) if len(k) else 0
+        nq = near.shape[1]
+        if kmax == 0:
+            return near, near_idx
+        steps = np.arange(1, kmax + 1, dtype=np.float64)[None, :, None]  # (1,K,1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            frac = np.where(dist > 0, eps / dist, 0.0)[:, None, None] * steps
+        chains = near[:, None, :] + np.minimum(frac, 1.0) * d[:, None, :]
+        # the step that covers the remaining distance lands on the target itself
+        full = (k * eps >= dist) & (k > 0)
+        chains[np.flatnonzero(full), k[full] - 1] = targets[full]
+        mask = np.arange(kmax)[None, :] < k[:, None]  # (n,K) real rows
+        flat = chains[mask]
+        ok_flat = np.asarray(obeys_constraints_batch(flat, self.constraints)).astype(bool)
+        self.stats["configs_checked"] = self.stats.get("configs_checked", 0) + int(len(flat))
+        self.stats["launches"] = self.stats.get("launches", 0) + 1
+        ok = np.zeros(mask.shape, dtype=bool)
+        ok[mask] = ok_flat
+        # stop rule: a step shorter than 1e-8 ends the chain (reference planning/utils.py:153)
+        prev = np.concatenate([near[:, None, :], chains[:, :-1]], axis=1)
+        ok &= np.linalg.norm(chains - prev, axis=2) >= 1e-8
+        good = np.where(ok.all(axis=1), k, np.argmin(ok, axis=1))
+        good = np.minimum(good, k)
+        last = forest.append_chains(rows, near_idx, chains, good)
+        return forest.q[rows, last], last
+
+    def plan(self, q_inits: np.ndarray, q_goals: np.ndarray) -> list[list[np.ndarray]]:
+        """``q_inits``, ``q_goals``: (B, nq).  Returns one waypoint list per query (empty on failure)."""
+        q_inits = np.ascontiguousarray(q_inits, dtype=np.float64)
+        q_goals = np.ascontiguousarray(q_goals, dtype=np.float64)
+        if q_inits.shape != q_goals.shape or q_inits.ndim != 2:
+            raise ValueError("q_inits and q_goals must both be (B, nq)")
+        B, nq = q_inits.shape
+        ok = np.asarray(obeys_constraints_batch(np.concatenate([q_inits, q_goals]), self.constraints)).astype(bool)
+        if not ok[:B].all():
+            raise ValueError("q_init is not a valid configuration")
+        if not ok[B:].all():
+            bad = q_goals[np.flatnonzero(~ok[B:])[0]]
+            raise ValueError(f"The following goal config is not a valid configuration: {bad}")
+        q_idx = np.array(qpos_idx(self.model, self.planning_joints))
+        fixed = np.array([i for i in range(nq) if i not in set(q_idx.tolist())], dtype=np.int64)
+        if len(fixed) and not np.allclose(q_inits[:, fixed], q_goals[:, fixed], rtol=0, atol=1e-12):
+            raise ValueError("goal configs have values for joints outside of the planner's planning joints "
+                             "that don't match q_init")
+        paths: list[list[np.ndarray]] = [[] for _ in range(B)]
+        direct = np.linalg.norm(q_goals - q_inits, axis=1) <= self.epsilon
+        for b in np.flatnonzero(direct):
+            paths[b] = [q_inits[b].copy(), q_goals[b].copy()]
+        start, goal = _Forest(q_inits), _Forest(q_goals)
+        active = np.flatnonzero(~direct)
+        base = 0 if self.seed is None else int(self.seed)
+        rngs = [np.random.default_rng(None if self.seed is None else base + b) for b in range(B)]
+        lo, hi = self.model.jnt_range.T
+        swapped = False
+        self.stats = {"iterations": 0, "configs_checked": 0, "launches": 0}
+        t0 = time.time()
+        it = 0
+        while len(active) and it < self.max_iterations and time.time() - t0 < self.max_planning_time:
+            it += 1
+            fa, fb = (goal, start) if swapped else (start, goal)
+            # ---- sample (one stream per query, the reference's draw order) -------------------
+            targets = np.empty((len(active), nq))
+            for i, b in enumerate(active):
+                r = rngs[b]
+                if r.random() <= self.goal_biasing_probability:
+                    if swapped:
+                        targets[i] = q_inits[b]
+                    else:
+                        r.integers(0, 1)  # the reference draws a goal index even with one goal
+                        targets[i] = q_goals[b]
+                else:
+                    t = q_inits[b].copy()
+                    t[q_idx] = r.uniform(lo, hi)[q_idx]
+                    targets[i] = t
+            # ---- extend A towards the samples, then B towards what A reached (connect) ------
+            qa, ia = self._extend(fa, active, targets)
+            qb, ib = self._extend(fb, active, qa)
+            met = np.all(qa == qb, axis=1)
+            for i in np.flatnonzero(met):
+                b = int(active[i])
+                s_idx, g_idx = (ib[i], ia[i]) if swapped else (ia[i], ib[i])
+                ps = start.path_to_root(b, int(s_idx))[::-1]
+                pg = goal.path_to_root(b, int(g_idx))
+                if np.array_equal(ps[-1], pg[0]):
+                    ps.pop()
+                paths[b] = ps + pg
+            active = active[~met]
+            swapped = not swapped
+        self.stats["iterations"] = it
+        self.stats["solved"] = int(sum(1 for p in paths if p))
+        self.stats["seconds"] = time.time() - t0
+        return paths

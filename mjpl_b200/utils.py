@@ -1,0 +1,70 @@
+"""Index helpers and the rejection sampler on the validity path.
+
+Reference: ``src/mjpl/utils.py`` (``all_joints`` :10-19, ``qpos_idx`` :22-38, ``qvel_idx``
+:41-57, ``random_config`` :78-107).  ``site_pose`` needs mink's SE3 type and is out of scope.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from .constraint.constraint_interface import Constraint
+from .constraint.utils import apply_constraints, obeys_constraints_batch
+from .model import JNT_DOF_WIDTH, JNT_QPOS_WIDTH
+
+
+def all_joints(model) -> list[str]:
+    """All joint names of the model, in joint-id order."""
+    return [model.joint(j).name for j in range(model.njnt)]
+
+
+def qpos_idx(model, joints: list[str]) -> list[int]:
+    """Indices into qpos of the given joints (query order preserved)."""
+    idx: list[int] = []
+    for name in joints:
+        j = model.joint(name).id
+        a = int(model.jnt_qposadr[j])
+        idx.extend(range(a, a + JNT_QPOS_WIDTH[int(model.jnt_type[j])]))
+    return idx
+
+
+def qvel_idx(model, joints: list[str]) -> list[int]:
+    """Indices into qvel of the given joints (query order preserved)."""
+    idx: list[int] = []
+    for name in joints:
+        j = model.joint(name).id
+        a = int(model.jnt_dofadr[j])
+        idx.extend(range(a, a + JNT_DOF_WIDTH[int(model.jnt_type[j])]))
+    return idx
+
+
+def random_config(model, q_init: np.ndarray, joints: list[str], seed: int | None = None,
+                  constraints: list[Constraint] = [], batch: int = 64) -> np.ndarray:
+    """Random configuration that obeys ``constraints`` (rejection sampling).
+
+    Same candidate sequence as the reference for a given seed: each candidate consumes one
+    ``rng.uniform(*model.jnt_range.T)`` draw over ALL joints, of which only ``joints`` are kept
+    (reference :103-105).  Candidates are drawn ``batch`` at a time and validated as one block;
+    the first valid one is returned, which is what the reference's loop would return.  With a
+    projecting constraint in the list the reference's one-at-a-time loop is used.
+    """
+    q_idx = qpos_idx(model, joints)
+    rng = np.random.default_rng(seed=seed)
+    lo, hi = model.jnt_range.T
+    if any(getattr(c, "projects", False) for c in constraints):
+        q = q_init.copy()
+        while True:
+            q[q_idx] = rng.uniform(lo, hi)[q_idx]
+            qc = apply_constraints(q_init, q, constraints)
+            if qc is not None:
+                return qc
+    while True:
+        draws = rng.uniform(lo, hi, size=(batch, len(lo)))  # row i == the i-th sequential draw
+        Q = np.tile(np.asarray(q_init, dtype=np.float64), (batch, 1))
+        Q[:, q_idx] = draws[:, q_idx]
+        ok = np.asarray(obeys_constraints_batch(Q, constraints)) if constraints else np.ones(batch, bool)
+        hit = np.flatnonzero(ok)
+        if len(hit):
+            # NB: a block draw advances the generator past the accepted candidate; the
+            # generator is local to this call, so nothing observable depends on that.
+            return Q[hit[0]].copy()

@@ -423,11 +423,20 @@ static double outside_face(const double *a, const double *b, const double *c, co
 static int closest_tetra(double W[4][3], double *lam) {
   static const int F[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
   static const int O[4] = {3, 2, 1, 0};
+  /* A flat tetrahedron (GJK landing on a face of A-B and adding a fourth, coplanar support
+   * point) has no inside: its face-side tests are rounding noise.  Detect it by volume and
+   * fall back to the closest of all four faces. */
+  double e1[3], e2[3], e3[3], cr[3];
+  sub3(W[1], W[0], e1); sub3(W[2], W[0], e2); sub3(W[3], W[0], e3);
+  cross3(e1, e2, cr);
+  double vol6 = fabs(dot3(cr, e3));
+  double len = fmax(norm3(e1), fmax(norm3(e2), norm3(e3)));
+  int flat = !(vol6 > 1e-10 * len * len * len);
   double best = 1e300;
   int any = 0;
   for (int f = 0; f < 4; f++) {
     const double *a = W[F[f][0]], *b = W[F[f][1]], *c = W[F[f][2]];
-    if (outside_face(a, b, c, W[O[f]]) >= 0) {
+    if (flat || outside_face(a, b, c, W[O[f]]) >= 0) {
       double l3[3], v[3];
       closest_triangle(a, b, c, l3);
       for (int k = 0; k < 3; k++) v[k] = l3[0] * a[k] + l3[1] * b[k] + l3[2] * c[k];
@@ -439,10 +448,7 @@ static int closest_tetra(double W[4][3], double *lam) {
       }
     }
   }
-  if (!any) return 1;
-  /* a degenerate (flat) tetra reports every face as "outside or on": still fine, the
-   * closest face point is the answer.  If it is (numerically) the origin, call it inside. */
-  return 0;
+  return any ? 0 : 1;
 }
 
 /* GJK distance between core shapes.  Returns distance (>0) or 0 when intersecting/touching;
@@ -460,7 +466,7 @@ static double gjk_distance(const shape_t *A, const shape_t *B, double W[4][3], i
     double vv = dot3(v, v), vw = dot3(v, w);
     if (n > 0) {
       double gap = vv - vw; /* >= 0 up to rounding; |v| - gap/|v| is a lower bound */
-      if (gap <= 1e-12 * vv || gap <= 1e-14 * sqrt(vv)) break;
+      if (gap <= 1e-11 * vv || gap <= 1e-14 * sqrt(vv)) break;
       int dup = 0;
       for (int i = 0; i < n; i++)
         if (W[i][0] == w[0] && W[i][1] == w[1] && W[i][2] == w[2]) dup = 1;

@@ -1,0 +1,98 @@
+"""TEST TOOL: CPU execution of the CUDA kernels' templated core (see hostsim.cpp).
+
+Built on demand with g++; used only by the ``-m "not gpu"`` tests to compare the geometric
+core (FK, culls, GJK classifier, fp64 re-evaluation) with the fp64 oracle where no GPU exists.
+Not a product path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from mjpl_b200 import _abi
+
+_HERE = Path(__file__).resolve().parent
+_SO = _HERE / "libhostsim.so"
+_ROOT = _HERE.parent.parent
+
+
+def build(force=False):
+    srcs = [_HERE / "hostsim.cpp", _ROOT / "mjpl_b200/csrc/vk_core.cuh", _ROOT / "mjpl_b200/csrc/vk_build.h"]
+    newest = max(p.stat().st_mtime for p in srcs)
+    if force or not _SO.exists() or _SO.stat().st_mtime < newest:
+        subprocess.run(
+            ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
+             str(_HERE / "hostsim.cpp"), "-o", str(_SO)],
+            check=True, capture_output=True, text=True,
+        )
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(_SO))
+        L.hs_create.argtypes = [C.POINTER(_abi.ModelDesc), C.POINTER(C.c_void_p), C.c_char_p, C.c_int]
+        L.hs_destroy.argtypes = [C.c_void_p]
+        L.hs_npair.argtypes = [C.c_void_p]
+        L.hs_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_fk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.hs_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.hs_pair_verdict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+class HostSim:
+    def __init__(self, model, allowed_collision_bodies=()):
+        allowed = [(model.body(a).id, model.body(b).id) for a, b in allowed_collision_bodies]
+        desc, keep = _abi.make_desc(model, allowed)
+        h = C.c_void_p()
+        err = C.create_string_buffer(256)
+        if lib().hs_create(C.byref(desc), C.byref(h), err, 256) != 0:
+            raise ValueError(err.value.decode())
+        self._h = h
+        self.model = model
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().hs_destroy(self._h)
+            self._h = None
+
+    def pairs(self):
+        n = lib().hs_npair(self._h)
+        g1, g2 = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        lib().hs_pairs(self._h, g1.ctypes.data, g2.ctypes.data)
+        return np.stack([g1, g2], 1)
+
+    def fk(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.model.nq)
+        n = len(q)
+        xpos = np.zeros((n, self.model.nbody, 3), np.float32)
+        xquat = np.zeros((n, self.model.nbody, 4), np.float32)
+        lib().hs_fk(self._h, q.ctypes.data, n, xpos.ctypes.data, xquat.ctypes.data)
+        return xpos, xquat
+
+    def check(self, q, flags=3, obb=True, recheck=True):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.model.nq)
+        n = len(q)
+        valid = np.zeros(n, np.uint8)
+        stats = np.zeros(8, np.int64)
+        lib().hs_check(self._h, q.ctypes.data, n, flags, int(obb), int(recheck), valid.ctypes.data, stats.ctypes.data)
+        names = "items gjk_iters uncertain_rows rows sphere_survivors gjk_calls max_gjk_iters uncertain_items".split()
+        return valid, dict(zip(names, stats.tolist()))
+
+    def pair_verdict(self, q, g1, g2, fp64=False):
+        """(verdict, iterations) of one geom pair: 0 separated, 1 contact, 2 uncertain."""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(self.model.nq)
+        it = C.c_int(0)
+        v = lib().hs_pair_verdict(self._h, q.ctypes.data, int(g1), int(g2), int(fp64), C.byref(it))
+        return v, it.value

@@ -1,0 +1,178 @@
+// hostsim.cpp -- TEST TOOL: runs the templated core of the CUDA kernels (vk_core.cuh,
+// vk_build.h) row by row on the CPU so the geometry can be compared with the fp64 oracle in the
+// `-m "not gpu"` suite, where no device exists.  It is NOT a product path: nothing in
+// mjpl_b200/ loads it, it is built only by tests/hostsim/__init__.py, and the shipped library
+// has no CPU fallback.
+//
+// Mirrors validity_kernel's per-row logic (P1 limits+FK, P2 sphere + OBB culls, P3 narrow
+// phase with certified verdicts, fp64 re-evaluation of uncertain rows).
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../mjpl_b200/csrc/vk_build.h"
+
+using namespace vk;
+
+struct Sim {
+  vkb::HostModel H;
+  FkTables<float> fk32;
+  std::vector<Shape<float>> s32;
+  std::vector<Vtx<float>> v32;
+};
+
+extern "C" {
+
+int hs_create(const mjb_model_desc *d, Sim **out, char *err, int errlen) {
+  Sim *s = new Sim();
+  if (!vkb::build_host_model(d, s->H)) {
+    snprintf(err, errlen, "%s", s->H.err.c_str());
+    delete s;
+    return 2;
+  }
+  s->fk32 = vkb::convert_fk<float>(s->H.fk);
+  for (auto &sh : s->H.shapes) s->s32.push_back(vkb::convert_shape<float>(sh));
+  for (auto &v : s->H.verts) { Vtx<float> f; f.x = (float)v.x; f.y = (float)v.y; f.z = (float)v.z; f.w = 0; s->v32.push_back(f); }
+  *out = s;
+  return 0;
+}
+void hs_destroy(Sim *s) { delete s; }
+int hs_npair(Sim *s) { return (int)s->H.pairs.size(); }
+void hs_pairs(Sim *s, int32_t *g1, int32_t *g2) {
+  for (size_t i = 0; i < s->H.pairs.size(); i++) { g1[i] = s->H.pair_g1[i]; g2[i] = s->H.pair_g2[i]; }
+}
+
+// xpos (n,nbody,3), xquat (n,nbody,4) in fp32 arithmetic
+void hs_fk(Sim *s, const float *q, int64_t n, float *xpos, float *xquat) {
+  const auto &H = s->H;
+  for (int64_t r = 0; r < n; r++) {
+    Pose<float> P[MAX_BODY], ident;
+    ident.p = mk<float>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+    for (int k = 0; k < H.nslot; k++) {
+      int ps = s->fk32.body_parent[k];
+      P[k] = fk_body(s->fk32, k, ps < 0 ? ident : P[ps], q + r * H.nq);
+    }
+    for (int b = 0; b < H.nbody; b++) {
+      float *xp = xpos + (r * H.nbody + b) * 3, *xq = xquat + (r * H.nbody + b) * 4;
+      int k = H.body_slot[b];
+      if (k >= 0) {
+        xp[0] = P[k].p.x; xp[1] = P[k].p.y; xp[2] = P[k].p.z;
+        xq[0] = P[k].q.w; xq[1] = P[k].q.x; xq[2] = P[k].q.y; xq[3] = P[k].q.z;
+      } else {
+        const auto &S = H.static_pose[b];
+        xp[0] = (float)S.p.x; xp[1] = (float)S.p.y; xp[2] = (float)S.p.z;
+        xq[0] = (float)S.q.w; xq[1] = (float)S.q.x; xq[2] = (float)S.q.y; xq[3] = (float)S.q.z;
+      }
+    }
+  }
+}
+
+}  // extern "C"
+
+template <typename T>
+static int row_verdict(const vkb::HostModel &H, const FkTables<T> &fk, const Shape<T> *shapes, const Vtx<T> *verts,
+                       const float *q, bool use_obb, int64_t *stats) {
+  // returns 0 = no contact, 1 = certain contact, 2 = uncertain (no certain contact)
+  Pose<T> P[MAX_BODY], ident;
+  ident.p = mk<T>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  for (int k = 0; k < H.nslot; k++) {
+    int ps = fk.body_parent[k];
+    P[k] = fk_body(fk, k, ps < 0 ? ident : P[ps], q);
+  }
+  const T slack = sizeof(T) == 4 ? T(1e-4) : T(1e-6);
+  bool unc = false;
+  for (size_t p = 0; p < H.pairs.size(); p++) {
+    const Pair pr = H.pairs[p];
+    const Shape<T> &A = shapes[pr.sa], &B = shapes[pr.sb];
+    const Pose<T> &PA = A.slot < 0 ? ident : P[A.slot];
+    const Pose<T> &PB = B.slot < 0 ? ident : P[B.slot];
+    const T bsum = sizeof(T) == 4 ? (T)pr.bsum : (T)H.pair_bsum64[p];
+    const T rsum = sizeof(T) == 4 ? (T)pr.rsum : (T)H.pair_rsum64[p];
+    V3<T> cB = PB.p + qrot(PB.q, mk<T>(B.bc[0], B.bc[1], B.bc[2]));
+    if (pr.kind == PK_PLANE) {
+      T d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
+      if (d > bsum + slack) continue;
+    } else {
+      V3<T> cA = PA.p + qrot(PA.q, mk<T>(A.bc[0], A.bc[1], A.bc[2]));
+      V3<T> dd = cA - cB;
+      if (dot(dd, dd) > (bsum + slack) * (bsum + slack)) continue;
+      if (stats) stats[4]++;
+      if (use_obb && (pr.flags & 1)) {
+        Rel<T> rel = relative_pose(PA, PB);
+        if (obb_disjoint(A, B, rel, rsum - swept_radius(A) - swept_radius(B) + slack)) continue;
+      }
+    }
+    if (stats) stats[0]++;
+    int v;
+    if (pr.kind == PK_GJK) {
+      int iters = 0;
+      Rel<T> rel = relative_pose(PA, PB);
+      v = gjk_classify(A, B, verts, rel, rsum, &iters);
+      if (stats) { stats[1] += iters; stats[5]++; if (iters > stats[6]) stats[6] = iters; }
+    } else {
+      v = narrow_item<T>(pr.kind, A, B, verts, PA, PB, rsum);
+    }
+    if (v == V_PEN) return 1;
+    if (v == V_UNC) { unc = true; if (stats) stats[7]++; }
+  }
+  return unc ? 2 : 0;
+}
+
+extern "C" {
+
+// valid[i]: 1 valid, 0 invalid.  stats: [0] narrow items, [1] gjk iterations, [2] uncertain rows,
+// [3] rows, [4] sphere survivors, [5] gjk calls, [6] max gjk iterations, [7] uncertain items
+void hs_check(Sim *s, const float *q, int64_t n, uint32_t flags, int use_obb, int use_recheck, uint8_t *valid,
+              int64_t *stats) {
+  const auto &H = s->H;
+  for (int64_t r = 0; r < n; r++) {
+    const float *qr = q + r * H.nq;
+    bool ok = true;
+    if (flags & 1u)
+      for (int j = 0; j < H.njnt; j++) ok = ok && ((double)qr[j] >= H.jnt_lo[j]) && ((double)qr[j] <= H.jnt_hi[j]);
+    int out = ok ? 1 : 0;
+    if (ok && (flags & 2u)) {
+      int v = row_verdict<float>(H, s->fk32, s->s32.data(), s->v32.data(), qr, use_obb != 0, stats);
+      if (v == 2) {
+        if (stats) stats[2]++;
+        if (use_recheck) v = row_verdict<double>(H, H.fk, H.shapes.data(), H.verts.data(), qr, false, nullptr) != 0 ? 1 : 0;
+      }
+      out = v == 0 ? 1 : (v == 1 ? 0 : 2);
+    }
+    valid[r] = (uint8_t)out;
+    if (stats) stats[3]++;
+  }
+}
+
+
+// verdict of one pair (by MuJoCo geom ids) at one row, in fp32 (prec=0) or fp64 (prec=1); -1 if no such pair
+int hs_pair_verdict(Sim *s, const float *q, int g1, int g2, int prec, int *iters) {
+  const auto &H = s->H;
+  for (size_t p = 0; p < H.pairs.size(); p++) {
+    if (!((H.pair_g1[p] == g1 && H.pair_g2[p] == g2) || (H.pair_g1[p] == g2 && H.pair_g2[p] == g1))) continue;
+    const Pair pr = H.pairs[p];
+    if (prec == 0) {
+      Pose<float> P[MAX_BODY], ident;
+      ident.p = mk<float>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+      for (int k = 0; k < H.nslot; k++) { int ps = s->fk32.body_parent[k]; P[k] = fk_body(s->fk32, k, ps < 0 ? ident : P[ps], q); }
+      const Shape<float> &A = s->s32[pr.sa], &B = s->s32[pr.sb];
+      const Pose<float> &PA = A.slot < 0 ? ident : P[A.slot];
+      const Pose<float> &PB = B.slot < 0 ? ident : P[B.slot];
+      if (pr.kind == PK_GJK) { Rel<float> rel = relative_pose(PA, PB); return gjk_classify(A, B, s->v32.data(), rel, pr.rsum, iters); }
+      return narrow_item<float>(pr.kind, A, B, s->v32.data(), PA, PB, pr.rsum);
+    } else {
+      Pose<double> P[MAX_BODY], ident;
+      ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+      for (int k = 0; k < H.nslot; k++) { int ps = H.fk.body_parent[k]; P[k] = fk_body(H.fk, k, ps < 0 ? ident : P[ps], q); }
+      const Shape<double> &A = H.shapes[pr.sa], &B = H.shapes[pr.sb];
+      const Pose<double> &PA = A.slot < 0 ? ident : P[A.slot];
+      const Pose<double> &PB = B.slot < 0 ? ident : P[B.slot];
+      if (pr.kind == PK_GJK) { Rel<double> rel = relative_pose(PA, PB); return gjk_classify(A, B, H.verts.data(), rel, H.pair_rsum64[p], iters); }
+      return narrow_item<double>(pr.kind, A, B, H.verts.data(), PA, PB, H.pair_rsum64[p]);
+    }
+  }
+  return -1;
+}
+
+}  // extern "C"
