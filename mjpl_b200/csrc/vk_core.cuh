@@ -170,8 +170,8 @@ template <typename T> struct Shape {
   T orot[9];       // OBB axes = columns, row-major 3x3
   T ohalf[3];      // OBB half extents (include swept radius)
   int geom;        // MuJoCo geom id
-  int pad;
 };
+static_assert(sizeof(Shape<float>) == 128, "Shape<float> must stay a multiple of 16 bytes (cp.async.bulk granularity)");
 
 struct Pair {
   uint16_t sa, sb;  // shape indices (sa: plane if any; else the one with more vertices first)

@@ -66,16 +66,21 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded spin: a copy that never lands (bad size / alignment) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++) {
+    if (spins > (1u << 26)) __trap();
+  }
 }
 // 1-D bulk async copy global -> shared (TMA engine; SASS: UBLKCP); bytes % 16 == 0, 16B aligned
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
@@ -196,7 +201,12 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
 
   for (;;) {
     // ---- tile ticket -------------------------------------------------------------------------------
-    if (tid == 0) *s_ticket = (long long)atomicAdd(&a.counters[C_TICKET], 1ull);
+    if (tid == 0) {
+      *s_ticket = (long long)atomicAdd(&a.counters[C_TICKET], 1ull);
+      s_misc[0] = 0;  // work-queue fill count
+    }
+    s_hit[tid] = 0;
+    s_unc[tid] = 0;
     __syncthreads();
     const long long tile = *s_ticket;
     if (tile >= ntiles) break;
@@ -223,10 +233,6 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
         __syncthreads();
       }
     }
-    if (tid == 0) s_misc[0] = 0;
-    s_hit[tid] = 0;
-    s_unc[tid] = 0;
-
     // ---- P1: limits + FK -----------------------------------------------------------------------------------
     float *q = s_q + tid * nq;  // this lane's row (stride nq words: conflict free for odd nq)
     long long e_idx = 0;

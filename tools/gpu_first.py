@@ -33,7 +33,11 @@ def run(name, allowed, n=200000):
 
 if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
-    run("two_dof_ball", [], 20000)
+    quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    run("two_dof_ball", [], 2000 if quick else 20000)
+    if quick:
+        run("franka_scene", [], 3000)
+        sys.exit(0)
     run("ur5e_scene", [])
     run("franka_scene", [])
     run("franka_scene_with_obstacles", [("left_finger", "right_finger")])
