@@ -1,0 +1,51 @@
+"""Test doubles: Constraint implementations backed by the fp64 CPU oracle.
+
+They let the host-side planner logic (chain building, stop rules, tree bookkeeping, batched
+lock-step RRT) run in the ``-m "not gpu"`` suite.  Test infrastructure only -- the product's
+constraints call the CUDA engine and have no CPU path.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+import oracle
+from mjpl_b200.constraint.constraint_interface import Constraint
+
+
+class OracleJointLimitConstraint(Constraint):
+    def __init__(self, model):
+        self.model = model
+        self.orc = oracle.Oracle(model)
+
+    def valid_config(self, q):
+        return bool(self.orc.check(np.asarray(q, float), oracle.CHECK_LIMITS)[0])
+
+    def valid_configs(self, Q):
+        Q = np.asarray(Q, float)
+        return self.orc.check(Q, oracle.CHECK_LIMITS) if len(Q) else np.zeros(0, bool)
+
+    def apply(self, q_old, q):
+        return q if self.valid_config(q) else None
+
+
+class OracleCollisionConstraint(Constraint):
+    def __init__(self, model, allowed_collision_bodies=()):
+        self.model = model
+        self.orc = oracle.Oracle(model, allowed_collision_bodies)
+
+    def valid_config(self, q):
+        return bool(self.orc.check(np.asarray(q, float), oracle.CHECK_COLLISION)[0])
+
+    def valid_configs(self, Q):
+        Q = np.asarray(Q, float)
+        return self.orc.check(Q, oracle.CHECK_COLLISION) if len(Q) else np.zeros(0, bool)
+
+    def valid_edges(self, Q0, Q1, step_dist, want_first_bad=False):
+        res = [oracle.valid_collision_interval(self.orc, a, b, step_dist) for a, b in zip(np.asarray(Q0, float), np.asarray(Q1, float))]
+        v = np.array([r[0] for r in res], dtype=bool)
+        fb = np.array([r[1] for r in res], dtype=np.int32)
+        return (v, fb) if want_first_bad else v
+
+    def apply(self, q_old, q):
+        return q if self.valid_config(q) else None

@@ -1,0 +1,235 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the fp64 oracle.
+
+Bar (north star): FK body poses within 1e-5 m / 1e-5 rad; validity booleans identical except
+for rows whose oracle signed distance lies within 1e-5 of the margin, which are counted.
+"""
+
+import numpy as np
+import pytest
+
+import oracle
+import mjpl_b200 as mj
+from mjpl_b200 import _abi, mjcf, models
+from mjpl_b200.engine import sweep_rows_host
+
+from . import toy_models as toys
+
+pytestmark = pytest.mark.gpu
+GOLDEN = __import__("pathlib").Path(__file__).parent / "golden"
+BAND = 1e-5
+
+CASES = [
+    ("franka_scene", []),
+    ("franka_scene", [("left_finger", "right_finger")]),
+    ("franka_scene_with_obstacles", [("left_finger", "right_finger")]),
+    ("ur5e_scene", []),
+    ("two_dof_ball", []),
+    ("one_dof_ball", []),
+]
+
+
+def rows(model, n, seed):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(model.jnt_range[:, 0], model.jnt_range[:, 1], size=(n, model.nq)).astype(np.float32)
+
+
+def compare(got, want, dist):
+    bad = np.asarray(got, bool) != want
+    outside = bad & (np.abs(dist) >= BAND)
+    return int(bad.sum()), int(outside.sum())
+
+
+@pytest.mark.parametrize("mname,allowed", CASES)
+def test_validity_matches_oracle(mname, allowed):
+    import torch
+
+    model = models.load(mname)
+    eng = mj.get_engine(model, allowed)
+    orc = oracle.Oracle(model, allowed)
+    oracle.Oracle.set_threads(8)
+    assert set(map(tuple, eng.pairs().tolist())) == set(map(tuple, orc.pairs().tolist()))
+    Q = rows(model, 60000, 11)
+    # widen a little beyond the limits so the limit mask is exercised too
+    Q[::17] *= 1.05
+    want, dist, _ = orc.check(Q.astype(np.float64), 3, want_dist=True)
+    got = eng.valid_configs(torch.from_numpy(Q).cuda(), 3).cpu().numpy()
+    nbad, nout = compare(got, want, dist)
+    inband = int((np.abs(dist) < BAND).sum())
+    print(f"{mname}: mismatches={nbad} outside band={nout} rows in band={inband} valid={got.mean():.3f}")
+    assert nout == 0
+    assert nbad <= inband
+    # the OBB mid-phase is a pure cull: switching it off must not change a single row
+    got2 = eng.valid_configs(torch.from_numpy(Q).cuda(), 3 | _abi.NO_OBB_CULL).cpu().numpy()
+    assert compare(got2, want, dist)[1] == 0
+    # separate constraints == fused
+    lim = eng.valid_configs(torch.from_numpy(Q).cuda(), _abi.CHECK_LIMITS).cpu().numpy()
+    col = eng.valid_configs(torch.from_numpy(Q).cuda(), _abi.CHECK_COLLISION).cpu().numpy()
+    np.testing.assert_array_equal(lim, orc.check(Q.astype(np.float64), 1))
+    np.testing.assert_array_equal(lim & col, got)
+
+
+@pytest.mark.parametrize("mname,allowed", CASES[:4])
+def test_fk_matches_oracle(mname, allowed):
+    model = models.load(mname)
+    eng = mj.get_engine(model, allowed)
+    orc = oracle.Oracle(model, allowed)
+    Q = rows(model, 20000, 5)
+    xpos, xquat = eng.fk(Q)
+    op, oq = orc.fk(Q.astype(np.float64))
+    assert np.abs(xpos - op).max() < 1e-5
+    dq = np.minimum(np.abs(xquat - oq).max(-1), np.abs(xquat + oq).max(-1))
+    assert dq.max() < 1e-5  # quaternion component error bounds the rotation angle error (2x)
+    assert xpos.shape == (20000, model.nbody, 3) and xquat.shape == (20000, model.nbody, 4)
+
+
+def test_primitive_zoo_all_pair_types():
+    model = mjcf.from_xml_string(toys.PRIMITIVE_ARM)
+    eng = mj.ValidityEngine(model)
+    orc = oracle.Oracle(model)
+    Q = rows(model, 50000, 2)
+    want, dist, _ = orc.check(Q.astype(np.float64), 3, want_dist=True)
+    got = eng.valid_configs(Q)
+    assert compare(got, want, dist)[1] == 0
+    assert 0.2 < got.mean() < 0.95
+
+
+@pytest.mark.parametrize("name,mname,allowed", [
+    ("franka_scene", "franka_scene", []),
+    ("franka_obstacles", "franka_scene_with_obstacles", [("left_finger", "right_finger")]),
+    ("ur5e_scene", "ur5e_scene", []),
+    ("two_dof_ball", "two_dof_ball", []),
+])
+def test_golden_vectors(name, mname, allowed):
+    g = np.load(GOLDEN / f"{name}.npz")
+    eng = mj.get_engine(models.load(mname), allowed)
+    got = eng.valid_configs(g["q"])
+    assert compare(got, g["valid"], g["dist"])[1] == 0
+    xpos, _ = eng.fk(g["q"][: len(g["xpos"])])
+    assert np.abs(xpos - g["xpos"]).max() < 1e-5
+    mjf = GOLDEN / f"{name}_mujoco.npz"
+    if mjf.exists():
+        r = np.load(mjf)
+        got = eng.valid_configs(r["q"])
+        assert (got != r["valid"]).mean() < 1e-3
+
+
+def test_edge_cases_sizes_strides_and_containers():
+    import torch
+
+    model = models.load("franka_scene")
+    eng = mj.get_engine(model, [])
+    orc = oracle.Oracle(model)
+    base = rows(model, 1500, 9)
+    want = orc.check(base.astype(np.float64), 3)
+    assert eng.valid_configs(np.zeros((0, 9), np.float32)).shape == (0,)
+    for n in (1, 2, 31, 32, 33, 255, 256, 257, 511, 512, 513, 1025, 1500):
+        np.testing.assert_array_equal(eng.valid_configs(base[:n]), want[:n])
+    # float64 numpy, CPU tensor, CUDA tensor, strided rows, host-buffer entry point
+    np.testing.assert_array_equal(eng.valid_configs(base.astype(np.float64)), want)
+    assert eng.valid_configs(torch.from_numpy(base)).device.type == "cpu"
+    wide = torch.zeros((1500, 16), dtype=torch.float32, device="cuda")
+    wide[:, :9] = torch.from_numpy(base).cuda()
+    strided = wide[:, :9]
+    assert not strided.is_contiguous()
+    np.testing.assert_array_equal(eng.valid_configs(strided).cpu().numpy(), want)
+    np.testing.assert_array_equal(eng.valid_configs_host(base), want)
+    with pytest.raises(ValueError):
+        eng.valid_configs(np.zeros((3, 5)))
+    # idempotence: same rows, same answer, any batch split
+    a = eng.valid_configs(base)
+    b = np.concatenate([eng.valid_configs(base[:700]), eng.valid_configs(base[700:])])
+    np.testing.assert_array_equal(a, b)
+
+
+def test_constraint_api_known_answers():
+    # reference test/test_collision_constraint.py:17-33, test/test_joint_limit_constraint.py:15-31
+    model = models.load("two_dof_ball")
+    cc, jl = mj.CollisionConstraint(model), mj.JointLimitConstraint(model)
+    q = np.array([0.0, 0.0])
+    assert cc.valid_config(q) and jl.valid_config(q)
+    assert cc.apply(np.array([]), q) is q and jl.apply(np.array([]), q) is q
+    assert not cc.valid_config(np.array([0.6, 0.0])) and cc.apply(np.array([]), np.array([0.6, 0.0])) is None
+    assert not jl.valid_config(np.array([2.5, 0.0])) and jl.apply(np.array([]), np.array([2.5, 0.0])) is None
+    assert mj.obeys_constraints(q, [jl, cc]) and not mj.obeys_constraints(np.array([0.6, 0.0]), [jl, cc])
+    Q = np.array([[0.0, 0.0], [0.6, 0.0], [2.5, 0.0], [1.0, 1.9], [2.0, -2.0]])
+    np.testing.assert_array_equal(mj.obeys_constraints_batch(Q, [jl, cc]), [True, False, False, True, True])
+    # home keyframes of the shipped robots are valid (rrt.py:154-155 would raise otherwise)
+    f = models.load("franka_scene")
+    assert mj.obeys_constraints(f.keyframe("home").qpos, [mj.JointLimitConstraint(f), mj.CollisionConstraint(f)])
+    u = models.load("ur5e_scene")
+    assert mj.obeys_constraints(u.keyframe("home").qpos, [mj.JointLimitConstraint(u), mj.CollisionConstraint(u)])
+    with pytest.raises(KeyError):
+        mj.CollisionConstraint(f, [("hand", "nope")])
+
+
+def test_edges_match_reference_loop():
+    model = models.load("ur5e_scene")
+    eng = mj.get_engine(model, [])
+    orc = oracle.Oracle(model)
+    rng = np.random.default_rng(0)
+    E = 1500
+    q0 = rng.uniform(-3.1415, 3.1415, size=(E, 6)).astype(np.float32)
+    q1 = rng.uniform(-3.1415, 3.1415, size=(E, 6)).astype(np.float32)
+    q1[:10] = q0[:10] + 0.01  # shorter than one step: no interior waypoint -> valid
+    got, fb = eng.valid_edges(q0, q1, 0.05, want_first_bad=True)
+    want, wfb, band = [], [], 0
+    for a, b in zip(q0.astype(np.float64), q1.astype(np.float64)):
+        wps = oracle.interval_waypoints(a, b, 0.05)
+        if not wps:
+            want.append(True); wfb.append(-1); continue
+        v, d, _ = orc.check(np.array(wps), 2, want_dist=True)
+        bad = np.flatnonzero(~v)
+        want.append(len(bad) == 0); wfb.append(int(bad[0]) if len(bad) else -1)
+        band += int((np.abs(d) < 1e-4).any())
+    want, wfb = np.array(want), np.array(wfb)
+    dis = np.flatnonzero((got != want) | (fb != wfb))
+    print(f"edges: {E}, valid={got.mean():.3f}, disagreements={len(dis)}, edges with a waypoint near the band={band}")
+    assert got[:10].all() and (fb[:10] == -1).all()
+    assert len(dis) <= band
+    with pytest.raises(ValueError, match="step_dist"):
+        eng.valid_edges(q0, q1, 0.0)
+    # reference known answers (test_planning_utils.py:321-344)
+    cc = mj.CollisionConstraint(models.load("one_dof_ball"))
+    v = cc.valid_edges(np.array([[0.8], [0.8], [0.0]]), np.array([[1.5], [1.5], [0.2]]), 0.1)
+    assert v.tolist() == [False, False, True]
+    assert cc.valid_edges(np.array([[0.8]]), np.array([[1.5]]), 0.2).tolist() == [True]
+
+
+def test_sweep_rows_and_masks():
+    model = models.load("franka_scene_with_obstacles")
+    allowed = [("left_finger", "right_finger")]
+    eng = mj.get_engine(model, allowed)
+    n = 300000
+    q_dev = eng.sweep_rows(123, 1000, 4096).cpu().numpy()
+    np.testing.assert_array_equal(q_dev, sweep_rows_host(model, 123, 1000, 4096))  # bit-identical mirror
+    mask = eng.sweep(123, 0, n).cpu().numpy()
+    # chunked == one shot (rows are keyed by global id), and == dense check of the same rows
+    parts = [eng.sweep(123, lo, min(70001, n - lo)).cpu().numpy() for lo in range(0, n, 70001)]
+    np.testing.assert_array_equal(np.concatenate(parts), mask)
+    dense = eng.valid_configs(sweep_rows_host(model, 123, 0, 50000))
+    np.testing.assert_array_equal(dense, mask[:50000].astype(bool))
+    orc = oracle.Oracle(model, allowed)
+    oracle.Oracle.set_threads(8)
+    want, dist, _ = orc.check(sweep_rows_host(model, 123, 0, 50000).astype(np.float64), 3, want_dist=True)
+    assert compare(mask[:50000], want, dist)[1] == 0
+
+
+def test_full_size_sweep_properties():
+    """BASELINE config 2 at full size (1M rows): determinism, fused == limits & collision,
+    OBB on == OBB off, and the checksum of the mask equals the sum of chunk checksums."""
+    model = models.load("franka_scene_with_obstacles")
+    eng = mj.get_engine(model, [("left_finger", "right_finger")])
+    n = 1_000_000
+    a = eng.sweep(0, 0, n)
+    b = eng.sweep(0, 0, n)
+    assert bool((a == b).all())
+    c = eng.sweep(0, 0, n, 3 | _abi.NO_OBB_CULL)
+    assert bool((a == c).all())
+    lim = eng.sweep(0, 0, n, _abi.CHECK_LIMITS)
+    col = eng.sweep(0, 0, n, _abi.CHECK_COLLISION)
+    assert bool(((lim & col) == a).all())
+    total = int(a.sum())
+    assert total == sum(int(eng.sweep(0, lo, 250000).sum()) for lo in range(0, n, 250000))
+    assert 0.55 < total / n < 0.70
+    st = eng.stats()
+    assert st["uncertain_rows"] < 0.05 * st["rows"]

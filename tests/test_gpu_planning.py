@@ -1,0 +1,109 @@
+"""Planners on the real CUDA constraints; every returned path must replay as valid under the
+fp64 oracle (the "reference checker" stand-in)."""
+
+import numpy as np
+import pytest
+
+import oracle
+import mjpl_b200 as mj
+from mjpl_b200 import models
+from mjpl_b200.planning.tree import Node, Tree
+from mjpl_b200.planning.utils import _constrained_extend, _valid_collision_interval
+
+pytestmark = pytest.mark.gpu
+
+
+def replay_valid(model, allowed, path, eps):
+    orc = oracle.Oracle(model, allowed)
+    P = np.array(path)
+    assert orc.check(P, 3).all()
+    assert (np.linalg.norm(np.diff(P, axis=0), axis=1) <= eps + 1e-9).all()
+
+
+def test_reference_planning_utils_cases():
+    # reference test/test_planning_utils.py:207-344 on the CUDA constraints
+    model = models.load("one_dof_ball")
+    c = [mj.JointLimitConstraint(model), mj.CollisionConstraint(model)]
+    tree = Tree(Node(np.array([-0.1])))
+    q_goal = np.array([0.15])
+    np.testing.assert_equal(_constrained_extend(q_goal, tree, 0.1, c), q_goal)
+    path = [n.q for n in tree.get_path(tree.nearest_neighbor(q_goal))]
+    for p, e in zip(path, [[0.15], [0.1], [0.0], [-0.1]]):
+        np.testing.assert_allclose(p, e, atol=1e-9)
+    tree = Tree(Node(np.array([0.0])))
+    r = _constrained_extend(np.array([1.0]), tree, 0.1, c)
+    assert 0.0 < r[0] < 0.85
+    tree = Tree(Node(np.array([0.8])))
+    np.testing.assert_equal(_constrained_extend(np.array([1.8]), tree, np.inf, c, (0.3, c[1])), [1.8])
+    tree = Tree(Node(np.array([0.8])))
+    np.testing.assert_equal(_constrained_extend(np.array([1.8]), tree, np.inf, c, (0.1, c[1])), [0.8])
+    assert not _valid_collision_interval(np.array([0.8]), np.array([1.5]), 0.1, c[1])
+    assert _valid_collision_interval(np.array([0.8]), np.array([1.5]), 0.2, c[1])
+    assert _valid_collision_interval(np.array([0.0]), np.array([0.2]), 0.01, c[1])
+    with pytest.raises(ValueError, match="step_dist"):
+        _valid_collision_interval(np.array([0.0]), np.array([0.2]), 0.0, c[1])
+
+
+def test_smooth_path_two_dof():
+    model = models.load("two_dof_ball")
+    c = [mj.JointLimitConstraint(model), mj.CollisionConstraint(model)]
+    wps = [np.array(p) for p in [[0.0, 0.0], [0.25, 0.0], [0.25, 1.5], [0.5, 1.5], [1.0, 1.5], [1.0, 0.0], [1.0, 0.0]]]
+    out = mj.smooth_path(wps, c, eps=0.1, seed=5)
+    assert mj.path_length(out) < mj.path_length(wps) and len(out) > 2
+    replay_valid(model, [], out, 0.1)
+
+
+def test_rrt_franka_benchmark_query():
+    """BASELINE config 1 (examples/benchmark.py:28-48), goal given as the configuration
+    random_config(seed=42) produces (the reference converts it to a pose and runs IK)."""
+    model = models.load("franka_scene")
+    joints = [f"joint{i}" for i in range(1, 8)]
+    c = [mj.JointLimitConstraint(model), mj.CollisionConstraint(model)]
+    q_init = model.keyframe("home").qpos.copy()
+    q_goal = mj.random_config(model, q_init, joints, 42, c)
+    assert mj.obeys_constraints(q_goal, c)
+    np.testing.assert_equal(q_goal[7:], q_init[7:])
+    planner = mj.RRT(model, joints, c, max_planning_time=10, epsilon=0.05, seed=42, goal_biasing_probability=0.1)
+    path = planner.plan_to_config(q_init, q_goal)
+    assert path, "planner timed out"
+    np.testing.assert_equal(path[0], q_init)
+    np.testing.assert_equal(path[-1], q_goal)
+    replay_valid(model, [], path, 0.05)
+    short = mj.smooth_path(path, c, eps=0.05, seed=42)
+    assert mj.path_length(short) <= mj.path_length(path)
+    replay_valid(model, [], short, 0.05)
+
+
+def test_smooth_path_ur5e():
+    # reference test_planning_utils.py:154-182 on the local ur5e.xml
+    model = models.load("ur5e_scene")
+    c = [mj.JointLimitConstraint(model), mj.CollisionConstraint(model)]
+    wps = [model.keyframe("home").qpos.copy()]
+    for i in range(5):
+        wps.append(mj.random_config(model, np.zeros(model.nq), mj.all_joints(model), 42 + i, c))
+    assert len({tuple(w) for w in wps}) == 6
+    out = mj.smooth_path(wps, c, seed=42)
+    assert mj.path_length(out) <= mj.path_length(wps)
+    np.testing.assert_equal(out[0], wps[0])
+    np.testing.assert_equal(out[-1], wps[-1])
+    assert oracle.Oracle(model).check(np.array(out), 3).all()
+
+
+def test_batched_rrt_franka_queries():
+    model = models.load("franka_scene_with_obstacles")
+    allowed = [("left_finger", "right_finger")]
+    joints = [f"joint{i}" for i in range(1, 8)]
+    c = [mj.JointLimitConstraint(model), mj.CollisionConstraint(model, allowed)]
+    q_init = model.keyframe("home").qpos.copy()
+    B = 32
+    goals = np.array([mj.random_config(model, q_init, joints, s, c) for s in range(B)])
+    planner = mj.BatchedRRT(model, joints, c, max_planning_time=60, epsilon=0.05, seed=0, goal_biasing_probability=0.1)
+    paths = planner.plan(np.tile(q_init, (B, 1)), goals)
+    solved = [p for p in paths if p]
+    print("batched rrt:", planner.stats)
+    assert len(solved) >= B - 2
+    for p, g in zip(paths, goals):
+        if p:
+            np.testing.assert_equal(p[0], q_init)
+            np.testing.assert_equal(p[-1], g)
+            replay_valid(model, allowed, p, 0.05)

@@ -1,0 +1,358 @@
+"""Host-side planner logic on CPU, with oracle-backed constraint doubles.
+
+These restate the reference's planning tests (test/test_planning_utils.py, test/test_rrt.py,
+test/test_tree.py, test/test_utils.py::test_random_config) on the bundled ball models.
+"""
+
+import numpy as np
+import pytest
+
+import mjpl_b200 as mj
+from mjpl_b200 import models
+from mjpl_b200.planning.batched_rrt import BatchedRRT
+from mjpl_b200.planning.rrt import RRT
+from mjpl_b200.planning.tree import Node, Tree
+from mjpl_b200.planning.utils import (
+    _chain,
+    _combine_paths,
+    _constrained_extend,
+    _step,
+    _valid_collision_interval,
+    path_length,
+    smooth_path,
+)
+
+from .doubles import OracleCollisionConstraint, OracleJointLimitConstraint
+
+
+def cons(model, allowed=()):
+    return [OracleJointLimitConstraint(model), OracleCollisionConstraint(model, allowed)]
+
+
+# ------------------------------------------------------------------ tree (reference test/test_tree.py)
+def test_node_equality_and_hash():
+    a = Node(np.array([0, 1, 2]), None)
+    b = Node(np.array([0, 1, 2]), a)
+    c = Node(np.array([3, 4, 5]), a)
+    assert a == b and a != c and c == Node(np.array([3, 4, 5]), b) and a != 5
+    assert hash(a) == hash(b)
+
+
+def test_tree_invariants():
+    root = Node(np.array([0.0, 0.0]))
+    n1, n2 = Node(np.array([1.0, 0.0]), root), Node(np.array([0.0, 1.0]), root)
+    n3 = Node(np.array([2.0, 0.0]), n1)
+    with pytest.raises(ValueError, match="root node should have no parent"):
+        Tree(Node(np.array([1.0]), parent=Node(np.array([0.0]))))
+    t = Tree(root)
+    for n in (n1, n2, n3):
+        t.add_node(n)
+    assert len(t.nodes) == 4 and root in t
+    with pytest.raises(ValueError, match="already exists"):
+        t.add_node(Node(n2.q, n3))
+    with pytest.raises(ValueError, match="does not have a parent"):
+        t.add_node(Node(np.array([5.0, 5.0])))
+    with pytest.raises(ValueError, match="parent is not in the tree"):
+        t.add_node(Node(np.array([5.0, 5.0]), Node(np.array([9.0, 9.0]), root)))
+    assert t.nearest_neighbor(np.array([1.9, 0.1])) == n3
+    assert t.nearest_neighbor(np.array([0.1, 0.8])) == n2
+    assert [n.q.tolist() for n in t.get_path(n3)] == [[2, 0], [1, 0], [0, 0]]
+    with pytest.raises(ValueError, match="not in the tree"):
+        t.get_path(Node(np.array([7.0, 7.0]), root))
+    # +inf sink never wins (reference rrt.py:184-188)
+    sink = Node(np.ones(2) * np.inf)
+    g = Tree(sink)
+    g.add_node(Node(np.array([3.0, 3.0]), sink))
+    assert g.nearest_neighbor(np.zeros(2)).q.tolist() == [3.0, 3.0]
+
+
+# ------------------------------------------------------------------ step / chain
+def test_step():
+    start, target = np.array([0.0, 0.0]), np.array([0.5, 0.0])
+    np.testing.assert_equal(_step(start, target, 5.0), target)
+    np.testing.assert_allclose(_step(start, target, 0.1), [0.1, 0.0], atol=1e-8)
+    np.testing.assert_equal(_step(target, target, np.inf), target)
+    with pytest.raises(ValueError, match="`max_step_dist` must be > 0.0"):
+        _step(start, target, 0.0)
+
+
+def test_chain_matches_repeated_step():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        a, b = rng.uniform(-3, 3, 6), rng.uniform(-3, 3, 6)
+        eps = float(rng.uniform(0.03, 0.5))
+        ch = _chain(a, b, eps)
+        q, seq = a, []
+        while not np.array_equal(q, b):
+            q = _step(q, b, eps)
+            seq.append(q)
+        assert len(seq) == len(ch)
+        np.testing.assert_allclose(np.array(seq), ch, atol=1e-12)
+        np.testing.assert_equal(ch[-1], b)
+        assert np.all(np.linalg.norm(np.diff(np.vstack([a, ch]), axis=0), axis=1) <= eps + 1e-12)
+    assert _chain(a, a, 0.1).shape == (0, 6)
+
+
+# ------------------------------------------------------------------ extend / interval (reference test_planning_utils.py:207-344)
+def test_constrained_extend_reaches_target():
+    model = models.load("one_dof_ball")
+    tree = Tree(Node(np.array([-0.1])))
+    q_goal = np.array([0.15])
+    q_reached = _constrained_extend(q_goal, tree, 0.1, cons(model))
+    np.testing.assert_equal(q_reached, q_goal)
+    path = [n.q for n in tree.get_path(tree.nearest_neighbor(q_goal))]
+    expected = [q_goal, np.array([0.1]), np.array([0.0]), np.array([-0.1])]
+    assert len(path) == len(expected)
+    for p, e in zip(path, expected):
+        np.testing.assert_allclose(p, e, rtol=0, atol=1e-9)
+
+
+def test_constrained_extend_stops_before_obstacle():
+    model = models.load("one_dof_ball")
+    obstacle = model.geom("wall_obstacle")
+    min_x = obstacle.pos[0] - obstacle.size[0]
+    tree = Tree(Node(np.array([0.0])))
+    q_reached = _constrained_extend(np.array([1.0]), tree, 0.1, cons(model))
+    assert 0.0 < q_reached[0] < min_x
+
+
+def test_constrained_extend_with_interval_check():
+    model = models.load("one_dof_ball")
+    c = cons(model)
+    q_init, q_goal = np.array([0.8]), np.array([1.8])
+    assert mj.obeys_constraints(q_init, c) and mj.obeys_constraints(q_goal, c)
+    tree = Tree(Node(q_init))
+    np.testing.assert_equal(_constrained_extend(q_goal, tree, np.inf, c, (0.3, c[1])), q_goal)
+    tree = Tree(Node(q_init))
+    np.testing.assert_equal(_constrained_extend(q_goal, tree, np.inf, c, (0.1, c[1])), q_init)
+
+
+def test_constrained_extend_towards_existing_config():
+    model = models.load("one_dof_ball")
+    root = Node(np.array([0.0]))
+    tree = Tree(root)
+    np.testing.assert_equal(_constrained_extend(root.q, tree, 0.1, cons(model)), root.q)
+    assert tree.nodes == {root}
+
+
+def test_valid_collision_interval():
+    model = models.load("one_dof_ball")
+    c = OracleCollisionConstraint(model)
+    assert not _valid_collision_interval(np.array([0.8]), np.array([1.5]), 0.1, c)
+    assert _valid_collision_interval(np.array([0.8]), np.array([1.5]), 0.2, c)
+    assert _valid_collision_interval(np.array([0.0]), np.array([0.2]), 0.01, c)
+    with pytest.raises(ValueError, match="step_dist"):
+        _valid_collision_interval(np.array([0.0]), np.array([0.2]), 0.0, c)
+
+
+def test_combine_paths():
+    rs, rg = Node(np.array([0.0])), Node(np.array([0.3]))
+    cs, cg = Node(np.array([0.1]), rs), Node(np.array([0.2]), rg)
+    st, gt = Tree(rs), Tree(rg)
+    st.add_node(cs)
+    gt.add_node(cg)
+    assert [p.tolist() for p in _combine_paths(st, cs, gt, cg)] == [[0.0], [0.1], [0.2], [0.3]]
+    q_new = np.array([0.15])
+    gs, gg = Node(q_new, cs), Node(q_new, cg)
+    st.add_node(gs)
+    gt.add_node(gg)
+    assert [p.tolist() for p in _combine_paths(st, gs, gt, gg)] == [[0.0], [0.1], [0.15], [0.2], [0.3]]
+
+
+def test_path_length():
+    wps = [np.array([0.0, 0, 0]), np.array([1.0, 0, 0]), np.array([1.0, 1, 0]), np.array([1.0, 1, 1])]
+    assert path_length(wps) == pytest.approx(3.0)
+
+
+# ------------------------------------------------------------------ smoothing (reference test_planning_utils.py:72-196)
+def _check_smoothed(smoothed, original, c, eps):
+    assert path_length(smoothed) < path_length(original)
+    np.testing.assert_equal(smoothed[0], original[0])
+    np.testing.assert_equal(smoothed[-1], original[-1])
+    for a, b in zip(smoothed[:-1], smoothed[1:]):
+        assert np.linalg.norm(b - a) <= eps + 1e-8
+    for wp in smoothed:
+        assert mj.obeys_constraints(wp, c)
+
+
+def test_smooth_path_directly_connectable():
+    model = models.load("two_dof_ball")
+    c = cons(model)
+    wps = [np.array(p) for p in [[0.0, 0.0], [0.25, 0.0], [0.25, 0.75], [0.5, 0.75], [1.0, 0.75], [1.0, -0.75], [0.5, -0.75]]]
+    out = smooth_path(wps, c, eps=0.1, seed=5)
+    assert len(out) > 2
+    _check_smoothed(out, wps, c, 0.1)
+    sparse = smooth_path(wps, c, eps=0.1, seed=5, sparse=True)
+    assert len(sparse) == 2 and sparse[0] is wps[0] and sparse[1] is wps[-1]
+
+
+def test_smooth_path_around_obstacle():
+    model = models.load("two_dof_ball")
+    c = cons(model)
+    wps = [np.array(p) for p in [[0.0, 0.0], [0.25, 0.0], [0.25, 1.5], [0.5, 1.5], [1.0, 1.5], [1.0, 0.0], [1.0, 0.0]]]
+    out = smooth_path(wps, c, eps=0.1, seed=5)
+    assert len(out) > 2
+    _check_smoothed(out, wps, c, 0.1)
+    sparse = smooth_path(wps, c, eps=0.1, seed=5, sparse=True)
+    assert len(sparse) > 2 and path_length(sparse) < path_length(wps)
+    for wp in sparse:
+        assert mj.obeys_constraints(wp, c)
+
+
+def test_smooth_path_invalid_args():
+    with pytest.raises(ValueError, match="waypoints"):
+        smooth_path([], [])
+    wps = [np.zeros(6), np.ones(6)]
+    with pytest.raises(ValueError, match="eps"):
+        smooth_path(wps, [], eps=0.0)
+    with pytest.raises(ValueError, match="num_tries"):
+        smooth_path(wps, [], num_tries=0)
+
+
+# ------------------------------------------------------------------ RRT (reference test/test_rrt.py)
+def _check_plan(wps, q_init, q_goal, eps, c):
+    assert len(wps) >= 2
+    np.testing.assert_equal(wps[0], q_init)
+    np.testing.assert_equal(wps[-1], q_goal)
+    for a, b in zip(wps[:-1], wps[1:]):
+        assert np.linalg.norm(b - a) <= eps + 1e-12
+    for wp in wps:
+        assert mj.obeys_constraints(wp, c)
+
+
+def test_run_rrt():
+    model = models.load("one_dof_ball")
+    c = cons(model)
+    planner = RRT(model, mj.all_joints(model), c, max_planning_time=5.0, epsilon=0.1, seed=42)
+    wps = planner.plan_to_config(np.array([-0.2]), np.array([0.35]))
+    assert len(wps) > 2
+    _check_plan(wps, np.array([-0.2]), np.array([0.35]), 0.1, c)
+
+
+def test_run_rrt_subset_joints_and_trivial():
+    model = models.load("two_dof_ball")
+    c = cons(model)
+    planner = RRT(model, ["ball_slide_x"], c, max_planning_time=5.0, epsilon=0.1, seed=42)
+    wps = planner.plan_to_config(np.array([0.0, 0.0]), np.array([0.3, 0.0]))
+    assert len(wps) > 2
+    _check_plan(wps, np.array([0.0, 0.0]), np.array([0.3, 0.0]), 0.1, c)
+    wps = planner.plan_to_config(np.array([0.0, 0.0]), np.array([0.05, 0.0]))
+    assert len(wps) == 2
+
+
+def test_rrt_around_wall_2dof():
+    model = models.load("two_dof_ball")
+    c = cons(model)
+    planner = RRT(model, mj.all_joints(model), c, max_planning_time=20.0, epsilon=0.1, seed=3)
+    q0, q1 = np.array([0.0, 0.0]), np.array([1.2, 0.0])
+    wps = planner.plan_to_config(q0, q1)
+    assert wps, "planner timed out"
+    _check_plan(wps, q0, q1, 0.1, c)
+    assert path_length(wps) > 1.2  # had to go around the wall
+
+
+def test_rrt_invalid_args():
+    model = models.load("one_dof_ball")
+    joints = mj.all_joints(model)
+    with pytest.raises(ValueError, match="max_planning_time"):
+        RRT(model, joints, [], max_planning_time=0.0)
+    with pytest.raises(ValueError, match="epsilon"):
+        RRT(model, joints, [], epsilon=0.0)
+    with pytest.raises(ValueError, match="goal_biasing_probability"):
+        RRT(model, joints, [], goal_biasing_probability=2.0)
+    with pytest.raises(ValueError, match="planning_joints"):
+        RRT(model, [], [])
+    model = models.load("two_dof_ball")
+    planner = RRT(model, ["ball_slide_y"], [], max_planning_time=5.0, epsilon=0.1, seed=42)
+    with pytest.raises(ValueError, match="values for joints outside of the planner's planning joints"):
+        planner.plan_to_config(np.array([0.0, 0.0]), np.array([0.1, 0.0]))
+    c = cons(model)
+    planner = RRT(model, mj.all_joints(model), c, seed=1)
+    with pytest.raises(ValueError, match="q_init is not a valid configuration"):
+        planner.plan_to_config(np.array([0.6, 0.0]), np.array([0.0, 0.0]))
+    with pytest.raises(ValueError, match="goal config is not a valid configuration"):
+        planner.plan_to_config(np.array([0.0, 0.0]), np.array([0.6, 0.0]))
+
+
+# ------------------------------------------------------------------ random_config (reference test/test_utils.py:104-129)
+def test_random_config():
+    model = models.load("two_dof_ball")
+    c = cons(model)
+    joints = mj.all_joints(model)
+    q_init = np.zeros(model.nq)
+    a = mj.random_config(model, q_init, joints, 42, c)
+    b = mj.random_config(model, q_init, joints, 42, c)
+    np.testing.assert_equal(a, b)
+    assert mj.obeys_constraints(a, c)
+    # same candidate sequence as the reference's one-at-a-time loop
+    rng = np.random.default_rng(42)
+    while True:
+        cand = rng.uniform(*model.jnt_range.T)
+        if mj.obeys_constraints(cand, c):
+            break
+    np.testing.assert_equal(a, cand)
+    q = mj.random_config(model, q_init, ["ball_slide_y"], 42, c)
+    assert q[mj.qpos_idx(model, ["ball_slide_x"])[0]] == 0.0 and mj.obeys_constraints(q, c)
+
+
+# ------------------------------------------------------------------ batched lock-step RRT
+def test_batched_rrt_many_queries():
+    model = models.load("two_dof_ball")
+    c = cons(model)
+    rng = np.random.default_rng(0)
+    qi, qg = [], []
+    while len(qi) < 24:
+        a, b = rng.uniform(-1.5, 1.5, 2), rng.uniform(-1.5, 1.5, 2)
+        if mj.obeys_constraints(a, c) and mj.obeys_constraints(b, c):
+            qi.append(a)
+            qg.append(b)
+    qi[0], qg[0] = np.array([0.0, 0.0]), np.array([1.2, 0.0])  # wall in between
+    qi[1], qg[1] = np.array([0.1, 0.1]), np.array([0.12, 0.1])  # trivially connectable
+    planner = BatchedRRT(model, mj.all_joints(model), c, max_planning_time=60.0, epsilon=0.1, seed=11)
+    paths = planner.plan(np.array(qi), np.array(qg))
+    assert planner.stats["solved"] == 24
+    assert len(paths[1]) == 2
+    for p, a, b in zip(paths, qi, qg):
+        _check_plan(p, a, b, 0.1, c)
+    assert path_length(paths[0]) > 1.2
+    # far fewer validity launches than configurations checked: chains are evaluated as blocks
+    assert planner.stats["launches"] * 10 < planner.stats["configs_checked"]
+    with pytest.raises(ValueError, match="q_init is not a valid configuration"):
+        planner.plan(np.array([[0.6, 0.0]]), np.array([[0.0, 0.0]]))
+
+
+def test_obeys_constraints_batch_generic_and_fused_paths():
+    model = models.load("two_dof_ball")
+    c = cons(model)
+    Q = np.array([[0.0, 0.0], [0.6, 0.0], [2.5, 0.0], [1.0, 1.9]])
+    np.testing.assert_array_equal(mj.obeys_constraints_batch(Q, c), [True, False, False, True])
+    np.testing.assert_array_equal(mj.obeys_constraints_batch(Q, []), [True] * 4)
+    assert [mj.obeys_constraints(q, c) for q in Q] == [True, False, False, True]
+    q0 = Q[0].copy()
+    assert mj.apply_constraints(q0, q0, c) is q0  # the same array object comes back when valid
+    assert mj.apply_constraints(q0, Q[1].copy(), c) is None
+
+
+def test_collision_ruleset_semantics():
+    # reference test/test_collision_constraint.py:36-192 on the bundled Franka tables
+    from mjpl_b200.constraint.collision_constraint import CollisionRuleset
+
+    m = models.load("franka_scene")
+    g = {n: m.body_geomadr[m.body(n).id] for n in ("link1", "link2", "link3", "link4", "link5", "link6", "link7", "left_finger", "right_finger")}
+    cr = CollisionRuleset(m, [("link1", "link2")])
+    assert cr.obeys_ruleset(np.empty((0, 2)))
+    assert cr.obeys_ruleset(np.array([[g["link1"], g["link2"]]]))
+    assert cr.obeys_ruleset(np.array([[g["link2"], g["link1"]], [g["link1"], g["link2"]]]))
+    assert not cr.obeys_ruleset(np.array([[g["left_finger"], g["right_finger"]]]))
+    assert not cr.obeys_ruleset(np.array([[g["link1"], g["link2"]], [g["link1"], g["link5"]]]))
+    cr = CollisionRuleset(m, [("link1", "link2"), ("link6", "link7"), ("left_finger", "right_finger")])
+    assert cr.obeys_ruleset(np.array([[g["left_finger"], g["right_finger"]], [g["link7"], g["link6"]], [g["link2"], g["link1"]]]))
+    assert not cr.obeys_ruleset(np.array([[g["link2"], g["link3"]]]))
+    cr = CollisionRuleset(m)
+    assert cr.obeys_ruleset(np.empty((0, 2))) and not cr.obeys_ruleset(np.array([[g["link3"], g["link2"]]]))
+    with pytest.raises(ValueError, match="nx2"):
+        cr.obeys_ruleset(np.zeros((1, 3)))
+    with pytest.raises(ValueError, match="nx2"):
+        cr.obeys_ruleset(np.zeros((1, 2, 1)))
+    with pytest.raises(KeyError):
+        CollisionRuleset(m, [("link1", "nope")])
