@@ -164,6 +164,9 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   k.shapes = m->d_shapes32; k.verts = m->d_verts32; k.pairs = m->d_pairs;
   k.nshape = (int)H.shapes.size(); k.nmoving = H.nmoving_shapes; k.nvert = (int)H.verts.size();
   k.npair = (int)H.pairs.size(); k.nslot = H.nslot;
+  k.nrounds = H.nrounds;
+  for (int r = 0; r <= H.nrounds; r++) k.round_start[r] = H.round_start[r];
+  for (int r = 0; r < H.nrounds; r++) k.round_gjk[r] = H.round_gjk[r];
   k.pose_scratch = m->d_pose; k.counters = m->d_counters;
   RArgs &ra = m->rargs;
   memset(&ra, 0, sizeof ra);
@@ -219,7 +222,7 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
   CU(cudaGetLastError());
   m->launches++;
   if ((k.flags & F_COLLISION) && !(k.flags & F_NO_RECHECK)) {
-    recheck_kernel<<<m->num_sms * 2, 64, 0, st>>>(r);
+    recheck_kernel<<<m->num_sms * 4, 128, 0, st>>>(r);
     CU(cudaGetLastError());
     m->launches++;
   }

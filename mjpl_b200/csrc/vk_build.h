@@ -37,6 +37,10 @@ struct HostModel {
   std::vector<Pair> pairs;              // processing order
   std::vector<int> pair_g1, pair_g2;    // MuJoCo geom ids, same order as `pairs`
   std::vector<double> pair_rsum64, pair_bsum64;  // fp64 copies of Pair::rsum / bsum
+  int nrounds = 0;
+  int round_start[MAX_ROUNDS + 1] = {0};  // pair index range of each round
+  int round_gjk[MAX_ROUNDS] = {0};        // 1: the round holds GJK pairs, 0: plane / segment pairs
+  double calib_sphere_per_row = 0, calib_items_per_row = 0, calib_pen_rows = 0;
   std::string err;
 };
 
@@ -165,6 +169,32 @@ inline void fit_bounds(Shape<double> &s, const std::vector<Vtx<double>> &verts) 
       for (int k = 0; k < 3; k++) s.oc[k] = Rc[3 * k] * cen[0] + Rc[3 * k + 1] * cen[1] + Rc[3 * k + 2] * cen[2];
     }
   }
+}
+
+template <typename T> inline FkTables<T> convert_fk(const FkTables<double> &s) {
+  FkTables<T> o; memset(&o, 0, sizeof o);
+  o.nq = s.nq; o.nbody = s.nbody; o.njnt = s.njnt;
+  for (int i = 0; i < MAX_BODY; i++) {
+    o.body_parent[i] = s.body_parent[i]; o.body_jntadr[i] = s.body_jntadr[i];
+    o.body_jntnum[i] = s.body_jntnum[i]; o.body_slot[i] = s.body_slot[i];
+    for (int k = 0; k < 3; k++) o.body_pos[i][k] = (T)s.body_pos[i][k];
+    for (int k = 0; k < 4; k++) o.body_quat[i][k] = (T)s.body_quat[i][k];
+  }
+  for (int j = 0; j < MAX_JNT; j++) {
+    o.jnt_type[j] = s.jnt_type[j]; o.jnt_qadr[j] = s.jnt_qadr[j];
+    for (int k = 0; k < 3; k++) { o.jnt_pos[j][k] = (T)s.jnt_pos[j][k]; o.jnt_axis[j][k] = (T)s.jnt_axis[j][k]; }
+    o.jnt_lo[j] = (T)s.jnt_lo[j]; o.jnt_hi[j] = (T)s.jnt_hi[j]; o.qpos0[j] = (T)s.qpos0[j];
+  }
+  return o;
+}
+
+template <typename T> inline Shape<T> convert_shape(const Shape<double> &s) {
+  Shape<T> o; memset(&o, 0, sizeof o);
+  o.kind = s.kind; o.slot = s.slot; o.vadr = s.vadr; o.nvert = s.nvert; o.geom = s.geom;
+  o.radius = (T)s.radius; o.halflen = (T)s.halflen; o.brad = (T)s.brad;
+  for (int k = 0; k < 3; k++) { o.c[k] = (T)s.c[k]; o.ax[k] = (T)s.ax[k]; o.bc[k] = (T)s.bc[k]; o.oc[k] = (T)s.oc[k]; o.ohalf[k] = (T)s.ohalf[k]; }
+  for (int k = 0; k < 9; k++) o.orot[k] = (T)s.orot[k];
+  return o;
 }
 
 inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
@@ -374,50 +404,108 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
       t.rsum = ra + rb + margin;
       t.bsum = A->brad + B->brad + margin;
       int cost = (A->kind == SK_CYL ? 16 : A->nvert) + (B->kind == SK_CYL ? 16 : B->nvert);
-      t.p.flags = (!seg && cost >= 12) ? 1 : 0;
+      t.p.flags = (!seg && cost >= 12) ? PF_OBB : 0;
       t.key = seg ? 1 : 1000 + cost;
     }
     t.p.rsum = (float)t.rsum;
     t.p.bsum = (float)t.bsum;
     tp.push_back(t);
   }
-  std::stable_sort(tp.begin(), tp.end(), [](const Tmp &x, const Tmp &y) {
-    if (x.key != y.key) return x.key < y.key;
-    if (x.p.sa != y.p.sa) return x.p.sa < y.p.sa;
-    return x.p.sb < y.p.sb;
-  });
   for (auto &t : tp) {
+    const Shape<double> &A = H.shapes[t.p.sa], &B = H.shapes[t.p.sb];
+    if (A.slot < 0) t.p.flags |= PF_A_STATIC;
+    if (B.slot < 0) t.p.flags |= PF_B_STATIC;
+  }
+  // ---- calibration: run the same fp32 core on seeded rows (uniform in the joint ranges) to
+  // learn, per pair, how often it survives the sphere cull / the OBB cull / ends in contact.
+  // This only ORDERS the work (likely contacts first => early exit; bounded work-queue fill
+  // per round); it never decides a result.
+  const int NCAL = 2048;
+  std::vector<double> n_sph(tp.size(), 0), n_obb(tp.size(), 0), n_pen(tp.size(), 0);
+  {
+    FkTables<float> fk32 = convert_fk<float>(H.fk);
+    std::vector<Shape<float>> s32; std::vector<Vtx<float>> v32;
+    for (auto &sh : H.shapes) s32.push_back(convert_shape<float>(sh));
+    for (auto &v : H.verts) { Vtx<float> f; f.x = (float)v.x; f.y = (float)v.y; f.z = (float)v.z; f.w = 0; v32.push_back(f); }
+    Pose<float> ident; ident.p = mk<float>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+    for (int r = 0; r < NCAL; r++) {
+      float q[MAX_JNT];
+      for (int j = 0; j < d->nq; j++) {
+        float lo = (float)H.jnt_lo[j], hi = (float)H.jnt_hi[j];
+        if (!(hi > lo)) { lo = -3.14159f; hi = 3.14159f; }
+        q[j] = sweep_value(0x5eedull, (uint64_t)r, (uint32_t)j, lo, hi);
+      }
+      Pose<float> P[MAX_BODY];
+      for (int k = 0; k < H.nslot; k++) { int ps = fk32.body_parent[k]; P[k] = fk_body(fk32, k, ps < 0 ? ident : P[ps], q); }
+      bool row_pen = false;
+      for (size_t p = 0; p < tp.size(); p++) {
+        const Pair &pr = tp[p].p;
+        const Shape<float> &A = s32[pr.sa], &B = s32[pr.sb];
+        const Pose<float> &PA = A.slot < 0 ? ident : P[A.slot];
+        const Pose<float> &PB = B.slot < 0 ? ident : P[B.slot];
+        V3<float> cB = PB.p + qrot(PB.q, mk<float>(B.bc[0], B.bc[1], B.bc[2]));
+        const float slack = 1e-4f;
+        if (pr.kind == PK_PLANE) {
+          float dd = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
+          if (dd > pr.bsum + slack) continue;
+          n_sph[p]++;
+        } else {
+          V3<float> cA = PA.p + qrot(PA.q, mk<float>(A.bc[0], A.bc[1], A.bc[2]));
+          V3<float> dd = cA - cB;
+          if (dot(dd, dd) > (pr.bsum + slack) * (pr.bsum + slack)) continue;
+          n_sph[p]++;
+          if (pr.flags & PF_OBB) {
+            Rel<float> rel = relative_pose(PA, PB);
+            if (obb_disjoint(A, B, rel, pr.rsum - swept_radius(A) - swept_radius(B) + slack)) continue;
+          }
+        }
+        n_obb[p]++;
+        int v = narrow_item<float>(pr.kind, A, B, v32.data(), PA, PB, pr.rsum);
+        if (v == V_PEN) { n_pen[p]++; row_pen = true; }
+      }
+      H.calib_pen_rows += row_pen;
+    }
+    for (size_t p = 0; p < tp.size(); p++) { H.calib_sphere_per_row += n_sph[p] / NCAL; H.calib_items_per_row += n_obb[p] / NCAL; }
+    H.calib_pen_rows /= NCAL;
+  }
+  // ---- order: cheap analytic kinds first, then GJK pairs by contact likelihood (descending),
+  // ties by fewer narrow-phase items and fewer vertices
+  std::vector<int> ord(tp.size());
+  for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
+  std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
+    bool gx = tp[x].p.kind == PK_GJK, gy = tp[y].p.kind == PK_GJK;
+    if (gx != gy) return !gx;
+    if (n_pen[x] != n_pen[y]) return n_pen[x] > n_pen[y];
+    if (n_obb[x] != n_obb[y]) return n_obb[x] < n_obb[y];
+    if (tp[x].key != tp[y].key) return tp[x].key < tp[y].key;
+    if (tp[x].p.sa != tp[y].p.sa) return tp[x].p.sa < tp[y].p.sa;
+    return tp[x].p.sb < tp[y].p.sb;
+  });
+  // ---- rounds: bounded expected queue fill per row (sphere survivors <= 3, items <= 1.5)
+  H.nrounds = 0;
+  double acc_s = 0, acc_o = 0;
+  int cur_gjk = -1;
+  for (size_t k = 0; k < ord.size(); k++) {
+    int i = ord[k];
+    int g = tp[i].p.kind == PK_GJK ? 1 : 0;
+    double es = n_sph[i] / NCAL, eo = n_obb[i] / NCAL;
+    bool fresh = (k == 0) || (g != cur_gjk) || (acc_s + es > 3.0) || (acc_o + eo > 1.5);
+    if (fresh && H.nrounds < MAX_ROUNDS) {
+      H.round_start[H.nrounds] = (int)k;
+      H.round_gjk[H.nrounds] = g;
+      H.nrounds++;
+      acc_s = acc_o = 0;
+      cur_gjk = g;
+    }
+    acc_s += es; acc_o += eo;
+    Tmp &t = tp[i];
+    t.p.round = (uint16_t)(H.nrounds - 1);
     H.pairs.push_back(t.p); H.pair_g1.push_back(t.g1); H.pair_g2.push_back(t.g2);
     H.pair_rsum64.push_back(t.rsum); H.pair_bsum64.push_back(t.bsum);
   }
+  H.round_start[H.nrounds] = (int)ord.size();
   if (H.pairs.size() > 60000) { H.err = "too many geom pairs"; return false; }
   return true;
-}
-
-template <typename T> inline FkTables<T> convert_fk(const FkTables<double> &s) {
-  FkTables<T> o; memset(&o, 0, sizeof o);
-  o.nq = s.nq; o.nbody = s.nbody; o.njnt = s.njnt;
-  for (int i = 0; i < MAX_BODY; i++) {
-    o.body_parent[i] = s.body_parent[i]; o.body_jntadr[i] = s.body_jntadr[i];
-    o.body_jntnum[i] = s.body_jntnum[i]; o.body_slot[i] = s.body_slot[i];
-    for (int k = 0; k < 3; k++) o.body_pos[i][k] = (T)s.body_pos[i][k];
-    for (int k = 0; k < 4; k++) o.body_quat[i][k] = (T)s.body_quat[i][k];
-  }
-  for (int j = 0; j < MAX_JNT; j++) {
-    o.jnt_type[j] = s.jnt_type[j]; o.jnt_qadr[j] = s.jnt_qadr[j];
-    for (int k = 0; k < 3; k++) { o.jnt_pos[j][k] = (T)s.jnt_pos[j][k]; o.jnt_axis[j][k] = (T)s.jnt_axis[j][k]; }
-    o.jnt_lo[j] = (T)s.jnt_lo[j]; o.jnt_hi[j] = (T)s.jnt_hi[j]; o.qpos0[j] = (T)s.qpos0[j];
-  }
-  return o;
-}
-
-template <typename T> inline Shape<T> convert_shape(const Shape<double> &s) {
-  Shape<T> o; memset(&o, 0, sizeof o);
-  o.kind = s.kind; o.slot = s.slot; o.vadr = s.vadr; o.nvert = s.nvert; o.geom = s.geom;
-  o.radius = (T)s.radius; o.halflen = (T)s.halflen; o.brad = (T)s.brad;
-  for (int k = 0; k < 3; k++) { o.c[k] = (T)s.c[k]; o.ax[k] = (T)s.ax[k]; o.bc[k] = (T)s.bc[k]; o.oc[k] = (T)s.oc[k]; o.ohalf[k] = (T)s.ohalf[k]; }
-  for (int k = 0; k < 9; k++) o.orot[k] = (T)s.orot[k];
-  return o;
 }
 
 }  // namespace vkb

@@ -175,11 +175,15 @@ static_assert(sizeof(Shape<float>) == 128, "Shape<float> must stay a multiple of
 
 struct Pair {
   uint16_t sa, sb;  // shape indices (sa: plane if any; else the one with more vertices first)
-  uint16_t kind;    // PairKind
-  uint16_t flags;   // bit0: OBB mid-phase is worthwhile
+  uint8_t kind;     // PairKind
+  uint8_t flags;    // PF_* bits
+  uint16_t round;   // processing round (pairs are sorted by round)
   float rsum;       // swept radii + margin: contact iff core distance <= rsum
   float bsum;       // bounding radii sum + margin
 };
+static_assert(sizeof(Pair) == 16, "Pair is loaded as one 16-byte word");
+constexpr uint8_t PF_OBB = 1, PF_A_STATIC = 2, PF_B_STATIC = 4;
+constexpr int MAX_ROUNDS = 32;
 
 // ------------------------------------------------------------------------------ forward kinematics
 // One body of mj_kinematics (engine_core_smooth.c), SURVEY.md A.1: parent pose -> body pose.
@@ -377,71 +381,86 @@ template <typename T> VK_HD Rel<T> relative_pose(const Pose<T> &A, const Pose<T>
 }
 
 // ------------------------------------------------------------------------------ GJK three-way classifier
-// A in its own frame, B through `rel`.  R = swept radii + margin.  `iters` (optional) counts
-// support evaluations.
+// A in its own frame, B through `rel`.  R = swept radii + margin.  The loop is exposed as
+// init + step so the kernel can run ONE iteration per trip of a persistent-lane loop (lanes
+// that finish fetch the next work item instead of idling until the slowest lane is done).
+template <typename T> struct GjkState {
+  V3<T> v, p0, p1, p2, p3;
+  int n, it;
+};
+
+template <typename T>
+VK_HD void gjk_init(GjkState<T> &s, const Shape<T> &A, const Shape<T> &B, const Rel<T> &rel) {
+  V3<T> cA = mk<T>(A.bc[0], A.bc[1], A.bc[2]);
+  V3<T> cB = mul(rel.R, mk<T>(B.bc[0], B.bc[1], B.bc[2])) + rel.t;
+  s.v = cA - cB;
+  if (!(dot(s.v, s.v) > Num<T>::tiny)) s.v = mk<T>(T(1), T(0), T(0));
+  s.p0 = s.p1 = s.p2 = s.p3 = s.v;
+  s.n = 0;
+  s.it = 0;
+}
+
+// one iteration; returns -1 to continue or the verdict
+template <typename T>
+VK_HD int gjk_step(GjkState<T> &s, const Shape<T> &A, const Shape<T> &B, const Vtx<T> *__restrict__ verts,
+                   const Rel<T> &rel, T R) {
+  const T tol = Num<T>::tol;
+  if (s.it >= Num<T>::maxit) return V_UNC;
+  s.it++;
+  // support of A-B along -v
+  V3<T> v = s.v;
+  V3<T> sa = support_shape(A, verts, -v);
+  V3<T> sb = mul(rel.R, support_shape(B, verts, mulT(rel.R, v))) + rel.t;
+  V3<T> w = sa - sb;
+  T vv = dot(v, v), vw = dot(v, w);
+  // every x in A-B has x.v >= v.w  =>  distance >= v.w/|v|
+  if (vw > T(0)) {
+    T lim = R + tol;
+    if (vw * vw > lim * lim * vv) return V_SEP;
+  }
+  // converged: |v| is the core distance up to rounding and it sits inside the tol band
+  // (otherwise SEP above or PEN below would have fired) -> uncertain
+  if (s.n > 0 && (vv - vw) <= Num<T>::conv_rel * vv) return V_UNC;
+  // append w and solve for the closest point of the simplex
+  T l0 = T(0), l1 = T(0), l2 = T(0), l3 = T(0);
+  bool inside = false;
+  if (s.n == 0) { s.p0 = w; l0 = T(1); }
+  else if (s.n == 1) { s.p1 = w; solve1(s.p0, s.p1, l0, l1); }
+  else if (s.n == 2) { s.p2 = w; solve2(s.p0, s.p1, s.p2, l0, l1, l2); }
+  else { s.p3 = w; inside = solve3(s.p0, s.p1, s.p2, s.p3, l0, l1, l2, l3); }
+  if (inside) {
+    // origin enclosed by the core tetrahedron: depth >= min face distance
+    T dep = vk_min(vk_min(plane_dist(s.p1, s.p2, s.p3), plane_dist(s.p0, s.p2, s.p3)),
+                   vk_min(plane_dist(s.p0, s.p1, s.p3), plane_dist(s.p0, s.p1, s.p2)));
+    return (dep + R > tol) ? V_PEN : V_UNC;
+  }
+  v = s.p0 * l0 + s.p1 * l1 + s.p2 * l2 + s.p3 * l3;
+  s.v = v;
+  // v is a point of A-B: core distance <= |v|
+  T nvv = dot(v, v);
+  if (R > tol && nvv < (R - tol) * (R - tol)) return V_PEN;
+  if (!(nvv > tol * tol)) return V_UNC;  // cores (nearly) touching: cannot be certified either way
+  // compact the simplex: keep vertices with positive weight at the front
+  bool k0 = l0 > T(0), k1 = l1 > T(0), k2 = l2 > T(0), k3 = l3 > T(0);
+  { bool c = !k0 && k1; cswap(c, s.p0, s.p1); cswap(c, k0, k1); }
+  { bool c = !k1 && k2; cswap(c, s.p1, s.p2); cswap(c, k1, k2); }
+  { bool c = !k2 && k3; cswap(c, s.p2, s.p3); cswap(c, k2, k3); }
+  { bool c = !k0 && k1; cswap(c, s.p0, s.p1); cswap(c, k0, k1); }
+  { bool c = !k1 && k2; cswap(c, s.p1, s.p2); cswap(c, k1, k2); }
+  { bool c = !k0 && k1; cswap(c, s.p0, s.p1); cswap(c, k0, k1); }
+  s.n = int(k0) + int(k1) + int(k2) + int(k3);
+  if (s.n == 4) return V_UNC;  // cannot happen unless solve3 misreported
+  return -1;
+}
+
 template <typename T>
 VK_HD int gjk_classify(const Shape<T> &A, const Shape<T> &B, const Vtx<T> *__restrict__ verts,
                        const Rel<T> &rel, T R, int *iters) {
-  const T tol = Num<T>::tol;
-  V3<T> cA = mk<T>(A.bc[0], A.bc[1], A.bc[2]);
-  V3<T> cB = mul(rel.R, mk<T>(B.bc[0], B.bc[1], B.bc[2])) + rel.t;
-  V3<T> v = cA - cB;
-  if (!(dot(v, v) > Num<T>::tiny)) v = mk<T>(T(1), T(0), T(0));
-  V3<T> p0 = v, p1 = v, p2 = v, p3 = v;
-  int n = 0;
-  int verdict = V_UNC;
-  int it = 0;
-  for (; it < Num<T>::maxit; it++) {
-    // support of A-B along -v
-    V3<T> nv = -v;
-    V3<T> sa = support_shape(A, verts, nv);
-    V3<T> sb = mul(rel.R, support_shape(B, verts, mulT(rel.R, v))) + rel.t;
-    V3<T> w = sa - sb;
-    T vv = dot(v, v), vw = dot(v, w);
-    // every x in A-B has x.v >= v.w  =>  distance >= v.w/|v|
-    if (vw > T(0)) {
-      T lim = R + tol;
-      if (vw * vw > lim * lim * vv) { verdict = V_SEP; break; }
-    }
-    if (n > 0 && (vv - vw) <= Num<T>::conv_rel * vv) {
-      // converged: |v| is the core distance up to rounding; it is inside the tol band
-      // (otherwise SEP above or PEN below would have fired) -> uncertain
-      verdict = V_UNC;
-      break;
-    }
-    // append w and solve
-    T l0 = T(0), l1 = T(0), l2 = T(0), l3 = T(0);
-    bool inside = false;
-    if (n == 0) { p0 = w; l0 = T(1); }
-    else if (n == 1) { p1 = w; solve1(p0, p1, l0, l1); }
-    else if (n == 2) { p2 = w; solve2(p0, p1, p2, l0, l1, l2); }
-    else { p3 = w; inside = solve3(p0, p1, p2, p3, l0, l1, l2, l3); }
-    n++;
-    if (inside) {
-      // origin enclosed by the core tetrahedron: depth >= min face distance
-      T dep = vk_min(vk_min(plane_dist(p1, p2, p3), plane_dist(p0, p2, p3)),
-                     vk_min(plane_dist(p0, p1, p3), plane_dist(p0, p1, p2)));
-      verdict = (dep + R > tol) ? V_PEN : V_UNC;
-      break;
-    }
-    v = p0 * l0 + p1 * l1 + p2 * l2 + p3 * l3;
-    // v is a point of A-B: core distance <= |v|
-    T nvv = dot(v, v);
-    if (R > tol && nvv < (R - tol) * (R - tol)) { verdict = V_PEN; break; }
-    if (!(nvv > Num<T>::tiny)) { verdict = V_UNC; break; }  // touching cores
-    // compact the simplex: keep vertices with positive weight at the front
-    bool k0 = l0 > T(0), k1 = l1 > T(0), k2 = l2 > T(0), k3 = l3 > T(0);
-    // bubble empties to the back (stable enough: order is irrelevant to the solver)
-    { bool s = !k0 && k1; cswap(s, p0, p1); cswap(s, k0, k1); }
-    { bool s = !k1 && k2; cswap(s, p1, p2); cswap(s, k1, k2); }
-    { bool s = !k2 && k3; cswap(s, p2, p3); cswap(s, k2, k3); }
-    { bool s = !k0 && k1; cswap(s, p0, p1); cswap(s, k0, k1); }
-    { bool s = !k1 && k2; cswap(s, p1, p2); cswap(s, k1, k2); }
-    { bool s = !k0 && k1; cswap(s, p0, p1); cswap(s, k0, k1); }
-    n = int(k0) + int(k1) + int(k2) + int(k3);
-    if (n == 4) { verdict = V_UNC; break; }  // cannot happen unless solve3 misreported
-  }
-  if (iters) *iters = it + 1;
+  GjkState<T> s;
+  gjk_init(s, A, B, rel);
+  int verdict;
+  do { verdict = gjk_step(s, A, B, verts, rel, R); } while (verdict < 0);
+  if (iters) *iters = s.it;
   return verdict;
 }
 

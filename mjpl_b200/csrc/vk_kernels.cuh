@@ -31,7 +31,8 @@ namespace vk {
 
 constexpr int MODE_DENSE = 0, MODE_EDGES = 1, MODE_SWEEP = 2;
 constexpr uint32_t F_LIMITS = 1u, F_COLLISION = 2u, F_NO_OBB = 4u, F_NO_RECHECK = 8u;
-constexpr int QUEUE_PER_ROW = 8;  // shared work-queue capacity = QUEUE_PER_ROW * TILE items
+constexpr int Q1_PER_ROW = 8;   // sphere-survivor queue capacity per round = Q1_PER_ROW * TILE items
+constexpr int Q2_PER_ROW = 4;   // narrow-phase queue capacity per round = Q2_PER_ROW * TILE items
 
 struct KArgs {
   FkTables<float> fk;
@@ -41,6 +42,9 @@ struct KArgs {
   const Vtx<float> *verts;
   const Pair *pairs;
   int nshape, nmoving, nvert, npair, nslot;
+  int nrounds;
+  int round_start[MAX_ROUNDS + 1];
+  int round_gjk[MAX_ROUNDS];
   int mode;
   // row sources
   const float *q; int ldq; long long n;                       // dense
@@ -95,7 +99,7 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 // dynamic shared memory carve-up (host and device agree through this one function)
 struct SmemLayout {
-  size_t verts, shapes, pairs, cen, qtile, queue, hit, bars, total;
+  size_t verts, shapes, pairs, cen, qtile, queue1, queue2, hit, bars, total;
 };
 template <int TILE>
 __host__ __device__ inline SmemLayout smem_layout(int nvert, int nshape, int npair, int nmoving, int nq) {
@@ -106,9 +110,10 @@ __host__ __device__ inline SmemLayout smem_layout(int nvert, int nshape, int npa
   L.pairs = o; o = align_up(o + (size_t)npair * sizeof(Pair), 128);
   L.cen = o; o = align_up(o + (size_t)(nmoving > 0 ? nmoving : 1) * 3 * TILE * sizeof(float), 128);
   L.qtile = o; o = align_up(o + (size_t)TILE * nq * sizeof(float), 128);
-  L.queue = o; o = align_up(o + (size_t)QUEUE_PER_ROW * TILE * sizeof(uint32_t), 128);
-  L.hit = o; o = align_up(o + (size_t)2 * TILE, 128);
-  L.bars = o; o = align_up(o + 64, 128);
+  L.queue1 = o; o = align_up(o + (size_t)Q1_PER_ROW * TILE * sizeof(uint32_t), 128);
+  L.queue2 = o; o = align_up(o + (size_t)Q2_PER_ROW * TILE * sizeof(uint32_t), 128);
+  L.hit = o;
+  L.bars = o; o = align_up(o + 64 + 8 * (TILE / 32), 128);  // [0] tables, then one row-load barrier per warp
   L.total = o;
   return L;
 }
@@ -151,6 +156,19 @@ __device__ __forceinline__ Pose<float> load_pose(const float *ps, int slot, int 
 }
 
 // ---------------------------------------------------------------------------- main kernel
+// Work-queue items: row-in-warp in the low 16 bits, pair index in the high 16 bits.
+// Queues are WARP-LOCAL (each warp owns 32 rows and a private slice of shared memory), so a
+// push is a ballot + popc with the fill count held in a warp-uniform register: no atomics, no
+// CTA barriers between stages; warps drift apart and hide each other's latency.
+__device__ __forceinline__ bool warp_push(bool want, uint32_t item, uint32_t *queue, int &count, int cap, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, want);
+  const int idx = count + __popc(m & ((1u << lane) - 1u));
+  count += __popc(m);
+  if (!want) return true;
+  if (idx < cap) { queue[idx] = item; return true; }
+  return false;
+}
+
 template <int TILE>
 __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -161,79 +179,79 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
   Pair *s_pairs = reinterpret_cast<Pair *>(smem + L.pairs);
   float *s_cen = reinterpret_cast<float *>(smem + L.cen);
   float *s_q = reinterpret_cast<float *>(smem + L.qtile);
-  uint32_t *s_queue = reinterpret_cast<uint32_t *>(smem + L.queue);
-  uint8_t *s_hit = smem + L.hit;
-  uint8_t *s_unc = s_hit + TILE;
-  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.bars);       // [0] tables, [1] rows
-  int *s_misc = reinterpret_cast<int *>(smem + L.bars + 16);           // [0] queue count, [1..2] ticket
-  long long *s_ticket = reinterpret_cast<long long *>(smem + L.bars + 32);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.bars);       // [0] tables, [8 + w] rows of warp w
+  constexpr int Q1CAP = Q1_PER_ROW * 32, Q2CAP = Q2_PER_ROW * 32;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int wrow0 = tid & ~31;  // first row (within the tile) owned by this warp
+  uint32_t *q1 = reinterpret_cast<uint32_t *>(smem + L.queue1) + (tid >> 5) * Q1CAP;  // sphere-cull survivors
+  uint32_t *q2 = reinterpret_cast<uint32_t *>(smem + L.queue2) + (tid >> 5) * Q2CAP;  // narrow-phase items
   float *pose = a.pose_scratch + (size_t)blockIdx.x * a.nslot * 7 * TILE;
 
   // ---- one-time: model tables -> shared memory through the bulk-copy engine ---------------------
   const uint32_t bytes_v = (uint32_t)(a.nvert * sizeof(Vtx<float>));
   const uint32_t bytes_s = (uint32_t)(a.nshape * sizeof(Shape<float>));
-  const uint32_t bytes_p = (uint32_t)align_up((size_t)a.npair * sizeof(Pair), 16);
+  const uint32_t bytes_p = (uint32_t)(a.npair * sizeof(Pair));
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
     fence_barrier_init();
   }
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(&s_bar[0], bytes_v + bytes_s + bytes_p);
     if (bytes_v) bulk_g2s(s_verts, a.verts, bytes_v, &s_bar[0]);
-    bulk_g2s(s_shapes, a.shapes, bytes_s, &s_bar[0]);
-    bulk_g2s(s_pairs, a.pairs, bytes_p, &s_bar[0]);
+    if (bytes_s) bulk_g2s(s_shapes, a.shapes, bytes_s, &s_bar[0]);
+    if (bytes_p) bulk_g2s(s_pairs, a.pairs, bytes_p, &s_bar[0]);
   }
   mbar_wait(&s_bar[0], 0);
 
   // total number of rows (edges: read from the device-side prefix sums)
   long long nrows = a.n;
   if (a.mode == MODE_EDGES) nrows = a.edge_prefix[a.nedge];
-  const long long ntiles = (nrows + TILE - 1) / TILE;
+  const long long ntiles = (nrows + 31) / 32;   // a tile = the 32 rows one warp owns
   uint32_t row_parity = 0;
-  const bool dense_bulk = (a.mode == MODE_DENSE) && (a.ldq == nq) && ((reinterpret_cast<uintptr_t>(a.q) & 15) == 0) &&
-                          ((TILE * nq * sizeof(float)) % 16 == 0);
+  const bool dense_bulk = (a.mode == MODE_DENSE) && (a.ldq == nq) && ((reinterpret_cast<uintptr_t>(a.q) & 15) == 0);
   long long items_total = 0;
+  const bool use_obb = !(a.flags & F_NO_OBB);
+  const float slack = 1e-4f;
+  uint64_t *wbar = s_bar + 8 + (tid >> 5);       // this warp's row-load barrier
+  float *wq = s_q + (size_t)wrow0 * nq;          // this warp's 32 rows
+  if (lane == 0) mbar_init(wbar, 1);
+  fence_barrier_init();
+  __syncwarp();
 
   for (;;) {
-    // ---- tile ticket -------------------------------------------------------------------------------
-    if (tid == 0) {
-      *s_ticket = (long long)atomicAdd(&a.counters[C_TICKET], 1ull);
-      s_misc[0] = 0;  // work-queue fill count
-    }
-    s_hit[tid] = 0;
-    s_unc[tid] = 0;
-    __syncthreads();
-    const long long tile = *s_ticket;
+    // ---- tile ticket: warps are fully independent from here on (no CTA-wide barrier) ------------
+    long long tile = 0;
+    if (lane == 0) tile = (long long)atomicAdd(&a.counters[C_TICKET], 1ull);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= ntiles) break;
-    const long long row_base = tile * TILE;
-    const int rows_here = (int)((nrows - row_base) < TILE ? (nrows - row_base) : TILE);
-    const long long row = row_base + tid;
-    const bool active = tid < rows_here;
+    const long long row_base = tile * 32;
+    const int rows_here = (int)((nrows - row_base) < 32 ? (nrows - row_base) : 32);
+    const long long row = row_base + lane;
+    const bool active = lane < rows_here;
 
-    // ---- P0: rows -> shared ----------------------------------------------------------------------------
+    // ---- P0: the warp's rows -> shared (one TMA bulk copy per warp tile) -----------------------------
     if (a.mode == MODE_DENSE) {
-      if (dense_bulk && rows_here == TILE) {
-        if (tid == 0) {
+      if (dense_bulk && rows_here == 32) {
+        if (lane == 0) {
           fence_proxy_async();
-          mbar_expect_tx(&s_bar[1], (uint32_t)(TILE * nq * sizeof(float)));
-          bulk_g2s(s_q, a.q + row_base * nq, (uint32_t)(TILE * nq * sizeof(float)), &s_bar[1]);
+          mbar_expect_tx(wbar, (uint32_t)(32 * nq * sizeof(float)));
+          bulk_g2s(wq, a.q + row_base * nq, (uint32_t)(32 * nq * sizeof(float)), wbar);
         }
-        mbar_wait(&s_bar[1], row_parity);
+        mbar_wait(wbar, row_parity);
         row_parity ^= 1;
       } else {
-        for (int i = tid; i < rows_here * nq; i += TILE) {
+        for (int i = lane; i < rows_here * nq; i += 32) {
           int r = i / nq, j = i - r * nq;
-          s_q[i] = a.q[(row_base + r) * a.ldq + j];
+          wq[i] = a.q[(row_base + r) * a.ldq + j];
         }
-        __syncthreads();
       }
+      __syncwarp();
     }
-    // ---- P1: limits + FK -----------------------------------------------------------------------------------
+
+    // ---- P1: limits + FK, one lane per row ---------------------------------------------------------------
     float *q = s_q + tid * nq;  // this lane's row (stride nq words: conflict free for odd nq)
     long long e_idx = 0;
     int e_k = 0;
@@ -279,87 +297,168 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
         }
       }
     }
+    __syncwarp();  // poses (global scratch) and centres of this warp's rows are visible to its lanes
 
-    // ---- P2: broad phase + queue compaction -------------------------------------------------------------------
-    const float slack = 1e-4f;
-    bool overflow = false;
+    // ---- rounds over the (contact-likelihood ordered) pair list, all warp-local --------------------
+    unsigned hit_mask = 0;  // warp-uniform: bit r = row r of this warp has a certain contact
+    unsigned unc_mask = 0;  //               bit r = row r has an uncertain item
+    unsigned ovf_mask = 0;  //               bit r = an item of row r did not fit in a queue
+    int n2 = 0;             // q2 fill (warp-uniform)
+    const unsigned coll_mask = __ballot_sync(0xffffffffu, do_coll);
 #pragma unroll 1
-    for (int p = 0; p < a.npair; p++) {
-      const Pair pr = s_pairs[p];
-      bool survive = false;
-      if (do_coll) {
-        const Shape<float> &A = s_shapes[pr.sa];
-        const Shape<float> &B = s_shapes[pr.sb];
-        V3<float> cB;
-        if (B.slot >= 0) {
-          const float *cc = s_cen + (size_t)pr.sb * 3 * TILE + tid;
-          cB = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
-        } else cB = mk<float>(B.bc[0], B.bc[1], B.bc[2]);
-        if (pr.kind == PK_PLANE) {
-          float d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
-          survive = d <= pr.bsum + slack;
-        } else {
-          V3<float> cA;
-          if (A.slot >= 0) {
-            const float *cc = s_cen + (size_t)pr.sa * 3 * TILE + tid;
-            cA = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
-          } else cA = mk<float>(A.bc[0], A.bc[1], A.bc[2]);
-          V3<float> d = cA - cB;
-          float lim = pr.bsum + slack;
-          survive = dot(d, d) <= lim * lim;
-          if (survive && (pr.flags & 1) && !(a.flags & F_NO_OBB)) {
-            Pose<float> PA = load_pose(pose, A.slot, tid, TILE);
-            Pose<float> PB = load_pose(pose, B.slot, tid, TILE);
-            Rel<float> rel = relative_pose(PA, PB);
-            survive = !obb_disjoint(A, B, rel, pr.rsum - swept_radius(A) - swept_radius(B) + slack);
+    for (int rd = 0; rd < a.nrounds && (coll_mask & ~hit_mask); rd++) {
+      // A: sphere cull, lane = row.  Rows that already have a certain contact drop out.
+      const bool live = do_coll && !((hit_mask >> lane) & 1u);
+      int n1 = 0;
+      bool lost = false;
+      const int p1 = a.round_start[rd + 1];
+#pragma unroll 1
+      for (int p = a.round_start[rd]; p < p1; p++) {
+        const Pair pr = s_pairs[p];
+        bool survive = false;
+        if (live) {
+          const Shape<float> &B = s_shapes[pr.sb];
+          V3<float> cB;
+          if (pr.flags & PF_B_STATIC) cB = mk<float>(B.bc[0], B.bc[1], B.bc[2]);
+          else {
+            const float *cc = s_cen + (size_t)pr.sb * 3 * TILE + tid;
+            cB = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
+          }
+          const Shape<float> &A = s_shapes[pr.sa];
+          if (pr.kind == PK_PLANE) {
+            float d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
+            survive = d <= pr.bsum + slack;
+          } else {
+            V3<float> cA;
+            if (pr.flags & PF_A_STATIC) cA = mk<float>(A.bc[0], A.bc[1], A.bc[2]);
+            else {
+              const float *cc = s_cen + (size_t)pr.sa * 3 * TILE + tid;
+              cA = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
+            }
+            V3<float> d = cA - cB;
+            float lim = pr.bsum + slack;
+            survive = dot(d, d) <= lim * lim;
           }
         }
+        if (!warp_push(survive, (uint32_t)lane | ((uint32_t)p << 16), q1, n1, Q1CAP, lane)) lost = true;
       }
-      const unsigned m = __ballot_sync(0xffffffffu, survive);
-      if (m) {
-        int base = 0;
-        if (lane == (__ffs(m) - 1)) base = atomicAdd(&s_misc[0], __popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (survive) {
-          int idx = base + __popc(m & ((1u << lane) - 1u));
-          if (idx < QUEUE_PER_ROW * TILE) s_queue[idx] = (uint32_t)tid | ((uint32_t)p << 16);
-          else overflow = true;
+      ovf_mask |= __ballot_sync(0xffffffffu, lost);
+      if (n1 > Q1CAP) n1 = Q1CAP;
+      __syncwarp();
+      // B: OBB separating-axis cull, lane = surviving (row, pair)
+#pragma unroll 1
+      for (int base = 0; base < n1; base += 32) {
+        const int i = base + lane;
+        bool keep = false;
+        uint32_t it = 0;
+        if (i < n1) {
+          it = q1[i];
+          const int r = it & 0xffff;
+          const Pair pr = s_pairs[it >> 16];
+          keep = true;
+          if (use_obb && (pr.flags & PF_OBB)) {
+            const Shape<float> &A = s_shapes[pr.sa];
+            const Shape<float> &B = s_shapes[pr.sb];
+            Pose<float> PA = load_pose(pose, A.slot, wrow0 + r, TILE);
+            Pose<float> PB = load_pose(pose, B.slot, wrow0 + r, TILE);
+            Rel<float> rel = relative_pose(PA, PB);
+            keep = !obb_disjoint(A, B, rel, pr.rsum - swept_radius(A) - swept_radius(B) + slack);
+          }
+        }
+        const bool fit = warp_push(keep, it, q2, n2, Q2CAP, lane);
+        ovf_mask |= __reduce_or_sync(0xffffffffu, fit ? 0u : (1u << (it & 31)));
+      }
+      if (n2 > Q2CAP) n2 = Q2CAP;
+      __syncwarp();
+      // C: narrow phase.  Early rounds (most likely contacts) are flushed right away so that hit
+      // rows stop generating work; later rounds accumulate items for better lane balance.
+      const bool flush = (rd < 3) || (n2 >= Q2CAP / 2) || (rd + 1 == a.nrounds) || (a.round_gjk[rd] == 0);
+      if (!flush) continue;
+      items_total += n2;
+      if (!a.round_gjk[rd]) {
+        // plane / segment items: closed forms, one lane per item
+#pragma unroll 1
+        for (int base = 0; base < n2; base += 32) {
+          const int i = base + lane;
+          unsigned hb = 0, ub = 0;
+          if (i < n2) {
+            const uint32_t it = q2[i];
+            const int r = it & 0xffff;
+            const Pair pr = s_pairs[it >> 16];
+            const Shape<float> &SA = s_shapes[pr.sa];
+            const Shape<float> &SB = s_shapes[pr.sb];
+            Pose<float> PA = load_pose(pose, SA.slot, wrow0 + r, TILE);
+            Pose<float> PB = load_pose(pose, SB.slot, wrow0 + r, TILE);
+            const int v = narrow_item<float>(pr.kind, SA, SB, s_verts, PA, PB, pr.rsum);
+            if (v == V_PEN) hb = 1u << r;
+            else if (v == V_UNC) ub = 1u << r;
+          }
+          hit_mask |= __reduce_or_sync(0xffffffffu, hb);
+          unc_mask |= __reduce_or_sync(0xffffffffu, ub);
+        }
+      } else {
+        // GJK items with persistent lanes: every trip runs ONE GJK iteration per lane; a lane
+        // whose item is decided fetches the next one, so lanes do not idle while the slowest
+        // item of the warp converges.
+        GjkState<float> gs;
+        Rel<float> rel;
+        const Shape<float> *SA = s_shapes, *SB = s_shapes;
+        float R = 0.f;
+        int r = 0;
+        bool have = false;
+        int head = 0;  // warp-uniform
+#pragma unroll 1
+        for (;;) {
+          const unsigned need = __ballot_sync(0xffffffffu, !have);
+          if (need == 0xffffffffu && head >= n2) break;
+          if (!have) {
+            const int i = head + __popc(need & ((1u << lane) - 1u));
+            if (i < n2) {
+              const uint32_t it = q2[i];
+              r = it & 0xffff;
+              if (!((hit_mask >> r) & 1u)) {
+                const Pair pr = s_pairs[it >> 16];
+                SA = s_shapes + pr.sa;
+                SB = s_shapes + pr.sb;
+                R = pr.rsum;
+                Pose<float> PA = load_pose(pose, SA->slot, wrow0 + r, TILE);
+                Pose<float> PB = load_pose(pose, SB->slot, wrow0 + r, TILE);
+                rel = relative_pose(PA, PB);
+                gjk_init(gs, *SA, *SB, rel);
+                have = true;
+              }
+            }
+          }
+          head += __popc(need);
+          unsigned hb = 0, ub = 0;
+          if (have) {
+            const int v = gjk_step(gs, *SA, *SB, s_verts, rel, R);
+            if (v >= 0) {
+              if (v == V_PEN) hb = 1u << r;
+              else if (v == V_UNC) ub = 1u << r;
+              have = false;
+            }
+          }
+          hit_mask |= __reduce_or_sync(0xffffffffu, hb);
+          unc_mask |= __reduce_or_sync(0xffffffffu, ub);
+          if (have && ((hit_mask >> r) & 1u)) have = false;  // another pair already decided this row
         }
       }
+      n2 = 0;
+      __syncwarp();
     }
-    if (overflow) s_unc[tid] = 2;  // could not be queued: let the fp64 kernel decide the whole row
-    __syncthreads();  // queue + poses of all rows visible
 
-    // ---- P3: narrow phase over the queue ----------------------------------------------------------------------
-    int nitems = s_misc[0];
-    if (nitems > QUEUE_PER_ROW * TILE) nitems = QUEUE_PER_ROW * TILE;
-    items_total += (tid == 0) ? nitems : 0;
-#pragma unroll 1
-    for (int i = tid; i < nitems; i += TILE) {
-      const uint32_t it = s_queue[i];
-      const int cfg = it & 0xffff;
-      if (s_hit[cfg]) continue;  // early exit: the row already has a certain contact
-      const Pair pr = s_pairs[it >> 16];
-      const Shape<float> &SA = s_shapes[pr.sa];
-      const Shape<float> &SB = s_shapes[pr.sb];
-      Pose<float> PA = load_pose(pose, SA.slot, cfg, TILE);
-      Pose<float> PB = load_pose(pose, SB.slot, cfg, TILE);
-      const int v = narrow_item<float>(pr.kind, SA, SB, s_verts, PA, PB, pr.rsum);
-      if (v == V_PEN) s_hit[cfg] = 1;
-      else if (v == V_UNC) s_unc[cfg] = 1;
-    }
-    __syncthreads();
-
-    // ---- P4: results -----------------------------------------------------------------------------------------------
+    // ---- P4: results, lane = row ---------------------------------------------------------------------------------
     if (active) {
-      const bool hit = s_hit[tid] != 0;
-      const int unc = s_unc[tid];
+      const bool hit = (hit_mask >> lane) & 1u;
+      const bool ovf = (ovf_mask >> lane) & 1u;
+      const bool unc = ((unc_mask >> lane) & 1u) || ovf;
       bool ok = lim_ok && !hit;
-      bool pending = lim_ok && !hit && unc != 0;
+      bool pending = lim_ok && !hit && unc;
       if (pending && !(a.flags & F_NO_RECHECK)) {
         unsigned long long slot = atomicAdd(&a.counters[C_RECHECK], 1ull);
         a.recheck_rows[slot] = row;
-        if (unc == 2) atomicAdd(&a.counters[C_OVERFLOW], 1ull);
+        if (ovf) atomicAdd(&a.counters[C_OVERFLOW], 1ull);
       }
       if (a.mode == MODE_EDGES) {
         if (!ok && !pending) atomicMin(&a.first_bad[e_idx], e_k);
@@ -368,9 +467,8 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
         a.valid[row] = pending ? (uint8_t)((a.flags & F_NO_RECHECK) ? 2 : 1) : (uint8_t)(ok ? 1 : 0);
       }
     }
-    __syncthreads();
   }
-  if (tid == 0 && items_total) atomicAdd(&a.counters[C_ITEMS], (unsigned long long)items_total);
+  if (lane == 0 && items_total) atomicAdd(&a.counters[C_ITEMS], (unsigned long long)items_total);
 }
 
 // ---------------------------------------------------------------------------- fp64 re-evaluation
@@ -391,12 +489,17 @@ struct RArgs {
   const long long *recheck_rows;
 };
 
-__global__ void __launch_bounds__(64) recheck_kernel(const RArgs a) {
+// One WARP per listed row: every lane rebuilds the row and its fp64 poses (cheap, redundant),
+// then the 32 lanes split the static pair list; a contact found by any lane ends the row.
+__global__ void __launch_bounds__(128) recheck_kernel(const RArgs a) {
   const FkTables<double> &fk = *a.fk;
   const unsigned long long total = a.counters[C_RECHECK];
   if (blockIdx.x == 0 && threadIdx.x == 0 && total) atomicAdd(&a.counters[C_UNCERTAIN], total);
+  const int lane = threadIdx.x & 31;
   for (;;) {
-    unsigned long long t = atomicAdd(&a.counters[C_RTICKET], 1ull);
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(&a.counters[C_RTICKET], 1ull);
+    t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= total) break;
     const long long row = a.recheck_rows[t];
     double q[MAX_JNT];
@@ -420,31 +523,37 @@ __global__ void __launch_bounds__(64) recheck_kernel(const RArgs a) {
       P[s] = fk_body(fk, s, ps < 0 ? ident : P[ps], q);
     }
     bool contact = false;
-    for (int p = 0; p < a.npair && !contact; p++) {
-      Pair pr = a.pairs[p];
-      const Shape<double> &A = a.shapes[pr.sa];
-      const Shape<double> &B = a.shapes[pr.sb];
-      const Pose<double> &PA = A.slot < 0 ? ident : P[A.slot];
-      const Pose<double> &PB = B.slot < 0 ? ident : P[B.slot];
-      V3<double> cB = PB.p + qrot(PB.q, mk<double>(B.bc[0], B.bc[1], B.bc[2]));
-      const double bsum = a.pair_bsum[p];
-      if (pr.kind == PK_PLANE) {
-        double d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
-        if (d > bsum + 1e-6) continue;
-      } else {
-        V3<double> cA = PA.p + qrot(PA.q, mk<double>(A.bc[0], A.bc[1], A.bc[2]));
-        V3<double> d = cA - cB;
-        if (dot(d, d) > (bsum + 1e-6) * (bsum + 1e-6)) continue;
+    for (int base = 0; base < a.npair; base += 32) {
+      const int p = base + lane;
+      if (p < a.npair) {
+        const Pair pr = a.pairs[p];
+        const Shape<double> &A = a.shapes[pr.sa];
+        const Shape<double> &B = a.shapes[pr.sb];
+        const Pose<double> &PA = A.slot < 0 ? ident : P[A.slot];
+        const Pose<double> &PB = B.slot < 0 ? ident : P[B.slot];
+        V3<double> cB = PB.p + qrot(PB.q, mk<double>(B.bc[0], B.bc[1], B.bc[2]));
+        const double bsum = a.pair_bsum[p];
+        bool near;
+        if (pr.kind == PK_PLANE) {
+          double d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
+          near = d <= bsum + 1e-6;
+        } else {
+          V3<double> cA = PA.p + qrot(PA.q, mk<double>(A.bc[0], A.bc[1], A.bc[2]));
+          V3<double> d = cA - cB;
+          near = dot(d, d) <= (bsum + 1e-6) * (bsum + 1e-6);
+        }
+        // same classifier in fp64 with the fp64 radii.  "Uncertain" in fp64 means touching to
+        // within rounding: MuJoCo reports a contact for distance <= margin, so it counts.
+        if (near && narrow_item<double>(pr.kind, A, B, a.verts, PA, PB, a.pair_rsum[p]) != V_SEP) contact = true;
       }
-      // same classifier in fp64 with the fp64 radii.  "Uncertain" in fp64 means touching to
-      // within rounding: MuJoCo reports a contact for distance <= margin, so it counts.
-      const int v = narrow_item<double>(pr.kind, A, B, a.verts, PA, PB, a.pair_rsum[p]);
-      if (v != V_SEP) contact = true;
+      if (__any_sync(0xffffffffu, contact)) { contact = true; break; }
     }
-    if (a.mode == MODE_EDGES) {
-      if (contact) atomicMin(&a.first_bad[e_idx], e_k);
-    } else {
-      a.valid[row] = contact ? 0 : 1;
+    if (lane == 0) {
+      if (a.mode == MODE_EDGES) {
+        if (contact) atomicMin(&a.first_bad[e_idx], e_k);
+      } else {
+        a.valid[row] = contact ? 0 : 1;
+      }
     }
   }
 }

@@ -98,7 +98,7 @@ static int row_verdict(const vkb::HostModel &H, const FkTables<T> &fk, const Sha
       V3<T> dd = cA - cB;
       if (dot(dd, dd) > (bsum + slack) * (bsum + slack)) continue;
       if (stats) stats[4]++;
-      if (use_obb && (pr.flags & 1)) {
+      if (use_obb && (pr.flags & PF_OBB)) {
         Rel<T> rel = relative_pose(PA, PB);
         if (obb_disjoint(A, B, rel, rsum - swept_radius(A) - swept_radius(B) + slack)) continue;
       }
