@@ -57,13 +57,20 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.skip = 0
 
     def start(self):
+        """Launch the poller and wait for its first sample, so that NVML start-up (which can stall
+        kernel launches for milliseconds) happens BEFORE the timed region, not inside it."""
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 5.0:
+                time.sleep(0.01)
+            self.skip = len(self.lines)  # samples taken while the GPU was still idle
         except Exception:
             self.proc = None
 
@@ -77,7 +84,7 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons, power = [], [], set(), []
-        for ln in self.lines:
+        for ln in self.lines[self.skip:]:
             p = [x.strip() for x in ln.split(",")]
             if len(p) < 9:
                 continue
@@ -134,7 +141,7 @@ def run_reference(args):
     orc.check(rows[:20000].astype(np.float64), flags)
     rate = 20000 / (time.perf_counter() - t0)
     budget = 120.0 / max(1, args.steps + args.warmup)
-    n = int(min(ROWS_PER_STEP, max(20000, rate * min(budget, 15.0))))
+    n = int(min(ROWS_PER_STEP, max(2000, rate * min(budget, 15.0))))
     sample = rows[:n].astype(np.float64)
     for _ in range(args.warmup):
         orc.check(sample, flags)
@@ -158,8 +165,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

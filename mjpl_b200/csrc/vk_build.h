@@ -397,6 +397,7 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
       t.rsum = (B->kind == SK_VERTS ? B->radius : 0.0) + margin;
       t.bsum = B->brad + margin;
       t.key = 0;
+      if (B->kind == SK_VERTS && B->nvert >= 8) t.p.flags = PF_OBB;  // OBB-above-plane test before the vertex scan
     } else {
       bool seg = A->kind == SK_VERTS && B->kind == SK_VERTS && A->nvert <= 2 && B->nvert <= 2;
       t.p.kind = seg ? PK_SEGSEG : PK_GJK;
@@ -448,17 +449,13 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
         if (pr.kind == PK_PLANE) {
           float dd = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
           if (dd > pr.bsum + slack) continue;
-          n_sph[p]++;
         } else {
           V3<float> cA = PA.p + qrot(PA.q, mk<float>(A.bc[0], A.bc[1], A.bc[2]));
           V3<float> dd = cA - cB;
           if (dot(dd, dd) > (pr.bsum + slack) * (pr.bsum + slack)) continue;
-          n_sph[p]++;
-          if (pr.flags & PF_OBB) {
-            Rel<float> rel = relative_pose(PA, PB);
-            if (obb_disjoint(A, B, rel, pr.rsum - swept_radius(A) - swept_radius(B) + slack)) continue;
-          }
         }
+        n_sph[p]++;
+        if (midphase_cull(pr, A, B, PA, PB, pr.rsum - swept_radius(A) - swept_radius(B), slack)) continue;
         n_obb[p]++;
         int v = narrow_item<float>(pr.kind, A, B, v32.data(), PA, PB, pr.rsum);
         if (v == V_PEN) { n_pen[p]++; row_pen = true; }

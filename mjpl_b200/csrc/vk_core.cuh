@@ -401,16 +401,16 @@ VK_HD void gjk_init(GjkState<T> &s, const Shape<T> &A, const Shape<T> &B, const 
 }
 
 // one iteration; returns -1 to continue or the verdict
-template <typename T>
-VK_HD int gjk_step(GjkState<T> &s, const Shape<T> &A, const Shape<T> &B, const Vtx<T> *__restrict__ verts,
-                   const Rel<T> &rel, T R) {
+// supA(d): support point of A along d (A frame); supB(d): support point of B along d (B frame).
+template <typename T, typename SupA, typename SupB>
+VK_HD int gjk_step_impl(GjkState<T> &s, const Rel<T> &rel, T R, SupA supA, SupB supB) {
   const T tol = Num<T>::tol;
   if (s.it >= Num<T>::maxit) return V_UNC;
   s.it++;
   // support of A-B along -v
   V3<T> v = s.v;
-  V3<T> sa = support_shape(A, verts, -v);
-  V3<T> sb = mul(rel.R, support_shape(B, verts, mulT(rel.R, v))) + rel.t;
+  V3<T> sa = supA(-v);
+  V3<T> sb = mul(rel.R, supB(mulT(rel.R, v))) + rel.t;
   V3<T> w = sa - sb;
   T vv = dot(v, v), vw = dot(v, w);
   // every x in A-B has x.v >= v.w  =>  distance >= v.w/|v|
@@ -451,6 +451,13 @@ VK_HD int gjk_step(GjkState<T> &s, const Shape<T> &A, const Shape<T> &B, const V
   s.n = int(k0) + int(k1) + int(k2) + int(k3);
   if (s.n == 4) return V_UNC;  // cannot happen unless solve3 misreported
   return -1;
+}
+
+template <typename T>
+VK_HD int gjk_step(GjkState<T> &s, const Shape<T> &A, const Shape<T> &B, const Vtx<T> *__restrict__ verts,
+                   const Rel<T> &rel, T R) {
+  return gjk_step_impl(
+      s, rel, R, [&](V3<T> d) { return support_shape(A, verts, d); }, [&](V3<T> d) { return support_shape(B, verts, d); });
 }
 
 template <typename T>
@@ -538,38 +545,69 @@ VK_HD bool obb_disjoint(const Shape<T> &A, const Shape<T> &B, const Rel<T> &rel,
 }
 
 // ------------------------------------------------------------------------------ narrow phase of one item
+// plane (A, world fixed) against B.  mjc_PlaneConvex / PlaneSphere / PlaneCapsule / PlaneBox:
+// deepest point of B along -n;  mjc_PlaneCylinder analytic.  supB as in gjk_step_impl.
+template <typename T, typename SupB>
+VK_HD int plane_classify(const Shape<T> &A, const Shape<T> &B, const Pose<T> &PB, T R, SupB supB) {
+  const T tol = Num<T>::tol;
+  V3<T> n = mk<T>(A.ax[0], A.ax[1], A.ax[2]);
+  V3<T> c = mk<T>(A.c[0], A.c[1], A.c[2]);
+  T dist;
+  if (B.kind == SK_CYL) {
+    V3<T> ax = qrot(PB.q, mk<T>(B.ax[0], B.ax[1], B.ax[2]));
+    V3<T> cb = PB.p + qrot(PB.q, mk<T>(B.c[0], B.c[1], B.c[2]));
+    T na = dot(n, ax);
+    T rad = T(1) - na * na;
+    dist = dot(n, cb - c) - vk_abs(na) * B.halflen - B.radius * vk_sqrt(rad > T(0) ? rad : T(0));
+  } else {
+    V3<T> nl = qrot(qconj(PB.q), n);  // plane normal in B's frame
+    V3<T> sp = supB(-nl);
+    dist = dot(n, PB.p + qrot(PB.q, sp) - c);
+  }
+  if (dist > R + tol) return V_SEP;
+  if (dist < R - tol) return V_PEN;
+  return V_UNC;
+}
+
+// conservative cull: true => B's OBB is certainly above the plane by more than `slack`
+template <typename T>
+VK_HD bool obb_above_plane(const Shape<T> &A, const Shape<T> &B, const Pose<T> &PB, T slack) {
+  V3<T> n = mk<T>(A.ax[0], A.ax[1], A.ax[2]);
+  V3<T> nl = qrot(qconj(PB.q), n);
+  T ext = vk_abs(nl.x * B.orot[0] + nl.y * B.orot[3] + nl.z * B.orot[6]) * B.ohalf[0] +
+          vk_abs(nl.x * B.orot[1] + nl.y * B.orot[4] + nl.z * B.orot[7]) * B.ohalf[1] +
+          vk_abs(nl.x * B.orot[2] + nl.y * B.orot[5] + nl.z * B.orot[8]) * B.ohalf[2];
+  T cen = dot(n, PB.p - mk<T>(A.c[0], A.c[1], A.c[2])) + dot(nl, mk<T>(B.oc[0], B.oc[1], B.oc[2]));
+  return cen - ext > slack + T(1e-6);
+}
+
+// segment-segment item (sphere / capsule cores), world frame
+template <typename T>
+VK_HD int segseg_item(const Shape<T> &A, const Shape<T> &B, const Vtx<T> *verts, const Pose<T> &PA, const Pose<T> &PB, T R) {
+  Vtx<T> a0 = verts[A.vadr], a1 = verts[A.vadr + A.nvert - 1];
+  Vtx<T> b0 = verts[B.vadr], b1 = verts[B.vadr + B.nvert - 1];
+  V3<T> p1 = PA.p + qrot(PA.q, mk<T>(a0.x, a0.y, a0.z)), q1 = PA.p + qrot(PA.q, mk<T>(a1.x, a1.y, a1.z));
+  V3<T> p2 = PB.p + qrot(PB.q, mk<T>(b0.x, b0.y, b0.z)), q2 = PB.p + qrot(PB.q, mk<T>(b1.x, b1.y, b1.z));
+  return segseg_classify(p1, q1, p2, q2, R);
+}
+
+// the mid-phase cull of one surviving (row, pair): true => certainly no contact
+template <typename T>
+VK_HD bool midphase_cull(const Pair &pr, const Shape<T> &A, const Shape<T> &B, const Pose<T> &PA, const Pose<T> &PB,
+                         T margin, T slack) {
+  if (!(pr.flags & PF_OBB)) return false;
+  if (pr.kind == PK_PLANE) return obb_above_plane(A, B, PB, margin + slack);
+  Rel<T> rel = relative_pose(PA, PB);
+  return obb_disjoint(A, B, rel, margin + slack);
+}
+
+// ------------------------------------------------------------------------------ narrow phase of one item (scalar)
 template <typename T>
 VK_HD int narrow_item(int kind, const Shape<T> &A, const Shape<T> &B, const Vtx<T> *verts,
-                                           const Pose<T> &PA, const Pose<T> &PB, T R) {
-  const T tol = Num<T>::tol;
-  if (kind == PK_PLANE) {
-    // plane A is world fixed (PA identity).  mjc_PlaneConvex / PlaneSphere / PlaneCapsule /
-    // PlaneBox: deepest point of B along -n;  mjc_PlaneCylinder analytic.
-    V3<T> n = mk<T>(A.ax[0], A.ax[1], A.ax[2]);
-    V3<T> c = mk<T>(A.c[0], A.c[1], A.c[2]);
-    T dist;
-    if (B.kind == SK_CYL) {
-      V3<T> ax = qrot(PB.q, mk<T>(B.ax[0], B.ax[1], B.ax[2]));
-      V3<T> cb = PB.p + qrot(PB.q, mk<T>(B.c[0], B.c[1], B.c[2]));
-      T na = dot(n, ax);
-      T rad = T(1) - na * na;
-      dist = dot(n, cb - c) - vk_abs(na) * B.halflen - B.radius * vk_sqrt(rad > T(0) ? rad : T(0));
-    } else {
-      V3<T> nl = qrot(qconj(PB.q), n);  // plane normal in B's frame
-      V3<T> s = support_verts(verts + B.vadr, B.nvert, -nl);
-      dist = dot(n, PB.p + qrot(PB.q, s) - c);
-    }
-    if (dist > R + tol) return V_SEP;
-    if (dist < R - tol) return V_PEN;
-    return V_UNC;
-  }
-  if (kind == PK_SEGSEG) {
-    Vtx<T> a0 = verts[A.vadr], a1 = verts[A.vadr + A.nvert - 1];
-    Vtx<T> b0 = verts[B.vadr], b1 = verts[B.vadr + B.nvert - 1];
-    V3<T> p1 = PA.p + qrot(PA.q, mk<T>(a0.x, a0.y, a0.z)), q1 = PA.p + qrot(PA.q, mk<T>(a1.x, a1.y, a1.z));
-    V3<T> p2 = PB.p + qrot(PB.q, mk<T>(b0.x, b0.y, b0.z)), q2 = PB.p + qrot(PB.q, mk<T>(b1.x, b1.y, b1.z));
-    return segseg_classify(p1, q1, p2, q2, R);
-  }
+                      const Pose<T> &PA, const Pose<T> &PB, T R) {
+  if (kind == PK_PLANE)
+    return plane_classify(A, B, PB, R, [&](V3<T> d) { return support_verts(verts + B.vadr, B.nvert, d); });
+  if (kind == PK_SEGSEG) return segseg_item(A, B, verts, PA, PB, R);
   Rel<T> rel = relative_pose(PA, PB);
   return gjk_classify(A, B, verts, rel, R, (int *)nullptr);
 }

@@ -169,6 +169,39 @@ __device__ __forceinline__ bool warp_push(bool want, uint32_t item, uint32_t *qu
   return false;
 }
 
+// Lanes-per-item of the narrow phase: GRP consecutive lanes cooperate on one (row, pair) item.
+// They split every support scan (hull vertices) GRP ways and butterfly-reduce the arg-max, then
+// run the (cheap, identical) simplex update redundantly, so a warp works on 32/GRP items at
+// once with every lane busy during the scans that dominate the cost.
+constexpr int GRP = 4;
+
+__device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const Vtx<float> *__restrict__ verts, V3<float> d,
+                                                  int gl, unsigned gmask) {
+  if (s.kind == SK_CYL) return support_cyl(s, d);
+  const Vtx<float> *__restrict__ v = verts + s.vadr;
+  const int n = s.nvert;
+  float best = -3.0e38f;
+  int bi = 0;
+#pragma unroll 2
+  for (int i = gl; i < n; i += GRP) {
+    const Vtx<float> p = v[i];
+    const float t = p.x * d.x + p.y * d.y + p.z * d.z;
+    const bool g = t > best;
+    best = g ? t : best;
+    bi = g ? i : bi;
+  }
+#pragma unroll
+  for (int o = GRP / 2; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(gmask, best, o);
+    const int oi = __shfl_xor_sync(gmask, bi, o);
+    const bool take = (ob > best) || (ob == best && oi < bi);
+    best = take ? ob : best;
+    bi = take ? oi : bi;
+  }
+  const Vtx<float> w = v[bi];
+  return mk<float>(w.x, w.y, w.z);
+}
+
 template <int TILE>
 __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -361,8 +394,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
             const Shape<float> &B = s_shapes[pr.sb];
             Pose<float> PA = load_pose(pose, A.slot, wrow0 + r, TILE);
             Pose<float> PB = load_pose(pose, B.slot, wrow0 + r, TILE);
-            Rel<float> rel = relative_pose(PA, PB);
-            keep = !obb_disjoint(A, B, rel, pr.rsum - swept_radius(A) - swept_radius(B) + slack);
+            keep = !midphase_cull(pr, A, B, PA, PB, pr.rsum - swept_radius(A) - swept_radius(B), slack);
           }
         }
         const bool fit = warp_push(keep, it, q2, n2, Q2CAP, lane);
@@ -372,34 +404,15 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
       __syncwarp();
       // C: narrow phase.  Early rounds (most likely contacts) are flushed right away so that hit
       // rows stop generating work; later rounds accumulate items for better lane balance.
-      const bool flush = (rd < 3) || (n2 >= Q2CAP / 2) || (rd + 1 == a.nrounds) || (a.round_gjk[rd] == 0);
+      const bool flush = (rd < 2) || (n2 >= Q2CAP / 2) || (rd + 1 == a.nrounds);
       if (!flush) continue;
       items_total += n2;
-      if (!a.round_gjk[rd]) {
-        // plane / segment items: closed forms, one lane per item
-#pragma unroll 1
-        for (int base = 0; base < n2; base += 32) {
-          const int i = base + lane;
-          unsigned hb = 0, ub = 0;
-          if (i < n2) {
-            const uint32_t it = q2[i];
-            const int r = it & 0xffff;
-            const Pair pr = s_pairs[it >> 16];
-            const Shape<float> &SA = s_shapes[pr.sa];
-            const Shape<float> &SB = s_shapes[pr.sb];
-            Pose<float> PA = load_pose(pose, SA.slot, wrow0 + r, TILE);
-            Pose<float> PB = load_pose(pose, SB.slot, wrow0 + r, TILE);
-            const int v = narrow_item<float>(pr.kind, SA, SB, s_verts, PA, PB, pr.rsum);
-            if (v == V_PEN) hb = 1u << r;
-            else if (v == V_UNC) ub = 1u << r;
-          }
-          hit_mask |= __reduce_or_sync(0xffffffffu, hb);
-          unc_mask |= __reduce_or_sync(0xffffffffu, ub);
-        }
-      } else {
-        // GJK items with persistent lanes: every trip runs ONE GJK iteration per lane; a lane
-        // whose item is decided fetches the next one, so lanes do not idle while the slowest
-        // item of the warp converges.
+      {
+        // Persistent lane groups: every trip runs ONE GJK iteration per group; a group whose
+        // item is decided fetches the next one, so lanes do not idle while the slowest item of
+        // the warp converges.  Plane and segment items are decided in the fetch step.
+        const int gl = lane & (GRP - 1);
+        const unsigned gmask = ((1u << GRP) - 1u) << (lane & ~(GRP - 1));
         GjkState<float> gs;
         Rel<float> rel;
         const Shape<float> *SA = s_shapes, *SB = s_shapes;
@@ -409,10 +422,11 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
         int head = 0;  // warp-uniform
 #pragma unroll 1
         for (;;) {
-          const unsigned need = __ballot_sync(0xffffffffu, !have);
+          const unsigned need = __ballot_sync(0xffffffffu, !have);   // group-uniform bits
           if (need == 0xffffffffu && head >= n2) break;
+          unsigned hb = 0, ub = 0;
           if (!have) {
-            const int i = head + __popc(need & ((1u << lane) - 1u));
+            const int i = head + __popc(need & ((1u << (lane & ~(GRP - 1))) - 1u)) / GRP;
             if (i < n2) {
               const uint32_t it = q2[i];
               r = it & 0xffff;
@@ -423,16 +437,30 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
                 R = pr.rsum;
                 Pose<float> PA = load_pose(pose, SA->slot, wrow0 + r, TILE);
                 Pose<float> PB = load_pose(pose, SB->slot, wrow0 + r, TILE);
-                rel = relative_pose(PA, PB);
-                gjk_init(gs, *SA, *SB, rel);
-                have = true;
+                if (pr.kind == PK_GJK) {
+                  rel = relative_pose(PA, PB);
+                  gjk_init(gs, *SA, *SB, rel);
+                  have = true;
+                } else {
+                  int v;
+                  if (pr.kind == PK_PLANE) {
+                    const Shape<float> &Bs = *SB;
+                    v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support(Bs, s_verts, d, gl, gmask); });
+                  } else {
+                    v = segseg_item(*SA, *SB, s_verts, PA, PB, R);
+                  }
+                  if (v == V_PEN) hb = 1u << r;
+                  else if (v == V_UNC) ub = 1u << r;
+                }
               }
             }
           }
-          head += __popc(need);
-          unsigned hb = 0, ub = 0;
+          head += __popc(need) / GRP;
           if (have) {
-            const int v = gjk_step(gs, *SA, *SB, s_verts, rel, R);
+            const Shape<float> &As = *SA, &Bs = *SB;
+            const int v = gjk_step_impl(
+                gs, rel, R, [&](V3<float> d) { return group_support(As, s_verts, d, gl, gmask); },
+                [&](V3<float> d) { return group_support(Bs, s_verts, d, gl, gmask); });
             if (v >= 0) {
               if (v == V_PEN) hb = 1u << r;
               else if (v == V_UNC) ub = 1u << r;

@@ -97,12 +97,9 @@ static int row_verdict(const vkb::HostModel &H, const FkTables<T> &fk, const Sha
       V3<T> cA = PA.p + qrot(PA.q, mk<T>(A.bc[0], A.bc[1], A.bc[2]));
       V3<T> dd = cA - cB;
       if (dot(dd, dd) > (bsum + slack) * (bsum + slack)) continue;
-      if (stats) stats[4]++;
-      if (use_obb && (pr.flags & PF_OBB)) {
-        Rel<T> rel = relative_pose(PA, PB);
-        if (obb_disjoint(A, B, rel, rsum - swept_radius(A) - swept_radius(B) + slack)) continue;
-      }
     }
+    if (stats) stats[4]++;
+    if (use_obb && midphase_cull(pr, A, B, PA, PB, rsum - swept_radius(A) - swept_radius(B), slack)) continue;
     if (stats) stats[0]++;
     int v;
     if (pr.kind == PK_GJK) {
