@@ -160,13 +160,12 @@ __device__ __forceinline__ Pose<float> load_pose(const float *ps, int slot, int 
 // Queues are WARP-LOCAL (each warp owns 32 rows and a private slice of shared memory), so a
 // push is a ballot + popc with the fill count held in a warp-uniform register: no atomics, no
 // CTA barriers between stages; warps drift apart and hide each other's latency.
-__device__ __forceinline__ bool warp_push(bool want, uint32_t item, uint32_t *queue, int &count, int cap, int lane) {
+// The caller guarantees count + 32 <= cap before the push, so nothing can be dropped.
+__device__ __forceinline__ void warp_push(bool want, uint32_t item, uint32_t *queue, int &count, int cap, int lane) {
   const unsigned m = __ballot_sync(0xffffffffu, want);
   const int idx = count + __popc(m & ((1u << lane) - 1u));
   count += __popc(m);
-  if (!want) return true;
-  if (idx < cap) { queue[idx] = item; return true; }
-  return false;
+  if (want && idx < cap) queue[idx] = item;
 }
 
 // Lanes-per-item of the narrow phase: GRP consecutive lanes cooperate on one (row, pair) item.
@@ -333,160 +332,167 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
     __syncwarp();  // poses (global scratch) and centres of this warp's rows are visible to its lanes
 
     // ---- rounds over the (contact-likelihood ordered) pair list, all warp-local --------------------
+    // Stage A fills q1 (sphere-cull survivors), stage B drains q1 into q2 (mid-phase survivors),
+    // stage C consumes q2 (narrow phase).  Every stage stops while the next queue still has room
+    // for a full warp of pushes, so NO item is ever dropped, whatever the rows look like
+    // (correlated rows of a planner chain fill the queues far beyond the calibrated average).
     unsigned hit_mask = 0;  // warp-uniform: bit r = row r of this warp has a certain contact
     unsigned unc_mask = 0;  //               bit r = row r has an uncertain item
-    unsigned ovf_mask = 0;  //               bit r = an item of row r did not fit in a queue
+    int n1 = 0, b_pos = 0;  // q1 fill and the next q1 index stage B will take (warp-uniform)
     int n2 = 0;             // q2 fill (warp-uniform)
     const unsigned coll_mask = __ballot_sync(0xffffffffu, do_coll);
+    const int gl = lane & (GRP - 1);
+    const unsigned gmask = ((1u << GRP) - 1u) << (lane & ~(GRP - 1));
 #pragma unroll 1
     for (int rd = 0; rd < a.nrounds && (coll_mask & ~hit_mask); rd++) {
-      // A: sphere cull, lane = row.  Rows that already have a certain contact drop out.
-      const bool live = do_coll && !((hit_mask >> lane) & 1u);
-      int n1 = 0;
-      bool lost = false;
+      int p = a.round_start[rd];
       const int p1 = a.round_start[rd + 1];
+      // early rounds (most likely contacts) are flushed right away so that hit rows stop
+      // generating work; later rounds accumulate items for better lane balance
+      const bool flush_round = (rd < 2) || (rd + 1 == a.nrounds);
 #pragma unroll 1
-      for (int p = a.round_start[rd]; p < p1; p++) {
-        const Pair pr = s_pairs[p];
-        bool survive = false;
-        if (live) {
-          const Shape<float> &B = s_shapes[pr.sb];
-          V3<float> cB;
-          if (pr.flags & PF_B_STATIC) cB = mk<float>(B.bc[0], B.bc[1], B.bc[2]);
-          else {
-            const float *cc = s_cen + (size_t)pr.sb * 3 * TILE + tid;
-            cB = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
-          }
-          const Shape<float> &A = s_shapes[pr.sa];
-          if (pr.kind == PK_PLANE) {
-            float d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
-            survive = d <= pr.bsum + slack;
-          } else {
-            V3<float> cA;
-            if (pr.flags & PF_A_STATIC) cA = mk<float>(A.bc[0], A.bc[1], A.bc[2]);
-            else {
-              const float *cc = s_cen + (size_t)pr.sa * 3 * TILE + tid;
-              cA = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
+      for (;;) {
+        // A: sphere cull, lane = row.  Rows that already have a certain contact drop out.
+        if (b_pos >= n1) {
+          n1 = 0;
+          b_pos = 0;
+          const bool live = do_coll && !((hit_mask >> lane) & 1u);
+#pragma unroll 1
+          for (; p < p1 && n1 + 32 <= Q1CAP; p++) {
+            const Pair pr = s_pairs[p];
+            bool survive = false;
+            if (live) {
+              const Shape<float> &B = s_shapes[pr.sb];
+              V3<float> cB;
+              if (pr.flags & PF_B_STATIC) cB = mk<float>(B.bc[0], B.bc[1], B.bc[2]);
+              else {
+                const float *cc = s_cen + (size_t)pr.sb * 3 * TILE + tid;
+                cB = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
+              }
+              const Shape<float> &A = s_shapes[pr.sa];
+              if (pr.kind == PK_PLANE) {
+                float d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
+                survive = d <= pr.bsum + slack;
+              } else {
+                V3<float> cA;
+                if (pr.flags & PF_A_STATIC) cA = mk<float>(A.bc[0], A.bc[1], A.bc[2]);
+                else {
+                  const float *cc = s_cen + (size_t)pr.sa * 3 * TILE + tid;
+                  cA = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
+                }
+                V3<float> d = cA - cB;
+                float lim = pr.bsum + slack;
+                survive = dot(d, d) <= lim * lim;
+              }
             }
-            V3<float> d = cA - cB;
-            float lim = pr.bsum + slack;
-            survive = dot(d, d) <= lim * lim;
+            warp_push(survive, (uint32_t)lane | ((uint32_t)p << 16), q1, n1, Q1CAP, lane);
           }
+          __syncwarp();
         }
-        if (!warp_push(survive, (uint32_t)lane | ((uint32_t)p << 16), q1, n1, Q1CAP, lane)) lost = true;
-      }
-      ovf_mask |= __ballot_sync(0xffffffffu, lost);
-      if (n1 > Q1CAP) n1 = Q1CAP;
-      __syncwarp();
-      // B: OBB separating-axis cull, lane = surviving (row, pair)
+        // B: mid-phase cull (OBB-OBB separating axes / OBB above plane), lane = surviving (row, pair)
 #pragma unroll 1
-      for (int base = 0; base < n1; base += 32) {
-        const int i = base + lane;
-        bool keep = false;
-        uint32_t it = 0;
-        if (i < n1) {
-          it = q1[i];
-          const int r = it & 0xffff;
-          const Pair pr = s_pairs[it >> 16];
-          keep = true;
-          if (use_obb && (pr.flags & PF_OBB)) {
-            const Shape<float> &A = s_shapes[pr.sa];
-            const Shape<float> &B = s_shapes[pr.sb];
-            Pose<float> PA = load_pose(pose, A.slot, wrow0 + r, TILE);
-            Pose<float> PB = load_pose(pose, B.slot, wrow0 + r, TILE);
-            keep = !midphase_cull(pr, A, B, PA, PB, pr.rsum - swept_radius(A) - swept_radius(B), slack);
+        for (; b_pos < n1 && n2 + 32 <= Q2CAP; b_pos += 32) {
+          const int i = b_pos + lane;
+          bool keep = false;
+          uint32_t it = 0;
+          if (i < n1) {
+            it = q1[i];
+            const int r = it & 0xffff;
+            const Pair pr = s_pairs[it >> 16];
+            keep = !((hit_mask >> r) & 1u);
+            if (keep && use_obb && (pr.flags & PF_OBB)) {
+              const Shape<float> &A = s_shapes[pr.sa];
+              const Shape<float> &B = s_shapes[pr.sb];
+              Pose<float> PA = load_pose(pose, A.slot, wrow0 + r, TILE);
+              Pose<float> PB = load_pose(pose, B.slot, wrow0 + r, TILE);
+              keep = !midphase_cull(pr, A, B, PA, PB, pr.rsum - swept_radius(A) - swept_radius(B), slack);
+            }
           }
+          warp_push(keep, it, q2, n2, Q2CAP, lane);
         }
-        const bool fit = warp_push(keep, it, q2, n2, Q2CAP, lane);
-        ovf_mask |= __reduce_or_sync(0xffffffffu, fit ? 0u : (1u << (it & 31)));
-      }
-      if (n2 > Q2CAP) n2 = Q2CAP;
-      __syncwarp();
-      // C: narrow phase.  Early rounds (most likely contacts) are flushed right away so that hit
-      // rows stop generating work; later rounds accumulate items for better lane balance.
-      const bool flush = (rd < 2) || (n2 >= Q2CAP / 2) || (rd + 1 == a.nrounds);
-      if (!flush) continue;
-      items_total += n2;
-      {
-        // Persistent lane groups: every trip runs ONE GJK iteration per group; a group whose
-        // item is decided fetches the next one, so lanes do not idle while the slowest item of
-        // the warp converges.  Plane and segment items are decided in the fetch step.
-        const int gl = lane & (GRP - 1);
-        const unsigned gmask = ((1u << GRP) - 1u) << (lane & ~(GRP - 1));
-        GjkState<float> gs;
-        Rel<float> rel;
-        const Shape<float> *SA = s_shapes, *SB = s_shapes;
-        float R = 0.f;
-        int r = 0;
-        bool have = false;
-        int head = 0;  // warp-uniform
+        __syncwarp();
+        const bool a_done = (p >= p1) && (b_pos >= n1);
+        const bool run_c = (b_pos < n1) /* q2 has no room */ || (a_done && (flush_round || n2 >= Q2CAP / 2));
+        if (run_c) {
+          // C: narrow phase with persistent lane groups: every trip runs ONE GJK iteration per
+          // group; a group whose item is decided fetches the next one, so lanes do not idle
+          // while the slowest item of the warp converges.  Plane and segment items are decided
+          // in the fetch step.
+          items_total += n2;
+          GjkState<float> gs;
+          Rel<float> rel;
+          const Shape<float> *SA = s_shapes, *SB = s_shapes;
+          float R = 0.f;
+          int r = 0;
+          bool have = false;
+          int head = 0;  // warp-uniform
 #pragma unroll 1
-        for (;;) {
-          const unsigned need = __ballot_sync(0xffffffffu, !have);   // group-uniform bits
-          if (need == 0xffffffffu && head >= n2) break;
-          unsigned hb = 0, ub = 0;
-          if (!have) {
-            const int i = head + __popc(need & ((1u << (lane & ~(GRP - 1))) - 1u)) / GRP;
-            if (i < n2) {
-              const uint32_t it = q2[i];
-              r = it & 0xffff;
-              if (!((hit_mask >> r) & 1u)) {
-                const Pair pr = s_pairs[it >> 16];
-                SA = s_shapes + pr.sa;
-                SB = s_shapes + pr.sb;
-                R = pr.rsum;
-                Pose<float> PA = load_pose(pose, SA->slot, wrow0 + r, TILE);
-                Pose<float> PB = load_pose(pose, SB->slot, wrow0 + r, TILE);
-                if (pr.kind == PK_GJK) {
-                  rel = relative_pose(PA, PB);
-                  gjk_init(gs, *SA, *SB, rel);
-                  have = true;
-                } else {
-                  int v;
-                  if (pr.kind == PK_PLANE) {
-                    const Shape<float> &Bs = *SB;
-                    v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support(Bs, s_verts, d, gl, gmask); });
+          for (;;) {
+            const unsigned need = __ballot_sync(0xffffffffu, !have);   // group-uniform bits
+            if (need == 0xffffffffu && head >= n2) break;
+            unsigned hb = 0, ub = 0;
+            if (!have) {
+              const int i = head + __popc(need & ((1u << (lane & ~(GRP - 1))) - 1u)) / GRP;
+              if (i < n2) {
+                const uint32_t it = q2[i];
+                r = it & 0xffff;
+                if (!((hit_mask >> r) & 1u)) {
+                  const Pair pr = s_pairs[it >> 16];
+                  SA = s_shapes + pr.sa;
+                  SB = s_shapes + pr.sb;
+                  R = pr.rsum;
+                  Pose<float> PA = load_pose(pose, SA->slot, wrow0 + r, TILE);
+                  Pose<float> PB = load_pose(pose, SB->slot, wrow0 + r, TILE);
+                  if (pr.kind == PK_GJK) {
+                    rel = relative_pose(PA, PB);
+                    gjk_init(gs, *SA, *SB, rel);
+                    have = true;
                   } else {
-                    v = segseg_item(*SA, *SB, s_verts, PA, PB, R);
+                    int v;
+                    if (pr.kind == PK_PLANE) {
+                      const Shape<float> &Bs = *SB;
+                      v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support(Bs, s_verts, d, gl, gmask); });
+                    } else {
+                      v = segseg_item(*SA, *SB, s_verts, PA, PB, R);
+                    }
+                    if (v == V_PEN) hb = 1u << r;
+                    else if (v == V_UNC) ub = 1u << r;
                   }
-                  if (v == V_PEN) hb = 1u << r;
-                  else if (v == V_UNC) ub = 1u << r;
                 }
               }
             }
-          }
-          head += __popc(need) / GRP;
-          if (have) {
-            const Shape<float> &As = *SA, &Bs = *SB;
-            const int v = gjk_step_impl(
-                gs, rel, R, [&](V3<float> d) { return group_support(As, s_verts, d, gl, gmask); },
-                [&](V3<float> d) { return group_support(Bs, s_verts, d, gl, gmask); });
-            if (v >= 0) {
-              if (v == V_PEN) hb = 1u << r;
-              else if (v == V_UNC) ub = 1u << r;
-              have = false;
+            head += __popc(need) / GRP;
+            if (have) {
+              const Shape<float> &As = *SA, &Bs = *SB;
+              const int v = gjk_step_impl(
+                  gs, rel, R, [&](V3<float> d) { return group_support(As, s_verts, d, gl, gmask); },
+                  [&](V3<float> d) { return group_support(Bs, s_verts, d, gl, gmask); });
+              if (v >= 0) {
+                if (v == V_PEN) hb = 1u << r;
+                else if (v == V_UNC) ub = 1u << r;
+                have = false;
+              }
             }
+            hit_mask |= __reduce_or_sync(0xffffffffu, hb);
+            unc_mask |= __reduce_or_sync(0xffffffffu, ub);
+            if (have && ((hit_mask >> r) & 1u)) have = false;  // another pair already decided this row
           }
-          hit_mask |= __reduce_or_sync(0xffffffffu, hb);
-          unc_mask |= __reduce_or_sync(0xffffffffu, ub);
-          if (have && ((hit_mask >> r) & 1u)) have = false;  // another pair already decided this row
+          n2 = 0;
+          __syncwarp();
         }
+        if (a_done) break;
       }
-      n2 = 0;
-      __syncwarp();
     }
 
     // ---- P4: results, lane = row ---------------------------------------------------------------------------------
     if (active) {
       const bool hit = (hit_mask >> lane) & 1u;
-      const bool ovf = (ovf_mask >> lane) & 1u;
-      const bool unc = ((unc_mask >> lane) & 1u) || ovf;
+      const bool unc = (unc_mask >> lane) & 1u;
       bool ok = lim_ok && !hit;
       bool pending = lim_ok && !hit && unc;
       if (pending && !(a.flags & F_NO_RECHECK)) {
         unsigned long long slot = atomicAdd(&a.counters[C_RECHECK], 1ull);
         a.recheck_rows[slot] = row;
-        if (ovf) atomicAdd(&a.counters[C_OVERFLOW], 1ull);
       }
       if (a.mode == MODE_EDGES) {
         if (!ok && !pending) atomicMin(&a.first_bad[e_idx], e_k);
