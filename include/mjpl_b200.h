@@ -121,6 +121,16 @@ int mjb_check_sweep(mjb_model *m, uint64_t seed, int64_t row0, int64_t n, uint8_
                     uint32_t flags, void *stream);
 int mjb_sweep_rows(mjb_model *m, uint64_t seed, int64_t row0, int64_t n, float *d_q, void *stream);
 
+/*
+ * Tree.nearest_neighbor (src/mjpl/planning/tree.py:57-66) for n queries at once.  Trees are
+ * rows of a padded (ntrees, cap, nq) fp64 array with per-tree node counts; d_rows (optional)
+ * selects the tree of each query (NULL: query i uses tree i).  d_out[i] = index of the nearest
+ * node (squared Euclidean distance, lowest index wins ties; non-finite nodes never win).
+ */
+int mjb_nearest_batch(const double *d_nodes, int64_t cap, int32_t nq, const int64_t *d_count,
+                      const int64_t *d_rows, const double *d_targets, int64_t n, int64_t *d_out,
+                      void *stream);
+
 int mjb_get_stats(mjb_model *m, mjb_stats *out);   /* synchronises the handle's last stream */
 int mjb_reset_stats(mjb_model *m);
 

@@ -32,30 +32,23 @@ def apply_constraints(q_old: np.ndarray, q: np.ndarray, constraints: list[Constr
 
 
 def _fusable(constraints):
-    """[JointLimitConstraint, CollisionConstraint] on one model -> (engine, flags) for a single
-    fused kernel launch (limits + FK + collision), else None."""
+    """``[JointLimitConstraint, CollisionConstraint]`` (any order, at most one of each) on ONE model
+    -> ``(engine, flags)`` for a single fused kernel launch (limits + FK + collision); else None."""
     if not constraints:
         return None
-    flags, eng = 0, None
+    flags, eng, model = 0, None, None
     for c in constraints:
-        if type(c) is JointLimitConstraint:
+        if type(c) is JointLimitConstraint and not flags & _engine.CHECK_LIMITS:
             flags |= _engine.CHECK_LIMITS
-            model = c.model
-        elif type(c) is CollisionConstraint:
-            if flags & _engine.CHECK_COLLISION:
-                return None
+        elif type(c) is CollisionConstraint and not flags & _engine.CHECK_COLLISION:
             flags |= _engine.CHECK_COLLISION
             eng = c.engine
-            model = c.model
         else:
             return None
-        if eng is not None and model is not eng.model:
+        if model is not None and c.model is not model:
             return None
-    if eng is None:
-        eng = constraints[0].engine
-    if any(c.model is not eng.model for c in constraints):
-        return None
-    return eng, flags
+        model = c.model
+    return (eng if eng is not None else constraints[0].engine), flags
 
 
 def obeys_constraints_batch(Q, constraints: list[Constraint]):

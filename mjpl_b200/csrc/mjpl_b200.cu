@@ -402,3 +402,16 @@ extern "C" int mjb_reset_stats(mjb_model *m) {
   m->launches = 0;
   return MJB_OK;
 }
+
+extern "C" int mjb_nearest_batch(const double *d_nodes, int64_t cap, int32_t nq, const int64_t *d_count, const int64_t *d_rows,
+                                 const double *d_targets, int64_t n, int64_t *d_out, void *stream) {
+  if (n < 0 || cap < 1 || nq < 1) return fail(MJB_ERR_ARG, "bad n / cap / nq");
+  if (n == 0) return MJB_OK;
+  if (!d_nodes || !d_count || !d_targets || !d_out) return fail(MJB_ERR_ARG, "null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  nearest_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_count,
+                                                                  (const long long *)d_rows, d_targets, (long long)n,
+                                                                  (long long *)d_out);
+  CU(cudaGetLastError());
+  return MJB_OK;
+}

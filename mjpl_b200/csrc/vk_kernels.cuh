@@ -660,4 +660,37 @@ __global__ void sweep_rows_kernel(FkTables<float> fk, unsigned long long seed, l
   q[i] = sweep_value(seed, (uint64_t)(row0 + r), (uint32_t)j, fk.jnt_lo[j], fk.jnt_hi[j]);
 }
 
+// ---------------------------------------------------------------------------- batched nearest neighbour
+// Tree.nearest_neighbor (reference: src/mjpl/planning/tree.py:57-66) for many trees at once:
+// trees are rows of a padded (B, cap, nq) fp64 array; one warp scans one tree and keeps the
+// arg-min of the squared distance (lowest index wins ties).  Nodes with non-finite entries (the
+// +inf sink root of the reference's goal tree) can never win.
+__global__ void __launch_bounds__(128) nearest_kernel(const double *nodes, long long cap, int nq, const long long *count,
+                                                      const long long *rows, const double *targets, long long n,
+                                                      long long *out) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const long long tree = rows ? rows[w] : w;
+  const double *base = nodes + tree * cap * nq;
+  const double *t = targets + w * nq;
+  const long long cnt = count[tree];
+  double best = 1.0e300;
+  long long bi = 0;
+  for (long long i = lane; i < cnt; i += 32) {
+    double d2 = 0;
+    for (int j = 0; j < nq; j++) {
+      double d = base[i * nq + j] - t[j];
+      d2 += d * d;
+    }
+    if (d2 < best) { best = d2; bi = i; }   // NaN / inf never pass
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if (lane == 0) out[w] = bi;
+}
+
 }  // namespace vk

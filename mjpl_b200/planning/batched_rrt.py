@@ -10,6 +10,17 @@ random stream seeded ``seed + i``), so they shard across GPUs without communicat
 
 Trees are stored as padded ``(nqueries, capacity, nq)`` arrays; nearest neighbours are one
 vectorised reduction per iteration for all queries.
+
+Two drivers share the algorithm:
+
+* the **device driver** (used when the constraints are this package's CUDA constraints on one
+  model): forests live in HBM as fp64 tensors, nearest neighbours come from
+  ``mjb_nearest_batch`` (one warp per tree), chains are built, validated
+  (``mjb_check_configs``) and appended without leaving the GPU; the host only learns, once per
+  iteration, which queries have met.  Sampling uses one vectorised random stream for all queries.
+* the **host driver** (any other ``Constraint``, e.g. the oracle-backed doubles of the CPU test
+  suite): the same steps in numpy with one ``valid_configs`` call per extend phase and one random
+  stream per query (``seed + i``).
 """
 
 from __future__ import annotations
@@ -19,7 +30,7 @@ import time
 import numpy as np
 
 from ..constraint.constraint_interface import Constraint
-from ..constraint.utils import obeys_constraints_batch
+from ..constraint.utils import _fusable, obeys_constraints_batch
 from ..utils import qpos_idx
 
 
@@ -80,8 +91,8 @@ class BatchedRRT:
 
     def __init__(self, model, planning_joints: list[str], constraints: list[Constraint],
                  max_planning_time: float = 10.0, epsilon: float = 0.05, seed: int | None = None,
-                 goal_biasing_probability: float = 0.05, max_iterations: int = 100000,
-                 max_chain: int = 512) -> None:
+                 goal_biasing_probability: float = 0.05, max_iterations: int = 1000000,
+                 max_chain: int = 512, max_active: int = 4096, max_iterations_per_query: int = 3000) -> None:
         if not planning_joints:
             raise ValueError("`planning_joints` cannot be empty.")
         if max_planning_time <= 0.0:
@@ -101,6 +112,8 @@ class BatchedRRT:
         self.goal_biasing_probability = goal_biasing_probability
         self.max_iterations = max_iterations
         self.max_chain = max_chain
+        self.max_active = max_active                              # slots of the device driver
+        self.max_iterations_per_query = max_iterations_per_query  # a query that exceeds it returns []
         self.stats: dict = {}
 
     # one extend for a set of queries: returns reached configs and node indices
@@ -144,6 +157,241 @@ class BatchedRRT:
         q_goals = np.ascontiguousarray(q_goals, dtype=np.float64)
         if q_inits.shape != q_goals.shape or q_inits.ndim != 2:
             raise ValueError("q_inits and q_goals must both be (B, nq)")
+        fused = _fusable(self.constraints)
+        if fused is not None:
+            return self._plan_device(q_inits, q_goals, *fused)
+        return self._plan_host(q_inits, q_goals)
+
+    # ------------------------------------------------------------------ device driver
+    def _plan_device(self, q_inits, q_goals, eng, flags):
+        import ctypes as C
+
+        import torch
+
+        from .. import _abi
+
+        dev, f64 = eng.torch_device, torch.float64
+        L = _abi.lib()
+        B, nq = q_inits.shape
+        eps = float(self.epsilon)
+        with torch.cuda.device(eng.device):
+            QI = torch.from_numpy(q_inits).to(dev)
+            QG = torch.from_numpy(q_goals).to(dev)
+            ok = eng.valid_configs(torch.cat([QI, QG]).float(), flags)
+            if not bool(ok[:B].all()):
+                raise ValueError("q_init is not a valid configuration")
+            if not bool(ok[B:].all()):
+                bad = q_goals[int((~ok[B:]).nonzero()[0])]
+                raise ValueError(f"The following goal config is not a valid configuration: {bad}")
+            q_idx = qpos_idx(self.model, self.planning_joints)
+            fixed = [i for i in range(nq) if i not in set(q_idx)]
+            if fixed and not np.allclose(q_inits[:, fixed], q_goals[:, fixed], rtol=0, atol=1e-12):
+                raise ValueError("goal configs have values for joints outside of the planner's planning joints "
+                                 "that don't match q_init")
+            plan_mask = torch.zeros(nq, dtype=torch.bool, device=dev)
+            plan_mask[q_idx] = True
+            lo = torch.from_numpy(np.ascontiguousarray(self.model.jnt_range[:, 0])).to(dev)
+            hi = torch.from_numpy(np.ascontiguousarray(self.model.jnt_range[:, 1])).to(dev)
+            gen = torch.Generator(device=dev)
+            if self.seed is not None:
+                gen.manual_seed(int(self.seed))
+
+            class Forest:
+                def __init__(self, roots, cap=1024):
+                    self.cap = cap
+                    self.q = torch.full((B, cap, nq), float("inf"), dtype=f64, device=dev)
+                    self.parent = torch.full((B, cap), -1, dtype=torch.int64, device=dev)
+                    self.count = torch.ones(B, dtype=torch.int64, device=dev)
+                    self.q[:, 0] = roots
+                    self.hi = 1  # host-side upper bound of count.max()
+
+                def reserve(self, extra):
+                    if self.hi + extra <= self.cap:
+                        return
+                    new = max(self.hi + extra, 2 * self.cap)
+                    q = torch.full((B, new, nq), float("inf"), dtype=f64, device=dev)
+                    q[:, : self.cap] = self.q
+                    p = torch.full((B, new), -1, dtype=torch.int64, device=dev)
+                    p[:, : self.cap] = self.parent
+                    self.q, self.parent, self.cap = q, p, new
+
+                def nearest(self, act, targets):
+                    out = torch.empty(len(act), dtype=torch.int64, device=dev)
+                    t = targets.contiguous()
+                    _abi.check(L.mjb_nearest_batch(self.q.data_ptr(), self.cap, nq, self.count.data_ptr(), act.data_ptr(),
+                                                   t.data_ptr(), len(act), out.data_ptr(),
+                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                    return out
+
+            def extend(F, act, targets):
+                n = len(act)
+                near_idx = F.nearest(act, targets)
+                near = F.q[act, near_idx]
+                d = targets - near
+                dist = torch.linalg.vector_norm(d, dim=1)
+                k = torch.ceil(dist / eps).clamp(max=self.max_chain).to(torch.int64)
+                kmax = int(k.max())
+                if kmax == 0:
+                    return near, near_idx
+                F.reserve(kmax)
+                ar = torch.arange(kmax, device=dev)
+                frac = torch.where(dist > 0, eps / dist, torch.zeros_like(dist))[:, None] * (ar + 1)[None, :].to(f64)
+                chains = near[:, None, :] + frac.clamp(max=1.0)[:, :, None] * d[:, None, :]
+                # the step that covers the remaining distance lands on the target itself
+                full = (k.to(f64) * eps >= dist) & (k > 0)
+                fi = full.nonzero(as_tuple=True)[0]
+                chains[fi, k[fi] - 1] = targets[fi]
+                mask = ar[None, :] < k[:, None]
+                flat = chains[mask]
+                okf = eng.valid_configs(flat.float(), flags)
+                self.stats["configs_checked"] += int(flat.shape[0])
+                self.stats["launches"] += 1
+                okm = torch.ones(mask.shape, dtype=torch.bool, device=dev)
+                okm[mask] = okf
+                prev = torch.cat([near[:, None, :], chains[:, :-1]], dim=1)
+                okm &= (torch.linalg.vector_norm(chains - prev, dim=2) >= 1e-8) | ~mask
+                good = torch.minimum(okm.to(torch.int64).cumprod(dim=1).sum(dim=1), k)
+                base = F.count[act]
+                m2 = ar[None, :] < good[:, None]
+                slot = base[:, None] + ar[None, :]
+                rows = act[:, None].expand(n, kmax)
+                par = torch.where(ar[None, :] == 0, near_idx[:, None].expand(n, kmax), slot - 1)
+                F.q[rows[m2], slot[m2]] = chains[m2]
+                F.parent[rows[m2], slot[m2]] = par[m2]
+                F.count[act] = base + good
+                F.hi += kmax
+                last = torch.where(good > 0, base + good - 1, near_idx)
+                return F.q[act, last], last
+
+            direct = torch.linalg.vector_norm(QG - QI, dim=1) <= eps
+            paths: list[list[np.ndarray]] = [[] for _ in range(B)]
+            for b in direct.nonzero(as_tuple=True)[0].tolist():
+                paths[b] = [q_inits[b].copy(), q_goals[b].copy()]
+            pending = (~direct).nonzero(as_tuple=True)[0].cpu().numpy().tolist()[::-1]  # pop() takes the lowest id
+            # ---- continuous batching: S slots, each holding one query's two trees; a slot whose
+            # query is solved (or out of budget) is handed to the next pending query at once, so
+            # the long tail of hard queries never idles the rest of the batch.
+            S = min(len(pending), int(self.max_active)) if pending else 0
+            self.stats = {"iterations": 0, "configs_checked": 0, "launches": 0, "driver": "device", "slots": S,
+                          "gave_up": 0}
+            t0 = time.time()
+            it = 0
+            if S:
+                slot_query = torch.full((S,), -1, dtype=torch.int64, device=dev)
+                slot_age = torch.zeros(S, dtype=torch.int64, device=dev)
+                first = [pending.pop() for _ in range(S)]
+                slot_query[:] = torch.tensor(first, device=dev)
+                SQI, SQG = QI[slot_query].clone(), QG[slot_query].clone()   # per-slot endpoints
+                B_forest = S
+
+                class SlotForest(Forest):
+                    def __init__(self, roots):
+                        self.cap = 1024
+                        self.q = torch.full((B_forest, self.cap, nq), float("inf"), dtype=f64, device=dev)
+                        self.parent = torch.full((B_forest, self.cap), -1, dtype=torch.int64, device=dev)
+                        self.count = torch.ones(B_forest, dtype=torch.int64, device=dev)
+                        self.q[:, 0] = roots
+                        self.hi = 1
+
+                    def reserve(self, extra):
+                        if self.hi + extra <= self.cap:
+                            return
+                        new = max(self.hi + extra, 2 * self.cap)
+                        q = torch.full((B_forest, new, nq), float("inf"), dtype=f64, device=dev)
+                        q[:, : self.cap] = self.q
+                        p = torch.full((B_forest, new), -1, dtype=torch.int64, device=dev)
+                        p[:, : self.cap] = self.parent
+                        self.q, self.parent, self.cap = q, p, new
+
+                start, goal = SlotForest(SQI), SlotForest(SQG)
+                live = torch.arange(S, device=dev)       # slots that hold a query
+                swapped = False
+                while len(live) and it < self.max_iterations and time.time() - t0 < self.max_planning_time:
+                    it += 1
+                    n = len(live)
+                    fa, fb = (goal, start) if swapped else (start, goal)
+                    u = torch.rand(n, generator=gen, device=dev, dtype=f64)
+                    rnd = lo[None, :] + (hi - lo)[None, :] * torch.rand((n, nq), generator=gen, device=dev, dtype=f64)
+                    qi_a = SQI[live]
+                    targets = torch.where(plan_mask[None, :], rnd, qi_a)
+                    bias = (u <= self.goal_biasing_probability)[:, None]
+                    targets = torch.where(bias, qi_a if swapped else SQG[live], targets)
+                    qa, ia = extend(fa, live, targets)
+                    qb, ib = extend(fb, live, qa)
+                    slot_age[live] += 1
+                    met = (qa == qb).all(dim=1)
+                    done = met | (slot_age[live] >= self.max_iterations_per_query)
+                    if bool(done.any()):
+                        di = done.nonzero(as_tuple=True)[0]
+                        dslots = live[di]
+                        dmet = met[di].cpu().numpy()
+                        dq = slot_query[dslots].cpu().numpy()
+                        s_idx, g_idx = (ib, ia) if swapped else (ia, ib)
+                        ds, dg = s_idx[di].cpu().numpy(), g_idx[di].cpu().numpy()
+                        hi_s = int(start.count[dslots].max())
+                        hi_g = int(goal.count[dslots].max())
+                        sp = start.parent[dslots, :hi_s].cpu().numpy()
+                        gp = goal.parent[dslots, :hi_g].cpu().numpy()
+                        want_s, want_g, who = [], [], []
+                        for k in range(len(di)):
+                            if not dmet[k]:
+                                self.stats["gave_up"] += 1
+                                continue
+                            a, si = [], int(ds[k])
+                            while si >= 0:
+                                a.append(si)
+                                si = int(sp[k, si])
+                            g, gi = [], int(dg[k])
+                            while gi >= 0:
+                                g.append(gi)
+                                gi = int(gp[k, gi])
+                            want_s.append((int(dslots[k]), a[::-1]))
+                            want_g.append((int(dslots[k]), g))
+                            who.append(int(dq[k]))
+
+                        def gather(F, lists):
+                            if not lists:
+                                return []
+                            bb = np.concatenate([np.full(len(ix), sl) for sl, ix in lists])
+                            ii = np.concatenate([np.asarray(ix) for _, ix in lists])
+                            rows = F.q[torch.from_numpy(bb).to(dev), torch.from_numpy(ii).to(dev)].cpu().numpy()
+                            out, o = [], 0
+                            for _, ix in lists:
+                                out.append(rows[o : o + len(ix)])
+                                o += len(ix)
+                            return out
+
+                        for qid, ps, pg in zip(who, gather(start, want_s), gather(goal, want_g)):
+                            ps, pg = list(ps), list(pg)
+                            if np.array_equal(ps[-1], pg[0]):
+                                ps.pop()
+                            paths[qid] = ps + pg
+                        # hand the freed slots to pending queries (or retire them)
+                        refill = [pending.pop() for _ in range(min(len(pending), len(dslots)))]
+                        nr = len(refill)
+                        if nr:
+                            rs = dslots[:nr]
+                            rq = torch.tensor(refill, device=dev)
+                            slot_query[rs] = rq
+                            SQI[rs], SQG[rs] = QI[rq], QG[rq]
+                            for F, roots in ((start, QI[rq]), (goal, QG[rq])):
+                                F.q[rs, 0] = roots
+                                F.count[rs] = 1
+                                F.parent[rs, 0] = -1
+                            slot_age[rs] = 0
+                        start.hi, goal.hi = int(start.count.max()), int(goal.count.max())  # exact again
+                        if nr < len(dslots):
+                            keep = torch.ones(n, dtype=torch.bool, device=dev)
+                            keep[di[nr:]] = False
+                            live = live[keep]
+                    swapped = not swapped
+            self.stats["iterations"] = it
+            self.stats["solved"] = int(sum(1 for p in paths if p))
+            self.stats["seconds"] = time.time() - t0
+            return paths
+
+    # ------------------------------------------------------------------ host driver
+    def _plan_host(self, q_inits, q_goals):
         B, nq = q_inits.shape
         ok = np.asarray(obeys_constraints_batch(np.concatenate([q_inits, q_goals]), self.constraints)).astype(bool)
         if not ok[:B].all():

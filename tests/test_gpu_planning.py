@@ -107,3 +107,61 @@ def test_batched_rrt_franka_queries():
             np.testing.assert_equal(p[0], q_init)
             np.testing.assert_equal(p[-1], g)
             replay_valid(model, allowed, p, 0.05)
+
+
+def test_nearest_batch_kernel_matches_numpy():
+    import ctypes as C
+
+    import torch
+
+    from mjpl_b200 import _abi
+
+    L = _abi.lib()
+    rng = np.random.default_rng(0)
+    B, cap, nq = 37, 300, 7
+    nodes = rng.normal(size=(B, cap, nq))
+    count = rng.integers(1, cap, size=B)
+    nodes[3, 0] = np.inf  # a sink root must never win
+    count[3] = max(count[3], 5)
+    targets = rng.normal(size=(B, nq))
+    dn, dc, dt = torch.from_numpy(nodes).cuda(), torch.from_numpy(count).cuda(), torch.from_numpy(targets).cuda()
+    out = torch.empty(B, dtype=torch.int64, device="cuda")
+    _abi.check(L.mjb_nearest_batch(dn.data_ptr(), cap, nq, dc.data_ptr(), None, dt.data_ptr(), B, out.data_ptr(),
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    want = []
+    for b in range(B):
+        with np.errstate(invalid="ignore"):
+            d2 = ((nodes[b, : count[b]] - targets[b]) ** 2).sum(1)
+        want.append(int(np.argmin(np.where(np.isfinite(d2), d2, np.inf))))
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    # with an explicit row selection
+    rows = torch.tensor([5, 5, 0, 36], device="cuda")
+    out2 = torch.empty(4, dtype=torch.int64, device="cuda")
+    t2 = dt[[1, 2, 3, 4]].contiguous()
+    _abi.check(L.mjb_nearest_batch(dn.data_ptr(), cap, nq, dc.data_ptr(), rows.data_ptr(), t2.data_ptr(), 4, out2.data_ptr(),
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    for k, (b, ti) in enumerate(zip([5, 5, 0, 36], [1, 2, 3, 4])):
+        d2 = ((nodes[b, : count[b]] - targets[ti]) ** 2).sum(1)
+        assert int(out2[k]) == int(np.argmin(d2))
+
+
+def test_batched_rrt_device_driver_many_queries():
+    model = models.load("franka_scene_with_obstacles")
+    allowed = [("left_finger", "right_finger")]
+    joints = [f"joint{i}" for i in range(1, 8)]
+    c = [mj.JointLimitConstraint(model), mj.CollisionConstraint(model, allowed)]
+    q_init = model.keyframe("home").qpos.copy()
+    rows = c[1].engine.sweep_rows(3, 0, 4096).double().cpu().numpy()
+    rows[:, 7:] = q_init[7:]
+    goals = rows[np.asarray(mj.obeys_constraints_batch(rows, c))][:256]
+    planner = mj.BatchedRRT(model, joints, c, max_planning_time=60, epsilon=0.05, seed=1, goal_biasing_probability=0.1)
+    paths = planner.plan(np.tile(q_init, (len(goals), 1)), goals)
+    print("batched rrt (device):", planner.stats)
+    assert planner.stats["driver"] == "device"
+    assert planner.stats["solved"] >= 0.95 * len(goals)
+    orc = oracle.Oracle(model, allowed)
+    for p, g in list(zip(paths, goals))[:64]:
+        if p:
+            np.testing.assert_equal(p[0], q_init)
+            np.testing.assert_equal(p[-1], g)
+            replay_valid(model, allowed, p, 0.05)
