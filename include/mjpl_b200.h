@@ -65,7 +65,7 @@ typedef struct mjb_stats {
   int64_t rows;            /* configurations submitted since the last reset */
   int64_t narrow_items;    /* (row, pair) items that reached the narrow phase */
   int64_t uncertain_rows;  /* rows re-evaluated by the fp64 kernel */
-  int64_t queue_overflow;  /* rows sent to the fp64 kernel because a tile queue filled up */
+  int64_t queue_overflow;  /* extend chains clipped because a tree was at capacity (mjb_rrt_extend) */
   int64_t launches;        /* kernels launched by this handle */
 } mjb_stats;
 
@@ -130,6 +130,21 @@ int mjb_sweep_rows(mjb_model *m, uint64_t seed, int64_t row0, int64_t n, float *
 int mjb_nearest_batch(const double *d_nodes, int64_t cap, int32_t nq, const int64_t *d_count,
                       const int64_t *d_rows, const double *d_targets, int64_t n, int64_t *d_out,
                       void *stream);
+
+/*
+ * One _constrained_extend (src/mjpl/planning/utils.py:105-164) for n trees at once, for
+ * non-projecting constraints, entirely on the device: nearest node, the chain
+ * near + k*eps*(target-near)/|target-near| (k = 1..min(ceil(dist/eps), kcap); the step that covers
+ * the remaining distance lands on the target itself), validity of every step with `flags`, the
+ * reference's stop rules, and the append of the valid prefix to the tree.
+ * Trees: d_nodes (ntrees, cap, nq) fp64, d_parent (ntrees, cap), d_count (ntrees); d_slots
+ * (optional) = tree of each query.  Out: d_reached (n,nq) = configuration reached (the nearest
+ * node itself if no step was valid), d_last (n,) = its node index.  The caller keeps
+ * count + kcap <= cap (chains are clipped at the capacity and counted in stats.queue_overflow).
+ */
+int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, int64_t *d_count, int64_t cap,
+                   const int64_t *d_slots, const double *d_targets, int64_t n, double eps,
+                   int32_t kcap, uint32_t flags, double *d_reached, int64_t *d_last, void *stream);
 
 int mjb_get_stats(mjb_model *m, mjb_stats *out);   /* synchronises the handle's last stream */
 int mjb_reset_stats(mjb_model *m);

@@ -95,7 +95,7 @@ _lib = None
 EXPORTS = (
     "mjb_last_error mjb_device_count mjb_model_create mjb_model_destroy mjb_model_npair "
     "mjb_model_pairs mjb_check_configs mjb_check_configs_host mjb_fk mjb_check_edges "
-    "mjb_check_sweep mjb_sweep_rows mjb_get_stats mjb_reset_stats mjb_nearest_batch"
+    "mjb_check_sweep mjb_sweep_rows mjb_get_stats mjb_reset_stats mjb_nearest_batch mjb_rrt_extend"
 ).split()
 
 
@@ -127,6 +127,7 @@ def lib():
     L.mjb_check_sweep.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, u8p, C.c_uint32, vp]
     L.mjb_sweep_rows.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, f32p, vp]
     L.mjb_nearest_batch.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, C.c_int64, vp, vp]
+    L.mjb_rrt_extend.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, C.c_int64, C.c_double, C.c_int32, C.c_uint32, vp, vp, vp]
     L.mjb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.mjb_reset_stats.argtypes = [vp]
     for n in EXPORTS:

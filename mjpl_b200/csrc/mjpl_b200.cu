@@ -49,6 +49,7 @@ struct mjb_model {
   long long *d_recheck = nullptr; size_t recheck_cap = 0;
   long long *d_edge_count = nullptr, *d_edge_prefix = nullptr; int *d_first_bad = nullptr; size_t edge_cap = 0;
   void *d_cub = nullptr; size_t cub_bytes = 0;
+  double *d_chain_near = nullptr; long long *d_chain_nn = nullptr; size_t chain_cap = 0;
   float *d_stage_q = nullptr; uint8_t *d_stage_v = nullptr; size_t stage_rows = 0;
   float *h_pin_q = nullptr; uint8_t *h_pin_v = nullptr; size_t pin_rows = 0;
   cudaStream_t own_stream = nullptr;
@@ -186,7 +187,7 @@ extern "C" void mjb_model_destroy(mjb_model *m) {
   cudaFree(m->d_verts64); cudaFree(m->d_fk64); cudaFree(m->d_rsum64); cudaFree(m->d_bsum64);
   cudaFree(m->d_body_slot); cudaFree(m->d_static_pose); cudaFree(m->d_pose); cudaFree(m->d_counters);
   cudaFree(m->d_recheck); cudaFree(m->d_edge_count); cudaFree(m->d_edge_prefix); cudaFree(m->d_first_bad);
-  cudaFree(m->d_cub); cudaFree(m->d_stage_q); cudaFree(m->d_stage_v);
+  cudaFree(m->d_cub); cudaFree(m->d_stage_q); cudaFree(m->d_stage_v); cudaFree(m->d_chain_near); cudaFree(m->d_chain_nn);
   if (m->h_pin_q) cudaFreeHost(m->h_pin_q);
   if (m->h_pin_v) cudaFreeHost(m->h_pin_v);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -200,6 +201,8 @@ extern "C" int mjb_model_pairs(const mjb_model *m, int32_t *g1, int32_t *g2) {
   for (size_t i = 0; i < m->H.pairs.size(); i++) { g1[i] = m->H.pair_g1[i]; g2[i] = m->H.pair_g2[i]; }
   return MJB_OK;
 }
+
+static int ensure_edge_buffers(mjb_model *m, size_t ne, cudaStream_t st);
 
 static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st) {
   if (rows <= m->recheck_cap) return MJB_OK;
@@ -307,20 +310,7 @@ extern "C" int mjb_check_edges(mjb_model *m, const float *d_q0, const float *d_q
   if (ne == 0) return MJB_OK;
   if (!d_q0 || !d_q1 || !d_valid) return fail(MJB_ERR_ARG, "null device pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if ((size_t)ne + 1 > m->edge_cap) {
-    CU(cudaStreamSynchronize(st));
-    cudaFree(m->d_edge_count); cudaFree(m->d_edge_prefix); cudaFree(m->d_first_bad); cudaFree(m->d_cub);
-    m->d_edge_count = m->d_edge_prefix = nullptr; m->d_first_bad = nullptr; m->d_cub = nullptr;
-    size_t cap = std::max<size_t>((size_t)ne + 1, 1 << 16);
-    CU(cudaMalloc((void **)&m->d_edge_count, cap * sizeof(long long)));
-    CU(cudaMalloc((void **)&m->d_edge_prefix, cap * sizeof(long long)));
-    CU(cudaMalloc((void **)&m->d_first_bad, cap * sizeof(int)));
-    size_t tb = 0;
-    CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, m->d_edge_count, m->d_edge_prefix, (int)cap, st));
-    CU(cudaMalloc(&m->d_cub, tb + 256));
-    m->cub_bytes = tb + 256;
-    m->edge_cap = cap;
-  }
+  if ((rc = ensure_edge_buffers(m, (size_t)ne, st))) return rc;
   const int nq = m->H.nq;
   edge_count_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(d_q0, d_q1, ne, nq, ldq, step, m->d_edge_count, m->d_first_bad);
   CU(cudaGetLastError());
@@ -385,7 +375,7 @@ extern "C" int mjb_get_stats(mjb_model *m, mjb_stats *out) {
   CU(cudaDeviceSynchronize());
   unsigned long long c[C_NCOUNTERS];
   CU(cudaMemcpy(c, m->d_counters, sizeof c, cudaMemcpyDeviceToHost));
-  out->rows = m->rows_total;
+  out->rows = (int64_t)c[C_ROWS];
   out->narrow_items = (int64_t)c[C_ITEMS];
   out->uncertain_rows = (int64_t)c[C_UNCERTAIN];
   out->queue_overflow = (int64_t)c[C_OVERFLOW];
@@ -413,5 +403,74 @@ extern "C" int mjb_nearest_batch(const double *d_nodes, int64_t cap, int32_t nq,
                                                                   (const long long *)d_rows, d_targets, (long long)n,
                                                                   (long long *)d_out);
   CU(cudaGetLastError());
+  return MJB_OK;
+}
+
+// grow the per-handle edge / chain buffers (count, prefix, first_bad, cub scratch) to `ne` entries
+static int ensure_edge_buffers(mjb_model *m, size_t ne, cudaStream_t st) {
+  if (ne + 1 <= m->edge_cap) return MJB_OK;
+  CU(cudaStreamSynchronize(st));
+  cudaFree(m->d_edge_count); cudaFree(m->d_edge_prefix); cudaFree(m->d_first_bad); cudaFree(m->d_cub);
+  m->d_edge_count = m->d_edge_prefix = nullptr; m->d_first_bad = nullptr; m->d_cub = nullptr;
+  size_t cap = std::max<size_t>(ne + 1, 1 << 16);
+  CU(cudaMalloc((void **)&m->d_edge_count, cap * sizeof(long long)));
+  CU(cudaMalloc((void **)&m->d_edge_prefix, cap * sizeof(long long)));
+  CU(cudaMalloc((void **)&m->d_first_bad, cap * sizeof(int)));
+  size_t tb = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, tb, m->d_edge_count, m->d_edge_prefix, (int)cap, st));
+  CU(cudaMalloc(&m->d_cub, tb + 256));
+  m->cub_bytes = tb + 256;
+  m->edge_cap = cap;
+  return MJB_OK;
+}
+
+extern "C" int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, int64_t *d_count, int64_t cap,
+                              const int64_t *d_slots, const double *d_targets, int64_t n, double eps, int32_t kcap,
+                              uint32_t flags, double *d_reached, int64_t *d_last, void *stream) {
+  int rc = check_common(m, flags);
+  if (rc) return rc;
+  // reference: ValueError("`max_step_dist` must be > 0.0") (src/mjpl/planning/utils.py:179-180)
+  if (!(eps > 0.0)) return fail(MJB_ERR_ARG, "`max_step_dist` must be > 0.0");
+  if (n < 0 || cap < 1 || kcap < 1) return fail(MJB_ERR_ARG, "bad n / cap / kcap");
+  if (n == 0) return MJB_OK;
+  if (!d_nodes || !d_parent || !d_count || !d_targets || !d_reached || !d_last) return fail(MJB_ERR_ARG, "null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nq = m->H.nq;
+  if ((rc = ensure_edge_buffers(m, (size_t)n, st))) return rc;
+  if ((size_t)n > m->chain_cap) {
+    CU(cudaStreamSynchronize(st));
+    cudaFree(m->d_chain_near); cudaFree(m->d_chain_nn);
+    m->d_chain_near = nullptr; m->d_chain_nn = nullptr;
+    size_t c = std::max<size_t>((size_t)n, 4096);
+    CU(cudaMalloc((void **)&m->d_chain_near, c * nq * sizeof(double)));
+    CU(cudaMalloc((void **)&m->d_chain_nn, c * sizeof(long long)));
+    m->chain_cap = c;
+  }
+  if ((rc = ensure_recheck(m, (size_t)n * (size_t)kcap, st))) return rc;  // worst case, no host read-back
+  // 1. nearest node of every query's tree   2. chain lengths + prefix sums
+  nearest_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_count,
+                                                                  (const long long *)d_slots, d_targets, (long long)n, m->d_chain_nn);
+  chain_setup_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_slots, m->d_chain_nn,
+                                                                 d_targets, (long long)n, eps, kcap, m->d_chain_near, m->d_edge_count,
+                                                                 m->d_first_bad);
+  CU(cudaGetLastError());
+  CU(cudaMemsetAsync(m->d_edge_count + n, 0, sizeof(long long), st));
+  size_t tb = m->cub_bytes;
+  CU(cub::DeviceScan::ExclusiveSum(m->d_cub, tb, m->d_edge_count, m->d_edge_prefix, (int)(n + 1), st));
+  // 3. validity of every chain step (rows generated on the device), first failing step per chain
+  KArgs k = m->kargs;
+  k.mode = MODE_CHAINS; k.c0 = m->d_chain_near; k.c1 = d_targets; k.ceps = eps; k.edge_prefix = m->d_edge_prefix; k.nedge = n;
+  k.first_bad = m->d_first_bad; k.flags = flags; k.ldq = nq;
+  RArgs r = m->rargs;
+  r.mode = MODE_CHAINS; r.c0 = m->d_chain_near; r.c1 = d_targets; r.ceps = eps; r.edge_prefix = m->d_edge_prefix; r.nedge = n;
+  r.first_bad = m->d_first_bad; r.ldq = nq;
+  if ((rc = launch_validity(m, k, r, st))) return rc;
+  // 4. append the valid prefixes
+  chain_append_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(
+      d_nodes, (long long *)d_parent, (long long *)d_count, (long long)cap, nq, (const long long *)d_slots, m->d_chain_nn,
+      m->d_chain_near, d_targets, m->d_edge_count, m->d_first_bad, (long long)n, eps, d_reached, (long long *)d_last,
+      m->d_counters + C_OVERFLOW);
+  CU(cudaGetLastError());
+  m->launches += 4;
   return MJB_OK;
 }

@@ -29,7 +29,7 @@
 
 namespace vk {
 
-constexpr int MODE_DENSE = 0, MODE_EDGES = 1, MODE_SWEEP = 2;
+constexpr int MODE_DENSE = 0, MODE_EDGES = 1, MODE_SWEEP = 2, MODE_CHAINS = 3;
 constexpr uint32_t F_LIMITS = 1u, F_COLLISION = 2u, F_NO_OBB = 4u, F_NO_RECHECK = 8u;
 constexpr int Q1_PER_ROW = 8;   // sphere-survivor queue capacity per round = Q1_PER_ROW * TILE items
 constexpr int Q2_PER_ROW = 4;   // narrow-phase queue capacity per round = Q2_PER_ROW * TILE items
@@ -50,6 +50,7 @@ struct KArgs {
   const float *q; int ldq; long long n;                       // dense
   const float *q0, *q1; const long long *edge_prefix; long long nedge; float step;  // edges
   unsigned long long seed; long long row0;                    // sweep
+  const double *c0, *c1; double ceps;                         // chains: fp64 end points (n,nq) and step
   // outputs
   uint8_t *valid; int *first_bad; uint32_t flags;
   // per-handle scratch
@@ -59,7 +60,7 @@ struct KArgs {
 };
 
 // counters layout
-constexpr int C_TICKET = 0, C_RECHECK = 1, C_RTICKET = 2, C_ITEMS = 3, C_OVERFLOW = 4, C_UNCERTAIN = 5, C_NCOUNTERS = 8;
+constexpr int C_TICKET = 0, C_RECHECK = 1, C_RTICKET = 2, C_ITEMS = 3, C_OVERFLOW = 4, C_UNCERTAIN = 5, C_ROWS = 6, C_NCOUNTERS = 8;
 constexpr int C_PER_LAUNCH = 3;  // counters [0, C_PER_LAUNCH) are cleared before every launch
 
 // ---------------------------------------------------------------------------- PTX helpers (sm_90+/sm_100a)
@@ -143,6 +144,27 @@ __device__ __forceinline__ void edge_row(const float *q0, const float *q1, int l
   for (int j = 0; j < nq; j++) {
     double x0 = q0[e * ldq + j], x1 = q1[e * ldq + j];
     q[j] = (T)(x0 + s * (x1 - x0));
+  }
+}
+
+// step k (0-based) of the extend chain of query e: near + (k+1)*eps*(target-near)/|target-near|,
+// and the target itself when that step covers the remaining distance.  Evaluated in fp64 exactly
+// like chain_append_kernel stores it, so the checked row is the fp32 rounding of the stored node.
+// reference: _constrained_extend / _step (src/mjpl/planning/utils.py:139-185)
+template <typename TO>
+__device__ __forceinline__ void chain_point(const double *c0, const double *c1, int nq, double eps, long long e, int k, TO *q) {
+  double d2 = 0;
+  for (int j = 0; j < nq; j++) {
+    double d = c1[e * nq + j] - c0[e * nq + j];
+    d2 += d * d;
+  }
+  const double dist = sqrt(d2);
+  const double reach = (double)(k + 1) * eps;
+  if (reach >= dist) {
+    for (int j = 0; j < nq; j++) q[j] = (TO)c1[e * nq + j];
+  } else {
+    const double s = reach / dist;
+    for (int j = 0; j < nq; j++) q[j] = (TO)(c0[e * nq + j] + s * (c1[e * nq + j] - c0[e * nq + j]));
   }
 }
 
@@ -240,11 +262,11 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
 
   // total number of rows (edges: read from the device-side prefix sums)
   long long nrows = a.n;
-  if (a.mode == MODE_EDGES) nrows = a.edge_prefix[a.nedge];
+  if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) nrows = a.edge_prefix[a.nedge];
   const long long ntiles = (nrows + 31) / 32;   // a tile = the 32 rows one warp owns
   uint32_t row_parity = 0;
   const bool dense_bulk = (a.mode == MODE_DENSE) && (a.ldq == nq) && ((reinterpret_cast<uintptr_t>(a.q) & 15) == 0);
-  long long items_total = 0;
+  long long items_total = 0, rows_total = 0;
   const bool use_obb = !(a.flags & F_NO_OBB);
   const float slack = 1e-4f;
   uint64_t *wbar = s_bar + 8 + (tid >> 5);       // this warp's row-load barrier
@@ -263,6 +285,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
     const int rows_here = (int)((nrows - row_base) < 32 ? (nrows - row_base) : 32);
     const long long row = row_base + lane;
     const bool active = lane < rows_here;
+    rows_total += rows_here;
 
     // ---- P0: the warp's rows -> shared (one TMA bulk copy per warp tile) -----------------------------
     if (a.mode == MODE_DENSE) {
@@ -292,6 +315,9 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
       if (a.mode == MODE_EDGES) {
         edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
         edge_row<float>(a.q0, a.q1, a.ldq, nq, a.step, e_idx, e_k, q);
+      } else if (a.mode == MODE_CHAINS) {
+        edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
+        chain_point<float>(a.c0, a.c1, nq, a.ceps, e_idx, e_k, q);
       } else if (a.mode == MODE_SWEEP) {
 #pragma unroll 1
         for (int j = 0; j < nq; j++)
@@ -494,7 +520,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
         unsigned long long slot = atomicAdd(&a.counters[C_RECHECK], 1ull);
         a.recheck_rows[slot] = row;
       }
-      if (a.mode == MODE_EDGES) {
+      if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) {
         if (!ok && !pending) atomicMin(&a.first_bad[e_idx], e_k);
         else if (pending && (a.flags & F_NO_RECHECK)) atomicMin(&a.first_bad[e_idx], e_k);
       } else {
@@ -503,6 +529,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
     }
   }
   if (lane == 0 && items_total) atomicAdd(&a.counters[C_ITEMS], (unsigned long long)items_total);
+  if (lane == 0 && rows_total) atomicAdd(&a.counters[C_ROWS], (unsigned long long)rows_total);
 }
 
 // ---------------------------------------------------------------------------- fp64 re-evaluation
@@ -517,6 +544,7 @@ struct RArgs {
   int mode;
   const float *q; int ldq;
   const float *q0, *q1; const long long *edge_prefix; long long nedge; float step;
+  const double *c0, *c1; double ceps;
   unsigned long long seed; long long row0;
   uint8_t *valid; int *first_bad;
   unsigned long long *counters;
@@ -546,6 +574,10 @@ __global__ void __launch_bounds__(128) recheck_kernel(const RArgs a) {
       float qf[MAX_JNT];
       edge_row<float>(a.q0, a.q1, a.ldq, fk.nq, a.step, e_idx, e_k, qf);
       for (int j = 0; j < fk.nq; j++) q[j] = (double)qf[j];
+    } else if (a.mode == MODE_CHAINS) {
+      edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
+      chain_point<double>(a.c0, a.c1, fk.nq, a.ceps, e_idx, e_k, q);
+      for (int j = 0; j < fk.nq; j++) q[j] = (double)(float)q[j];  // the fp32 row the fast path saw
     } else {
       for (int j = 0; j < fk.nq; j++)
         q[j] = (double)sweep_value(a.seed, (uint64_t)(a.row0 + row), (uint32_t)j, (float)fk.jnt_lo[j], (float)fk.jnt_hi[j]);
@@ -583,7 +615,7 @@ __global__ void __launch_bounds__(128) recheck_kernel(const RArgs a) {
       if (__any_sync(0xffffffffu, contact)) { contact = true; break; }
     }
     if (lane == 0) {
-      if (a.mode == MODE_EDGES) {
+      if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) {
         if (contact) atomicMin(&a.first_bad[e_idx], e_k);
       } else {
         a.valid[row] = contact ? 0 : 1;
@@ -658,6 +690,82 @@ __global__ void sweep_rows_kernel(FkTables<float> fk, unsigned long long seed, l
   long long r = i / fk.nq;
   int j = (int)(i - r * fk.nq);
   q[i] = sweep_value(seed, (uint64_t)(row0 + r), (uint32_t)j, fk.jnt_lo[j], fk.jnt_hi[j]);
+}
+
+// ---------------------------------------------------------------------------- RRT extend chains
+// near[i] = nodes[slot_i][nn[i]]; chain length K = min(ceil(|target-near|/eps), kcap) (0 if equal)
+__global__ void chain_setup_kernel(const double *nodes, long long cap, int nq, const long long *slots, const long long *nn,
+                                   const double *targets, long long n, double eps, int kcap, double *near, long long *count,
+                                   int *first_bad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long slot = slots ? slots[i] : i;
+  const double *src = nodes + (slot * cap + nn[i]) * nq;
+  double d2 = 0;
+  for (int j = 0; j < nq; j++) {
+    double x = src[j];
+    near[i * nq + j] = x;
+    double d = targets[i * nq + j] - x;
+    d2 += d * d;
+  }
+  const double dist = sqrt(d2);
+  long long k = dist > 0 ? (long long)ceil(dist / eps) : 0;
+  if (k > kcap) k = kcap;
+  count[i] = k;
+  first_bad[i] = 0x7fffffff;
+}
+
+// Append the valid prefix of every chain to its tree (reference stop rules,
+// src/mjpl/planning/utils.py:151-160: constraints failed -> first_bad; a final step shorter than
+// 1e-8 does not count), report the reached configuration and its node index.
+__global__ void chain_append_kernel(double *nodes, long long *parent, long long *tree_count, long long cap, int nq,
+                                    const long long *slots, const long long *nn, const double *near, const double *targets,
+                                    const long long *count, const int *first_bad, long long n, double eps, double *reached,
+                                    long long *last, unsigned long long *overflow) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const long long slot = slots ? slots[w] : w;
+  const long long K = count[w];
+  long long good = first_bad[w] == 0x7fffffff ? K : (long long)first_bad[w];
+  if (good > K) good = K;
+  double d2 = 0;
+  for (int j = 0; j < nq; j++) {
+    double d = targets[w * nq + j] - near[w * nq + j];
+    d2 += d * d;
+  }
+  const double dist = sqrt(d2);
+  // stop rule: the last step lands on the target; if that step is shorter than 1e-8 it is rejected
+  if (good == K && K > 0 && (double)K * eps >= dist && dist - (double)(K - 1) * eps < 1e-8) good = K - 1;
+  const long long base = tree_count[slot];
+  if (base + good > cap) {  // never write past the tree (the host grows trees ahead of time)
+    if (lane == 0) atomicAdd(overflow, 1ull);
+    good = cap - base;
+  }
+  double *dst = nodes + (slot * cap + base) * nq;
+  for (long long idx = lane; idx < good * nq; idx += 32) {
+    const long long k = idx / nq;
+    const int j = (int)(idx - k * nq);
+    const double reach = (double)(k + 1) * eps;
+    const double x0 = near[w * nq + j], x1 = targets[w * nq + j];
+    dst[idx] = reach >= dist ? x1 : x0 + (reach / dist) * (x1 - x0);
+  }
+  for (long long k = lane; k < good; k += 32) parent[slot * cap + base + k] = k == 0 ? nn[w] : base + k - 1;
+  __syncwarp();
+  const long long li = good > 0 ? base + good - 1 : nn[w];
+  if (lane == 0) {
+    tree_count[slot] = base + good;
+    last[w] = li;
+  }
+  for (int j = lane; j < nq; j += 32) {
+    double v;
+    if (good > 0) {
+      const double reach = (double)good * eps;
+      const double x0 = near[w * nq + j], x1 = targets[w * nq + j];
+      v = reach >= dist ? x1 : x0 + (reach / dist) * (x1 - x0);
+    } else v = near[w * nq + j];
+    reached[w * nq + j] = v;
+  }
 }
 
 // ---------------------------------------------------------------------------- batched nearest neighbour

@@ -223,45 +223,23 @@ class BatchedRRT:
                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
                     return out
 
+            kcap = int(self.max_chain)
+            eng.reset_stats()
+
             def extend(F, act, targets):
+                """One ``_constrained_extend`` per active slot, entirely on the device
+                (``mjb_rrt_extend``: nearest node, chain, validity, stop rules, append)."""
                 n = len(act)
-                near_idx = F.nearest(act, targets)
-                near = F.q[act, near_idx]
-                d = targets - near
-                dist = torch.linalg.vector_norm(d, dim=1)
-                k = torch.ceil(dist / eps).clamp(max=self.max_chain).to(torch.int64)
-                kmax = int(k.max())
-                if kmax == 0:
-                    return near, near_idx
-                F.reserve(kmax)
-                ar = torch.arange(kmax, device=dev)
-                frac = torch.where(dist > 0, eps / dist, torch.zeros_like(dist))[:, None] * (ar + 1)[None, :].to(f64)
-                chains = near[:, None, :] + frac.clamp(max=1.0)[:, :, None] * d[:, None, :]
-                # the step that covers the remaining distance lands on the target itself
-                full = (k.to(f64) * eps >= dist) & (k > 0)
-                fi = full.nonzero(as_tuple=True)[0]
-                chains[fi, k[fi] - 1] = targets[fi]
-                mask = ar[None, :] < k[:, None]
-                flat = chains[mask]
-                okf = eng.valid_configs(flat.float(), flags)
-                self.stats["configs_checked"] += int(flat.shape[0])
+                F.reserve(kcap)
+                reached = torch.empty((n, nq), dtype=f64, device=dev)
+                last = torch.empty(n, dtype=torch.int64, device=dev)
+                t = targets.contiguous()
+                _abi.check(L.mjb_rrt_extend(eng._h, F.q.data_ptr(), F.parent.data_ptr(), F.count.data_ptr(), F.cap,
+                                            act.data_ptr(), t.data_ptr(), n, eps, kcap, flags, reached.data_ptr(),
+                                            last.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                F.hi += kcap  # upper bound until the next exact refresh
                 self.stats["launches"] += 1
-                okm = torch.ones(mask.shape, dtype=torch.bool, device=dev)
-                okm[mask] = okf
-                prev = torch.cat([near[:, None, :], chains[:, :-1]], dim=1)
-                okm &= (torch.linalg.vector_norm(chains - prev, dim=2) >= 1e-8) | ~mask
-                good = torch.minimum(okm.to(torch.int64).cumprod(dim=1).sum(dim=1), k)
-                base = F.count[act]
-                m2 = ar[None, :] < good[:, None]
-                slot = base[:, None] + ar[None, :]
-                rows = act[:, None].expand(n, kmax)
-                par = torch.where(ar[None, :] == 0, near_idx[:, None].expand(n, kmax), slot - 1)
-                F.q[rows[m2], slot[m2]] = chains[m2]
-                F.parent[rows[m2], slot[m2]] = par[m2]
-                F.count[act] = base + good
-                F.hi += kmax
-                last = torch.where(good > 0, base + good - 1, near_idx)
-                return F.q[act, last], last
+                return reached, last
 
             direct = torch.linalg.vector_norm(QG - QI, dim=1) <= eps
             paths: list[list[np.ndarray]] = [[] for _ in range(B)]
@@ -321,7 +299,10 @@ class BatchedRRT:
                     slot_age[live] += 1
                     met = (qa == qb).all(dim=1)
                     done = met | (slot_age[live] >= self.max_iterations_per_query)
-                    if bool(done.any()):
+                    # the only host read-back of the iteration: any slot finished? + exact tree sizes
+                    info = torch.stack([done.any().to(torch.int64), start.count.max(), goal.count.max()]).cpu()
+                    start.hi, goal.hi = int(info[1]), int(info[2])
+                    if bool(info[0]):
                         di = done.nonzero(as_tuple=True)[0]
                         dslots = live[di]
                         dmet = met[di].cpu().numpy()
@@ -379,7 +360,6 @@ class BatchedRRT:
                                 F.count[rs] = 1
                                 F.parent[rs, 0] = -1
                             slot_age[rs] = 0
-                        start.hi, goal.hi = int(start.count.max()), int(goal.count.max())  # exact again
                         if nr < len(dslots):
                             keep = torch.ones(n, dtype=torch.bool, device=dev)
                             keep[di[nr:]] = False
@@ -388,6 +368,9 @@ class BatchedRRT:
             self.stats["iterations"] = it
             self.stats["solved"] = int(sum(1 for p in paths if p))
             self.stats["seconds"] = time.time() - t0
+            est = eng.stats()
+            self.stats["configs_checked"] = est["rows"]
+            self.stats["chains_clipped_at_capacity"] = est["queue_overflow"]
             return paths
 
     # ------------------------------------------------------------------ host driver
