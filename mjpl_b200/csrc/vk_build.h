@@ -482,6 +482,7 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
   H.nrounds = 0;
   double acc_s = 0, acc_o = 0;
   int cur_gjk = -1;
+  std::vector<int> round_of(ord.size(), 0);
   for (size_t k = 0; k < ord.size(); k++) {
     int i = ord[k];
     int g = tp[i].p.kind == PK_GJK ? 1 : 0;
@@ -495,8 +496,20 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
       cur_gjk = g;
     }
     acc_s += es; acc_o += eo;
-    Tmp &t = tp[i];
-    t.p.round = (uint16_t)(H.nrounds - 1);
+    round_of[k] = H.nrounds - 1;
+  }
+  // inside a round the order is free: sort by shape A so the sphere stage fetches A's centre
+  // once per run of pairs
+  for (int r = 0; r < H.nrounds; r++) {
+    int b = H.round_start[r], e = (r + 1 < H.nrounds) ? H.round_start[r + 1] : (int)ord.size();
+    std::stable_sort(ord.begin() + b, ord.begin() + e, [&](int x, int y) {
+      if (tp[x].p.sa != tp[y].p.sa) return tp[x].p.sa < tp[y].p.sa;
+      return tp[x].p.sb < tp[y].p.sb;
+    });
+  }
+  for (size_t k = 0; k < ord.size(); k++) {
+    Tmp &t = tp[ord[k]];
+    t.p.round = (uint16_t)round_of[k];
     H.pairs.push_back(t.p); H.pair_g1.push_back(t.g1); H.pair_g2.push_back(t.g2);
     H.pair_rsum64.push_back(t.rsum); H.pair_bsum64.push_back(t.bsum);
   }
