@@ -45,6 +45,7 @@ class ModelDesc(C.Structure):
         + [(n, _F64P) for n in _F64_ARRAYS_C]
         + [(n, _I32P) for n in _I32_ARRAYS_D]
         + [("mesh_vert", _F64P), ("exclude_signature", _I64P), ("allowed_body_pairs", _I32P)]
+        + [("mesh_graphadr", _I32P), ("mesh_graph", _I32P), ("nmeshgraph", C.c_int32)]
     )
 
 
@@ -87,6 +88,12 @@ def make_desc(model, allowed_body_ids):
     d.mesh_vert = mesh_vert.ctypes.data_as(_F64P)
     d.exclude_signature = excl.ctypes.data_as(_I64P)
     d.allowed_body_pairs = allowed.ctypes.data_as(_I32P)
+    graph = getattr(model, "mesh_graph", None)
+    gadr = getattr(model, "mesh_graphadr", None)
+    if graph is not None and gadr is not None and len(graph):
+        d.mesh_graphadr = arr(gadr, np.int32).ctypes.data_as(_I32P)
+        d.mesh_graph = arr(graph, np.int32).ctypes.data_as(_I32P)
+        d.nmeshgraph = len(graph)
     return d, keep
 
 

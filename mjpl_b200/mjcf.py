@@ -124,13 +124,39 @@ def load_mesh_vertices(path: Path) -> np.ndarray:
 
 def convex_hull_vertices(v: np.ndarray) -> np.ndarray:
     """Hull vertex subset (MuJoCo runs qhull on collision meshes; support = hull vertices)."""
+    return convex_hull(v)[0]
+
+
+def convex_hull(v: np.ndarray):
+    """-> (hull vertices (n,3), hull graph in MuJoCo's ``mesh_graph`` layout or None).
+
+    ``mesh_graph`` per mesh: ``nvert, nface, vert_edgeadr[nvert], vert_globalid[nvert],
+    edge_localid[nvert + 3*nface]`` (for every hull vertex the list of its neighbours, as local
+    ids, terminated by -1) ``, face_globalid[3*nface]``.  The engine uses the neighbour lists for
+    hill-climbing support queries.
+    """
     from scipy.spatial import ConvexHull
 
     v = np.unique(np.asarray(v, dtype=np.float64), axis=0)
     if len(v) < 4:
-        return v
-    hull = ConvexHull(v)
-    return v[np.sort(hull.vertices)]
+        return v, None
+    hull = ConvexHull(v)  # qhull 'Qt': triangulated facets
+    keep = np.sort(hull.vertices)
+    local = -np.ones(len(v), dtype=np.int64)
+    local[keep] = np.arange(len(keep))
+    faces = local[hull.simplices]
+    nv, nf = len(keep), len(faces)
+    nbr = [set() for _ in range(nv)]
+    for a, b, c in faces:
+        nbr[a].update((b, c)); nbr[b].update((a, c)); nbr[c].update((a, b))
+    edge_adr, edges = [], []
+    for i in range(nv):
+        edge_adr.append(len(edges))
+        edges.extend(sorted(nbr[i]))
+        edges.append(-1)
+    assert len(edges) == nv + 3 * nf  # Euler: 2E = 3F for a triangulated closed surface
+    graph = np.concatenate([[nv, nf], edge_adr, np.arange(nv), edges, faces.reshape(-1)]).astype(np.int32)
+    return v[keep], graph
 
 
 # --------------------------------------------------------------------- XML handling
@@ -452,17 +478,23 @@ def _compile(root: ET.Element, base: Path, name: str) -> Model:
     m.mesh_names = list(mesh_order)
     m.mesh_vertadr = np.zeros(m.nmesh, dtype=np.int32)
     m.mesh_vertnum = np.zeros(m.nmesh, dtype=np.int32)
-    verts = []
-    n = 0
+    m.mesh_graphadr = np.full(m.nmesh, -1, dtype=np.int32)
+    verts, graphs = [], []
+    n = ng = 0
     for i, mname in enumerate(mesh_order):
         m.mesh_vertadr[i] = n
         if mname in used_meshes:
             f, scale = mesh_files[mname]
-            hv = convex_hull_vertices(load_mesh_vertices(f) * scale)
+            hv, graph = convex_hull(load_mesh_vertices(f) * scale)
             verts.append(hv)
             m.mesh_vertnum[i] = len(hv)
             n += len(hv)
+            if graph is not None:
+                m.mesh_graphadr[i] = ng
+                graphs.append(graph)
+                ng += len(graph)
     m.mesh_vert = np.concatenate(verts) if verts else np.zeros((0, 3))
+    m.mesh_graph = np.concatenate(graphs).astype(np.int32) if graphs else np.zeros(0, np.int32)
 
     # ---- rbound (conservative, geom-frame origin) ---------------------------------------------
     rb = np.zeros(m.ngeom)

@@ -49,7 +49,7 @@ _ARRAY_FIELDS = (
     "body_pos body_quat jnt_type jnt_qposadr jnt_dofadr jnt_bodyid jnt_pos jnt_axis "
     "jnt_range jnt_limited qpos0 geom_type geom_bodyid geom_contype geom_conaffinity "
     "geom_size geom_pos geom_quat geom_rbound geom_margin geom_gap geom_dataid "
-    "mesh_vertadr mesh_vertnum mesh_vert site_bodyid site_pos site_quat key_qpos "
+    "mesh_vertadr mesh_vertnum mesh_vert mesh_graphadr mesh_graph site_bodyid site_pos site_quat key_qpos "
     "exclude_signature"
 ).split()
 _NAME_FIELDS = "body_names jnt_names geom_names site_names mesh_names key_names".split()
@@ -100,6 +100,9 @@ class Model:
     mesh_vertadr: np.ndarray = None
     mesh_vertnum: np.ndarray = None
     mesh_vert: np.ndarray = None  # (nmeshvert, 3) float64: convex-hull vertices only
+    mesh_graphadr: np.ndarray = None  # (nmesh,) start of each mesh's hull graph in mesh_graph, -1 = none
+    mesh_graph: np.ndarray = None  # MuJoCo layout per mesh: nvert, nface, vert_edgeadr[nvert], vert_globalid[nvert],
+    #                                edge_localid[nvert+3*nface] (neighbour lists, -1 terminated), face_globalid[3*nface]
     site_bodyid: np.ndarray = None
     site_pos: np.ndarray = None
     site_quat: np.ndarray = None
@@ -235,24 +238,33 @@ class Model:
         for f in ("nq", "nv", "nbody", "njnt", "ngeom", "nsite", "nmesh", "nkey"):
             setattr(m, f, int(getattr(mj, f)))
         for f in _ARRAY_FIELDS:
-            if f in ("mesh_vert", "mesh_vertadr", "mesh_vertnum", "exclude_signature"):
+            if f in ("mesh_vert", "mesh_vertadr", "mesh_vertnum", "exclude_signature", "mesh_graphadr", "mesh_graph"):
                 continue
             setattr(m, f, np.array(getattr(mj, f)).copy())
         m.jnt_limited = m.jnt_limited.astype(np.int32)
         # hull vertex subsets
-        verts, adr, num = [], [], []
+        verts, adr, num, graphs, gadr = [], [], [], [], []
         for i in range(m.nmesh):
             va, vn = int(mj.mesh_vertadr[i]), int(mj.mesh_vertnum[i])
             v = np.array(mj.mesh_vert[va : va + vn], dtype=np.float64)
             ga = int(mj.mesh_graphadr[i])
             if ga >= 0:
-                g = mj.mesh_graph[ga:]
-                nhv = int(g[0])
-                idx = np.array(g[2 + nhv : 2 + 2 * nhv])  # vert_globalid
+                g = np.array(mj.mesh_graph[ga:], dtype=np.int32)
+                nhv, nhf = int(g[0]), int(g[1])
+                idx = g[2 + nhv : 2 + 2 * nhv]  # vert_globalid
                 v = v[idx]
+                size = 2 + 3 * nhv + 6 * nhf
+                gg = g[:size].copy()
+                gg[2 + nhv : 2 + 2 * nhv] = np.arange(nhv)  # mesh_vert now holds hull vertices only, in local order
+                gadr.append(sum(len(x) for x in graphs))
+                graphs.append(gg)
+            else:
+                gadr.append(-1)
             adr.append(sum(num))
             num.append(len(v))
             verts.append(v)
+        m.mesh_graphadr = np.array(gadr, dtype=np.int32)
+        m.mesh_graph = np.concatenate(graphs).astype(np.int32) if graphs else np.zeros(0, np.int32)
         m.mesh_vert = np.concatenate(verts) if verts else np.zeros((0, 3))
         m.mesh_vertadr = np.array(adr, dtype=np.int32)
         m.mesh_vertnum = np.array(num, dtype=np.int32)

@@ -46,6 +46,7 @@ def lib():
         L.hs_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_fk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.hs_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.hs_support_check.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_pair_verdict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -85,10 +86,15 @@ class HostSim:
         q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.model.nq)
         n = len(q)
         valid = np.zeros(n, np.uint8)
-        stats = np.zeros(8, np.int64)
+        stats = np.zeros(48, np.int64)
         lib().hs_check(self._h, q.ctypes.data, n, flags, int(obb), int(recheck), valid.ctypes.data, stats.ctypes.data)
         names = "items gjk_iters uncertain_rows rows sphere_survivors gjk_calls max_gjk_iters uncertain_items".split()
-        return valid, dict(zip(names, stats.tolist()))
+        d = dict(zip(names, stats[:8].tolist()))
+        d['gjk_iter_hist'] = stats[8:40].tolist()
+        d['gjk_verdicts_sep_pen_unc'] = stats[40:43].tolist()
+        d['gjk_iters_by_verdict'] = stats[44:47].tolist()
+        d['vertex_evals'] = int(stats[47])
+        return valid, d
 
     def pair_verdict(self, q, g1, g2, fp64=False):
         """(verdict, iterations) of one geom pair: 0 separated, 1 contact, 2 uncertain."""
@@ -96,3 +102,10 @@ class HostSim:
         it = C.c_int(0)
         v = lib().hs_pair_verdict(self._h, q.ctypes.data, int(g1), int(g2), int(fp64), C.byref(it))
         return v, it.value
+
+    def support_check(self, ndir=2000, seed=1):
+        """hill-climbing support vs full scan -> (shapes with a graph, max value shortfall, evals hill, evals scan)"""
+        gap = C.c_double(0)
+        eh, es = C.c_int64(0), C.c_int64(0)
+        n = lib().hs_support_check(self._h, ndir, seed, C.byref(gap), C.byref(eh), C.byref(es))
+        return n, gap.value, eh.value, es.value

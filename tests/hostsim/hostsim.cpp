@@ -106,7 +106,8 @@ static int row_verdict(const vkb::HostModel &H, const FkTables<T> &fk, const Sha
       int iters = 0;
       Rel<T> rel = relative_pose(PA, PB);
       v = gjk_classify(A, B, verts, rel, rsum, &iters);
-      if (stats) { stats[1] += iters; stats[5]++; if (iters > stats[6]) stats[6] = iters; }
+      if (stats) stats[47] += (long long)iters * (A.nvert + B.nvert);
+      if (stats) { stats[1] += iters; stats[5]++; if (iters > stats[6]) stats[6] = iters; stats[8 + (iters < 31 ? iters : 31)]++; stats[40 + v]++; stats[44 + v] += iters; }
     } else {
       v = narrow_item<T>(pr.kind, A, B, verts, PA, PB, rsum);
     }
@@ -170,6 +171,45 @@ int hs_pair_verdict(Sim *s, const float *q, int g1, int g2, int prec, int *iters
     }
   }
   return -1;
+}
+
+
+// hill-climbing support vs scanning all vertices, for every shape with a hull graph and `ndir`
+// random directions (cold start and warm start from the previous answer): returns the number of
+// shapes with a graph; max_gap = largest shortfall of the hill-climbed support value.
+int hs_support_check(Sim *s, int ndir, uint64_t seed, double *max_gap, int64_t *evals_hill, int64_t *evals_scan) {
+  const auto &H = s->H;
+  int ngraph = 0;
+  *max_gap = 0; *evals_hill = 0; *evals_scan = 0;
+  for (size_t k = 0; k < H.shapes.size(); k++) {
+    const Shape<float> &sh = s->s32[k];
+    if (!sh.graph) continue;
+    ngraph++;
+    const Vtx<float> *v = s->v32.data() + sh.vadr;
+    const uint16_t *as = H.adj_start.data() + sh.vadr;
+    int warm = -1;
+    for (int i = 0; i < ndir; i++) {
+      V3<float> d = mk<float>(sweep_value(seed, i, 0, -1.f, 1.f), sweep_value(seed, i, 1, -1.f, 1.f), sweep_value(seed, i, 2, -1.f, 1.f));
+      if (i % 3 == 2) { d.x *= 1e-3f; }              // near-axis directions
+      V3<float> brute = support_verts(v, sh.nvert, d);
+      int start = (i % 2 == 0 || warm < 0) ? hill_start(sh, d) : warm;
+      // count evaluations along the climb
+      int cur = start;
+      for (;;) {
+        int nxt = cur; float cb = v[cur].x * d.x + v[cur].y * d.y + v[cur].z * d.z;
+        for (int e = as[cur]; e < as[cur + 1]; e++) { int j = H.adj[e]; float t = v[j].x * d.x + v[j].y * d.y + v[j].z * d.z; (*evals_hill)++; if (t > cb) { cb = t; nxt = j; } }
+        if (nxt == cur) break;
+        cur = nxt;
+      }
+      int got = support_hill(v, as, H.adj.data(), d, start);
+      if (got != cur) return -1;
+      warm = got;
+      *evals_scan += sh.nvert;
+      double gap = (double)dot(brute, d) - (double)(v[got].x * d.x + v[got].y * d.y + v[got].z * d.z);
+      if (gap > *max_gap) *max_gap = gap;
+    }
+  }
+  return ngraph;
 }
 
 }  // extern "C"

@@ -233,3 +233,57 @@ def test_full_size_sweep_properties():
     assert 0.55 < total / n < 0.70
     st = eng.stats()
     assert st["uncertain_rows"] < 0.05 * st["rows"]
+
+
+def test_hill_climbing_support_path_on_device(monkeypatch):
+    """The hull-graph (hill-climbing) support query is switched on only for large hulls; force it
+    on for the Franka meshes and require the same parity."""
+    monkeypatch.setenv("MJB_HILL_MIN", "16")
+    model = models.load("franka_scene_with_obstacles")  # fresh object -> fresh engine
+    allowed = [("left_finger", "right_finger")]
+    eng = mj.ValidityEngine(model, allowed)
+    orc = oracle.Oracle(model, allowed)
+    Q = rows(model, 40000, 21)
+    want, dist, _ = orc.check(Q.astype(np.float64), 3, want_dist=True)
+    assert compare(eng.valid_configs(Q), want, dist)[1] == 0
+
+
+def test_full_size_sweep_against_oracle():
+    """BASELINE configs[1] at its full size: all 1,000,000 rows of the benchmark block against
+    the fp64 oracle (multi-threaded), validity identical outside the 1e-5 band."""
+    import os
+
+    from bench import ALLOWED, MODEL, make_rows
+
+    model = models.load(MODEL)
+    eng = mj.get_engine(model, ALLOWED)
+    orc = oracle.Oracle(model, ALLOWED)
+    oracle.Oracle.set_threads(len(os.sched_getaffinity(0)))
+    Q = make_rows(model, 1_000_000)
+    got = eng.valid_configs(Q)
+    want, dist, _ = orc.check(Q.astype(np.float64), 3, want_dist=True)
+    nbad, nout = compare(got, want, dist)
+    inband = int((np.abs(dist) < BAND).sum())
+    print(f"1M rows: mismatches={nbad} outside band={nout} rows in band={inband} valid={got.mean():.4f}")
+    assert nout == 0 and nbad <= inband
+
+
+def test_full_size_edge_batch_properties():
+    """BASELINE configs[2] at its full size (100k UR5e edges, step 0.05): chunked == one shot,
+    first_bad consistent with valid, and a reversed edge has the same validity."""
+    import torch
+
+    model = models.load("ur5e_scene")
+    eng = mj.get_engine(model, [])
+    rng = np.random.default_rng(0)
+    E = 100_000
+    q0 = torch.from_numpy(rng.uniform(-3.1415, 3.1415, size=(E, 6)).astype(np.float32)).cuda()
+    q1 = torch.from_numpy(rng.uniform(-3.1415, 3.1415, size=(E, 6)).astype(np.float32)).cuda()
+    v, fb = eng.valid_edges(q0, q1, 0.05, want_first_bad=True)
+    assert bool(((fb < 0) == v).all())
+    parts = [eng.valid_edges(q0[i : i + 33333], q1[i : i + 33333], 0.05) for i in range(0, E, 33333)]
+    assert bool((torch.cat(parts) == v).all())
+    vr = eng.valid_edges(q1, q0, 0.05)
+    # the waypoint sets of an edge and its reverse coincide up to rounding: allow a handful of flips
+    assert int((vr != v).sum()) <= 20
+    assert 0.05 < float(v.float().mean()) < 0.5

@@ -251,3 +251,17 @@ def test_unsupported_models_are_rejected():
         oracle.Oracle(m)
     with pytest.raises(ValueError, match="hinge and slide"):
         HostSim(m)
+
+
+def test_hill_climbing_support_equals_full_scan(monkeypatch):
+    """The hull graphs (MuJoCo mesh_graph layout) and the hill-climbing support query return a true
+    support vertex for every mesh and 3000 directions (cold and warm starts)."""
+    monkeypatch.setenv("MJB_HILL_MIN", "16")
+    m = models.load("franka_scene_with_obstacles")
+    assert (m.mesh_graphadr >= 0).sum() == 12
+    h = HostSim(m, [("left_finger", "right_finger")])
+    nshape, gap, evals_hill, evals_scan = h.support_check(3000, seed=5)
+    assert nshape == 13 and gap == 0.0
+    assert evals_hill * 3 < evals_scan
+    monkeypatch.setenv("MJB_HILL_MIN", "100000")
+    assert HostSim(m).support_check(10)[0] == 0  # switched off -> no shape uses a graph
