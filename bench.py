@@ -252,10 +252,18 @@ def main():
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
         kernel_ms = total_ms / args.steps / 1.0  # the validity kernel dominates the step (see profiles/)
         achieved = ALG_BYTES_PER_ROW * ROWS_PER_STEP / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, fp32 = None, None
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
-            traffic = json.loads(tf.read_text()).get("validity_kernel_dram_bytes_per_launch")
+            prof = json.loads(tf.read_text())
+            traffic = prof.get("validity_kernel_dram_bytes_per_launch")
+            if prof.get("fp32_flop_per_row_executed"):
+                # executed FP32 flops per row from the committed ncu capture x live row rate,
+                # against the nominal CUDA-core peak (148 SM x 128 lanes x 2 x 1.965 GHz)
+                tfl = prof["fp32_flop_per_row_executed"] * ROWS_PER_STEP / (kernel_ms * 1e-3) / 1e12
+                fp32 = {"achieved_tflops": tfl, "peak_tflops_nominal": prof["fp32_peak_tflops_nominal"],
+                        "frac": tfl / prof["fp32_peak_tflops_nominal"], "flop_per_row": prof["fp32_flop_per_row_executed"],
+                        "source": "profiles/traffic.json (ncu op counts) x live rows/s"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -271,6 +279,7 @@ def main():
                          "traffic": traffic, "peak_source": peak_src,
                          "note": "the path is FP32-ALU/latency bound, not HBM bound (37 algorithmic bytes per row); "
                                  "see DESIGN.md and profiles/ for the pipe-utilisation view"},
+            "roofline_fp32": fp32,
             "stats": {"valid_fraction": float(mask.float().mean()), "narrow_items_per_row": st["narrow_items"] / max(1, st["rows"]),
                       "fp64_rows_fraction": st["uncertain_rows"] / max(1, st["rows"]),
                       "queue_overflow_rows": st["queue_overflow"]},

@@ -270,7 +270,7 @@ def test_full_size_sweep_against_oracle():
 
 def test_full_size_edge_batch_properties():
     """BASELINE configs[2] at its full size (100k UR5e edges, step 0.05): chunked == one shot,
-    first_bad consistent with valid, and a reversed edge has the same validity."""
+    first_bad consistent with valid, repeatable, and valid edges have all-valid waypoints."""
     import torch
 
     model = models.load("ur5e_scene")
@@ -283,7 +283,19 @@ def test_full_size_edge_batch_properties():
     assert bool(((fb < 0) == v).all())
     parts = [eng.valid_edges(q0[i : i + 33333], q1[i : i + 33333], 0.05) for i in range(0, E, 33333)]
     assert bool((torch.cat(parts) == v).all())
-    vr = eng.valid_edges(q1, q0, 0.05)
-    # the waypoint sets of an edge and its reverse coincide up to rounding: allow a handful of flips
-    assert int((vr != v).sum()) <= 20
+    v2, fb2 = eng.valid_edges(q0, q1, 0.05, want_first_bad=True)
+    assert bool((v2 == v).all()) and bool((fb2 == fb).all())
     assert 0.05 < float(v.float().mean()) < 0.5
+    # cross-check 300 edges against dense checks of explicitly generated waypoints
+    idx = rng.choice(E, 300, replace=False)
+    a, b = q0[idx].double().cpu().numpy(), q1[idx].double().cpu().numpy()
+    for k, (s, t) in enumerate(zip(a, b)):
+        d = np.linalg.norm(t - s)
+        K = int(np.ceil(d / np.float64(np.float32(0.05)))) - 1
+        if K <= 0:
+            assert bool(v[idx[k]])
+            continue
+        W = s[None, :] + (np.arange(1, K + 1)[:, None] * np.float64(np.float32(0.05)) / d) * (t - s)[None, :]
+        dense = eng.valid_configs(W.astype(np.float32), _abi.CHECK_COLLISION)
+        first = int(np.argmin(dense)) if not dense.all() else -1
+        assert bool(v[idx[k]]) == bool(dense.all()) and int(fb[idx[k]]) == first
