@@ -57,6 +57,10 @@ typedef struct mjb_model_desc {
   const double *mesh_vert;                          /* (nmeshvert,3) */
   const int64_t *exclude_signature;                 /* (b1<<16)+b2 per <exclude> */
   const int32_t *allowed_body_pairs;                /* (nallowed,2) body ids */
+  /* optional hull graphs (MjModel.mesh_graphadr / mesh_graph, local ids over the hull vertices
+   * above): neighbour lists for hill-climbing support queries; NULL / -1 = scan all vertices */
+  const int32_t *mesh_graphadr, *mesh_graph;
+  int32_t nmeshgraph;
 } mjb_model_desc;
 
 typedef struct mjb_model mjb_model;

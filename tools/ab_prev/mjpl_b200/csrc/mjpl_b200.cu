@@ -43,6 +43,7 @@ struct mjb_model {
   Shape<double> *d_shapes64 = nullptr; Vtx<double> *d_verts64 = nullptr; FkTables<double> *d_fk64 = nullptr;
   double *d_rsum64 = nullptr, *d_bsum64 = nullptr;
   int *d_body_slot = nullptr; float *d_static_pose = nullptr;
+  uint16_t *d_adj_start = nullptr; uint8_t *d_adj = nullptr;
   // scratch
   float *d_pose = nullptr;
   unsigned long long *d_counters = nullptr;
@@ -74,7 +75,8 @@ template <typename T> static int upload(T **dst, const std::vector<T> &src) {
 
 // rows resident per SM with TILE rows per CTA, or -1 if the tables do not fit
 template <int TILE> static int try_tile(const vkb::HostModel &H, int max_smem_optin, int *ctas, size_t *smem) {
-  SmemLayout L = smem_layout<TILE>((int)H.verts.size(), (int)H.shapes.size(), (int)H.pairs.size(), H.nmoving_shapes, H.nq);
+  SmemLayout L = smem_layout<TILE>((int)H.verts.size(), (int)H.shapes.size(), (int)H.pairs.size(), H.nmoving_shapes, H.nq,
+                                   (int)H.adj.size());
   if ((int)L.total > max_smem_optin) return -1;
   if (cudaFuncSetAttribute(validity_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
     cudaGetLastError();
@@ -137,6 +139,12 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   }
   if ((rc = upload(&m->d_static_pose, sp))) return bail(rc);
   if ((rc = upload(&m->d_body_slot, H.body_slot))) return bail(rc);
+  {  // padded to 16-byte multiples: the kernel bulk-copies whole 16-byte units
+    std::vector<uint16_t> as = H.adj_start; as.resize(align_up(as.size(), 8), 0);
+    std::vector<uint8_t> ad = H.adj; ad.resize(align_up(std::max<size_t>(ad.size(), 1), 16), 0);
+    if ((rc = upload(&m->d_adj_start, as))) return bail(rc);
+    if ((rc = upload(&m->d_adj, ad))) return bail(rc);
+  }
 
   // kernel configuration: the tile (rows per CTA) that keeps most rows resident per SM
   int optin = 0;
@@ -163,6 +171,7 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   for (int j = 0; j < H.njnt; j++) { k.jnt_lo[j] = H.jnt_lo[j]; k.jnt_hi[j] = H.jnt_hi[j]; }
   for (int s = 0; s < H.nslot; s++) { k.slot_shape_adr[s] = H.slot_shape_adr[s]; k.slot_shape_num[s] = H.slot_shape_num[s]; }
   k.shapes = m->d_shapes32; k.verts = m->d_verts32; k.pairs = m->d_pairs;
+  k.adj_start = m->d_adj_start; k.adj = m->d_adj; k.nadj = (int)H.adj.size();
   k.nshape = (int)H.shapes.size(); k.nmoving = H.nmoving_shapes; k.nvert = (int)H.verts.size();
   k.npair = (int)H.pairs.size(); k.nslot = H.nslot;
   k.nrounds = H.nrounds;
@@ -185,7 +194,7 @@ extern "C" void mjb_model_destroy(mjb_model *m) {
   if (!m) return;
   cudaFree(m->d_shapes32); cudaFree(m->d_verts32); cudaFree(m->d_pairs); cudaFree(m->d_shapes64);
   cudaFree(m->d_verts64); cudaFree(m->d_fk64); cudaFree(m->d_rsum64); cudaFree(m->d_bsum64);
-  cudaFree(m->d_body_slot); cudaFree(m->d_static_pose); cudaFree(m->d_pose); cudaFree(m->d_counters);
+  cudaFree(m->d_body_slot); cudaFree(m->d_static_pose); cudaFree(m->d_adj_start); cudaFree(m->d_adj); cudaFree(m->d_pose); cudaFree(m->d_counters);
   cudaFree(m->d_recheck); cudaFree(m->d_edge_count); cudaFree(m->d_edge_prefix); cudaFree(m->d_first_bad);
   cudaFree(m->d_cub); cudaFree(m->d_stage_q); cudaFree(m->d_stage_v); cudaFree(m->d_chain_near); cudaFree(m->d_chain_nn);
   if (m->h_pin_q) cudaFreeHost(m->h_pin_q);
@@ -380,6 +389,9 @@ extern "C" int mjb_get_stats(mjb_model *m, mjb_stats *out) {
   out->uncertain_rows = (int64_t)c[C_UNCERTAIN];
   out->queue_overflow = (int64_t)c[C_OVERFLOW];
   out->launches = m->launches;
+#ifdef VK_STATS
+  out->launches = (int64_t)c[7];  // debug build: GJK loop trips
+#endif
   return MJB_OK;
 }
 

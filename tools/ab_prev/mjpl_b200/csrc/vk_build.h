@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -34,6 +35,8 @@ struct HostModel {
   int nmoving_shapes = 0;
   std::vector<int> slot_shape_adr, slot_shape_num;
   std::vector<Vtx<double>> verts;
+  std::vector<uint16_t> adj_start;      // per vertex (+1 sentinel per table end): offsets into adj; all zero w/o graphs
+  std::vector<uint8_t> adj;             // local neighbour ids
   std::vector<Pair> pairs;              // processing order
   std::vector<int> pair_g1, pair_g2;    // MuJoCo geom ids, same order as `pairs`
   std::vector<double> pair_rsum64, pair_bsum64;  // fp64 copies of Pair::rsum / bsum
@@ -191,6 +194,7 @@ template <typename T> inline FkTables<T> convert_fk(const FkTables<double> &s) {
 template <typename T> inline Shape<T> convert_shape(const Shape<double> &s) {
   Shape<T> o; memset(&o, 0, sizeof o);
   o.kind = s.kind; o.slot = s.slot; o.vadr = s.vadr; o.nvert = s.nvert; o.geom = s.geom;
+  o.graph = s.graph; memcpy(o.ext, s.ext, sizeof o.ext);
   o.radius = (T)s.radius; o.halflen = (T)s.halflen; o.brad = (T)s.brad;
   for (int k = 0; k < 3; k++) { o.c[k] = (T)s.c[k]; o.ax[k] = (T)s.ax[k]; o.bc[k] = (T)s.bc[k]; o.oc[k] = (T)s.oc[k]; o.ohalf[k] = (T)s.ohalf[k]; }
   for (int k = 0; k < 9; k++) o.orot[k] = (T)s.orot[k];
@@ -379,6 +383,75 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
     }
   }
   if (H.shapes.size() > 4096) { H.err = "too many collision geoms"; return false; }
+
+  // ---- hull graphs -> per-vertex neighbour lists (hill-climbing support queries) ----------------
+  // One offset per vertex of the global vertex table (+1 sentinel); a shape's list for local
+  // vertex i is adj[adj_start[vadr+i] .. adj_start[vadr+i+1]).  Graphs are validated (ids in range,
+  // symmetric, every vertex has a neighbour); anything else falls back to scanning all vertices.
+  H.adj_start.assign(H.verts.size() + 1, 0);
+  // Measured on B200 (1M Franka rows, hulls of 41-152 vertices): hill-climbing needs 3.8x fewer
+  // dot products than scanning, but its dependent load chain is latency bound at 16 warps/SM and the
+  // step got SLOWER (5.2 ms vs 2.9 ms).  It is therefore only switched on for large hulls.
+  const char *hm = getenv("MJB_HILL_MIN");
+  const int hill_min = hm ? atoi(hm) : 200;
+  {
+    std::vector<std::vector<uint8_t>> lists(H.verts.size());
+    for (auto &sh : H.shapes) {
+      sh.graph = 0;
+      if (sh.kind != SK_VERTS || d->geom_type[sh.geom] != G_MESH || !d->mesh_graph || !d->mesh_graphadr) continue;
+      const int id = d->geom_dataid[sh.geom];
+      const int ga = d->mesh_graphadr[id];
+      const int nv = sh.nvert;
+      if (ga < 0 || nv < hill_min || nv > 256 || ga + 2 > d->nmeshgraph) continue;
+      const int32_t *g = d->mesh_graph + ga;
+      const int gnv = g[0], gnf = g[1];
+      if (gnv != nv || ga + 2 + 3 * gnv + 6 * gnf > d->nmeshgraph) continue;
+      const int32_t *edgeadr = g + 2, *globalid = g + 2 + gnv, *edges = g + 2 + 2 * gnv;
+      const int nedge = gnv + 3 * gnf;
+      bool ok = true;
+      std::vector<std::vector<uint8_t>> loc(nv);
+      for (int i = 0; i < nv && ok; i++) {
+        if (globalid[i] != i) ok = false;  // mesh_vert must already be in hull-local order
+        for (int e = edgeadr[i]; ok; e++) {
+          if (e < 0 || e >= nedge) { ok = false; break; }
+          int j = edges[e];
+          if (j < 0) break;
+          if (j >= nv || j == i) { ok = false; break; }
+          loc[i].push_back((uint8_t)j);
+        }
+        if (loc[i].empty()) ok = false;
+      }
+      for (int i = 0; i < nv && ok; i++)
+        for (uint8_t j : loc[i])
+          if (std::find(loc[j].begin(), loc[j].end(), (uint8_t)i) == loc[j].end()) ok = false;
+      if (!ok) continue;
+      for (int i = 0; i < nv; i++) lists[sh.vadr + i] = loc[i];
+      sh.graph = 1;
+      for (int k = 0; k < 3; k++)
+        for (int sgn = 0; sgn < 2; sgn++) {
+          int bi = 0; double bv = -1e300;
+          for (int i = 0; i < nv; i++) {
+            const Vtx<double> &p = H.verts[sh.vadr + i];
+            double c = k == 0 ? p.x : (k == 1 ? p.y : p.z);
+            if (sgn) c = -c;
+            if (c > bv) { bv = c; bi = i; }
+          }
+          sh.ext[2 * k + sgn] = (uint8_t)bi;
+        }
+    }
+    size_t total = 0;
+    for (auto &l : lists) total += l.size();
+    if (total > 65000) {  // offsets are 16 bit: give up on graphs for huge models
+      for (auto &sh : H.shapes) sh.graph = 0;
+      for (auto &l : lists) l.clear();
+    }
+    for (size_t i = 0; i < lists.size(); i++) {
+      H.adj_start[i] = (uint16_t)H.adj.size();
+      for (uint8_t j : lists[i]) H.adj.push_back(j);
+    }
+    H.adj_start[lists.size()] = (uint16_t)H.adj.size();
+  }
+  for (auto &sh : H.shapes) sh.pad = 0;
 
   // ---- pairs in processing order --------------------------------------------------------------------
   struct Tmp { Pair p; int g1, g2; long key; double rsum, bsum; };

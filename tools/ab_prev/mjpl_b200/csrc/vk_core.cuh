@@ -170,8 +170,11 @@ template <typename T> struct Shape {
   T orot[9];       // OBB axes = columns, row-major 3x3
   T ohalf[3];      // OBB half extents (include swept radius)
   int geom;        // MuJoCo geom id
+  int graph;       // 1: hull adjacency available (hill-climbing support), 0: scan all vertices
+  uint8_t ext[8];  // graph: local ids of the extreme vertices along +x,-x,+y,-y,+z,-z (start points)
+  int pad;
 };
-static_assert(sizeof(Shape<float>) == 128, "Shape<float> must stay a multiple of 16 bytes (cp.async.bulk granularity)");
+static_assert(sizeof(Shape<float>) == 144, "Shape<float> must stay a multiple of 16 bytes (cp.async.bulk granularity)");
 
 struct Pair {
   uint16_t sa, sb;  // shape indices (sa: plane if any; else the one with more vertices first)
@@ -348,6 +351,38 @@ VK_HD V3<T> support_verts(const Vtx<T> *__restrict__ v, int n, V3<T> d) {
     bp.x = g ? p.x : bp.x; bp.y = g ? p.y : bp.y; bp.z = g ? p.z : bp.z;
   }
   return bp;
+}
+
+// Hill-climbing support on the hull's vertex graph: from `start`, move to the best strictly
+// better neighbour until none is better.  On a convex polytope with its full edge graph a vertex
+// without a better neighbour is a global maximiser of the linear function, so this returns a
+// true support vertex (up to rounding of the dot products).  adj_start is indexed by local
+// vertex id (nvert+1 entries for this shape), adj holds local neighbour ids.
+template <typename T>
+VK_HD int support_hill(const Vtx<T> *__restrict__ v, const uint16_t *__restrict__ adj_start,
+                       const uint8_t *__restrict__ adj, V3<T> d, int start) {
+  int cur = start;
+  T best = v[cur].x * d.x + v[cur].y * d.y + v[cur].z * d.z;
+  for (;;) {
+    int cj = cur;
+    T cb = best;
+    for (int e = adj_start[cur]; e < adj_start[cur + 1]; e++) {
+      const int j = adj[e];
+      const T t = v[j].x * d.x + v[j].y * d.y + v[j].z * d.z;
+      if (t > cb) { cb = t; cj = j; }
+    }
+    if (cj == cur) return cur;
+    cur = cj;
+    best = cb;
+  }
+}
+
+// start vertex for a cold query: the precomputed extreme vertex along the dominant axis of d
+template <typename T> VK_HD int hill_start(const Shape<T> &s, V3<T> d) {
+  const T ax = vk_abs(d.x), ay = vk_abs(d.y), az = vk_abs(d.z);
+  int k = (ax >= ay && ax >= az) ? 0 : (ay >= az ? 1 : 2);
+  const T c = k == 0 ? d.x : (k == 1 ? d.y : d.z);
+  return s.ext[2 * k + (c < T(0) ? 1 : 0)];
 }
 
 template <typename T> VK_HD V3<T> support_cyl(const Shape<T> &s, V3<T> d) {

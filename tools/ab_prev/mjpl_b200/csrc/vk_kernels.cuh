@@ -47,6 +47,9 @@ struct KArgs {
   const Shape<float> *shapes;
   const Vtx<float> *verts;
   const Pair *pairs;
+  const uint16_t *adj_start;            // hull graphs: nvert+1 offsets into adj
+  const uint8_t *adj;                   // local neighbour ids
+  int nadj;
   int nshape, nmoving, nvert, npair, nslot;
   int nrounds;
   int round_start[MAX_ROUNDS + 1];
@@ -106,15 +109,17 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 
 // dynamic shared memory carve-up (host and device agree through this one function)
 struct SmemLayout {
-  size_t verts, shapes, pairs, cen, qtile, queue1, queue2, hit, bars, total;
+  size_t verts, shapes, pairs, adjs, adj, cen, qtile, queue1, queue2, hit, bars, total;
 };
 template <int TILE>
-__host__ __device__ inline SmemLayout smem_layout(int nvert, int nshape, int npair, int nmoving, int nq) {
+__host__ __device__ inline SmemLayout smem_layout(int nvert, int nshape, int npair, int nmoving, int nq, int nadj) {
   SmemLayout L;
   size_t o = 0;
   L.verts = o; o = align_up(o + (size_t)nvert * sizeof(Vtx<float>), 128);
   L.shapes = o; o = align_up(o + (size_t)nshape * sizeof(Shape<float>), 128);
   L.pairs = o; o = align_up(o + (size_t)npair * sizeof(Pair), 128);
+  L.adjs = o; o = align_up(o + (size_t)(nvert + 1) * sizeof(uint16_t), 128);
+  L.adj = o; o = align_up(o + (size_t)nadj, 128);
   L.cen = o; o = align_up(o + (size_t)(nmoving > 0 ? nmoving : 1) * 3 * TILE * sizeof(float), 128);
   L.qtile = o; o = align_up(o + (size_t)TILE * nq * sizeof(float), 128);
   L.queue1 = o; o = align_up(o + (size_t)Q1_PER_ROW * TILE * sizeof(uint32_t), 128);
@@ -206,28 +211,61 @@ __device__ __forceinline__ void warp_push(bool want, uint32_t item, uint32_t *qu
 #endif
 constexpr int GRP = VK_GRP;
 
-__device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const Vtx<float> *__restrict__ verts, V3<float> d,
-                                                  int gl, unsigned gmask) {
+// `warm` carries the last support vertex of this shape within one GJK run (-1 = cold start).
+__device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const Vtx<float> *__restrict__ verts,
+                                                  const uint16_t *__restrict__ adjs, const uint8_t *__restrict__ adj,
+                                                  V3<float> d, int gl, unsigned gmask, int &warm) {
   if (s.kind == SK_CYL) return support_cyl(s, d);
   const Vtx<float> *__restrict__ v = verts + s.vadr;
-  const int n = s.nvert;
-  float best = -3.0e38f;
   int bi = 0;
-#pragma unroll 2
-  for (int i = gl; i < n; i += GRP) {
-    const Vtx<float> p = v[i];
-    const float t = p.x * d.x + p.y * d.y + p.z * d.z;
-    const bool g = t > best;
-    best = g ? t : best;
-    bi = g ? i : bi;
-  }
+  if (s.graph) {
+    // hill-climbing on the hull graph; the lanes of the group split each neighbour list
+    const uint16_t *__restrict__ as = adjs + s.vadr;
+    bi = warm >= 0 ? warm : hill_start(s, d);
+    const Vtx<float> p0 = v[bi];
+    float best = p0.x * d.x + p0.y * d.y + p0.z * d.z;
+    for (;;) {
+      int cj = bi;
+      float cb = best;
+      const int e1 = as[bi + 1];
+      for (int e = as[bi] + gl; e < e1; e += GRP) {
+        const int j = adj[e];
+        const Vtx<float> p = v[j];
+        const float t = p.x * d.x + p.y * d.y + p.z * d.z;
+        if (t > cb) { cb = t; cj = j; }
+      }
 #pragma unroll
-  for (int o = GRP / 2; o > 0; o >>= 1) {
-    const float ob = __shfl_xor_sync(gmask, best, o);
-    const int oi = __shfl_xor_sync(gmask, bi, o);
-    const bool take = (ob > best) || (ob == best && oi < bi);
-    best = take ? ob : best;
-    bi = take ? oi : bi;
+      for (int o = GRP / 2; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(gmask, cb, o);
+        const int oj = __shfl_xor_sync(gmask, cj, o);
+        const bool take = (ob > cb) || (ob == cb && oj < cj);
+        cb = take ? ob : cb;
+        cj = take ? oj : cj;
+      }
+      if (cj == bi) break;
+      bi = cj;
+      best = cb;
+    }
+    warm = bi;
+  } else {
+    const int n = s.nvert;
+    float best = -3.0e38f;
+#pragma unroll 2
+    for (int i = gl; i < n; i += GRP) {
+      const Vtx<float> p = v[i];
+      const float t = p.x * d.x + p.y * d.y + p.z * d.z;
+      const bool g = t > best;
+      best = g ? t : best;
+      bi = g ? i : bi;
+    }
+#pragma unroll
+    for (int o = GRP / 2; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(gmask, best, o);
+      const int oi = __shfl_xor_sync(gmask, bi, o);
+      const bool take = (ob > best) || (ob == best && oi < bi);
+      best = take ? ob : best;
+      bi = take ? oi : bi;
+    }
   }
   const Vtx<float> w = v[bi];
   return mk<float>(w.x, w.y, w.z);
@@ -237,10 +275,12 @@ template <int TILE>
 __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int nq = a.fk.nq;
-  const SmemLayout L = smem_layout<TILE>(a.nvert, a.nshape, a.npair, a.nmoving, nq);
+  const SmemLayout L = smem_layout<TILE>(a.nvert, a.nshape, a.npair, a.nmoving, nq, a.nadj);
   Vtx<float> *s_verts = reinterpret_cast<Vtx<float> *>(smem + L.verts);
   Shape<float> *s_shapes = reinterpret_cast<Shape<float> *>(smem + L.shapes);
   Pair *s_pairs = reinterpret_cast<Pair *>(smem + L.pairs);
+  uint16_t *s_adjs = reinterpret_cast<uint16_t *>(smem + L.adjs);
+  uint8_t *s_adj = smem + L.adj;
   float *s_cen = reinterpret_cast<float *>(smem + L.cen);
   float *s_q = reinterpret_cast<float *>(smem + L.qtile);
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.bars);       // [0] tables, [8 + w] rows of warp w
@@ -262,11 +302,15 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
     fence_barrier_init();
   }
   __syncthreads();
+  const uint32_t bytes_as = (uint32_t)align_up((size_t)(a.nvert + 1) * sizeof(uint16_t), 16);  // device arrays are padded
+  const uint32_t bytes_a = (uint32_t)align_up((size_t)a.nadj, 16);
   if (tid == 0) {
-    mbar_expect_tx(&s_bar[0], bytes_v + bytes_s + bytes_p);
+    mbar_expect_tx(&s_bar[0], bytes_v + bytes_s + bytes_p + bytes_as + bytes_a);
     if (bytes_v) bulk_g2s(s_verts, a.verts, bytes_v, &s_bar[0]);
     if (bytes_s) bulk_g2s(s_shapes, a.shapes, bytes_s, &s_bar[0]);
     if (bytes_p) bulk_g2s(s_pairs, a.pairs, bytes_p, &s_bar[0]);
+    bulk_g2s(s_adjs, a.adj_start, bytes_as, &s_bar[0]);
+    if (bytes_a) bulk_g2s(s_adj, a.adj, bytes_a, &s_bar[0]);
   }
   mbar_wait(&s_bar[0], 0);
 
@@ -277,6 +321,9 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
   uint32_t row_parity = 0;
   const bool dense_bulk = (a.mode == MODE_DENSE) && (a.ldq == nq) && ((reinterpret_cast<uintptr_t>(a.q) & 15) == 0);
   long long items_total = 0, rows_total = 0;
+#ifdef VK_STATS
+  long long st_trips = 0, st_busy = 0, st_flushes = 0, st_bbatches = 0, st_bbusy = 0;
+#endif
   const bool use_obb = !(a.flags & F_NO_OBB);
   const float slack = 1e-4f;
   uint64_t *wbar = s_bar + 8 + (tid >> 5);       // this warp's row-load barrier
@@ -461,11 +508,15 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
           // while the slowest item of the warp converges.  Plane and segment items are decided
           // in the fetch step.
           items_total += n2;
+#ifdef VK_STATS
+          st_flushes++;
+#endif
           GjkState<float> gs;
           Rel<float> rel;
           const Shape<float> *SA = s_shapes, *SB = s_shapes;
           float R = 0.f;
           int r = 0;
+          int wa = -1, wb = -1;  // warm-start vertices of the current item's two shapes
           bool have = false;
           int head = 0;  // warp-uniform
 #pragma unroll 1
@@ -488,12 +539,14 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
                   if (pr.kind == PK_GJK) {
                     rel = relative_pose(PA, PB);
                     gjk_init(gs, *SA, *SB, rel);
+                    wa = wb = -1;
                     have = true;
                   } else {
                     int v;
                     if (pr.kind == PK_PLANE) {
                       const Shape<float> &Bs = *SB;
-                      v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support(Bs, s_verts, d, gl, gmask); });
+                      int cold = -1;
+                      v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, cold); });
                     } else {
                       v = segseg_item(*SA, *SB, s_verts, PA, PB, R);
                     }
@@ -504,11 +557,14 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
               }
             }
             head += __popc(need) / GRP;
+#ifdef VK_STATS
+            st_trips++; st_busy += __popc(__ballot_sync(0xffffffffu, have)) / GRP;
+#endif
             if (have) {
               const Shape<float> &As = *SA, &Bs = *SB;
               const int v = gjk_step_impl(
-                  gs, rel, R, [&](V3<float> d) { return group_support(As, s_verts, d, gl, gmask); },
-                  [&](V3<float> d) { return group_support(Bs, s_verts, d, gl, gmask); });
+                  gs, rel, R, [&](V3<float> d) { return group_support(As, s_verts, s_adjs, s_adj, d, gl, gmask, wa); },
+                  [&](V3<float> d) { return group_support(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, wb); });
               if (v >= 0) {
                 if (v == V_PEN) hb = 1u << r;
                 else if (v == V_UNC) ub = 1u << r;
@@ -546,6 +602,9 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
   }
   if (lane == 0 && items_total) atomicAdd(&a.counters[C_ITEMS], (unsigned long long)items_total);
   if (lane == 0 && rows_total) atomicAdd(&a.counters[C_ROWS], (unsigned long long)rows_total);
+#ifdef VK_STATS
+  if (lane == 0) { atomicAdd(&a.counters[7], (unsigned long long)st_trips); atomicAdd(&a.counters[C_OVERFLOW], (unsigned long long)st_busy); atomicAdd(&a.counters[C_UNCERTAIN], (unsigned long long)st_flushes); }
+#endif
 }
 
 // ---------------------------------------------------------------------------- fp64 re-evaluation
