@@ -28,9 +28,15 @@
 #if defined(__CUDACC__)
 #define VK_HD __host__ __device__ __forceinline__
 #define VK_HD_NOINLINE __host__ __device__ __noinline__
+#ifndef VK_SOLVE_INLINE
+#define VK_SOLVE_HD VK_HD_NOINLINE
+#else
+#define VK_SOLVE_HD VK_HD
+#endif
 #else
 #define VK_HD inline
 #define VK_HD_NOINLINE
+#define VK_SOLVE_HD inline
 #endif
 
 namespace vk {
@@ -240,7 +246,9 @@ template <typename T> VK_HD T comb2(V3<T> a, V3<T> b, T la, T lb) {
   return dot(v, v);
 }
 
-template <typename T> VK_HD void solve2(V3<T> a, V3<T> b, V3<T> c, T &la, T &lb, T &lc) {
+// solve2/solve3 are big and sit on rarely-taken paths: kept out of line so the kernel's hot loops
+// stay small (instruction-fetch stalls were the second largest stall reason in the ncu capture)
+template <typename T> VK_SOLVE_HD void solve2(V3<T> a, V3<T> b, V3<T> c, T &la, T &lb, T &lc) {
   V3<T> n = cross(b - a, c - a);
   T nn = dot(n, n);
   bool inside = false;
@@ -285,7 +293,7 @@ template <typename T> VK_HD T comb3(V3<T> a, V3<T> b, V3<T> c, T la, T lb, T lc)
 
 // returns true when the origin is inside the tetrahedron (weights then all > 0)
 template <typename T>
-VK_HD bool solve3(V3<T> a, V3<T> b, V3<T> c, V3<T> d, T &la, T &lb, T &lc, T &ld) {
+VK_SOLVE_HD bool solve3(V3<T> a, V3<T> b, V3<T> c, V3<T> d, T &la, T &lb, T &lc, T &ld) {
   T Ca = -det3(b, c, d), Cb = det3(a, c, d), Cc = -det3(a, b, d), Cd = det3(a, b, c);
   T dm = Ca + Cb + Cc + Cd;
   // scale for the degeneracy test: product of edge lengths ~ volume scale

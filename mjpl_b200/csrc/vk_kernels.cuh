@@ -203,13 +203,22 @@ __device__ __forceinline__ void warp_push(bool want, uint32_t item, uint32_t *qu
 }
 
 // Lanes-per-item of the narrow phase: GRP consecutive lanes cooperate on one (row, pair) item
-// (measured on B200, 1M Franka rows: GRP=2 3.24 ms, GRP=4 3.54 ms, GRP=8 4.08 ms per step).
+// (measured on B200, 1M Franka rows, same box: GRP=1 with the scan unrolled x4 3.34 ms, GRP=2 3.52 ms,
+// GRP=4 3.8 ms, GRP=8 4.4 ms per step; hulls here have 41-152 vertices -- larger hulls favour GRP > 1).
 // They split every support scan (hull vertices) GRP ways and butterfly-reduce the arg-max, then
 // run the (cheap, identical) simplex update redundantly, so a warp works on 32/GRP items at
 // once with every lane busy during the scans that dominate the cost.
 #ifndef VK_GRP
-#define VK_GRP 2
+#define VK_GRP 1
 #endif
+#ifndef VK_SCAN_UNROLL
+#define VK_SCAN_UNROLL 4
+#endif
+#ifndef VK_A_UNROLL
+#define VK_A_UNROLL 1
+#endif
+#define VK_PRAGMA(x) _Pragma(#x)
+#define VK_UNROLL(n) VK_PRAGMA(unroll n)
 constexpr int GRP = VK_GRP;
 
 // `warm` carries the last support vertex of this shape within one GJK run (-1 = cold start).
@@ -251,7 +260,7 @@ __device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const 
   } else {
     const int n = s.nvert;
     float best = -3.0e38f;
-#pragma unroll 2
+    VK_UNROLL(VK_SCAN_UNROLL)
     for (int i = gl; i < n; i += GRP) {
       const Vtx<float> p = v[i];
       const float t = p.x * d.x + p.y * d.y + p.z * d.z;
@@ -453,7 +462,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
           int cached_sa = -1;          // pairs of a round are sorted by shape A: its centre is
           V3<float> cA = mk<float>(0.f, 0.f, 0.f);  // fetched once per run of pairs (warp-uniform test)
           const int stat_off = a.nmoving * 3 * TILE - a.nmoving;  // static centre k sits at stat_off + shape index
-#pragma unroll 1
+          VK_UNROLL(VK_A_UNROLL)
           for (; p < p1 && n1 + 32 <= Q1CAP; p++) {
             const Pair pr = s_pairs[p];
             if ((int)pr.sa != cached_sa) {

@@ -78,6 +78,7 @@ template <int TILE> static int try_tile(const vkb::HostModel &H, int max_smem_op
   SmemLayout L = smem_layout<TILE>((int)H.verts.size(), (int)H.shapes.size(), (int)H.pairs.size(), H.nmoving_shapes, H.nq,
                                    (int)H.adj.size());
   if ((int)L.total > max_smem_optin) return -1;
+  if ((int)H.shapes.size() - H.nmoving_shapes > TILE) return -1;  // static centres share one [xyz][TILE] block
   if (cudaFuncSetAttribute(validity_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
     cudaGetLastError();
     return -1;

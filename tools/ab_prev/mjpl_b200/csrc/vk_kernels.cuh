@@ -120,7 +120,7 @@ __host__ __device__ inline SmemLayout smem_layout(int nvert, int nshape, int npa
   L.pairs = o; o = align_up(o + (size_t)npair * sizeof(Pair), 128);
   L.adjs = o; o = align_up(o + (size_t)(nvert + 1) * sizeof(uint16_t), 128);
   L.adj = o; o = align_up(o + (size_t)nadj, 128);
-  L.cen = o; o = align_up(o + (size_t)(nmoving > 0 ? nmoving : 1) * 3 * TILE * sizeof(float), 128);
+  L.cen = o; o = align_up(o + (size_t)(nmoving + 1) * 3 * TILE * sizeof(float), 128);  // + one block of static centres
   L.qtile = o; o = align_up(o + (size_t)TILE * nq * sizeof(float), 128);
   L.queue1 = o; o = align_up(o + (size_t)Q1_PER_ROW * TILE * sizeof(uint32_t), 128);
   L.queue2 = o; o = align_up(o + (size_t)Q2_PER_ROW * TILE * sizeof(uint32_t), 128);
@@ -196,6 +196,7 @@ __device__ __forceinline__ Pose<float> load_pose(const float *ps, int slot, int 
 // The caller guarantees count + 32 <= cap before the push, so nothing can be dropped.
 __device__ __forceinline__ void warp_push(bool want, uint32_t item, uint32_t *queue, int &count, int cap, int lane) {
   const unsigned m = __ballot_sync(0xffffffffu, want);
+  if (m == 0) return;  // warp-uniform: the common case in the sphere stage
   const int idx = count + __popc(m & ((1u << lane) - 1u));
   count += __popc(m);
   if (want && idx < cap) queue[idx] = item;
@@ -313,6 +314,15 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
     if (bytes_a) bulk_g2s(s_adj, a.adj, bytes_a, &s_bar[0]);
   }
   mbar_wait(&s_bar[0], 0);
+  // static (world-fixed) shapes: their centres never change; they live in one extra [xyz][TILE]
+  // block of the centre array, indexed by (shape - nmoving), so the sphere stage addresses moving
+  // and static centres the same way
+  for (int k = tid; k < a.nshape - a.nmoving; k += TILE) {
+    const Shape<float> &S = s_shapes[a.nmoving + k];
+    float *cc = s_cen + (size_t)a.nmoving * 3 * TILE + k;
+    cc[0] = S.bc[0]; cc[TILE] = S.bc[1]; cc[2 * TILE] = S.bc[2];
+  }
+  __syncthreads();
 
   // total number of rows (edges: read from the device-side prefix sums)
   long long nrows = a.n;
@@ -442,37 +452,26 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
           const bool live = do_coll && !((hit_mask >> lane) & 1u);
           int cached_sa = -1;          // pairs of a round are sorted by shape A: its centre is
           V3<float> cA = mk<float>(0.f, 0.f, 0.f);  // fetched once per run of pairs (warp-uniform test)
+          const int stat_off = a.nmoving * 3 * TILE - a.nmoving;  // static centre k sits at stat_off + shape index
 #pragma unroll 1
           for (; p < p1 && n1 + 32 <= Q1CAP; p++) {
             const Pair pr = s_pairs[p];
             if ((int)pr.sa != cached_sa) {
               cached_sa = pr.sa;
-              const Shape<float> &A = s_shapes[pr.sa];
-              if (pr.flags & PF_A_STATIC) cA = mk<float>(A.bc[0], A.bc[1], A.bc[2]);
-              else {
-                const float *cc = s_cen + (size_t)pr.sa * 3 * TILE + tid;
-                cA = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
-              }
+              const float *cc = s_cen + ((pr.flags & PF_A_STATIC) ? stat_off + (int)pr.sa : (int)pr.sa * 3 * TILE + tid);
+              cA = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
             }
-            bool survive = false;
-            if (live) {
-              V3<float> cB;
-              if (pr.flags & PF_B_STATIC) {
-                const Shape<float> &B = s_shapes[pr.sb];
-                cB = mk<float>(B.bc[0], B.bc[1], B.bc[2]);
-              } else {
-                const float *cc = s_cen + (size_t)pr.sb * 3 * TILE + tid;
-                cB = mk<float>(cc[0], cc[TILE], cc[2 * TILE]);
-              }
-              if (pr.kind == PK_PLANE) {
-                const Shape<float> &A = s_shapes[pr.sa];
-                float d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
-                survive = d <= pr.bsum + slack;
-              } else {
-                V3<float> d = cA - cB;
-                float lim = pr.bsum + slack;
-                survive = dot(d, d) <= lim * lim;
-              }
+            const float *cb = s_cen + ((pr.flags & PF_B_STATIC) ? stat_off + (int)pr.sb : (int)pr.sb * 3 * TILE + tid);
+            const V3<float> cB = mk<float>(cb[0], cb[TILE], cb[2 * TILE]);
+            const float lim = pr.bsum + slack;
+            bool survive;
+            if (pr.kind == PK_PLANE) {
+              const Shape<float> &A = s_shapes[pr.sa];
+              const float d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
+              survive = live && d <= lim;
+            } else {
+              const V3<float> d = cA - cB;
+              survive = live && dot(d, d) <= lim * lim;
             }
             warp_push(survive, (uint32_t)lane | ((uint32_t)p << 16), q1, n1, Q1CAP, lane);
           }
