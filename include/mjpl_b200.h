@@ -150,6 +150,33 @@ int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, int64_t *d_
                    const int64_t *d_slots, const double *d_targets, int64_t n, double eps,
                    int32_t kcap, uint32_t flags, double *d_reached, int64_t *d_last, void *stream);
 
+/*
+ * PoseConstraint (src/mjpl/constraint/pose_constraint.py:11-171): a site must stay inside a box
+ * of translations and roll/pitch/yaw expressed in a constraint frame.  fp64, rows (n,nq) of
+ * doubles.  mjb_pose_valid = valid_config (:72-76: joint limits, then |displacement| <=
+ * tolerance); mjb_pose_project = apply (:78-91): q -= J^T pinv(J J^T) dx until the displacement
+ * is within tolerance (ok=1, row written to d_q_out) or the row leaves the joint limits / moves
+ * more than 2*q_step from q_old / exceeds max_iters (ok=0: the reference returns None).
+ */
+typedef struct mjb_pose_spec {
+  int32_t site_bodyid;                /* model.site_bodyid[site]  (pose_constraint.py:70) */
+  double site_pos[3], site_quat[4];   /* model.site_pos / site_quat */
+  double ref_pos[3], ref_quat[4];     /* reference_frame (world_T_C), quaternion wxyz */
+  double lower[6], upper[6];          /* x, y, z, roll, pitch, yaw limits (may be +-inf) */
+  double tolerance, q_step;
+} mjb_pose_spec;
+
+/* site_pose (src/mjpl/utils.py:60-75) for a block of fp64 rows: world position (n,3) and
+ * quaternion (n,4 wxyz) of a site given by its body id and local pose. */
+int mjb_site_pose(mjb_model *m, int32_t site_bodyid, const double *site_pos, const double *site_quat,
+                  const double *d_q, int64_t n, double *d_pos, double *d_quat, void *stream);
+
+int mjb_pose_valid(mjb_model *m, const mjb_pose_spec *spec, const double *d_q, int64_t n,
+                   uint8_t *d_valid, void *stream);
+int mjb_pose_project(mjb_model *m, const mjb_pose_spec *spec, const double *d_q_old,
+                     const double *d_q, int64_t n, int32_t max_iters, double *d_q_out,
+                     uint8_t *d_ok, int32_t *d_iters, void *stream);
+
 int mjb_get_stats(mjb_model *m, mjb_stats *out);   /* synchronises the handle's last stream */
 int mjb_reset_stats(mjb_model *m);
 

@@ -13,14 +13,16 @@ from .constraint import (
     CollisionRuleset,
     Constraint,
     JointLimitConstraint,
+    PoseConstraint,
     apply_constraints,
     obeys_constraints,
     obeys_constraints_batch,
 )
+from .lie import SE3, SO3
 from .engine import EngineUnavailable, ValidityEngine, get_engine
 from .model import Model
 from .planning import RRT, BatchedRRT, path_length, smooth_path
-from .utils import all_joints, qpos_idx, qvel_idx, random_config
+from .utils import all_joints, qpos_idx, qvel_idx, random_config, site_pose
 
 __all__ = (
     "BatchedRRT",
@@ -30,6 +32,9 @@ __all__ = (
     "EngineUnavailable",
     "JointLimitConstraint",
     "Model",
+    "PoseConstraint",
+    "SE3",
+    "SO3",
     "RRT",
     "ValidityEngine",
     "all_joints",
@@ -43,5 +48,6 @@ __all__ = (
     "qpos_idx",
     "qvel_idx",
     "random_config",
+    "site_pose",
     "smooth_path",
 )

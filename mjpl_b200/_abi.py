@@ -53,6 +53,14 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in "rows narrow_items uncertain_rows queue_overflow launches".split()]
 
 
+class PoseSpec(C.Structure):
+    """``mjb_pose_spec``"""
+
+    _fields_ = [("site_bodyid", C.c_int32), ("site_pos", C.c_double * 3), ("site_quat", C.c_double * 4),
+                ("ref_pos", C.c_double * 3), ("ref_quat", C.c_double * 4), ("lower", C.c_double * 6),
+                ("upper", C.c_double * 6), ("tolerance", C.c_double), ("q_step", C.c_double)]
+
+
 class EngineUnavailable(RuntimeError):
     """The CUDA engine cannot run here (library not built, or no GPU).  Never caught internally."""
 
@@ -102,7 +110,7 @@ _lib = None
 EXPORTS = (
     "mjb_last_error mjb_device_count mjb_model_create mjb_model_destroy mjb_model_npair "
     "mjb_model_pairs mjb_check_configs mjb_check_configs_host mjb_fk mjb_check_edges "
-    "mjb_check_sweep mjb_sweep_rows mjb_get_stats mjb_reset_stats mjb_nearest_batch mjb_rrt_extend"
+    "mjb_check_sweep mjb_sweep_rows mjb_get_stats mjb_reset_stats mjb_nearest_batch mjb_rrt_extend mjb_pose_valid mjb_pose_project mjb_site_pose"
 ).split()
 
 
@@ -135,6 +143,9 @@ def lib():
     L.mjb_sweep_rows.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, f32p, vp]
     L.mjb_nearest_batch.argtypes = [vp, C.c_int64, C.c_int32, vp, vp, vp, C.c_int64, vp, vp]
     L.mjb_rrt_extend.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, C.c_int64, C.c_double, C.c_int32, C.c_uint32, vp, vp, vp]
+    L.mjb_site_pose.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, C.c_int64, vp, vp, vp]
+    L.mjb_pose_valid.argtypes = [vp, C.POINTER(PoseSpec), vp, C.c_int64, vp, vp]
+    L.mjb_pose_project.argtypes = [vp, C.POINTER(PoseSpec), vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp]
     L.mjb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.mjb_reset_stats.argtypes = [vp]
     for n in EXPORTS:

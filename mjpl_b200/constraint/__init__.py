@@ -1,6 +1,7 @@
 from .collision_constraint import CollisionConstraint, CollisionRuleset
 from .constraint_interface import Constraint
 from .joint_limit_constraint import JointLimitConstraint
+from .pose_constraint import PoseConstraint
 from .utils import apply_constraints, obeys_constraints, obeys_constraints_batch
 
 __all__ = (
@@ -8,6 +9,7 @@ __all__ = (
     "CollisionConstraint",
     "CollisionRuleset",
     "JointLimitConstraint",
+    "PoseConstraint",
     "apply_constraints",
     "obeys_constraints",
     "obeys_constraints_batch",

@@ -79,7 +79,9 @@ template <int TILE> static int try_tile(const vkb::HostModel &H, int max_smem_op
                                    (int)H.adj.size());
   if ((int)L.total > max_smem_optin) return -1;
   if ((int)H.shapes.size() - H.nmoving_shapes > TILE) return -1;  // static centres share one [xyz][TILE] block
-  if (cudaFuncSetAttribute(validity_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess) {
+  // the attribute is per kernel function, shared by every handle in the process: always ask for
+  // the device maximum so that handles with different table sizes can coexist
+  if (cudaFuncSetAttribute(validity_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }
@@ -485,5 +487,63 @@ extern "C" int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, 
       m->d_counters + C_OVERFLOW);
   CU(cudaGetLastError());
   m->launches += 4;
+  return MJB_OK;
+}
+
+// ---- PoseConstraint --------------------------------------------------------------------------------
+static int fill_pose_spec(mjb_model *m, const mjb_pose_spec *in, PoseSpec &sp) {
+  std::string err;
+  if (!vkb::make_pose_spec(m->H, in, sp, err)) return fail(MJB_ERR_ARG, err);
+  return MJB_OK;
+}
+
+static int launch_pose(mjb_model *m, const mjb_pose_spec *spec, const double *d_q_old, const double *d_q, int64_t n, int project,
+                       int32_t max_iters, double *d_q_out, uint8_t *d_ok, int32_t *d_iters, void *stream) {
+  int rc = check_common(m, MJB_CHECK_LIMITS);
+  if (rc) return rc;
+  if (n < 0) return fail(MJB_ERR_ARG, "bad n");
+  PoseArgs a;
+  memset(&a, 0, sizeof a);
+  if ((rc = fill_pose_spec(m, spec, a.spec))) return rc;
+  if (n == 0) return MJB_OK;
+  if (!d_q || !d_ok || (project && (!d_q_old || !d_q_out))) return fail(MJB_ERR_ARG, "null device pointer");
+  a.fk = m->d_fk64; a.nslot = m->H.nslot; a.q_old = d_q_old; a.q = d_q; a.n = n; a.project = project;
+  a.max_iters = max_iters > 0 ? max_iters : 1000; a.q_out = d_q_out; a.ok = d_ok; a.iters = d_iters;
+  cudaStream_t st = (cudaStream_t)stream;
+  pose_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(a);
+  CU(cudaGetLastError());
+  m->launches++;
+  m->last_stream = st;
+  return MJB_OK;
+}
+
+extern "C" int mjb_pose_valid(mjb_model *m, const mjb_pose_spec *spec, const double *d_q, int64_t n, uint8_t *d_valid, void *stream) {
+  return launch_pose(m, spec, nullptr, d_q, n, 0, 0, nullptr, d_valid, nullptr, stream);
+}
+
+extern "C" int mjb_pose_project(mjb_model *m, const mjb_pose_spec *spec, const double *d_q_old, const double *d_q, int64_t n,
+                                int32_t max_iters, double *d_q_out, uint8_t *d_ok, int32_t *d_iters, void *stream) {
+  return launch_pose(m, spec, d_q_old, d_q, n, 1, max_iters, d_q_out, d_ok, d_iters, stream);
+}
+
+extern "C" int mjb_site_pose(mjb_model *m, int32_t site_bodyid, const double *site_pos, const double *site_quat, const double *d_q,
+                             int64_t n, double *d_pos, double *d_quat, void *stream) {
+  int rc = check_common(m, MJB_CHECK_LIMITS);
+  if (rc) return rc;
+  if (n < 0 || !site_pos || !site_quat) return fail(MJB_ERR_ARG, "bad argument");
+  mjb_pose_spec in;
+  memset(&in, 0, sizeof in);
+  in.site_bodyid = site_bodyid;
+  memcpy(in.site_pos, site_pos, sizeof in.site_pos);
+  memcpy(in.site_quat, site_quat, sizeof in.site_quat);
+  in.ref_quat[0] = 1.0; in.q_step = 1.0;
+  PoseSpec sp;
+  if ((rc = fill_pose_spec(m, &in, sp))) return rc;
+  if (n == 0) return MJB_OK;
+  if (!d_q || !d_pos || !d_quat) return fail(MJB_ERR_ARG, "null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  site_pose_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(m->d_fk64, m->H.nslot, sp, d_q, (long long)n, d_pos, d_quat);
+  CU(cudaGetLastError());
+  m->launches++;
   return MJB_OK;
 }

@@ -591,4 +591,37 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
   return true;
 }
 
+// mjb_pose_spec (caller's view: site in its body frame, reference frame world_T_C) -> PoseSpec
+// (kernel's view: pose slot, C_T_world, joints that move the site)
+inline bool make_pose_spec(const HostModel &H, const mjb_pose_spec *in, PoseSpec &sp, std::string &err) {
+  if (!in) { err = "null pose spec"; return false; }
+  // reference: ValueError texts of PoseConstraint.__init__ (pose_constraint.py:51-54)
+  if (in->tolerance < 0.0) { err = "`tolerance` must be >= 0."; return false; }
+  if (!(in->q_step > 0.0)) { err = "`q_step` must be > 0."; return false; }
+  if (in->site_bodyid < 0 || in->site_bodyid >= H.nbody) { err = "bad site body id"; return false; }
+  memset(&sp, 0, sizeof sp);
+  const int b = in->site_bodyid;
+  sp.site_slot = H.body_slot[b];
+  Pose<double> S; S.p = mk<double>(in->site_pos[0], in->site_pos[1], in->site_pos[2]);
+  S.q = qnormalize(qd(in->site_quat));
+  if (sp.site_slot < 0) {  // world-fixed body: fold its pose in
+    const Pose<double> &Pb = H.static_pose[b];
+    Pose<double> W; W.p = Pb.p + qrot(Pb.q, S.p); W.q = qnormalize(qmul(Pb.q, S.q));
+    S = W;
+  }
+  sp.site_pos[0] = S.p.x; sp.site_pos[1] = S.p.y; sp.site_pos[2] = S.p.z;
+  sp.site_quat[0] = S.q.w; sp.site_quat[1] = S.q.x; sp.site_quat[2] = S.q.y; sp.site_quat[3] = S.q.z;
+  // C_T_world = inverse(reference frame)
+  Q4<double> iq = qconj(qnormalize(qd(in->ref_quat)));
+  V3<double> ip = -qrot(iq, mk<double>(in->ref_pos[0], in->ref_pos[1], in->ref_pos[2]));
+  sp.cw_pos[0] = ip.x; sp.cw_pos[1] = ip.y; sp.cw_pos[2] = ip.z;
+  sp.cw_quat[0] = iq.w; sp.cw_quat[1] = iq.x; sp.cw_quat[2] = iq.y; sp.cw_quat[3] = iq.z;
+  for (int i = 0; i < 6; i++) { sp.lo[i] = in->lower[i]; sp.hi[i] = in->upper[i]; }
+  sp.tolerance = in->tolerance; sp.q_step = in->q_step;
+  // joints that move the site: joints of the site's body and of all its ancestors
+  for (int s = sp.site_slot; s >= 0; s = H.fk.body_parent[s])
+    for (int k = 0; k < H.fk.body_jntnum[s]; k++) sp.jnt_mask |= 1u << (H.fk.body_jntadr[s] + k);
+  return true;
+}
+
 }  // namespace vkb

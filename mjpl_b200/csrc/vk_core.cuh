@@ -655,6 +655,225 @@ VK_HD int narrow_item(int kind, const Shape<T> &A, const Shape<T> &B, const Vtx<
   return gjk_classify(A, B, verts, rel, R, (int *)nullptr);
 }
 
+// ------------------------------------------------------------------------------ pose constraint (CBiRRT projection)
+// PoseConstraint (reference: src/mjpl/constraint/pose_constraint.py): a site must stay inside
+// a box of translations / roll-pitch-yaw expressed in a constraint frame C.
+//   _displacement_from_constraint :93-123, _get_jacobian :125-147, _e_rpy :150-171,
+//   valid_config :72-76, apply :78-91 (Newton-like projection q -= J^T pinv(J J^T) dx).
+// fp64 throughout, one lane per row (the iteration is a short dense-algebra loop per row).
+struct PoseSpec {
+  int site_slot;            // pose slot of the site's body, -1 = world fixed
+  unsigned jnt_mask;        // bit j: joint j moves the site (ancestor joints of its body)
+  double site_pos[3], site_quat[4];   // site in its body frame (world frame if site_slot < 0)
+  double cw_pos[3], cw_quat[4];       // C_T_world = inverse of the reference frame
+  double lo[6], hi[6];                // allowed x, y, z, roll, pitch, yaw in C
+  double tolerance, q_step;
+};
+
+VK_HD void quat2rpy(const Q4<double> &q, double &roll, double &pitch, double &yaw) {
+  // mink / jaxlie SO3.as_rpy_radians (quaternion wxyz)
+  roll = atan2(2.0 * (q.w * q.x + q.y * q.z), 1.0 - 2.0 * (q.x * q.x + q.y * q.y));
+  double sp = 2.0 * (q.w * q.y - q.z * q.x);
+  sp = sp > 1.0 ? 1.0 : (sp < -1.0 ? -1.0 : sp);
+  pitch = asin(sp);
+  yaw = atan2(2.0 * (q.w * q.z + q.x * q.y), 1.0 - 2.0 * (q.y * q.y + q.z * q.z));
+}
+
+// FK of all slots + world anchors/axes of every joint (mj_kinematics' xanchor / xaxis)
+VK_HD void fk_with_joints(const FkTables<double> &fk, int nslot, const double *q, Pose<double> *P,
+                                               V3<double> *anchor, V3<double> *axis) {
+  Pose<double> ident; ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  for (int s = 0; s < nslot; s++) {
+    const int ps = fk.body_parent[s];
+    const Pose<double> &par = ps < 0 ? ident : P[ps];
+    Pose<double> o;
+    o.p = par.p + qrot(par.q, mk<double>(fk.body_pos[s][0], fk.body_pos[s][1], fk.body_pos[s][2]));
+    Q4<double> bq; bq.w = fk.body_quat[s][0]; bq.x = fk.body_quat[s][1]; bq.y = fk.body_quat[s][2]; bq.z = fk.body_quat[s][3];
+    o.q = qmul(par.q, bq);
+    for (int k = 0; k < fk.body_jntnum[s]; k++) {
+      const int j = fk.body_jntadr[s] + k, a = fk.jnt_qadr[j];
+      V3<double> jp = mk<double>(fk.jnt_pos[j][0], fk.jnt_pos[j][1], fk.jnt_pos[j][2]);
+      V3<double> jax = mk<double>(fk.jnt_axis[j][0], fk.jnt_axis[j][1], fk.jnt_axis[j][2]);
+      anchor[j] = o.p + qrot(o.q, jp);
+      axis[j] = qrot(o.q, jax);
+      const double dq = q[a] - fk.qpos0[a];
+      if (fk.jnt_type[j] == JK_SLIDE) o.p = o.p + axis[j] * dq;
+      else {
+        double sn, cs;
+        vk_sincos(0.5 * dq, &sn, &cs);
+        Q4<double> ql; ql.w = cs; ql.x = jax.x * sn; ql.y = jax.y * sn; ql.z = jax.z * sn;
+        o.q = qmul(o.q, ql);
+        o.p = anchor[j] - qrot(o.q, jp);
+      }
+    }
+    o.q = qnormalize(o.q);
+    P[s] = o;
+  }
+}
+
+// displacement of the site from the constraint box, and the site's world pose
+VK_HD double pose_displacement(const PoseSpec &sp, const Pose<double> *P, double *dx, Pose<double> &site) {
+  Pose<double> ident; ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  const Pose<double> &B = sp.site_slot < 0 ? ident : P[sp.site_slot];
+  Q4<double> sq; sq.w = sp.site_quat[0]; sq.x = sp.site_quat[1]; sq.y = sp.site_quat[2]; sq.z = sp.site_quat[3];
+  site.p = B.p + qrot(B.q, mk<double>(sp.site_pos[0], sp.site_pos[1], sp.site_pos[2]));
+  site.q = qnormalize(qmul(B.q, sq));
+  Q4<double> cq; cq.w = sp.cw_quat[0]; cq.x = sp.cw_quat[1]; cq.y = sp.cw_quat[2]; cq.z = sp.cw_quat[3];
+  V3<double> t = mk<double>(sp.cw_pos[0], sp.cw_pos[1], sp.cw_pos[2]) + qrot(cq, site.p);
+  Q4<double> r = qmul(cq, site.q);
+  double d[6] = {t.x, t.y, t.z, 0, 0, 0};
+  quat2rpy(r, d[3], d[4], d[5]);
+  double n2 = 0;
+  for (int i = 0; i < 6; i++) {
+    dx[i] = d[i] > sp.hi[i] ? d[i] - sp.hi[i] : (d[i] < sp.lo[i] ? d[i] - sp.lo[i] : 0.0);
+    n2 += dx[i] * dx[i];
+  }
+  return sqrt(n2);
+}
+
+// y = pinv(A) x for a symmetric 6x6 A (cyclic Jacobi eigen-decomposition; eigenvalues below
+// 6*eps*max are dropped, which is numpy.linalg.pinv's default cut-off).
+// The loops are deliberately NOT unrolled (runtime indices into local arrays): the fully
+// unrolled form of this routine was miscompiled for sm_100a by nvcc 12.9 at every optimisation
+// level except -G (host and device disagreed on well-conditioned inputs; tools/dbg/pinv_dbg.cu).
+VK_HD void sym6_pinv_apply(double Ain[6][6], const double *x, double *y) {
+  double A[36], V[36];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int i = 0; i < 36; i++) { A[i] = Ain[i / 6][i % 6]; V[i] = (i / 6 == i % 6) ? 1.0 : 0.0; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int sweep = 0; sweep < 12; sweep++) {
+    double off = 0, dg = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 0; i < 36; i++) {
+      const double a2 = A[i] * A[i];
+      if (i / 6 == i % 6) dg += a2; else off += a2;
+    }
+    if (off <= 2e-30 * dg || off == 0.0) break;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int pq = 0; pq < 36; pq++) {
+      const int p = pq / 6, q = pq % 6;
+      if (q <= p) continue;
+      const double apq = A[p * 6 + q];
+      if (fabs(apq) < 1e-300) continue;
+      const double th = (A[q * 6 + q] - A[p * 6 + p]) / (2.0 * apq);
+      const double t = (th >= 0 ? 1.0 : -1.0) / (fabs(th) + sqrt(th * th + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int k = 0; k < 6; k++) {
+        const double akp = A[k * 6 + p], akq = A[k * 6 + q];
+        A[k * 6 + p] = c * akp - s * akq;
+        A[k * 6 + q] = s * akp + c * akq;
+        const double vkp = V[k * 6 + p], vkq = V[k * 6 + q];
+        V[k * 6 + p] = c * vkp - s * vkq;
+        V[k * 6 + q] = s * vkp + c * vkq;
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int k = 0; k < 6; k++) {
+        const double apk = A[p * 6 + k], aqk = A[q * 6 + k];
+        A[p * 6 + k] = c * apk - s * aqk;
+        A[q * 6 + k] = s * apk + c * aqk;
+      }
+    }
+  }
+  double lmax = 0;
+  for (int i = 0; i < 6; i++) lmax = fmax(lmax, fabs(A[i * 6 + i]));
+  const double cut = 6.0 * 2.220446049250313e-16 * lmax;
+  for (int i = 0; i < 6; i++) y[i] = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 6; k++) {
+    const double lam = A[k * 6 + k];
+    if (!(fabs(lam) > cut)) continue;
+    double cc = 0;
+    for (int i = 0; i < 6; i++) cc += V[i * 6 + k] * x[i];
+    cc /= lam;
+    for (int i = 0; i < 6; i++) y[i] += V[i * 6 + k] * cc;
+  }
+}
+
+// valid_config of one row (:72-76)
+VK_HD bool pose_valid_row(const FkTables<double> &fk, int nslot, const PoseSpec &spec, const double *qin) {
+  for (int j = 0; j < fk.njnt; j++)
+    if (!(qin[j] >= fk.jnt_lo[j] && qin[j] <= fk.jnt_hi[j])) return false;
+  Pose<double> P[MAX_BODY];
+  V3<double> anchor[MAX_JNT], axis[MAX_JNT];
+  fk_with_joints(fk, nslot, qin, P, anchor, axis);
+  double dx[6];
+  Pose<double> site;
+  return pose_displacement(spec, P, dx, site) <= spec.tolerance;
+}
+
+// apply of one row (:78-91); q is updated in place; returns true when the projection succeeded
+VK_HD bool pose_project_row(const FkTables<double> &fk, int nslot, const PoseSpec &spec, const double *q_old, double *q,
+                            int max_iters, int *iters_out) {
+  const int nq = fk.nq;
+  Pose<double> P[MAX_BODY];
+  V3<double> anchor[MAX_JNT], axis[MAX_JNT];
+  int it = 0;
+  bool ok = false;
+  for (; it < max_iters; it++) {
+    fk_with_joints(fk, nslot, q, P, anchor, axis);
+    double dx[6];
+    Pose<double> site;
+    if (pose_displacement(spec, P, dx, site) <= spec.tolerance) { ok = true; break; }
+    // RPY Jacobian of the site: E_rpy(world rpy of the site) @ [jacp; jacr]  (:125-171).
+    // NB the reference's E_rpy has cos(pitch) at [4,4] where the exact inverse has cos(yaw)
+    // (pose_constraint.py:165); restated as is.
+    double roll, pitch, yaw;
+    quat2rpy(site.q, roll, pitch, yaw);
+    const double cp = cos(pitch), sp_ = sin(pitch), cy = cos(yaw), sy = sin(yaw);
+    const double E[3][3] = {{cy / cp, sy / cp, 0.0}, {-sy, cp, 0.0}, {cy * (sp_ / cp), sy * (sp_ / cp), 1.0}};
+    double J[6][MAX_JNT];
+    for (int j = 0; j < fk.njnt; j++) {
+      V3<double> jp = mk<double>(0, 0, 0), jr = mk<double>(0, 0, 0);
+      if ((spec.jnt_mask >> j) & 1u) {
+        if (fk.jnt_type[j] == JK_SLIDE) jp = axis[j];
+        else { jr = axis[j]; jp = cross(axis[j], site.p - anchor[j]); }
+      }
+      const int c = fk.jnt_qadr[j];  // dof index == qpos index for hinge / slide
+      J[0][c] = jp.x; J[1][c] = jp.y; J[2][c] = jp.z;
+      J[3][c] = E[0][0] * jr.x + E[0][1] * jr.y + E[0][2] * jr.z;
+      J[4][c] = E[1][0] * jr.x + E[1][1] * jr.y + E[1][2] * jr.z;
+      J[5][c] = E[2][0] * jr.x + E[2][1] * jr.y + E[2][2] * jr.z;
+    }
+    double A[6][6];
+    for (int i = 0; i < 6; i++)
+      for (int k = i; k < 6; k++) {
+        double acc = 0;
+        for (int c = 0; c < nq; c++) acc += J[i][c] * J[k][c];
+        A[i][k] = A[k][i] = acc;
+      }
+    double y[6];
+    sym6_pinv_apply(A, dx, y);
+    double far2 = 0;
+    bool lim = true;
+    for (int c = 0; c < nq; c++) {
+      double e = 0;
+      for (int i = 0; i < 6; i++) e += J[i][c] * y[i];
+      q[c] -= e;
+      const double d = q[c] - q_old[c];
+      far2 += d * d;
+    }
+    for (int j = 0; j < fk.njnt; j++) lim = lim && q[j] >= fk.jnt_lo[j] && q[j] <= fk.jnt_hi[j];
+    if (!lim || sqrt(far2) > 2.0 * spec.q_step) break;  // :88-91
+  }
+  if (iters_out) *iters_out = it;
+  return ok;
+}
+
 // ------------------------------------------------------------------------------ counter-based row generator
 // splitmix64 finaliser over (seed, row, joint) -> 24-bit uniform in [0,1)
 VK_HD uint32_t sweep_bits(uint64_t seed, uint64_t row, uint32_t j) {

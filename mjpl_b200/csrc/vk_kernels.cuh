@@ -775,6 +775,56 @@ __global__ void sweep_rows_kernel(FkTables<float> fk, unsigned long long seed, l
   q[i] = sweep_value(seed, (uint64_t)(row0 + r), (uint32_t)j, fk.jnt_lo[j], fk.jnt_hi[j]);
 }
 
+// ---------------------------------------------------------------------------- pose constraint kernels (math in vk_core.cuh)
+// world pose of a site for a block of rows (fp64) -- site_pose (reference: src/mjpl/utils.py:60-75)
+__global__ void site_pose_kernel(const FkTables<double> *fkp, int nslot, PoseSpec spec, const double *q, long long n,
+                                 double *pos, double *quat) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  const FkTables<double> &fk = *fkp;
+  Pose<double> P[MAX_BODY];
+  V3<double> anchor[MAX_JNT], axis[MAX_JNT];
+  fk_with_joints(fk, nslot, q + row * fk.nq, P, anchor, axis);
+  Pose<double> ident; ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  const Pose<double> &B = spec.site_slot < 0 ? ident : P[spec.site_slot];
+  Q4<double> sq; sq.w = spec.site_quat[0]; sq.x = spec.site_quat[1]; sq.y = spec.site_quat[2]; sq.z = spec.site_quat[3];
+  V3<double> p = B.p + qrot(B.q, mk<double>(spec.site_pos[0], spec.site_pos[1], spec.site_pos[2]));
+  Q4<double> r = qnormalize(qmul(B.q, sq));
+  pos[row * 3] = p.x; pos[row * 3 + 1] = p.y; pos[row * 3 + 2] = p.z;
+  quat[row * 4] = r.w; quat[row * 4 + 1] = r.x; quat[row * 4 + 2] = r.y; quat[row * 4 + 3] = r.z;
+}
+
+struct PoseArgs {
+  const FkTables<double> *fk;
+  int nslot;
+  PoseSpec spec;
+  const double *q_old, *q;      // (n,nq)
+  long long n;
+  int project;                  // 0: valid_config only, 1: apply (projection)
+  int max_iters;
+  double *q_out;                // (n,nq) projected rows (project) -- untouched rows when !ok
+  uint8_t *ok;                  // valid / projection succeeded
+  int *iters;                   // optional
+};
+
+__global__ void __launch_bounds__(64) pose_kernel(const PoseArgs a) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= a.n) return;
+  const FkTables<double> &fk = *a.fk;
+  const int nq = fk.nq;
+  double q[MAX_JNT];
+  for (int j = 0; j < nq; j++) q[j] = a.q[row * nq + j];
+  if (!a.project) {
+    a.ok[row] = pose_valid_row(fk, a.nslot, a.spec, q) ? 1 : 0;
+    return;
+  }
+  int it = 0;
+  const bool ok = pose_project_row(fk, a.nslot, a.spec, a.q_old + row * nq, q, a.max_iters, &it);
+  a.ok[row] = ok ? 1 : 0;
+  if (a.iters) a.iters[row] = it;
+  if (ok) for (int j = 0; j < nq; j++) a.q_out[row * nq + j] = q[j];
+}
+
 // ---------------------------------------------------------------------------- RRT extend chains
 // near[i] = nodes[slot_i][nn[i]]; chain length K = min(ceil(|target-near|/eps), kcap) (0 if equal)
 __global__ void chain_setup_kernel(const double *nodes, long long cap, int nq, const long long *slots, const long long *nn,

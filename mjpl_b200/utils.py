@@ -1,7 +1,7 @@
 """Index helpers and the rejection sampler on the validity path.
 
 Reference: ``src/mjpl/utils.py`` (``all_joints`` :10-19, ``qpos_idx`` :22-38, ``qvel_idx``
-:41-57, ``random_config`` :78-107).  ``site_pose`` needs mink's SE3 type and is out of scope.
+:41-57, ``site_pose`` :60-75, ``random_config`` :78-107).
 """
 
 from __future__ import annotations
@@ -68,3 +68,30 @@ def random_config(model, q_init: np.ndarray, joints: list[str], seed: int | None
             # NB: a block draw advances the generator past the accepted candidate; the
             # generator is local to this call, so nothing observable depends on that.
             return Q[hit[0]].copy()
+
+
+def site_pose(model, q: np.ndarray, site_name: str):
+    """Pose of a site in the world frame at configuration ``q`` (fp64, ``mjb_site_pose``).
+
+    The reference reads it from an ``MjData`` after ``mj_kinematics`` (``utils.py:60-75``); there is
+    no ``MjData`` here, so this takes the configuration itself.
+    """
+    import ctypes as C
+
+    import torch
+
+    from . import _abi
+    from .engine import get_engine
+    from .lie import SE3, SO3
+
+    s = model.site(site_name).id
+    eng = get_engine(model, ())
+    with torch.cuda.device(eng.device):
+        qd = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64).reshape(1, -1)).to(eng.torch_device)
+        pos = torch.empty((1, 3), dtype=torch.float64, device=eng.torch_device)
+        quat = torch.empty((1, 4), dtype=torch.float64, device=eng.torch_device)
+        sp = (C.c_double * 3)(*[float(x) for x in model.site_pos[s]])
+        sq = (C.c_double * 4)(*[float(x) for x in model.site_quat[s]])
+        _abi.check(eng._L.mjb_site_pose(eng._h, int(model.site_bodyid[s]), sp, sq, qd.data_ptr(), 1, pos.data_ptr(),
+                                        quat.data_ptr(), eng._stream()))
+        return SE3(SO3(quat[0].cpu().numpy()), pos[0].cpu().numpy())

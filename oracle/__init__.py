@@ -275,3 +275,111 @@ def constrained_extend_chain(oracle: Oracle, q_near, q_target, eps, flags=CHECK_
         added.append(q)
         q_old = q
     return added, q_old
+
+
+# ------------------------------------------------------------------------------------------
+# PoseConstraint restated (reference: src/mjpl/constraint/pose_constraint.py)
+# ------------------------------------------------------------------------------------------
+def _q2mat(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _qmul(a, b):
+    aw, ax, ay, az = a
+    bw, bx, by, bz = b
+    return np.array([aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw])
+
+
+def _rpy(q):
+    """mink / jaxlie SO3.as_rpy_radians for a wxyz quaternion."""
+    w, x, y, z = q
+    return np.array([np.arctan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y)),
+                     np.arcsin(np.clip(2 * (w * y - z * x), -1, 1)),
+                     np.arctan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))])
+
+
+class PoseOracle:
+    """fp64 numpy restatement of ``PoseConstraint`` on top of the C oracle's ``mj_kinematics``.
+
+    ``ref_pos`` / ``ref_quat`` (wxyz) are the reference frame ``world_T_C``; ``C`` is the (6,2) box
+    of allowed x, y, z, roll, pitch, yaw.
+    """
+
+    def __init__(self, model, site, ref_pos, ref_quat, C, tolerance=0.001, q_step=0.05):
+        self.model, self.orc = model, Oracle(model)
+        self.sid = model.site(site).id
+        self.C = np.asarray(C, dtype=np.float64)
+        rq = np.asarray(ref_quat, float) / np.linalg.norm(ref_quat)
+        self.cw_quat = rq * np.array([1, -1, -1, -1.0])
+        self.cw_pos = -_q2mat(self.cw_quat) @ np.asarray(ref_pos, float)
+        self.tolerance, self.q_step = tolerance, q_step
+
+    def site_pose(self, q):
+        xpos, xquat = self.orc.fk(q)
+        b = int(self.model.site_bodyid[self.sid])
+        p = xpos[0, b] + _q2mat(xquat[0, b]) @ self.model.site_pos[self.sid]
+        r = _qmul(xquat[0, b], self.model.site_quat[self.sid])
+        return p, r / np.linalg.norm(r)
+
+    def displacement(self, q):
+        """``_displacement_from_constraint`` (pose_constraint.py:93-123)."""
+        p, r = self.site_pose(q)
+        d = np.concatenate([self.cw_pos + _q2mat(self.cw_quat) @ p, _rpy(_qmul(self.cw_quat, r))])
+        over, under = d > self.C[:, 1], d < self.C[:, 0]
+        dx = np.zeros(6)
+        dx[over] = d[over] - self.C[over, 1]
+        dx[under] = d[under] - self.C[under, 0]
+        return dx
+
+    def jacobian(self, q):
+        """``_get_jacobian`` + ``_e_rpy`` (pose_constraint.py:125-171): mj_jacSite restated
+        (hinge: jacr = axis, jacp = axis x (site - anchor); slide: jacp = axis)."""
+        m = self.model
+        xpos, xquat = self.orc.fk(q)
+        p, r = self.site_pose(q)
+        J = np.zeros((6, m.nv))
+        b = int(m.site_bodyid[self.sid])
+        while b > 0:
+            for k in range(int(m.body_jntnum[b])):
+                j = int(m.body_jntadr[b]) + k
+                # the joint's own motion does not move its anchor / axis: the body pose after the
+                # joint transform gives the same world axis, and the anchor from jnt_pos
+                R = _q2mat(xquat[0, b])
+                axis = R @ m.jnt_axis[j]
+                anchor = xpos[0, b] + R @ m.jnt_pos[j]
+                c = int(m.jnt_dofadr[j])
+                if int(m.jnt_type[j]) == 2:
+                    J[:3, c] = axis
+                else:
+                    J[:3, c] = np.cross(axis, p - anchor)
+                    J[3:, c] = axis
+            b = int(m.body_parentid[b])
+        _, pitch, yaw = _rpy(r)
+        cp, sp, cy, sy = np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+        E = np.eye(6)
+        E[3:6, 3:5] = np.array([[cy / cp, sy / cp], [-sy, cp], [cy * (sp / cp), sy * (sp / cp)]])
+        return E @ J
+
+    def limits_ok(self, q):
+        return bool(np.all((q >= self.model.jnt_range[:, 0]) & (q <= self.model.jnt_range[:, 1])))
+
+    def valid_config(self, q):
+        q = np.asarray(q, float)
+        return self.limits_ok(q) and np.linalg.norm(self.displacement(q)) <= self.tolerance
+
+    def apply(self, q_old, q, max_iters=1000):
+        """``apply`` (pose_constraint.py:78-91) -> projected q or None."""
+        q_old, qp = np.asarray(q_old, float), np.asarray(q, float).copy()
+        for _ in range(max_iters):
+            dx = self.displacement(qp)
+            if np.linalg.norm(dx) <= self.tolerance:
+                return qp
+            J = self.jacobian(qp)
+            qp = qp - J.T @ np.linalg.pinv(J @ J.T) @ dx
+            if not self.limits_ok(qp) or np.linalg.norm(qp - q_old) > 2 * self.q_step:
+                return None
+        return None

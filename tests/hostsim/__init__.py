@@ -47,6 +47,8 @@ def lib():
         L.hs_fk.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.hs_check.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.hs_support_check.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.hs_pose.argtypes = [C.c_void_p, C.POINTER(_abi.PoseSpec), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
         L.hs_pair_verdict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -109,3 +111,18 @@ class HostSim:
         eh, es = C.c_int64(0), C.c_int64(0)
         n = lib().hs_support_check(self._h, ndir, seed, C.byref(gap), C.byref(eh), C.byref(es))
         return n, gap.value, eh.value, es.value
+
+    def pose(self, spec, q_old, q, project=True, max_iters=1000):
+        """PoseConstraint rows through the kernel core on the CPU -> (q_out, ok, iters)"""
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(-1, self.model.nq)
+        q_old = np.ascontiguousarray(q_old, dtype=np.float64).reshape(-1, self.model.nq)
+        n = len(q)
+        out = q.copy()
+        ok = np.zeros(n, np.uint8)
+        iters = np.zeros(n, np.int32)
+        err = C.create_string_buffer(256)
+        rc = lib().hs_pose(self._h, C.byref(spec), q_old.ctypes.data, q.ctypes.data, n, int(project), max_iters,
+                           out.ctypes.data, ok.ctypes.data, iters.ctypes.data, err, 256)
+        if rc:
+            raise ValueError(err.value.decode())
+        return out, ok.astype(bool), iters

@@ -212,4 +212,25 @@ int hs_support_check(Sim *s, int ndir, uint64_t seed, double *max_gap, int64_t *
   return ngraph;
 }
 
+
+// PoseConstraint rows on the CPU through the same core (pose_valid_row / pose_project_row)
+int hs_pose(Sim *s, const mjb_pose_spec *spec, const double *q_old, const double *q, int64_t n, int project, int max_iters,
+            double *q_out, uint8_t *ok, int32_t *iters, char *err, int errlen) {
+  PoseSpec sp;
+  std::string e;
+  if (!vkb::make_pose_spec(s->H, spec, sp, e)) { snprintf(err, errlen, "%s", e.c_str()); return 1; }
+  const int nq = s->H.nq;
+  for (int64_t r = 0; r < n; r++) {
+    double row[MAX_JNT];
+    for (int j = 0; j < nq; j++) row[j] = q[r * nq + j];
+    if (!project) { ok[r] = pose_valid_row(s->H.fk, s->H.nslot, sp, row); continue; }
+    int it = 0;
+    bool good = pose_project_row(s->H.fk, s->H.nslot, sp, q_old + r * nq, row, max_iters, &it);
+    ok[r] = good;
+    if (iters) iters[r] = it;
+    for (int j = 0; j < nq; j++) q_out[r * nq + j] = good ? row[j] : q[r * nq + j];
+  }
+  return 0;
+}
+
 }  // extern "C"
