@@ -177,6 +177,33 @@ int mjb_pose_project(mjb_model *m, const mjb_pose_spec *spec, const double *d_q_
                      const double *d_q, int64_t n, int32_t max_iters, double *d_q_out,
                      uint8_t *d_ok, int32_t *d_iters, void *stream);
 
+/*
+ * IKSolver.solve_ik (src/mjpl/inverse_kinematics/ik_solver_interface.py:11-28) for n (target,
+ * initial guess) rows at once; replaces the per-attempt iteration loop of the stock solver
+ * (mink_ik_solver.py:93-108: iterate until |position error| <= pos_tolerance and |orientation
+ * error| <= ori_tolerance, at most `iterations` times).  The update is Levenberg-Marquardt damped
+ * least squares on the geometric site Jacobian, fp64, with every iterate clamped to the joint
+ * limits (the role of mink.ConfigurationLimit, :87); joints outside movable_mask are held fixed
+ * (the DampingTask of :64-70).  Retries from random configurations and the constraint check on
+ * the result (:99-116) are the caller's (mjpl_b200.inverse_kinematics).
+ * d_target_pos (n,3), d_target_quat (n,4 wxyz), d_q_init / d_q_out (n,nq) fp64; d_ok[i] = 1 iff
+ * row i converged; d_iters (optional); d_err (optional, (n,2)): final position / rotation error.
+ */
+typedef struct mjb_ik_spec {
+  int32_t site_bodyid;
+  double site_pos[3], site_quat[4];
+  uint32_t movable_mask;             /* bit j: joint id j may move */
+  double pos_tolerance, ori_tolerance;
+  double lm_damping;                 /* error-proportional damping (mink FrameTask lm_damping, :80); <0 = default 0.1 */
+  double damping;                    /* constant damping; <=0 = default 1e-9 */
+  double max_step;                   /* cap on |dq|_inf per iteration; <=0 = default 0.5 */
+  int32_t iterations;
+} mjb_ik_spec;
+
+int mjb_ik_solve(mjb_model *m, const mjb_ik_spec *spec, const double *d_target_pos,
+                 const double *d_target_quat, const double *d_q_init, int64_t n, double *d_q_out,
+                 uint8_t *d_ok, int32_t *d_iters, double *d_err, void *stream);
+
 int mjb_get_stats(mjb_model *m, mjb_stats *out);   /* synchronises the handle's last stream */
 int mjb_reset_stats(mjb_model *m);
 

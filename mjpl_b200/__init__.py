@@ -18,6 +18,7 @@ from .constraint import (
     obeys_constraints,
     obeys_constraints_batch,
 )
+from .inverse_kinematics import DLSIKSolver, IKSolver
 from .lie import SE3, SO3
 from .engine import EngineUnavailable, ValidityEngine, get_engine
 from .model import Model
@@ -28,6 +29,8 @@ __all__ = (
     "BatchedRRT",
     "CollisionConstraint",
     "CollisionRuleset",
+    "DLSIKSolver",
+    "IKSolver",
     "Constraint",
     "EngineUnavailable",
     "JointLimitConstraint",

@@ -61,6 +61,15 @@ class PoseSpec(C.Structure):
                 ("upper", C.c_double * 6), ("tolerance", C.c_double), ("q_step", C.c_double)]
 
 
+class IkSpec(C.Structure):
+    """``mjb_ik_spec``"""
+
+    _fields_ = [("site_bodyid", C.c_int32), ("site_pos", C.c_double * 3), ("site_quat", C.c_double * 4),
+                ("movable_mask", C.c_uint32), ("pos_tolerance", C.c_double), ("ori_tolerance", C.c_double),
+                ("lm_damping", C.c_double), ("damping", C.c_double), ("max_step", C.c_double),
+                ("iterations", C.c_int32)]
+
+
 class EngineUnavailable(RuntimeError):
     """The CUDA engine cannot run here (library not built, or no GPU).  Never caught internally."""
 
@@ -110,7 +119,8 @@ _lib = None
 EXPORTS = (
     "mjb_last_error mjb_device_count mjb_model_create mjb_model_destroy mjb_model_npair "
     "mjb_model_pairs mjb_check_configs mjb_check_configs_host mjb_fk mjb_check_edges "
-    "mjb_check_sweep mjb_sweep_rows mjb_get_stats mjb_reset_stats mjb_nearest_batch mjb_rrt_extend mjb_pose_valid mjb_pose_project mjb_site_pose"
+    "mjb_check_sweep mjb_sweep_rows mjb_get_stats mjb_reset_stats mjb_nearest_batch mjb_rrt_extend mjb_pose_valid mjb_pose_project mjb_site_pose "
+    "mjb_ik_solve"
 ).split()
 
 
@@ -146,6 +156,7 @@ def lib():
     L.mjb_site_pose.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, C.c_int64, vp, vp, vp]
     L.mjb_pose_valid.argtypes = [vp, C.POINTER(PoseSpec), vp, C.c_int64, vp, vp]
     L.mjb_pose_project.argtypes = [vp, C.POINTER(PoseSpec), vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp]
+    L.mjb_ik_solve.argtypes = [vp, C.POINTER(IkSpec), vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp]
     L.mjb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.mjb_reset_stats.argtypes = [vp]
     for n in EXPORTS:

@@ -526,6 +526,28 @@ extern "C" int mjb_pose_project(mjb_model *m, const mjb_pose_spec *spec, const d
   return launch_pose(m, spec, d_q_old, d_q, n, 1, max_iters, d_q_out, d_ok, d_iters, stream);
 }
 
+extern "C" int mjb_ik_solve(mjb_model *m, const mjb_ik_spec *spec, const double *d_target_pos, const double *d_target_quat,
+                            const double *d_q_init, int64_t n, double *d_q_out, uint8_t *d_ok, int32_t *d_iters, double *d_err,
+                            void *stream) {
+  int rc = check_common(m, MJB_CHECK_LIMITS);
+  if (rc) return rc;
+  if (n < 0) return fail(MJB_ERR_ARG, "bad n");
+  IkArgs a;
+  memset(&a, 0, sizeof a);
+  std::string err;
+  if (!vkb::make_ik_spec(m->H, spec, a.spec, err)) return fail(MJB_ERR_ARG, err);
+  if (n == 0) return MJB_OK;
+  if (!d_target_pos || !d_target_quat || !d_q_init || !d_q_out || !d_ok) return fail(MJB_ERR_ARG, "null device pointer");
+  a.fk = m->d_fk64; a.nslot = m->H.nslot; a.tpos = d_target_pos; a.tquat = d_target_quat; a.q_init = d_q_init; a.n = n;
+  a.q_out = d_q_out; a.ok = d_ok; a.iters = d_iters; a.err = d_err;
+  cudaStream_t st = (cudaStream_t)stream;
+  ik_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(a);
+  CU(cudaGetLastError());
+  m->launches++;
+  m->last_stream = st;
+  return MJB_OK;
+}
+
 extern "C" int mjb_site_pose(mjb_model *m, int32_t site_bodyid, const double *site_pos, const double *site_quat, const double *d_q,
                              int64_t n, double *d_pos, double *d_quat, void *stream) {
   int rc = check_common(m, MJB_CHECK_LIMITS);

@@ -624,4 +624,31 @@ inline bool make_pose_spec(const HostModel &H, const mjb_pose_spec *in, PoseSpec
   return true;
 }
 
+// mjb_ik_spec -> IkSpec (argument checks follow MinkIKSolver.__init__, mink_ik_solver.py:47-52)
+inline bool make_ik_spec(const HostModel &H, const mjb_ik_spec *in, IkSpec &out, std::string &err) {
+  if (!in) { err = "null ik spec"; return false; }
+  if (in->movable_mask == 0) { err = "`joints` cannot be empty."; return false; }
+  if (in->iterations < 1) { err = "`iterations` must be > 0."; return false; }
+  if (!(in->pos_tolerance >= 0.0) || !(in->ori_tolerance >= 0.0)) { err = "tolerances must be >= 0."; return false; }
+  mjb_pose_spec ps;
+  memset(&ps, 0, sizeof ps);
+  ps.site_bodyid = in->site_bodyid;
+  memcpy(ps.site_pos, in->site_pos, sizeof ps.site_pos);
+  memcpy(ps.site_quat, in->site_quat, sizeof ps.site_quat);
+  ps.ref_quat[0] = 1.0; ps.q_step = 1.0;
+  PoseSpec sp;
+  if (!make_pose_spec(H, &ps, sp, err)) return false;
+  memset(&out, 0, sizeof out);
+  out.site_slot = sp.site_slot;
+  out.jnt_mask = sp.jnt_mask & in->movable_mask;
+  memcpy(out.site_pos, sp.site_pos, sizeof sp.site_pos);
+  memcpy(out.site_quat, sp.site_quat, sizeof sp.site_quat);
+  out.pos_tol = in->pos_tolerance; out.ori_tol = in->ori_tolerance;
+  out.lm_damping = in->lm_damping >= 0.0 ? in->lm_damping : 0.1;
+  out.damping = in->damping > 0.0 ? in->damping : 1e-9;
+  out.max_step = in->max_step > 0.0 ? in->max_step : 0.5;
+  out.iterations = in->iterations;
+  return true;
+}
+
 }  // namespace vkb

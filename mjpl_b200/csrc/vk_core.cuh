@@ -874,6 +874,169 @@ VK_HD bool pose_project_row(const FkTables<double> &fk, int nslot, const PoseSpe
   return ok;
 }
 
+// ------------------------------------------------------------------------------ inverse kinematics (move-to-pose goals)
+// IKSolver.solve_ik (reference: src/mjpl/inverse_kinematics/ik_solver_interface.py:11-28; the
+// stock implementation, mink_ik_solver.py:74-117, iterates a QP-based differential IK from an
+// initial guess until the site's pose error is within pos/ori tolerance).  The contract, not the
+// QP, is what planners consume: a configuration whose site pose is within tolerance of the
+// target.  Here each row runs Levenberg-Marquardt damped least squares in fp64:
+//   e = [p_t - p; rotvec(R_t R^T)]   (world frame),  J = geometric site Jacobian (movable joints),
+//   dq = J^T (J J^T + (lm |e|^2 + damping) I)^-1 e,  |dq|_inf capped, q clamped to joint limits.
+struct IkSpec {
+  int site_slot;
+  unsigned jnt_mask;                 // ancestor joints of the site that are allowed to move
+  double site_pos[3], site_quat[4];
+  double pos_tol, ori_tol, lm_damping, damping, max_step;
+  int iterations;
+};
+
+// solve the SPD 6x6 system A y = x (Cholesky; runtime-indexed loops, see sym6_pinv_apply)
+VK_HD bool spd6_solve(const double *Ain, const double *x, double *y) {
+  double L[36];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int i = 0; i < 36; i++) L[i] = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int i = 0; i < 6; i++) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j <= i; j++) {
+      double s = Ain[i * 6 + j];
+      for (int k = 0; k < j; k++) s -= L[i * 6 + k] * L[j * 6 + k];
+      if (i == j) {
+        if (!(s > 0.0)) return false;
+        L[i * 6 + i] = sqrt(s);
+      } else L[i * 6 + j] = s / L[j * 6 + j];
+    }
+  }
+  double z[6];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int i = 0; i < 6; i++) {
+    double s = x[i];
+    for (int k = 0; k < i; k++) s -= L[i * 6 + k] * z[k];
+    z[i] = s / L[i * 6 + i];
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int i = 5; i >= 0; i--) {
+    double s = z[i];
+    for (int k = i + 1; k < 6; k++) s -= L[k * 6 + i] * y[k];
+    y[i] = s / L[i * 6 + i];
+  }
+  return true;
+}
+
+// pose error of the site against a target (world frame): e[0:3] = p_t - p, e[3:6] = rotation
+// vector of R_t R^T; returns the two norms
+VK_HD void ik_error(const IkSpec &sp, const Pose<double> *P, const double *tpos, const double *tquat, double *e,
+                    V3<double> &site_p, double &perr, double &oerr) {
+  Pose<double> ident; ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  const Pose<double> &B = sp.site_slot < 0 ? ident : P[sp.site_slot];
+  Q4<double> sq; sq.w = sp.site_quat[0]; sq.x = sp.site_quat[1]; sq.y = sp.site_quat[2]; sq.z = sp.site_quat[3];
+  site_p = B.p + qrot(B.q, mk<double>(sp.site_pos[0], sp.site_pos[1], sp.site_pos[2]));
+  const Q4<double> cq = qnormalize(qmul(B.q, sq));
+  Q4<double> tq; tq.w = tquat[0]; tq.x = tquat[1]; tq.y = tquat[2]; tq.z = tquat[3];
+  tq = qnormalize(tq);
+  Q4<double> d = qmul(tq, qconj(cq));
+  if (d.w < 0) { d.w = -d.w; d.x = -d.x; d.y = -d.y; d.z = -d.z; }
+  const double vn = sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+  const double ang = 2.0 * atan2(vn, d.w);
+  const double k = vn > 1e-12 ? ang / vn : 2.0;
+  e[0] = tpos[0] - site_p.x; e[1] = tpos[1] - site_p.y; e[2] = tpos[2] - site_p.z;
+  e[3] = k * d.x; e[4] = k * d.y; e[5] = k * d.z;
+  perr = sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+  oerr = ang;
+}
+
+VK_HD bool ik_row(const FkTables<double> &fk, int nslot, const IkSpec &spec, const double *tpos, const double *tquat,
+                  double *q, int *iters_out, double *perr_out, double *oerr_out) {
+  const int nq = fk.nq;
+  Pose<double> P[MAX_BODY];
+  V3<double> anchor[MAX_JNT], axis[MAX_JNT];
+  for (int j = 0; j < fk.njnt; j++) {  // start inside the limits
+    const int c = fk.jnt_qadr[j];
+    if ((spec.jnt_mask >> j) & 1u) q[c] = q[c] < fk.jnt_lo[j] ? fk.jnt_lo[j] : (q[c] > fk.jnt_hi[j] ? fk.jnt_hi[j] : q[c]);
+  }
+  int it = 0;
+  bool ok = false;
+  double perr = 0, oerr = 0;
+  for (;; it++) {
+    fk_with_joints(fk, nslot, q, P, anchor, axis);
+    double e[6];
+    V3<double> sp;
+    ik_error(spec, P, tpos, tquat, e, sp, perr, oerr);
+    if (perr <= spec.pos_tol && oerr <= spec.ori_tol) { ok = true; break; }
+    if (it >= spec.iterations) break;
+    // Active set over the joint limits (the role of mink.ConfigurationLimit in the reference's QP,
+    // mink_ik_solver.py:87): a joint that sits on a limit and would be pushed further out is
+    // frozen and the step re-solved, so that the other joints take up its share.
+    unsigned active = spec.jnt_mask;
+    double dq[MAX_JNT], sc = 1.0;
+    bool solved = false;
+    for (int pass = 0; pass < 4; pass++) {
+      double J[6][MAX_JNT];
+      for (int j = 0; j < fk.njnt; j++) {
+        V3<double> jp = mk<double>(0, 0, 0), jr = mk<double>(0, 0, 0);
+        if ((active >> j) & 1u) {
+          if (fk.jnt_type[j] == JK_SLIDE) jp = axis[j];
+          else { jr = axis[j]; jp = cross(axis[j], sp - anchor[j]); }
+        }
+        const int c = fk.jnt_qadr[j];
+        J[0][c] = jp.x; J[1][c] = jp.y; J[2][c] = jp.z;
+        J[3][c] = jr.x; J[4][c] = jr.y; J[5][c] = jr.z;
+      }
+      double A[36];
+      const double mu = spec.lm_damping * (perr * perr + oerr * oerr) + spec.damping;
+      for (int i = 0; i < 6; i++)
+        for (int k = i; k < 6; k++) {
+          double acc = 0;
+          for (int c = 0; c < nq; c++) acc += J[i][c] * J[k][c];
+          if (i == k) acc += mu;
+          A[i * 6 + k] = A[k * 6 + i] = acc;
+        }
+      double y[6];
+      if (!spd6_solve(A, e, y)) break;
+      solved = true;
+      double big = 0;
+      for (int c = 0; c < nq; c++) {
+        double s = 0;
+        for (int i = 0; i < 6; i++) s += J[i][c] * y[i];
+        dq[c] = s;
+        big = fmax(big, fabs(s));
+      }
+      sc = big > spec.max_step ? spec.max_step / big : 1.0;
+      unsigned blocked = 0;
+      for (int j = 0; j < fk.njnt; j++) {
+        if (!((active >> j) & 1u)) continue;
+        const int c = fk.jnt_qadr[j];
+        if ((q[c] <= fk.jnt_lo[j] && dq[c] < 0.0) || (q[c] >= fk.jnt_hi[j] && dq[c] > 0.0)) blocked |= 1u << j;
+      }
+      if (!blocked) break;
+      active &= ~blocked;
+      if (!active) { solved = false; break; }
+    }
+    if (!solved) break;
+    for (int j = 0; j < fk.njnt; j++) {
+      const int c = fk.jnt_qadr[j];
+      if (!((active >> j) & 1u)) continue;
+      double v = q[c] + sc * dq[c];
+      v = v < fk.jnt_lo[j] ? fk.jnt_lo[j] : (v > fk.jnt_hi[j] ? fk.jnt_hi[j] : v);
+      q[c] = v;
+    }
+  }
+  if (iters_out) *iters_out = it;
+  if (perr_out) *perr_out = perr;
+  if (oerr_out) *oerr_out = oerr;
+  return ok;
+}
+
 // ------------------------------------------------------------------------------ counter-based row generator
 // splitmix64 finaliser over (seed, row, joint) -> 24-bit uniform in [0,1)
 VK_HD uint32_t sweep_bits(uint64_t seed, uint64_t row, uint32_t j) {

@@ -825,6 +825,37 @@ __global__ void __launch_bounds__(64) pose_kernel(const PoseArgs a) {
   if (ok) for (int j = 0; j < nq; j++) a.q_out[row * nq + j] = q[j];
 }
 
+// ---------------------------------------------------------------------------- inverse kinematics
+// one lane per (target, initial guess) row; math in vk_core.cuh (ik_row)
+struct IkArgs {
+  const FkTables<double> *fk;
+  int nslot;
+  IkSpec spec;
+  const double *tpos, *tquat;   // (n,3), (n,4 wxyz) world-frame targets
+  const double *q_init;         // (n,nq)
+  long long n;
+  double *q_out;                // (n,nq): last iterate (a solution when ok)
+  uint8_t *ok;
+  int *iters;                   // optional
+  double *err;                  // optional (n,2): position / orientation error of q_out
+};
+
+__global__ void __launch_bounds__(64) ik_kernel(const IkArgs a) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= a.n) return;
+  const FkTables<double> &fk = *a.fk;
+  const int nq = fk.nq;
+  double q[MAX_JNT];
+  for (int j = 0; j < nq; j++) q[j] = a.q_init[row * nq + j];
+  int it = 0;
+  double pe = 0, oe = 0;
+  const bool ok = ik_row(fk, a.nslot, a.spec, a.tpos + row * 3, a.tquat + row * 4, q, &it, &pe, &oe);
+  a.ok[row] = ok ? 1 : 0;
+  if (a.iters) a.iters[row] = it;
+  if (a.err) { a.err[row * 2] = pe; a.err[row * 2 + 1] = oe; }
+  for (int j = 0; j < nq; j++) a.q_out[row * nq + j] = q[j];
+}
+
 // ---------------------------------------------------------------------------- RRT extend chains
 // near[i] = nodes[slot_i][nn[i]]; chain length K = min(ceil(|target-near|/eps), kcap) (0 if equal)
 __global__ void chain_setup_kernel(const double *nodes, long long cap, int nq, const long long *slots, const long long *nn,

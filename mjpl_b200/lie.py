@@ -87,6 +87,16 @@ class SO3:
     def apply(self, v):
         return self.as_matrix() @ np.asarray(v, dtype=np.float64)
 
+    def log(self) -> np.ndarray:
+        """Rotation vector (axis * angle), angle in [0, pi]."""
+        w, v = self.wxyz[0], self.wxyz[1:]
+        if w < 0:
+            w, v = -w, -v
+        n = np.linalg.norm(v)
+        if n < 1e-12:
+            return 2.0 * v
+        return (2.0 * np.arctan2(n, w) / n) * v
+
 
 class SE3:
     def __init__(self, rotation: SO3, translation):
@@ -119,6 +129,23 @@ class SE3:
         return SE3(self._r.multiply(other._r), self._t + self._r.apply(other._t))
 
     __matmul__ = multiply
+
+    def log(self) -> np.ndarray:
+        """se(3) tangent ``[v, omega]`` (translation part first, as in mink / jaxlie)."""
+        om = self._r.log()
+        th = np.linalg.norm(om)
+        K = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]])
+        if th < 1e-6:
+            Vinv = np.eye(3) - 0.5 * K + (K @ K) / 12.0
+        else:
+            half = 0.5 * th
+            Vinv = np.eye(3) - 0.5 * K + (1.0 - half * np.cos(half) / np.sin(half)) / (th * th) * (K @ K)
+        return np.concatenate([Vinv @ self._t, om])
+
+    def rminus(self, other) -> np.ndarray:
+        return other.inverse().multiply(self).log()
+
+    minus = rminus  # mink's SE3.minus is the right-minus
 
     @property
     def wxyz_xyz(self):

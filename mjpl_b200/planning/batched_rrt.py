@@ -162,6 +162,27 @@ class BatchedRRT:
             return self._plan_device(q_inits, q_goals, *fused)
         return self._plan_host(q_inits, q_goals)
 
+    def plan_to_poses(self, q_inits: np.ndarray, poses, site: str, solver=None) -> list[list[np.ndarray]]:
+        """One pose goal per query (the reference's ``RRT.plan_to_pose``, rrt.py:69-139, for a block of
+        queries): batched IK from each query's ``q_init``, then ``plan`` on the solved ones.  Queries
+        whose pose has no IK solution return ``[]``."""
+        q_inits = np.ascontiguousarray(q_inits, dtype=np.float64)
+        if q_inits.ndim != 2 or len(poses) != len(q_inits):
+            raise ValueError("q_inits must be (B, nq) with one pose per query")
+        if solver is None:
+            from ..inverse_kinematics import DLSIKSolver
+
+            solver = DLSIKSolver(model=self.model, joints=self.planning_joints, constraints=self.constraints,
+                                 seed=self.seed, max_attempts=5)
+        goals, solved = solver.solve_ik_batch(list(poses), site, q_inits)
+        out: list[list[np.ndarray]] = [[] for _ in range(len(q_inits))]
+        idx = np.flatnonzero(solved)
+        if len(idx):
+            for i, path in zip(idx, self.plan(q_inits[idx], goals[idx])):
+                out[i] = path
+        self.stats["ik_solved"] = int(solved.sum())
+        return out
+
     # ------------------------------------------------------------------ device driver
     def _plan_device(self, q_inits, q_goals, eng, flags):
         import ctypes as C

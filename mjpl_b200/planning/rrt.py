@@ -47,16 +47,21 @@ class RRT:
         self.seed = seed
         self.goal_biasing_probability = goal_biasing_probability
 
-    # ---- pose goals need an external IK solver ------------------------------------------------
+    # ---- pose goals: IK, then plan to the configurations (reference rrt.py:69-139) ----------------
     def plan_to_pose(self, q_init, pose, site: str, solver=None) -> list[np.ndarray]:
         return self.plan_to_poses(q_init, [pose], site, solver)
 
     def plan_to_poses(self, q_init, poses, site: str, solver=None) -> list[np.ndarray]:
         if solver is None:
-            raise NotImplementedError(
-                "plan_to_pose(s) needs an IK solver (an object with solve_ik(pose, site, q_init_guess)); "
-                "the reference's default MinkIKSolver depends on mink/daqp, which are out of scope here")
-        cands = [q for p in poses for q in solver.solve_ik(p, site, q_init_guess=q_init)]
+            from ..inverse_kinematics import DLSIKSolver
+
+            solver = DLSIKSolver(model=self.model, joints=self.planning_joints, constraints=self.constraints,
+                                 seed=self.seed, max_attempts=5)
+        if hasattr(solver, "solve_ik_batch"):
+            Q, solved = solver.solve_ik_batch(list(poses), site, np.asarray(q_init, dtype=np.float64))
+            cands = [q for q, k in zip(Q, solved) if k]
+        else:
+            cands = [q for p in poses for q in solver.solve_ik(p, site, q_init_guess=q_init)]
         if not cands:
             return []
         ok = np.asarray(obeys_constraints_batch(np.asarray(cands, dtype=np.float64), self.constraints))

@@ -49,6 +49,8 @@ def lib():
         L.hs_support_check.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_pose.argtypes = [C.c_void_p, C.POINTER(_abi.PoseSpec), C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.hs_ik.argtypes = [C.c_void_p, C.POINTER(_abi.IkSpec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
         L.hs_pair_verdict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -126,3 +128,20 @@ class HostSim:
         if rc:
             raise ValueError(err.value.decode())
         return out, ok.astype(bool), iters
+
+    def ik(self, spec, target_pos, target_quat, q_init):
+        """IK rows through the kernel core on the CPU -> (q_out, ok, iters, errs)"""
+        q = np.ascontiguousarray(q_init, dtype=np.float64).reshape(-1, self.model.nq)
+        tp = np.ascontiguousarray(target_pos, dtype=np.float64).reshape(-1, 3)
+        tq = np.ascontiguousarray(target_quat, dtype=np.float64).reshape(-1, 4)
+        n = len(q)
+        out = q.copy()
+        ok = np.zeros(n, np.uint8)
+        iters = np.zeros(n, np.int32)
+        errs = np.zeros((n, 2))
+        err = C.create_string_buffer(256)
+        rc = lib().hs_ik(self._h, C.byref(spec), tp.ctypes.data, tq.ctypes.data, q.ctypes.data, n, out.ctypes.data,
+                         ok.ctypes.data, iters.ctypes.data, errs.ctypes.data, err, 256)
+        if rc:
+            raise ValueError(err.value.decode())
+        return out, ok.astype(bool), iters, errs

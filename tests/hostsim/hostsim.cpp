@@ -233,4 +233,24 @@ int hs_pose(Sim *s, const mjb_pose_spec *spec, const double *q_old, const double
   return 0;
 }
 
+// IK rows on the CPU through the same core (ik_row)
+int hs_ik(Sim *s, const mjb_ik_spec *spec, const double *tpos, const double *tquat, const double *q_init, int64_t n,
+          double *q_out, uint8_t *ok, int32_t *iters, double *errs, char *err, int errlen) {
+  IkSpec sp;
+  std::string e;
+  if (!vkb::make_ik_spec(s->H, spec, sp, e)) { snprintf(err, errlen, "%s", e.c_str()); return 1; }
+  const int nq = s->H.nq;
+  for (int64_t r = 0; r < n; r++) {
+    double row[MAX_JNT];
+    for (int j = 0; j < nq; j++) row[j] = q_init[r * nq + j];
+    int it = 0;
+    double pe = 0, oe = 0;
+    ok[r] = ik_row(s->H.fk, s->H.nslot, sp, tpos + r * 3, tquat + r * 4, row, &it, &pe, &oe);
+    if (iters) iters[r] = it;
+    if (errs) { errs[r * 2] = pe; errs[r * 2 + 1] = oe; }
+    for (int j = 0; j < nq; j++) q_out[r * nq + j] = row[j];
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -105,11 +105,70 @@ def bench_plans(nq_queries=1024, time_limit=60.0):
                                    "what": "block-extend RRT host logic on the fp64 C oracle (not MuJoCo), sequential queries"}}))
 
 
+def bench_poses(nq_queries=1024, time_limit=60.0):
+    """BASELINE config #1 as the reference runs it (examples/benchmark.py): the goal is a POSE (the
+    end-effector pose of a random valid configuration); each query is IK + bi-RRT."""
+    model = models.load("franka_scene_with_obstacles")
+    allowed = [("left_finger", "right_finger")]
+    joints = [f"joint{i}" for i in range(1, 8)]
+    site = "ee_site"
+    c = [mj.JointLimitConstraint(model), mj.CollisionConstraint(model, allowed)]
+    eng = c[1].engine
+    q_init = model.keyframe("home").qpos.copy()
+    rows = eng.sweep_rows(11, 0, 8 * nq_queries).double().cpu().numpy()
+    rows[:, 7:] = q_init[7:]
+    ok = np.asarray(mj.obeys_constraints_batch(rows, c))
+    qg = rows[ok][:nq_queries]
+    B = len(qg)
+    # goal poses through the engine's fp64 site kinematics, one block
+    solver = mj.DLSIKSolver(model=model, joints=joints, constraints=c, seed=0, max_attempts=8)
+    po = oracle.PoseOracle(model, site, [0, 0, 0], [1, 0, 0, 0], [(-np.inf, np.inf)] * 6)
+    poses = []
+    for q in qg:
+        p, r = po.site_pose(q)
+        poses.append(mj.SE3(mj.SO3(r), p))
+    inits = np.tile(q_init, (B, 1))
+    solver.solve_ik_batch(poses[:8], site, inits[:8])  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Q, solved = solver.solve_ik_batch(poses, site, inits)
+    torch.cuda.synchronize()
+    ik_dt = time.perf_counter() - t0
+    # kernel-only rate of the IK launch (rows = queries x attempts)
+    tp = np.repeat(np.array([p.translation() for p in poses]), 8, axis=0)
+    tq = np.repeat(np.array([p.rotation().wxyz for p in poses]), 8, axis=0)
+    G = solver._guess_block(inits).reshape(-1, model.nq)
+    t1 = time.perf_counter()
+    solver.solve_rows(tp, tq, G, site)
+    rows_dt = time.perf_counter() - t1
+    bad = 0
+    for i in np.flatnonzero(solved)[:200]:
+        p, r = po.site_pose(Q[i])
+        e = poses[i].minus(mj.SE3(mj.SO3(r), p))
+        bad += not (np.linalg.norm(e[:3]) <= 1e-3 and np.linalg.norm(e[3:]) <= 1e-3)
+    planner = mj.BatchedRRT(model, joints, c, max_planning_time=time_limit, epsilon=0.05, seed=0, goal_biasing_probability=0.1,
+                            max_active=int(os.environ.get("MAX_ACTIVE", "4096")), max_iterations_per_query=int(os.environ.get("MAX_ITERS", "2000")))
+    planner.plan_to_poses(inits[:8], poses[:8], site, solver)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    paths = planner.plan_to_poses(inits, poses, site, solver)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t2
+    nsolved = sum(1 for p in paths if p)
+    print(json.dumps({"case": "move-to-pose queries (IK + batched bi-RRT), Franka scene_with_obstacles", "queries": B,
+                      "ik": {"solved": int(solved.sum()), "attempts_per_query": 8, "seconds": ik_dt, "poses_per_s": B / ik_dt,
+                             "kernel_call_rows": len(G), "kernel_call_seconds_incl_copies": rows_dt,
+                             "pose_check_failures_of_200": int(bad)},
+                      "solved": nsolved, "seconds": dt, "queries_per_s": nsolved / dt, "stats": planner.stats}))
+
+
 if __name__ == "__main__":
     args = sys.argv[1:]
     nqq = int(args[args.index("--queries") + 1]) if "--queries" in args else 1024
-    which = [a for a in args if a in ("edges", "plans")] or ["edges", "plans"]
+    which = [a for a in args if a in ("edges", "plans", "poses")] or ["edges", "plans"]
     if "edges" in which:
         bench_edges()
     if "plans" in which:
         bench_plans(nqq)
+    if "poses" in which:
+        bench_poses(nqq)
