@@ -976,56 +976,61 @@ VK_HD bool ik_row(const FkTables<double> &fk, int nslot, const IkSpec &spec, con
     if (it >= spec.iterations) break;
     // Active set over the joint limits (the role of mink.ConfigurationLimit in the reference's QP,
     // mink_ik_solver.py:87): a joint that sits on a limit and would be pushed further out is
-    // frozen and the step re-solved, so that the other joints take up its share.
-    unsigned active = spec.jnt_mask;
-    double dq[MAX_JNT], sc = 1.0;
+    // frozen and the step re-solved, so that the other joints take up its share.  The frozen set
+    // is a weight per column rather than a bit mask tested while rebuilding J inside the pass
+    // loop: that form came back from nvcc 12.9 (sm_100a, -O3) with the first pass's step reused
+    // on every later pass (tools/dbg/ik_dbg.py shows device and host iterates side by side).
+    double J[6][MAX_JNT], w[MAX_JNT], dq[MAX_JNT], sc = 1.0;
+    for (int c = 0; c < nq; c++) {
+      w[c] = 0.0;
+      for (int i = 0; i < 6; i++) J[i][c] = 0.0;
+    }
+    for (int j = 0; j < fk.njnt; j++) {
+      if (!((spec.jnt_mask >> j) & 1u)) continue;
+      const int c = fk.jnt_qadr[j];
+      V3<double> jp, jr = mk<double>(0, 0, 0);
+      if (fk.jnt_type[j] == JK_SLIDE) jp = axis[j];
+      else { jr = axis[j]; jp = cross(axis[j], sp - anchor[j]); }
+      J[0][c] = jp.x; J[1][c] = jp.y; J[2][c] = jp.z;
+      J[3][c] = jr.x; J[4][c] = jr.y; J[5][c] = jr.z;
+      w[c] = 1.0;
+    }
+    const double mu = spec.lm_damping * (perr * perr + oerr * oerr) + spec.damping;
     bool solved = false;
     for (int pass = 0; pass < 4; pass++) {
-      double J[6][MAX_JNT];
-      for (int j = 0; j < fk.njnt; j++) {
-        V3<double> jp = mk<double>(0, 0, 0), jr = mk<double>(0, 0, 0);
-        if ((active >> j) & 1u) {
-          if (fk.jnt_type[j] == JK_SLIDE) jp = axis[j];
-          else { jr = axis[j]; jp = cross(axis[j], sp - anchor[j]); }
-        }
-        const int c = fk.jnt_qadr[j];
-        J[0][c] = jp.x; J[1][c] = jp.y; J[2][c] = jp.z;
-        J[3][c] = jr.x; J[4][c] = jr.y; J[5][c] = jr.z;
-      }
       double A[36];
-      const double mu = spec.lm_damping * (perr * perr + oerr * oerr) + spec.damping;
       for (int i = 0; i < 6; i++)
         for (int k = i; k < 6; k++) {
           double acc = 0;
-          for (int c = 0; c < nq; c++) acc += J[i][c] * J[k][c];
+          for (int c = 0; c < nq; c++) acc += w[c] * J[i][c] * J[k][c];
           if (i == k) acc += mu;
           A[i * 6 + k] = A[k * 6 + i] = acc;
         }
       double y[6];
-      if (!spd6_solve(A, e, y)) break;
-      solved = true;
+      solved = spd6_solve(A, e, y);
+      if (!solved) break;
       double big = 0;
       for (int c = 0; c < nq; c++) {
         double s = 0;
         for (int i = 0; i < 6; i++) s += J[i][c] * y[i];
-        dq[c] = s;
-        big = fmax(big, fabs(s));
+        dq[c] = w[c] * s;
+        big = fmax(big, fabs(dq[c]));
       }
       sc = big > spec.max_step ? spec.max_step / big : 1.0;
-      unsigned blocked = 0;
+      int nblocked = 0, nfree = 0;
       for (int j = 0; j < fk.njnt; j++) {
-        if (!((active >> j) & 1u)) continue;
         const int c = fk.jnt_qadr[j];
-        if ((q[c] <= fk.jnt_lo[j] && dq[c] < 0.0) || (q[c] >= fk.jnt_hi[j] && dq[c] > 0.0)) blocked |= 1u << j;
+        if (w[c] == 0.0) continue;
+        if ((q[c] <= fk.jnt_lo[j] && dq[c] < 0.0) || (q[c] >= fk.jnt_hi[j] && dq[c] > 0.0)) { w[c] = 0.0; dq[c] = 0.0; nblocked++; }
+        else nfree++;
       }
-      if (!blocked) break;
-      active &= ~blocked;
-      if (!active) { solved = false; break; }
+      if (!nblocked) break;
+      if (!nfree) { solved = false; break; }
     }
     if (!solved) break;
     for (int j = 0; j < fk.njnt; j++) {
       const int c = fk.jnt_qadr[j];
-      if (!((active >> j) & 1u)) continue;
+      if (w[c] == 0.0) continue;
       double v = q[c] + sc * dq[c];
       v = v < fk.jnt_lo[j] ? fk.jnt_lo[j] : (v > fk.jnt_hi[j] ? fk.jnt_hi[j] : v);
       q[c] = v;

