@@ -394,6 +394,8 @@ extern "C" int mjb_get_stats(mjb_model *m, mjb_stats *out) {
   out->launches = m->launches;
 #ifdef VK_STATS
   out->launches = (int64_t)c[7];  // debug build: GJK loop trips
+  fprintf(stderr, "[vk_stats] trips by busy lanes <=4 / <=8 / <=16 / <=32: %llu %llu %llu %llu; lane-trips: %llu %llu %llu %llu\n",
+          c[8], c[9], c[10], c[11], c[12], c[13], c[14], c[15]);
 #endif
   return MJB_OK;
 }

@@ -69,7 +69,7 @@ struct KArgs {
 };
 
 // counters layout
-constexpr int C_TICKET = 0, C_RECHECK = 1, C_RTICKET = 2, C_ITEMS = 3, C_OVERFLOW = 4, C_UNCERTAIN = 5, C_ROWS = 6, C_NCOUNTERS = 8;
+constexpr int C_TICKET = 0, C_RECHECK = 1, C_RTICKET = 2, C_ITEMS = 3, C_OVERFLOW = 4, C_UNCERTAIN = 5, C_ROWS = 6, C_NCOUNTERS = 16;
 constexpr int C_PER_LAUNCH = 3;  // counters [0, C_PER_LAUNCH) are cleared before every launch
 
 // ---------------------------------------------------------------------------- PTX helpers (sm_90+/sm_100a)
@@ -124,7 +124,7 @@ __host__ __device__ inline SmemLayout smem_layout(int nvert, int nshape, int npa
   L.qtile = o; o = align_up(o + (size_t)TILE * nq * sizeof(float), 128);
   L.queue1 = o; o = align_up(o + (size_t)Q1_PER_ROW * TILE * sizeof(uint32_t), 128);
   L.queue2 = o; o = align_up(o + (size_t)Q2_PER_ROW * TILE * sizeof(uint32_t), 128);
-  L.hit = o;
+  L.hit = o; o = align_up(o + (size_t)TILE * sizeof(uint32_t), 128);  // per row: uncertain-item count << 16 | first such pair
   L.bars = o; o = align_up(o + 64 + 8 * (TILE / 32), 128);  // [0] tables, then one row-load barrier per warp
   L.total = o;
   return L;
@@ -193,6 +193,12 @@ __device__ __forceinline__ Pose<float> load_pose(const float *ps, int slot, int 
 // Queues are WARP-LOCAL (each warp owns 32 rows and a private slice of shared memory), so a
 // push is a ballot + popc with the fill count held in a warp-uniform register: no atomics, no
 // CTA barriers between stages; warps drift apart and hide each other's latency.
+// An item the fp32 path could not certify: count it for its row and remember the first such pair,
+// so that the fp64 pass re-evaluates one pair instead of the whole row when it is the only one.
+__device__ __forceinline__ void note_uncertain(uint32_t *w, int pair) {
+  if ((atomicAdd(w, 0x10000u) >> 16) == 0) atomicOr(w, (uint32_t)pair);
+}
+
 // The caller guarantees count + 32 <= cap before the push, so nothing can be dropped.
 __device__ __forceinline__ void warp_push(bool want, uint32_t item, uint32_t *queue, int &count, int cap, int lane) {
   const unsigned m = __ballot_sync(0xffffffffu, want);
@@ -216,6 +222,15 @@ __device__ __forceinline__ void warp_push(bool want, uint32_t item, uint32_t *qu
 #endif
 #ifndef VK_A_UNROLL
 #define VK_A_UNROLL 1
+#endif
+#ifndef VK_SUSPEND
+#define VK_SUSPEND 12   // leave stage C with at most this many unfinished items when the queue is empty
+#endif
+#ifndef VK_FLUSH_EARLY
+#define VK_FLUSH_EARLY 1   // rounds whose narrow-phase items are processed at once (early exit); B200: 1 -> 3.15 ms, 2 -> 3.35, 0 -> 3.26
+#endif
+#ifndef VK_FLUSH_FILL
+#define VK_FLUSH_FILL (3 * Q2CAP / 4)   // later rounds: run the narrow phase once this many items wait
 #endif
 #define VK_PRAGMA(x) _Pragma(#x)
 #define VK_UNROLL(n) VK_PRAGMA(unroll n)
@@ -294,6 +309,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
   float *s_cen = reinterpret_cast<float *>(smem + L.cen);
   float *s_q = reinterpret_cast<float *>(smem + L.qtile);
   uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.bars);       // [0] tables, [8 + w] rows of warp w
+  uint32_t *s_unc = reinterpret_cast<uint32_t *>(smem + L.hit);
   constexpr int Q1CAP = Q1_PER_ROW * 32, Q2CAP = Q2_PER_ROW * 32;
 
   const int tid = threadIdx.x;
@@ -342,6 +358,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
   long long items_total = 0, rows_total = 0;
 #ifdef VK_STATS
   long long st_trips = 0, st_busy = 0, st_flushes = 0, st_bbatches = 0, st_bbusy = 0;
+  long long st_hist[4] = {0, 0, 0, 0}, st_histb[4] = {0, 0, 0, 0};
 #endif
   const bool use_obb = !(a.flags & F_NO_OBB);
   const float slack = 1e-4f;
@@ -443,6 +460,18 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
     int n1 = 0, b_pos = 0;  // q1 fill and the next q1 index stage B will take (warp-uniform)
     int n2 = 0;             // q2 fill (warp-uniform)
     const unsigned coll_mask = __ballot_sync(0xffffffffu, do_coll);
+    // narrow-phase state of this lane's current GJK item.  It outlives one pass of stage C: when
+    // the item queue is empty and only a few lanes still iterate (the long tail of slow items),
+    // the warp goes back to produce more items and the unfinished ones resume with full lanes.
+    GjkState<float> gs;
+    Rel<float> rel;
+    const Shape<float> *SA = s_shapes, *SB = s_shapes;
+    float R = 0.f;
+    int r = 0;
+    int pidx = 0;          // pair index of the current item (reported if it ends uncertain)
+    int wa = -1, wb = -1;  // warm-start vertices of the current item's two shapes
+    bool have = false;
+    s_unc[tid] = 0;
     const int gl = lane & (GRP - 1);
     const unsigned gmask = ((1u << GRP) - 1u) << (lane & ~(GRP - 1));
 #pragma unroll 1
@@ -451,7 +480,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
       const int p1 = a.round_start[rd + 1];
       // early rounds (most likely contacts) are flushed right away so that hit rows stop
       // generating work; later rounds accumulate items for better lane balance
-      const bool flush_round = (rd < 2) || (rd + 1 == a.nrounds);
+      const bool flush_round = (rd < VK_FLUSH_EARLY) || (rd + 1 == a.nrounds);
 #pragma unroll 1
       for (;;) {
         // A: sphere cull, lane = row.  Rows that already have a certain contact drop out.
@@ -509,7 +538,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
         }
         __syncwarp();
         const bool a_done = (p >= p1) && (b_pos >= n1);
-        const bool run_c = (b_pos < n1) /* q2 has no room */ || (a_done && (flush_round || n2 >= Q2CAP / 2));
+        const bool run_c = (b_pos < n1) /* q2 has no room */ || (a_done && (flush_round || n2 >= VK_FLUSH_FILL));
         if (run_c) {
           // C: narrow phase with persistent lane groups: every trip runs ONE GJK iteration per
           // group; a group whose item is decided fetches the next one, so lanes do not idle
@@ -519,18 +548,13 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
 #ifdef VK_STATS
           st_flushes++;
 #endif
-          GjkState<float> gs;
-          Rel<float> rel;
-          const Shape<float> *SA = s_shapes, *SB = s_shapes;
-          float R = 0.f;
-          int r = 0;
-          int wa = -1, wb = -1;  // warm-start vertices of the current item's two shapes
-          bool have = false;
           int head = 0;  // warp-uniform
+          const bool drain = a_done && (rd + 1 == a.nrounds);
+          if (have && ((hit_mask >> r) & 1u)) have = false;  // decided while the item was parked
 #pragma unroll 1
           for (;;) {
             const unsigned need = __ballot_sync(0xffffffffu, !have);   // group-uniform bits
-            if (need == 0xffffffffu && head >= n2) break;
+            if (head >= n2 && (need == 0xffffffffu || (!drain && __popc(~need) <= VK_SUSPEND * GRP))) break;
             unsigned hb = 0, ub = 0;
             if (!have) {
               const int i = head + __popc(need & ((1u << (lane & ~(GRP - 1))) - 1u)) / GRP;
@@ -538,7 +562,8 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
                 const uint32_t it = q2[i];
                 r = it & 0xffff;
                 if (!((hit_mask >> r) & 1u)) {
-                  const Pair pr = s_pairs[it >> 16];
+                  pidx = (int)(it >> 16);
+                  const Pair pr = s_pairs[pidx];
                   SA = s_shapes + pr.sa;
                   SB = s_shapes + pr.sb;
                   R = pr.rsum;
@@ -559,14 +584,15 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
                       v = segseg_item(*SA, *SB, s_verts, PA, PB, R);
                     }
                     if (v == V_PEN) hb = 1u << r;
-                    else if (v == V_UNC) ub = 1u << r;
+                    else if (v == V_UNC) { ub = 1u << r; note_uncertain(s_unc + wrow0 + r, pidx); }
                   }
                 }
               }
             }
             head += __popc(need) / GRP;
 #ifdef VK_STATS
-            st_trips++; st_busy += __popc(__ballot_sync(0xffffffffu, have)) / GRP;
+            { const int nb = __popc(__ballot_sync(0xffffffffu, have)) / GRP; st_trips++; st_busy += nb;
+              const int bin = nb <= 4 ? 0 : (nb <= 8 ? 1 : (nb <= 16 ? 2 : 3)); st_hist[bin]++; st_histb[bin] += nb; }
 #endif
             if (have) {
               const Shape<float> &As = *SA, &Bs = *SB;
@@ -575,7 +601,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
                   [&](V3<float> d) { return group_support(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, wb); });
               if (v >= 0) {
                 if (v == V_PEN) hb = 1u << r;
-                else if (v == V_UNC) ub = 1u << r;
+                else if (v == V_UNC) { ub = 1u << r; note_uncertain(s_unc + wrow0 + r, pidx); }
                 have = false;
               }
             }
@@ -597,8 +623,11 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
       bool ok = lim_ok && !hit;
       bool pending = lim_ok && !hit && unc;
       if (pending && !(a.flags & F_NO_RECHECK)) {
+        // entry = row | (pair + 1) << 44 when exactly one item was uncertain, row alone otherwise
+        const uint32_t u = s_unc[tid];
+        const unsigned long long one = ((u >> 16) == 1u) ? (unsigned long long)((u & 0xffffu) + 1u) << 44 : 0ull;
         unsigned long long slot = atomicAdd(&a.counters[C_RECHECK], 1ull);
-        a.recheck_rows[slot] = row;
+        a.recheck_rows[slot] = (long long)((unsigned long long)row | one);
       }
       if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) {
         if (!ok && !pending) atomicMin(&a.first_bad[e_idx], e_k);
@@ -611,7 +640,8 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
   if (lane == 0 && items_total) atomicAdd(&a.counters[C_ITEMS], (unsigned long long)items_total);
   if (lane == 0 && rows_total) atomicAdd(&a.counters[C_ROWS], (unsigned long long)rows_total);
 #ifdef VK_STATS
-  if (lane == 0) { atomicAdd(&a.counters[7], (unsigned long long)st_trips); atomicAdd(&a.counters[C_OVERFLOW], (unsigned long long)st_busy); atomicAdd(&a.counters[C_UNCERTAIN], (unsigned long long)st_flushes); }
+  if (lane == 0) { atomicAdd(&a.counters[7], (unsigned long long)st_trips); atomicAdd(&a.counters[C_OVERFLOW], (unsigned long long)st_busy); atomicAdd(&a.counters[C_UNCERTAIN], (unsigned long long)st_flushes);
+    for (int b = 0; b < 4; b++) { atomicAdd(&a.counters[8 + b], (unsigned long long)st_hist[b]); atomicAdd(&a.counters[12 + b], (unsigned long long)st_histb[b]); } }
 #endif
 }
 
@@ -634,8 +664,35 @@ struct RArgs {
   const long long *recheck_rows;
 };
 
+// support point of a shape with the 32 lanes of a warp splitting the vertex scan (fp64); every
+// lane returns the same vertex (ties go to the lower index)
+__device__ __forceinline__ V3<double> warp_support64(const Shape<double> &s, const Vtx<double> *__restrict__ verts, V3<double> d,
+                                                    int lane) {
+  if (s.kind == SK_CYL) return support_cyl(s, d);
+  const Vtx<double> *__restrict__ v = verts + s.vadr;
+  double best = -1.0e300;
+  int bi = 0;
+  for (int i = lane; i < s.nvert; i += 32) {
+    const Vtx<double> p = v[i];
+    const double t = p.x * d.x + p.y * d.y + p.z * d.z;
+    if (t > best) { best = t; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    const bool take = (ob > best) || (ob == best && oi < bi);
+    best = take ? ob : best;
+    bi = take ? oi : bi;
+  }
+  const Vtx<double> p = v[bi];
+  return mk<double>(p.x, p.y, p.z);
+}
+
 // One WARP per listed row: every lane rebuilds the row and its fp64 poses (cheap, redundant),
 // then the 32 lanes split the static pair list; a contact found by any lane ends the row.
+// A row whose only uncertain item is known (the usual case) re-evaluates just that pair: all
+// its other pairs were certified separated by the fast path.
 __global__ void __launch_bounds__(128) recheck_kernel(const RArgs a) {
   const FkTables<double> &fk = *a.fk;
   const unsigned long long total = a.counters[C_RECHECK];
@@ -646,7 +703,9 @@ __global__ void __launch_bounds__(128) recheck_kernel(const RArgs a) {
     if (lane == 0) t = atomicAdd(&a.counters[C_RTICKET], 1ull);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= total) break;
-    const long long row = a.recheck_rows[t];
+    const unsigned long long entry = (unsigned long long)a.recheck_rows[t];
+    const long long row = (long long)(entry & ((1ull << 44) - 1ull));
+    const int only = (int)(entry >> 44) - 1;  // >= 0: the single pair the fast path was unsure about
     double q[MAX_JNT];
     long long e_idx = 0;
     int e_k = 0;
@@ -672,9 +731,30 @@ __global__ void __launch_bounds__(128) recheck_kernel(const RArgs a) {
       P[s] = fk_body(fk, s, ps < 0 ? ident : P[ps], q);
     }
     bool contact = false;
-    for (int base = 0; base < a.npair; base += 32) {
+    int p_lo = 0, p_hi = a.npair;
+    if (only >= 0) {
+      p_lo = only; p_hi = only + 1;
+      const Pair pr = a.pairs[only];
+      if (pr.kind == PK_GJK) {
+        // the usual case: one near-touching convex pair.  Such a pair needs many GJK iterations
+        // in fp64, so the whole warp runs ONE instance with the support scans split 32 ways.
+        const Shape<double> &A = a.shapes[pr.sa];
+        const Shape<double> &B = a.shapes[pr.sb];
+        const Rel<double> rel = relative_pose(A.slot < 0 ? ident : P[A.slot], B.slot < 0 ? ident : P[B.slot]);
+        GjkState<double> gs;
+        gjk_init(gs, A, B, rel);
+        int v;
+        do {
+          v = gjk_step_impl(gs, rel, a.pair_rsum[only], [&](V3<double> d) { return warp_support64(A, a.verts, d, lane); },
+                            [&](V3<double> d) { return warp_support64(B, a.verts, d, lane); });
+        } while (v < 0);
+        contact = v != V_SEP;
+        p_hi = p_lo;  // done
+      }
+    }
+    for (int base = p_lo; base < p_hi; base += 32) {
       const int p = base + lane;
-      if (p < a.npair) {
+      if (p < p_hi) {
         const Pair pr = a.pairs[p];
         const Shape<double> &A = a.shapes[pr.sa];
         const Shape<double> &B = a.shapes[pr.sb];

@@ -51,6 +51,7 @@ def lib():
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
         L.hs_ik.argtypes = [C.c_void_p, C.POINTER(_abi.IkSpec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L.hs_pair_census.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.hs_pair_verdict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -145,3 +146,11 @@ class HostSim:
         if rc:
             raise ValueError(err.value.decode())
         return out, ok.astype(bool), iters, errs
+
+    def pair_census(self, q):
+        """per pair (in the engine's pair order, see ``pairs()``): sphere survivors, narrow items,
+        vertex evaluations, contacts over the rows of ``q`` (no early exit)"""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.model.nq)
+        out = np.zeros((lib().hs_npair(self._h), 4), np.int64)
+        lib().hs_pair_census(self._h, q.ctypes.data, len(q), out.ctypes.data)
+        return out

@@ -253,4 +253,42 @@ int hs_ik(Sim *s, const mjb_ik_spec *spec, const double *tpos, const double *tqu
   return 0;
 }
 
+// per-pair work census (analysis aid): out[p*4 + {0,1,2,3}] = sphere survivors, narrow items,
+// vertex evaluations, contacts -- every pair evaluated on every row (no early exit)
+void hs_pair_census(Sim *s, const float *q, int64_t n, int64_t *out) {
+  const auto &H = s->H;
+  Pose<float> P[MAX_BODY], ident;
+  ident.p = mk<float>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  for (int64_t r = 0; r < n; r++) {
+    const float *qr = q + r * H.nq;
+    for (int k = 0; k < H.nslot; k++) { int ps = s->fk32.body_parent[k]; P[k] = fk_body(s->fk32, k, ps < 0 ? ident : P[ps], qr); }
+    for (size_t p = 0; p < H.pairs.size(); p++) {
+      const Pair pr = H.pairs[p];
+      const Shape<float> &A = s->s32[pr.sa], &B = s->s32[pr.sb];
+      const Pose<float> &PA = A.slot < 0 ? ident : P[A.slot];
+      const Pose<float> &PB = B.slot < 0 ? ident : P[B.slot];
+      const float slack = 1e-4f;
+      V3<float> cB = PB.p + qrot(PB.q, mk<float>(B.bc[0], B.bc[1], B.bc[2]));
+      if (pr.kind == PK_PLANE) {
+        float d = A.ax[0] * (cB.x - A.c[0]) + A.ax[1] * (cB.y - A.c[1]) + A.ax[2] * (cB.z - A.c[2]);
+        if (d > pr.bsum + slack) continue;
+      } else {
+        V3<float> cA = PA.p + qrot(PA.q, mk<float>(A.bc[0], A.bc[1], A.bc[2]));
+        V3<float> dd = cA - cB;
+        if (dot(dd, dd) > (pr.bsum + slack) * (pr.bsum + slack)) continue;
+      }
+      out[p * 4 + 0]++;
+      if (midphase_cull(pr, A, B, PA, PB, pr.rsum - swept_radius(A) - swept_radius(B), slack)) continue;
+      out[p * 4 + 1]++;
+      int v, iters = 0;
+      if (pr.kind == PK_GJK) {
+        Rel<float> rel = relative_pose(PA, PB);
+        v = gjk_classify(A, B, s->v32.data(), rel, pr.rsum, &iters);
+        out[p * 4 + 2] += (int64_t)iters * (A.nvert + B.nvert);
+      } else v = narrow_item<float>(pr.kind, A, B, s->v32.data(), PA, PB, pr.rsum);
+      if (v == V_PEN) out[p * 4 + 3]++;
+    }
+  }
+}
+
 }  // extern "C"

@@ -10,8 +10,9 @@ model = models.load(MODEL); eng = mj.get_engine(model, ALLOWED)
 q = torch.from_numpy(make_rows(model, 1_000_000)).cuda()
 out = torch.empty(len(q), dtype=torch.uint8, device="cuda")
 L = _abi.lib()
+FLAGS = int(sys.argv[1]) if len(sys.argv) > 1 else 3   # 11 = skip the fp64 re-evaluation kernel
 def raw():
-    _abi.check(L.mjb_check_configs(eng._h, q.data_ptr(), len(q), 9, out.data_ptr(), 3, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    _abi.check(L.mjb_check_configs(eng._h, q.data_ptr(), len(q), 9, out.data_ptr(), FLAGS, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
 for _ in range(10): raw()
 torch.cuda.synchronize()
 ts = []
