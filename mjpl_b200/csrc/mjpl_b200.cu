@@ -220,7 +220,7 @@ static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st) {
   if (rows <= m->recheck_cap) return MJB_OK;
   if (m->d_recheck) { CU(cudaStreamSynchronize(st)); CU(cudaFree(m->d_recheck)); m->d_recheck = nullptr; }
   size_t cap = std::max<size_t>(rows, 1 << 20);
-  CU(cudaMalloc((void **)&m->d_recheck, cap * sizeof(long long)));
+  CU(cudaMalloc((void **)&m->d_recheck, 2 * cap * sizeof(long long)));  // row list, then item list
   m->recheck_cap = cap;
   return MJB_OK;
 }
@@ -229,6 +229,9 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
   CU(cudaMemsetAsync(m->d_counters, 0, C_PER_LAUNCH * sizeof(unsigned long long), st));
   k.recheck_rows = m->d_recheck;
   r.recheck_rows = m->d_recheck;
+  k.recheck_items = (unsigned long long *)(m->d_recheck + m->recheck_cap);
+  r.recheck_items = k.recheck_items;
+  k.item_cap = r.item_cap = m->recheck_cap;
   switch (m->tile) {
     case 512: validity_kernel<512><<<m->grid, 512, m->smem_bytes, st>>>(k); break;
     case 256: validity_kernel<256><<<m->grid, 256, m->smem_bytes, st>>>(k); break;
@@ -393,9 +396,10 @@ extern "C" int mjb_get_stats(mjb_model *m, mjb_stats *out) {
   out->queue_overflow = (int64_t)c[C_OVERFLOW];
   out->launches = m->launches;
 #ifdef VK_STATS
-  out->launches = (int64_t)c[7];  // debug build: GJK loop trips
+  out->launches = (int64_t)c[C_TRIPS];  // debug build: GJK loop trips
+  out->uncertain_rows = (int64_t)c[C_HIST + 8];  // debug build: narrow-phase passes
   fprintf(stderr, "[vk_stats] trips by busy lanes <=4 / <=8 / <=16 / <=32: %llu %llu %llu %llu; lane-trips: %llu %llu %llu %llu\n",
-          c[8], c[9], c[10], c[11], c[12], c[13], c[14], c[15]);
+          c[C_HIST], c[C_HIST + 1], c[C_HIST + 2], c[C_HIST + 3], c[C_HIST + 4], c[C_HIST + 5], c[C_HIST + 6], c[C_HIST + 7]);
 #endif
   return MJB_OK;
 }

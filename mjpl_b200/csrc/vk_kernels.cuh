@@ -65,12 +65,15 @@ struct KArgs {
   // per-handle scratch
   float *pose_scratch;                  // [grid][nslot*7][TILE]
   unsigned long long *counters;         // see C_* below
-  long long *recheck_rows;              // capacity >= number of rows
+  long long *recheck_rows;              // rows to re-evaluate whole; capacity >= number of rows
+  unsigned long long *recheck_items;    // (row | pair << 44) items to re-evaluate; capacity item_cap
+  unsigned long long item_cap;
 };
 
 // counters layout
-constexpr int C_TICKET = 0, C_RECHECK = 1, C_RTICKET = 2, C_ITEMS = 3, C_OVERFLOW = 4, C_UNCERTAIN = 5, C_ROWS = 6, C_NCOUNTERS = 16;
-constexpr int C_PER_LAUNCH = 3;  // counters [0, C_PER_LAUNCH) are cleared before every launch
+constexpr int C_TICKET = 0, C_RECHECK = 1, C_RTICKET = 2, C_RITEMS = 3, C_RITICKET = 4;   // per launch
+constexpr int C_ITEMS = 5, C_OVERFLOW = 6, C_UNCERTAIN = 7, C_ROWS = 8, C_TRIPS = 9, C_HIST = 10, C_NCOUNTERS = 20;  // statistics
+constexpr int C_PER_LAUNCH = 5;  // counters [0, C_PER_LAUNCH) are cleared before every launch
 
 // ---------------------------------------------------------------------------- PTX helpers (sm_90+/sm_100a)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -193,10 +196,14 @@ __device__ __forceinline__ Pose<float> load_pose(const float *ps, int slot, int 
 // Queues are WARP-LOCAL (each warp owns 32 rows and a private slice of shared memory), so a
 // push is a ballot + popc with the fill count held in a warp-uniform register: no atomics, no
 // CTA barriers between stages; warps drift apart and hide each other's latency.
-// An item the fp32 path could not certify: count it for its row and remember the first such pair,
-// so that the fp64 pass re-evaluates one pair instead of the whole row when it is the only one.
-__device__ __forceinline__ void note_uncertain(uint32_t *w, int pair) {
-  if ((atomicAdd(w, 0x10000u) >> 16) == 0) atomicOr(w, (uint32_t)pair);
+// An item the fp32 path could not certify goes to the fp64 pass as (row, pair): all the other
+// pairs of its row were certified by the fast path, so one pair is all there is to redo.  If the
+// item list is full the row is flagged and re-evaluated whole (the row list holds every row).
+__device__ __forceinline__ void note_uncertain(unsigned long long *counters, unsigned long long *items, unsigned long long cap,
+                                               long long row, int pair, uint32_t *row_flag) {
+  const unsigned long long slot = atomicAdd(&counters[C_RITEMS], 1ull);
+  if (slot < cap) items[slot] = (unsigned long long)row | ((unsigned long long)pair << 44);
+  else atomicOr(row_flag, 1u);
 }
 
 // The caller guarantees count + 32 <= cap before the push, so nothing can be dropped.
@@ -584,7 +591,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
                       v = segseg_item(*SA, *SB, s_verts, PA, PB, R);
                     }
                     if (v == V_PEN) hb = 1u << r;
-                    else if (v == V_UNC) { ub = 1u << r; note_uncertain(s_unc + wrow0 + r, pidx); }
+                    else if (v == V_UNC) { ub = 1u << r; if (!(a.flags & F_NO_RECHECK)) note_uncertain(a.counters, a.recheck_items, a.item_cap, row_base + r, pidx, s_unc + wrow0 + r); }
                   }
                 }
               }
@@ -601,7 +608,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
                   [&](V3<float> d) { return group_support(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, wb); });
               if (v >= 0) {
                 if (v == V_PEN) hb = 1u << r;
-                else if (v == V_UNC) { ub = 1u << r; note_uncertain(s_unc + wrow0 + r, pidx); }
+                else if (v == V_UNC) { ub = 1u << r; if (!(a.flags & F_NO_RECHECK)) note_uncertain(a.counters, a.recheck_items, a.item_cap, row_base + r, pidx, s_unc + wrow0 + r); }
                 have = false;
               }
             }
@@ -622,12 +629,12 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
       const bool unc = (unc_mask >> lane) & 1u;
       bool ok = lim_ok && !hit;
       bool pending = lim_ok && !hit && unc;
+      if (pending) atomicAdd(&a.counters[C_UNCERTAIN], 1ull);
       if (pending && !(a.flags & F_NO_RECHECK)) {
-        // entry = row | (pair + 1) << 44 when exactly one item was uncertain, row alone otherwise
-        const uint32_t u = s_unc[tid];
-        const unsigned long long one = ((u >> 16) == 1u) ? (unsigned long long)((u & 0xffffu) + 1u) << 44 : 0ull;
-        unsigned long long slot = atomicAdd(&a.counters[C_RECHECK], 1ull);
-        a.recheck_rows[slot] = (long long)((unsigned long long)row | one);
+        if (s_unc[tid]) {  // its items did not fit the item list
+          unsigned long long slot = atomicAdd(&a.counters[C_RECHECK], 1ull);
+          a.recheck_rows[slot] = row;
+        }
       }
       if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) {
         if (!ok && !pending) atomicMin(&a.first_bad[e_idx], e_k);
@@ -640,8 +647,8 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
   if (lane == 0 && items_total) atomicAdd(&a.counters[C_ITEMS], (unsigned long long)items_total);
   if (lane == 0 && rows_total) atomicAdd(&a.counters[C_ROWS], (unsigned long long)rows_total);
 #ifdef VK_STATS
-  if (lane == 0) { atomicAdd(&a.counters[7], (unsigned long long)st_trips); atomicAdd(&a.counters[C_OVERFLOW], (unsigned long long)st_busy); atomicAdd(&a.counters[C_UNCERTAIN], (unsigned long long)st_flushes);
-    for (int b = 0; b < 4; b++) { atomicAdd(&a.counters[8 + b], (unsigned long long)st_hist[b]); atomicAdd(&a.counters[12 + b], (unsigned long long)st_histb[b]); } }
+  if (lane == 0) { atomicAdd(&a.counters[C_TRIPS], (unsigned long long)st_trips); atomicAdd(&a.counters[C_OVERFLOW], (unsigned long long)st_busy); atomicAdd(&a.counters[C_HIST + 8], (unsigned long long)st_flushes);
+    for (int b = 0; b < 4; b++) { atomicAdd(&a.counters[C_HIST + b], (unsigned long long)st_hist[b]); atomicAdd(&a.counters[C_HIST + 4 + b], (unsigned long long)st_histb[b]); } }
 #endif
 }
 
@@ -662,6 +669,8 @@ struct RArgs {
   uint8_t *valid; int *first_bad;
   unsigned long long *counters;
   const long long *recheck_rows;
+  const unsigned long long *recheck_items;
+  unsigned long long item_cap;
 };
 
 // support point of a shape with the 32 lanes of a warp splitting the vertex scan (fp64); every
@@ -689,72 +698,98 @@ __device__ __forceinline__ V3<double> warp_support64(const Shape<double> &s, con
   return mk<double>(p.x, p.y, p.z);
 }
 
-// One WARP per listed row: every lane rebuilds the row and its fp64 poses (cheap, redundant),
-// then the 32 lanes split the static pair list; a contact found by any lane ends the row.
-// A row whose only uncertain item is known (the usual case) re-evaluates just that pair: all
-// its other pairs were certified separated by the fast path.
+// the fp64 row the fast path saw (as fp32) and its place in an edge / chain, for any row source
+__device__ __forceinline__ void recheck_row(const RArgs &a, const FkTables<double> &fk, long long row, double *q, long long &e_idx,
+                                            int &e_k) {
+  e_idx = 0; e_k = 0;
+  if (a.mode == MODE_DENSE) {
+    for (int j = 0; j < fk.nq; j++) q[j] = (double)a.q[row * a.ldq + j];
+  } else if (a.mode == MODE_EDGES) {
+    edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
+    float qf[MAX_JNT];
+    edge_row<float>(a.q0, a.q1, a.ldq, fk.nq, a.step, e_idx, e_k, qf);
+    for (int j = 0; j < fk.nq; j++) q[j] = (double)qf[j];
+  } else if (a.mode == MODE_CHAINS) {
+    edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
+    chain_point<double>(a.c0, a.c1, fk.nq, a.ceps, e_idx, e_k, q);
+    for (int j = 0; j < fk.nq; j++) q[j] = (double)(float)q[j];
+  } else {
+    for (int j = 0; j < fk.nq; j++)
+      q[j] = (double)sweep_value(a.seed, (uint64_t)(a.row0 + row), (uint32_t)j, (float)fk.jnt_lo[j], (float)fk.jnt_hi[j]);
+  }
+}
+
+// fp64 re-evaluation, one WARP per unit of work, two passes:
+//  1. uncertain ITEMS (row, pair): every lane rebuilds the row and its fp64 poses (cheap,
+//     redundant).  A convex pair near touching needs many GJK iterations in fp64, so the whole
+//     warp runs ONE GJK instance with each support scan split 32 ways; other kinds are closed
+//     form.  "Uncertain" in fp64 means touching to within rounding: MuJoCo reports a contact for
+//     distance <= margin, so it counts as one.
+//  2. whole ROWS (only when the item list overflowed): the 32 lanes split the static pair list.
+// Both only ever turn a tentatively valid row invalid.
 __global__ void __launch_bounds__(128) recheck_kernel(const RArgs a) {
   const FkTables<double> &fk = *a.fk;
-  const unsigned long long total = a.counters[C_RECHECK];
-  if (blockIdx.x == 0 && threadIdx.x == 0 && total) atomicAdd(&a.counters[C_UNCERTAIN], total);
   const int lane = threadIdx.x & 31;
+  Pose<double> P[MAX_BODY];
+  Pose<double> ident; ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  double q[MAX_JNT];
+  long long e_idx;
+  int e_k;
+  unsigned long long nitems = a.counters[C_RITEMS];
+  if (nitems > a.item_cap) nitems = a.item_cap;
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(&a.counters[C_RITICKET], 1ull);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= nitems) break;
+    const unsigned long long entry = a.recheck_items[t];
+    const long long row = (long long)(entry & ((1ull << 44) - 1ull));
+    const int p = (int)(entry >> 44);
+    recheck_row(a, fk, row, q, e_idx, e_k);
+    const bool edges = a.mode == MODE_EDGES || a.mode == MODE_CHAINS;
+    if (!edges && a.valid[row] == 0) continue;  // the row already has a certain contact
+    for (int s = 0; s < a.nslot; s++) {
+      int ps = fk.body_parent[s];
+      P[s] = fk_body(fk, s, ps < 0 ? ident : P[ps], q);
+    }
+    const Pair pr = a.pairs[p];
+    const Shape<double> &A = a.shapes[pr.sa];
+    const Shape<double> &B = a.shapes[pr.sb];
+    const Pose<double> &PA = A.slot < 0 ? ident : P[A.slot];
+    const Pose<double> &PB = B.slot < 0 ? ident : P[B.slot];
+    int v;
+    if (pr.kind == PK_GJK) {
+      const Rel<double> rel = relative_pose(PA, PB);
+      GjkState<double> gs;
+      gjk_init(gs, A, B, rel);
+      do {
+        v = gjk_step_impl(gs, rel, a.pair_rsum[p], [&](V3<double> d) { return warp_support64(A, a.verts, d, lane); },
+                          [&](V3<double> d) { return warp_support64(B, a.verts, d, lane); });
+      } while (v < 0);
+    } else {
+      v = narrow_item<double>(pr.kind, A, B, a.verts, PA, PB, a.pair_rsum[p]);
+    }
+    if (lane == 0 && v != V_SEP) {
+      if (edges) atomicMin(&a.first_bad[e_idx], e_k);
+      else a.valid[row] = 0;
+    }
+  }
+  const unsigned long long total = a.counters[C_RECHECK];
   for (;;) {
     unsigned long long t = 0;
     if (lane == 0) t = atomicAdd(&a.counters[C_RTICKET], 1ull);
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= total) break;
-    const unsigned long long entry = (unsigned long long)a.recheck_rows[t];
-    const long long row = (long long)(entry & ((1ull << 44) - 1ull));
-    const int only = (int)(entry >> 44) - 1;  // >= 0: the single pair the fast path was unsure about
-    double q[MAX_JNT];
-    long long e_idx = 0;
-    int e_k = 0;
-    if (a.mode == MODE_DENSE) {
-      for (int j = 0; j < fk.nq; j++) q[j] = (double)a.q[row * a.ldq + j];
-    } else if (a.mode == MODE_EDGES) {
-      edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
-      float qf[MAX_JNT];
-      edge_row<float>(a.q0, a.q1, a.ldq, fk.nq, a.step, e_idx, e_k, qf);
-      for (int j = 0; j < fk.nq; j++) q[j] = (double)qf[j];
-    } else if (a.mode == MODE_CHAINS) {
-      edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
-      chain_point<double>(a.c0, a.c1, fk.nq, a.ceps, e_idx, e_k, q);
-      for (int j = 0; j < fk.nq; j++) q[j] = (double)(float)q[j];  // the fp32 row the fast path saw
-    } else {
-      for (int j = 0; j < fk.nq; j++)
-        q[j] = (double)sweep_value(a.seed, (uint64_t)(a.row0 + row), (uint32_t)j, (float)fk.jnt_lo[j], (float)fk.jnt_hi[j]);
-    }
-    Pose<double> P[MAX_BODY];
-    Pose<double> ident; ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+    const long long row = a.recheck_rows[t];
+    recheck_row(a, fk, row, q, e_idx, e_k);
     for (int s = 0; s < a.nslot; s++) {
       int ps = fk.body_parent[s];
       P[s] = fk_body(fk, s, ps < 0 ? ident : P[ps], q);
     }
     bool contact = false;
-    int p_lo = 0, p_hi = a.npair;
-    if (only >= 0) {
-      p_lo = only; p_hi = only + 1;
-      const Pair pr = a.pairs[only];
-      if (pr.kind == PK_GJK) {
-        // the usual case: one near-touching convex pair.  Such a pair needs many GJK iterations
-        // in fp64, so the whole warp runs ONE instance with the support scans split 32 ways.
-        const Shape<double> &A = a.shapes[pr.sa];
-        const Shape<double> &B = a.shapes[pr.sb];
-        const Rel<double> rel = relative_pose(A.slot < 0 ? ident : P[A.slot], B.slot < 0 ? ident : P[B.slot]);
-        GjkState<double> gs;
-        gjk_init(gs, A, B, rel);
-        int v;
-        do {
-          v = gjk_step_impl(gs, rel, a.pair_rsum[only], [&](V3<double> d) { return warp_support64(A, a.verts, d, lane); },
-                            [&](V3<double> d) { return warp_support64(B, a.verts, d, lane); });
-        } while (v < 0);
-        contact = v != V_SEP;
-        p_hi = p_lo;  // done
-      }
-    }
-    for (int base = p_lo; base < p_hi; base += 32) {
+    for (int base = 0; base < a.npair; base += 32) {
       const int p = base + lane;
-      if (p < p_hi) {
+      if (p < a.npair) {
         const Pair pr = a.pairs[p];
         const Shape<double> &A = a.shapes[pr.sa];
         const Shape<double> &B = a.shapes[pr.sb];
@@ -771,18 +806,13 @@ __global__ void __launch_bounds__(128) recheck_kernel(const RArgs a) {
           V3<double> d = cA - cB;
           near = dot(d, d) <= (bsum + 1e-6) * (bsum + 1e-6);
         }
-        // same classifier in fp64 with the fp64 radii.  "Uncertain" in fp64 means touching to
-        // within rounding: MuJoCo reports a contact for distance <= margin, so it counts.
         if (near && narrow_item<double>(pr.kind, A, B, a.verts, PA, PB, a.pair_rsum[p]) != V_SEP) contact = true;
       }
       if (__any_sync(0xffffffffu, contact)) { contact = true; break; }
     }
-    if (lane == 0) {
-      if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) {
-        if (contact) atomicMin(&a.first_bad[e_idx], e_k);
-      } else {
-        a.valid[row] = contact ? 0 : 1;
-      }
+    if (lane == 0 && contact) {
+      if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) atomicMin(&a.first_bad[e_idx], e_k);
+      else a.valid[row] = 0;
     }
   }
 }
