@@ -54,6 +54,8 @@ struct mjb_model {
   float *d_stage_q = nullptr; uint8_t *d_stage_v = nullptr; size_t stage_rows = 0;
   float *h_pin_q = nullptr; uint8_t *h_pin_v = nullptr; size_t pin_rows = 0;
   cudaStream_t own_stream = nullptr;
+  cudaStream_t copy_stream = nullptr; cudaEvent_t ev_ready_reset = nullptr;   // streamed host entry point
+  unsigned long long *d_rows_ready = nullptr, *h_progress = nullptr; size_t progress_cap = 0;
   cudaStream_t last_stream = nullptr;
   long long rows_total = 0, launches = 0;
 };
@@ -203,6 +205,8 @@ extern "C" void mjb_model_destroy(mjb_model *m) {
   if (m->h_pin_q) cudaFreeHost(m->h_pin_q);
   if (m->h_pin_v) cudaFreeHost(m->h_pin_v);
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
+  if (m->copy_stream) { cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_ready_reset); cudaFree(m->d_rows_ready); }
+  if (m->h_progress) cudaFreeHost(m->h_progress);
   cudaGetLastError();
   delete m;
 }
@@ -274,6 +278,13 @@ extern "C" int mjb_check_configs(mjb_model *m, const float *d_q, int64_t n, int3
   return launch_validity(m, k, r, st);
 }
 
+// Host buffers in, host mask out.  The rows are copied in chunks on a second stream while ONE
+// validity launch is already consuming them: after every chunk the copy stream publishes the number
+// of rows that have landed (an 8-byte copy from a pinned progress table), and a warp whose tile lies
+// beyond that mark waits for it (validity_kernel, P0).  Copy and compute overlap without cutting
+// the batch into several launches (each of which would end in a tail of idle SMs).
+static const int64_t HOST_CHUNK_ROWS = 65536;
+
 extern "C" int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n, uint8_t *h_valid, uint32_t flags) {
   int rc = check_common(m, flags);
   if (rc) return rc;
@@ -291,11 +302,51 @@ extern "C" int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n,
     CU(cudaMalloc((void **)&m->d_stage_v, cap));
     m->stage_rows = cap;
   }
-  CU(cudaMemcpyAsync(m->d_stage_q, h_q, (size_t)n * nq * sizeof(float), cudaMemcpyHostToDevice, st));
-  rc = mjb_check_configs(m, m->d_stage_q, n, nq, m->d_stage_v, flags, st);
-  if (rc) return rc;
+  const int64_t nchunk = (n + HOST_CHUNK_ROWS - 1) / HOST_CHUNK_ROWS;
+  if (nchunk < 2) {  // small batch: nothing to overlap
+    CU(cudaMemcpyAsync(m->d_stage_q, h_q, (size_t)n * nq * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = mjb_check_configs(m, m->d_stage_q, n, nq, m->d_stage_v, flags, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_valid, m->d_stage_v, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MJB_OK;
+  }
+  if (!m->copy_stream) {
+    CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&m->ev_ready_reset, cudaEventDisableTiming));
+    CU(cudaMalloc((void **)&m->d_rows_ready, sizeof(unsigned long long)));
+  }
+  if ((size_t)nchunk > m->progress_cap) {
+    CU(cudaStreamSynchronize(m->copy_stream));
+    if (m->h_progress) cudaFreeHost(m->h_progress);
+    m->h_progress = nullptr;
+    size_t cap = std::max<size_t>((size_t)nchunk, 64);
+    CU(cudaMallocHost((void **)&m->h_progress, cap * sizeof(unsigned long long)));
+    m->progress_cap = cap;
+  }
+  // compute stream: reset the progress word, then launch; the kernel starts polling right away
+  CU(cudaMemsetAsync(m->d_rows_ready, 0, sizeof(unsigned long long), st));
+  CU(cudaEventRecord(m->ev_ready_reset, st));
+  if ((rc = ensure_recheck(m, (size_t)n, st))) return rc;
+  KArgs k = m->kargs;
+  k.mode = MODE_DENSE; k.q = m->d_stage_q; k.ldq = nq; k.n = n; k.valid = m->d_stage_v; k.flags = flags;
+  k.rows_ready = m->d_rows_ready;
+  RArgs r = m->rargs;
+  r.mode = MODE_DENSE; r.q = m->d_stage_q; r.ldq = nq; r.valid = m->d_stage_v;
+  m->rows_total += n;
+  if ((rc = launch_validity(m, k, r, st))) return rc;
+  // copy stream: chunks in row order, each followed by its progress mark
+  CU(cudaStreamWaitEvent(m->copy_stream, m->ev_ready_reset, 0));
+  for (int64_t c = 0; c < nchunk; c++) {
+    const int64_t r0 = c * HOST_CHUNK_ROWS, r1 = std::min<int64_t>(n, r0 + HOST_CHUNK_ROWS);
+    m->h_progress[c] = (unsigned long long)r1;
+    CU(cudaMemcpyAsync(m->d_stage_q + (size_t)r0 * nq, h_q + (size_t)r0 * nq, (size_t)(r1 - r0) * nq * sizeof(float),
+                       cudaMemcpyHostToDevice, m->copy_stream));
+    CU(cudaMemcpyAsync(m->d_rows_ready, &m->h_progress[c], sizeof(unsigned long long), cudaMemcpyHostToDevice, m->copy_stream));
+  }
   CU(cudaMemcpyAsync(h_valid, m->d_stage_v, (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(m->copy_stream));
   return MJB_OK;
 }
 

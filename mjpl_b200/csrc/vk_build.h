@@ -587,7 +587,17 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
   // once per run of pairs
   for (int r = 0; r < H.nrounds; r++) {
     int b = H.round_start[r], e = (r + 1 < H.nrounds) ? H.round_start[r + 1] : (int)ord.size();
+    const char *so = getenv("MJB_ROUND_SORT");   // experiment: "size" = similar hull sizes adjacent
+    const bool by_size = so && !strcmp(so, "size");
     std::stable_sort(ord.begin() + b, ord.begin() + e, [&](int x, int y) {
+      if (by_size) {
+        const int ax = H.shapes[tp[x].p.sa].nvert, ay = H.shapes[tp[y].p.sa].nvert;
+        if (ax != ay) return ax > ay;
+        if (tp[x].p.sa != tp[y].p.sa) return tp[x].p.sa < tp[y].p.sa;
+        const int bx = H.shapes[tp[x].p.sb].nvert, by = H.shapes[tp[y].p.sb].nvert;
+        if (bx != by) return bx > by;
+        return tp[x].p.sb < tp[y].p.sb;
+      }
       if (tp[x].p.sa != tp[y].p.sa) return tp[x].p.sa < tp[y].p.sa;
       return tp[x].p.sb < tp[y].p.sb;
     });

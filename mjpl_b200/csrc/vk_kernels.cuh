@@ -57,6 +57,7 @@ struct KArgs {
   int mode;
   // row sources
   const float *q; int ldq; long long n;                       // dense
+  const unsigned long long *rows_ready;   // dense, optional: rows [0, *rows_ready) have landed (host copy in flight)
   const float *q0, *q1; const long long *edge_prefix; long long nedge; float step;  // edges
   unsigned long long seed; long long row0;                    // sweep
   const double *c0, *c1; double ceps;                         // chains: fp64 end points (n,nq) and step
@@ -92,6 +93,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n"
       "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
 }
 // bounded spin: a copy that never lands (bad size / alignment) traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -389,6 +395,21 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
 
     // ---- P0: the warp's rows -> shared (one TMA bulk copy per warp tile) -----------------------------
     if (a.mode == MODE_DENSE) {
+      if (a.rows_ready) {
+        // rows are still being copied host -> device on another stream (mjb_check_configs_host): the
+        // copy publishes its progress after every chunk; tiles are handed out in row order, so a
+        // warp only ever waits for the chunk that holds its own rows.  Bounded: a copy that never
+        // lands traps instead of hanging the GPU.
+        if (lane == 0) {
+          const unsigned long long need = (unsigned long long)(row_base + rows_here);
+          const long long t0 = clock64();
+          while (ld_acquire_sys(a.rows_ready) < need) {
+            __nanosleep(256);
+            if (clock64() - t0 > 8000000000ll) __trap();
+          }
+        }
+        __syncwarp();
+      }
       if (dense_bulk && rows_here == 32) {
         if (lane == 0) {
           fence_proxy_async();

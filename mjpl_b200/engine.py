@@ -51,6 +51,7 @@ class ValidityEngine:
             _abi.check(L.mjb_model_create(C.byref(desc), C.byref(h)))
         self._h = h
         self._L = L
+        self._host_mask = None   # pinned result buffer of the host entry point (grown on demand)
         del keep
 
     def close(self):
@@ -104,8 +105,14 @@ class ValidityEngine:
 
     # ------------------------------------------------------------------ entry points
     def valid_configs(self, Q, flags: int = CHECK_LIMITS | CHECK_COLLISION):
-        """(n,nq) -> (n,) bool, same container kind as the input (numpy / CPU tensor / CUDA tensor)."""
+        """(n,nq) -> (n,) bool, same container kind as the input (numpy / CPU tensor / CUDA tensor).
+
+        Host containers go through ``mjb_check_configs_host``: the rows are copied in chunks while the
+        (single) validity launch is already consuming them, so copy and compute overlap.
+        """
         torch = _torch()
+        if isinstance(Q, np.ndarray) or (torch.is_tensor(Q) and not Q.is_cuda):
+            return self._valid_host(Q, flags)
         with torch.cuda.device(self.device):
             q, kind = self._rows(Q)
             n = q.shape[0]
@@ -114,15 +121,30 @@ class ValidityEngine:
                 _abi.check(self._L.mjb_check_configs(self._h, q.data_ptr(), n, q.stride(0), out.data_ptr(), flags, self._stream()))
             return self._back(out.bool() if not (flags & _abi.NO_FP64_RECHECK) else out, kind)
 
+    def _valid_host(self, Q, flags: int):
+        torch = _torch()
+        is_np = isinstance(Q, np.ndarray)
+        if Q.ndim != 2 or Q.shape[1] != self.nq:
+            raise ValueError(f"expected an (n, {self.nq}) {'array' if is_np else 'tensor'} of configurations")
+        if is_np:
+            rows = np.ascontiguousarray(Q, dtype=np.float32)
+            ptr = rows.ctypes.data
+        else:
+            rows = Q.to(dtype=torch.float32).contiguous()
+            ptr = rows.data_ptr()
+        n = int(rows.shape[0])
+        if self._host_mask is None or self._host_mask.numel() < n:
+            self._host_mask = torch.empty(max(n, 4096), dtype=torch.uint8, pin_memory=True)
+        out = self._host_mask[:n]
+        if n:
+            with torch.cuda.device(self.device):
+                _abi.check(self._L.mjb_check_configs_host(self._h, ptr, n, out.data_ptr(), flags))
+        res = out.clone() if (flags & _abi.NO_FP64_RECHECK) else out.bool()
+        return res.numpy() if is_np else res
+
     def valid_configs_host(self, Q: np.ndarray, flags: int = CHECK_LIMITS | CHECK_COLLISION) -> np.ndarray:
         """Host buffers straight through ``mjb_check_configs_host`` (copies inside the call)."""
-        Q = np.ascontiguousarray(Q, dtype=np.float32)
-        if Q.ndim != 2 or Q.shape[1] != self.nq:
-            raise ValueError(f"expected an (n, {self.nq}) array of configurations")
-        out = np.empty(len(Q), np.uint8)
-        with _torch().cuda.device(self.device):
-            _abi.check(self._L.mjb_check_configs_host(self._h, Q.ctypes.data, len(Q), out.ctypes.data, flags))
-        return out.astype(bool)
+        return np.asarray(self._valid_host(np.asarray(Q), flags)).astype(bool)
 
     def fk(self, Q):
         """mj_kinematics for a block: -> xpos (n,nbody,3), xquat (n,nbody,4), fp32."""

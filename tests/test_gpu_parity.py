@@ -299,3 +299,28 @@ def test_full_size_edge_batch_properties():
         dense = eng.valid_configs(W.astype(np.float32), _abi.CHECK_COLLISION)
         first = int(np.argmin(dense)) if not dense.all() else -1
         assert bool(v[idx[k]]) == bool(dense.all()) and int(fb[idx[k]]) == first
+
+
+def test_streamed_host_entry_point_matches_device_path():
+    """mjb_check_configs_host copies rows chunk by chunk while one launch consumes them (progress
+    word polled by the kernel): same mask as the device-resident path for pageable numpy rows, pinned
+    CPU tensors, and sizes around the chunk boundaries; repeated calls reuse the staging buffers."""
+    import torch
+
+    model = models.load("franka_scene_with_obstacles")
+    eng = mj.get_engine(model, [("left_finger", "right_finger")])
+    big = rows(model, 300_001, 21)
+    want = eng.valid_configs(torch.from_numpy(big).cuda()).cpu().numpy()
+    for n in (65_535, 65_536, 65_537, 131_073, 300_001):
+        np.testing.assert_array_equal(eng.valid_configs(big[:n]), want[:n])
+    pinned = torch.from_numpy(big).pin_memory()
+    got = eng.valid_configs(pinned)
+    assert got.device.type == "cpu" and got.dtype == torch.bool
+    np.testing.assert_array_equal(got.numpy(), want)
+    for _ in range(3):
+        np.testing.assert_array_equal(eng.valid_configs_host(big), want)
+    # a shorter batch after a longer one, and limits-only / collision-only flags
+    np.testing.assert_array_equal(eng.valid_configs(big[:70_000]), want[:70_000])
+    lim = eng.valid_configs(big[:100_000], 1)
+    col = eng.valid_configs(big[:100_000], 2)
+    np.testing.assert_array_equal(lim & col, want[:100_000])
