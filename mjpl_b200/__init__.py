@@ -23,6 +23,7 @@ from .lie import SE3, SO3
 from .engine import EngineUnavailable, ValidityEngine, get_engine
 from .model import Model
 from .planning import RRT, BatchedRRT, path_length, smooth_path
+from .trajectory import Trajectory, TrajectoryGenerator, generate_constrained_trajectory
 from .utils import all_joints, qpos_idx, qvel_idx, random_config, site_pose
 
 __all__ = (
@@ -38,10 +39,13 @@ __all__ = (
     "PoseConstraint",
     "SE3",
     "SO3",
+    "Trajectory",
+    "TrajectoryGenerator",
     "RRT",
     "ValidityEngine",
     "all_joints",
     "apply_constraints",
+    "generate_constrained_trajectory",
     "get_engine",
     "mjcf",
     "models",

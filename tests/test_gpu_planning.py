@@ -165,3 +165,32 @@ def test_batched_rrt_device_driver_many_queries():
             np.testing.assert_equal(p[0], q_init)
             np.testing.assert_equal(p[-1], g)
             replay_valid(model, allowed, p, 0.05)
+
+
+def test_trajectory_revalidation_matches_oracle():
+    """trajectory/utils.py:40-41 as one block: the first invalid sample of a dense trajectory is the
+    one the reference's per-sample loop would stop at (checked with the CPU oracle)."""
+    import oracle
+    from mjpl_b200.trajectory import Trajectory, first_invalid_position
+
+    model = models.load("franka_scene_with_obstacles")
+    allowed = [("left_finger", "right_finger")]
+    cons = [mj.JointLimitConstraint(model), mj.CollisionConstraint(model, allowed)]
+    orc = oracle.Oracle(model, allowed)
+    q0 = model.keyframe("home").qpos.copy()
+    rng = np.random.default_rng(4)
+    hits = 0
+    for _ in range(6):
+        q1 = q0.copy()
+        q1[:7] = rng.uniform(model.jnt_range[:7, 0], model.jnt_range[:7, 1])
+        pos = q0[None, :] + np.linspace(0, 1, 2001)[1:, None] * (q1 - q0)[None, :]
+        traj = Trajectory(dt=0.002, q_init=q0, positions=[p for p in pos], velocities=[], accelerations=[])
+        got = first_invalid_position(traj, cons)
+        ok, dist, _ = orc.check(pos.astype(np.float32).astype(np.float64), 3, want_dist=True)
+        bad = np.flatnonzero(~ok)
+        want = int(bad[0]) if len(bad) else -1
+        if got != want:  # only a sample inside the 1e-5 band may differ
+            lo, hi = sorted((got if got >= 0 else len(pos) - 1, want if want >= 0 else len(pos) - 1))
+            assert np.abs(dist[lo:hi + 1]).min() < 1e-5
+        hits += want >= 0
+    assert hits >= 2
