@@ -22,7 +22,7 @@ from .inverse_kinematics import DLSIKSolver, IKSolver
 from .lie import SE3, SO3
 from .engine import EngineUnavailable, ValidityEngine, get_engine
 from .model import Model
-from .planning import RRT, BatchedRRT, path_length, smooth_path
+from .planning import RRT, BatchedRRT, cartesian_plan, path_length, smooth_path
 from .trajectory import Trajectory, TrajectoryGenerator, generate_constrained_trajectory
 from .utils import all_joints, qpos_idx, qvel_idx, random_config, site_pose
 
@@ -45,6 +45,7 @@ __all__ = (
     "ValidityEngine",
     "all_joints",
     "apply_constraints",
+    "cartesian_plan",
     "generate_constrained_trajectory",
     "get_engine",
     "mjcf",

@@ -75,6 +75,30 @@ class SO3:
             yaw=float(np.arctan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z))),
         )
 
+    @staticmethod
+    def exp(omega):
+        """Rotation of angle |omega| about omega."""
+        om = np.asarray(omega, dtype=np.float64).reshape(3)
+        th = np.linalg.norm(om)
+        if th < 1e-12:
+            return SO3(np.concatenate([[1.0], 0.5 * om]))
+        return SO3(np.concatenate([[np.cos(0.5 * th)], np.sin(0.5 * th) / th * om]))
+
+    @staticmethod
+    def from_x_radians(theta):
+        return SO3.exp([theta, 0.0, 0.0])
+
+    @staticmethod
+    def from_y_radians(theta):
+        return SO3.exp([0.0, theta, 0.0])
+
+    @staticmethod
+    def from_z_radians(theta):
+        return SO3.exp([0.0, 0.0, theta])
+
+    def parameters(self):
+        return self.wxyz
+
     def inverse(self):
         w, x, y, z = self.wxyz
         return SO3([w, -x, -y, -z])
@@ -141,6 +165,36 @@ class SE3:
             half = 0.5 * th
             Vinv = np.eye(3) - 0.5 * K + (1.0 - half * np.cos(half) / np.sin(half)) / (th * th) * (K @ K)
         return np.concatenate([Vinv @ self._t, om])
+
+    @staticmethod
+    def exp(tangent):
+        """Inverse of ``log``: tangent ``[v, omega]`` -> SE3."""
+        tg = np.asarray(tangent, dtype=np.float64).reshape(6)
+        v, om = tg[:3], tg[3:]
+        th = np.linalg.norm(om)
+        K = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]])
+        if th < 1e-6:
+            V = np.eye(3) + 0.5 * K + (K @ K) / 6.0
+        else:
+            V = np.eye(3) + (1.0 - np.cos(th)) / (th * th) * K + (th - np.sin(th)) / (th ** 3) * (K @ K)
+        return SE3(SO3.exp(om), V @ v)
+
+    def interpolate(self, other, alpha: float = 0.5):
+        """Geodesic interpolation: ``self @ exp(alpha * log(self^-1 @ other))``; the end points are
+        returned as they are."""
+        if alpha <= 0.0:
+            return self
+        if alpha >= 1.0:
+            return other
+        return self.multiply(SE3.exp(alpha * self.inverse().multiply(other).log()))
+
+    def __eq__(self, other):
+        if not isinstance(other, SE3):
+            return NotImplemented
+        same_rot = min(np.abs(self._r.wxyz - other._r.wxyz).max(), np.abs(self._r.wxyz + other._r.wxyz).max()) < 1e-12
+        return bool(same_rot and np.abs(self._t - other._t).max() < 1e-12)
+
+    __hash__ = None
 
     def rminus(self, other) -> np.ndarray:
         return other.inverse().multiply(self).log()

@@ -153,3 +153,28 @@ def test_ik_argument_errors():
         s.solve_rows(np.zeros((2, 3)), np.zeros((1, 4)), np.zeros((2, 6)), "attachment_site")
     with pytest.raises(KeyError):
         s.solve_rows(np.zeros((1, 3)), np.array([[1.0, 0, 0, 0]]), np.zeros((1, 6)), "nope")
+
+
+def test_cartesian_path():
+    # reference test/test_cartesian_planner.py:114-200, on the engine
+    model = models.load("ur5e_scene")
+    site = "attachment_site"
+    cons = [mj.JointLimitConstraint(model), mj.CollisionConstraint(model)]
+    q_init = model.keyframe("home").qpos.copy()
+    current = mj.site_pose(model, q_init, site)
+    nxt = current.multiply(SE3.from_translation(np.array([0.02, 0.0, 0.0])))
+    final = nxt.multiply(SE3.from_translation(np.array([0.0, 0.02, 0.0])))
+    mid = current.multiply(SE3.from_translation(np.array([0.02, 0.01, 0.0])))
+    solver = mj.DLSIKSolver(model=model, joints=mj.all_joints(model), constraints=[cons[1]], pos_tolerance=1e-3,
+                            ori_tolerance=1e-3, seed=12345, max_attempts=5)
+    wps = mj.cartesian_plan(q_init, [nxt, final], site, solver, cons, lin_threshold=0.01, ori_threshold=0.1,
+                            collision_interval_check=(0.01, cons[1]))
+    assert len(wps) == 4
+    assert mj.obeys_constraints_batch(np.asarray(wps), cons).all()
+    np.testing.assert_equal(wps[0], q_init)
+    po = _free(model, site)
+    for w, want in zip(wps[1:], (nxt, mid, final)):
+        e = _err(po, want, w)
+        assert np.linalg.norm(e[:3]) <= 1e-3 and np.linalg.norm(e[3:]) <= 1e-3
+    with pytest.raises(ValueError, match="site"):
+        mj.cartesian_plan(q_init, [], "", solver, [])
