@@ -15,6 +15,7 @@
 #include "vk_build.h"
 #include "vk_core.cuh"
 #include "vk_kernels.cuh"
+#include "vk_split.cuh"
 
 using namespace vk;
 
@@ -48,6 +49,10 @@ struct mjb_model {
   float *d_pose = nullptr;
   unsigned long long *d_counters = nullptr;
   long long *d_recheck = nullptr; size_t recheck_cap = 0;
+  // two-kernel pipeline (MJB_SPLIT=1): poses / item bins / row flags of one batch
+  bool split = false; int split_tile = 0; size_t split_smem = 0, narrow_smem = 0; int narrow_grid = 0;
+  float *d_pose8 = nullptr; unsigned long long *d_bins = nullptr; uint32_t *d_row_flags = nullptr; size_t split_cap = 0;
+  size_t cur_rows = 0, split_min = 0, bin_cap_override = 0; bool use_split = false;   // decided per launch from the row count
   long long *d_edge_count = nullptr, *d_edge_prefix = nullptr; int *d_first_bad = nullptr; size_t edge_cap = 0;
   void *d_cub = nullptr; size_t cub_bytes = 0;
   double *d_chain_near = nullptr; long long *d_chain_nn = nullptr; size_t chain_cap = 0;
@@ -95,6 +100,18 @@ template <int TILE> static int try_tile(const vkb::HostModel &H, int max_smem_op
   *ctas = occ;
   *smem = L.total;
   return occ * TILE;
+}
+
+template <int TILE> static bool try_split(const vkb::HostModel &H, int max_smem_optin, size_t *smem) {
+  BroadLayout L = broad_layout<TILE>((int)H.shapes.size(), (int)H.pairs.size(), H.nmoving_shapes, H.nq);
+  if ((int)L.total > max_smem_optin) return false;
+  if ((int)H.shapes.size() - H.nmoving_shapes > TILE) return false;
+  if (cudaFuncSetAttribute(broad_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  *smem = L.total;
+  return true;
 }
 
 extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
@@ -164,6 +181,33 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   if (best < 0) return bail(fail(MJB_ERR_MODEL, "model tables do not fit in shared memory"));
   m->grid = m->num_sms * m->ctas_per_sm;
 
+  {  // Two-kernel pipeline (vk_split.cuh) for large batches.  Measured on B200 against the single
+     // kernel: 1M Franka rows 2.93 vs 3.00 ms, 12M UR5e edge waypoints 3.7 vs 5.0 ms; small launches
+     // (the planner's extends, ~10k rows) are faster in one kernel.  MJB_SPLIT=0 never, =1 always,
+     // default: batches of at least MJB_SPLIT_MIN rows (131072).
+    const char *sp = getenv("MJB_SPLIT");
+    const char *smin = getenv("MJB_SPLIT_MIN");
+    const int mode = sp ? atoi(sp) : -1;
+    m->split_min = mode == 1 ? 0 : (smin ? (size_t)atoll(smin) : (size_t)131072);
+    const char *bc = getenv("MJB_BIN_CAP");   // testing: tiny bins force the on-the-spot path of full bins
+    m->bin_cap_override = bc ? (size_t)atoll(bc) : 0;
+    if (mode != 0) {
+      int st_ = 0;
+      size_t ss = 0;
+      if (try_split<512>(H, optin, &ss)) st_ = 512;
+      else if (try_split<256>(H, optin, &ss)) st_ = 256;
+      else if (try_split<128>(H, optin, &ss)) st_ = 128;
+      NarrowLayout NL = narrow_layout((int)H.verts.size(), (int)H.shapes.size(), (int)H.pairs.size(), (int)H.adj.size());
+      int nocc = 0;
+      if (st_ && (int)NL.total <= optin &&
+          cudaFuncSetAttribute(narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess &&
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nocc, narrow_kernel, NARROW_THREADS, NL.total) == cudaSuccess && nocc >= 1) {
+        m->split = true; m->split_tile = st_; m->split_smem = ss; m->narrow_smem = NL.total; m->narrow_grid = m->num_sms * nocc;
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
   CU(cudaMalloc((void **)&m->d_pose, (size_t)m->grid * std::max(H.nslot, 1) * 7 * m->tile * sizeof(float)));
   CU(cudaMalloc((void **)&m->d_counters, C_NCOUNTERS * sizeof(unsigned long long)));
   CU(cudaMemset(m->d_counters, 0, C_NCOUNTERS * sizeof(unsigned long long)));
@@ -200,6 +244,7 @@ extern "C" void mjb_model_destroy(mjb_model *m) {
   cudaFree(m->d_shapes32); cudaFree(m->d_verts32); cudaFree(m->d_pairs); cudaFree(m->d_shapes64);
   cudaFree(m->d_verts64); cudaFree(m->d_fk64); cudaFree(m->d_rsum64); cudaFree(m->d_bsum64);
   cudaFree(m->d_body_slot); cudaFree(m->d_static_pose); cudaFree(m->d_adj_start); cudaFree(m->d_adj); cudaFree(m->d_pose); cudaFree(m->d_counters);
+  cudaFree(m->d_pose8); cudaFree(m->d_bins); cudaFree(m->d_row_flags);
   cudaFree(m->d_recheck); cudaFree(m->d_edge_count); cudaFree(m->d_edge_prefix); cudaFree(m->d_first_bad);
   cudaFree(m->d_cub); cudaFree(m->d_stage_q); cudaFree(m->d_stage_v); cudaFree(m->d_chain_near); cudaFree(m->d_chain_nn);
   if (m->h_pin_q) cudaFreeHost(m->h_pin_q);
@@ -220,7 +265,28 @@ extern "C" int mjb_model_pairs(const mjb_model *m, int32_t *g1, int32_t *g2) {
 
 static int ensure_edge_buffers(mjb_model *m, size_t ne, cudaStream_t st);
 
-static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st) {
+// capacity of bin b for `rows` rows: twice the calibrated average plus a floor (uniform random rows
+// are what the calibration saw; planner chains near obstacles produce more, and a full bin only
+// costs speed -- its items are decided on the spot)
+static size_t bin_capacity(const vkb::HostModel &H, int b, size_t rows) {
+  return (size_t)((2.0 * H.bin_expect[b] + 0.25) * (double)rows) + 1024;
+}
+
+static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st, bool may_split = true) {
+  m->cur_rows = rows;
+  m->use_split = may_split && m->split && rows >= m->split_min;
+  if (m->use_split && rows > m->split_cap) {
+    CU(cudaStreamSynchronize(st));
+    cudaFree(m->d_pose8); cudaFree(m->d_bins); cudaFree(m->d_row_flags);
+    m->d_pose8 = nullptr; m->d_bins = nullptr; m->d_row_flags = nullptr;
+    size_t cap = std::max<size_t>(rows, 1 << 16);
+    CU(cudaMalloc((void **)&m->d_pose8, cap * std::max(m->H.nslot, 1) * 8 * sizeof(float)));
+    size_t tot = 0;
+    for (int b = 0; b < NBIN; b++) tot += bin_capacity(m->H, b, cap);
+    CU(cudaMalloc((void **)&m->d_bins, tot * sizeof(unsigned long long)));
+    CU(cudaMalloc((void **)&m->d_row_flags, align_up(cap, 4)));
+    m->split_cap = cap;
+  }
   if (rows <= m->recheck_cap) return MJB_OK;
   if (m->d_recheck) { CU(cudaStreamSynchronize(st)); CU(cudaFree(m->d_recheck)); m->d_recheck = nullptr; }
   size_t cap = std::max<size_t>(rows, 1 << 20);
@@ -236,13 +302,34 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
   k.recheck_items = (unsigned long long *)(m->d_recheck + m->recheck_cap);
   r.recheck_items = k.recheck_items;
   k.item_cap = r.item_cap = m->recheck_cap;
-  switch (m->tile) {
-    case 512: validity_kernel<512><<<m->grid, 512, m->smem_bytes, st>>>(k); break;
-    case 256: validity_kernel<256><<<m->grid, 256, m->smem_bytes, st>>>(k); break;
-    default: validity_kernel<128><<<m->grid, 128, m->smem_bytes, st>>>(k); break;
+  if (m->use_split && (k.flags & F_COLLISION)) {
+    // two-kernel pipeline: broad phase writes poses + binned items, narrow phase consumes them
+    k.pose8 = m->d_pose8; k.bin_items = m->d_bins; k.row_flags = m->d_row_flags;
+    size_t off = 0;
+    for (int b = 0; b < NBIN; b++) {
+      const size_t c = bin_capacity(m->H, b, m->split_cap);
+      k.bin_off[b] = off; k.bin_capv[b] = m->bin_cap_override ? std::min(c, m->bin_cap_override) : c;
+      off += c;
+    }
+    CU(cudaMemsetAsync(m->d_row_flags, 0, align_up(std::min(m->cur_rows, m->split_cap), 4), st));
+    switch (m->split_tile) {
+      case 512: broad_kernel<512><<<m->num_sms, 512, m->split_smem, st>>>(k); break;
+      case 256: broad_kernel<256><<<m->num_sms, 256, m->split_smem, st>>>(k); break;
+      default: broad_kernel<128><<<m->num_sms, 128, m->split_smem, st>>>(k); break;
+    }
+    CU(cudaGetLastError());
+    narrow_kernel<<<m->narrow_grid, NARROW_THREADS, m->narrow_smem, st>>>(k);
+    CU(cudaGetLastError());
+    m->launches += 2;
+  } else {
+    switch (m->tile) {
+      case 512: validity_kernel<512><<<m->grid, 512, m->smem_bytes, st>>>(k); break;
+      case 256: validity_kernel<256><<<m->grid, 256, m->smem_bytes, st>>>(k); break;
+      default: validity_kernel<128><<<m->grid, 128, m->smem_bytes, st>>>(k); break;
+    }
+    CU(cudaGetLastError());
+    m->launches++;
   }
-  CU(cudaGetLastError());
-  m->launches++;
   if ((k.flags & F_COLLISION) && !(k.flags & F_NO_RECHECK)) {
     recheck_kernel<<<m->num_sms * 4, 128, 0, st>>>(r);
     CU(cudaGetLastError());
@@ -518,7 +605,8 @@ extern "C" int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, 
     CU(cudaMalloc((void **)&m->d_chain_nn, c * sizeof(long long)));
     m->chain_cap = c;
   }
-  if ((rc = ensure_recheck(m, (size_t)n * (size_t)kcap, st))) return rc;  // worst case, no host read-back
+  // worst case, no host read-back; the actual chains are short, so always the single kernel
+  if ((rc = ensure_recheck(m, (size_t)n * (size_t)kcap, st, false))) return rc;
   // 1. nearest node of every query's tree   2. chain lengths + prefix sums
   nearest_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_count,
                                                                   (const long long *)d_slots, d_targets, (long long)n, m->d_chain_nn);

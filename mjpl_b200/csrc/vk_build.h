@@ -40,6 +40,7 @@ struct HostModel {
   std::vector<Pair> pairs;              // processing order
   std::vector<int> pair_g1, pair_g2;    // MuJoCo geom ids, same order as `pairs`
   std::vector<double> pair_rsum64, pair_bsum64;  // fp64 copies of Pair::rsum / bsum
+  double bin_expect[NBIN] = {0};   // calibrated narrow-phase items per row that land in each bin (vk_split.cuh)
   int nrounds = 0;
   int round_start[MAX_ROUNDS + 1] = {0};  // pair index range of each round
   int round_gjk[MAX_ROUNDS] = {0};        // 1: the round holds GJK pairs, 0: plane / segment pairs
@@ -535,7 +536,11 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
       }
       H.calib_pen_rows += row_pen;
     }
-    for (size_t p = 0; p < tp.size(); p++) { H.calib_sphere_per_row += n_sph[p] / NCAL; H.calib_items_per_row += n_obb[p] / NCAL; }
+    for (size_t p = 0; p < tp.size(); p++) {
+      H.calib_sphere_per_row += n_sph[p] / NCAL; H.calib_items_per_row += n_obb[p] / NCAL;
+      const Shape<double> &A = H.shapes[tp[p].p.sa], &B = H.shapes[tp[p].p.sb];
+      if (item_needs_scan(tp[p].p, B)) H.bin_expect[item_bin(tp[p].p, A, B)] += n_obb[p] / NCAL;
+    }
     H.calib_pen_rows /= NCAL;
   }
   // ---- order: cheap analytic kinds first, then GJK pairs by contact likelihood (descending),

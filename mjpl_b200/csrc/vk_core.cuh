@@ -1042,6 +1042,24 @@ VK_HD bool ik_row(const FkTables<double> &fk, int nslot, const IkSpec &spec, con
   return ok;
 }
 
+// ------------------------------------------------------------------------------ two-kernel pipeline: item bins
+// (shared by the device kernels in vk_split.cuh and the host-side capacity estimate in vk_build.h)
+constexpr int NBIN = 8;
+// does the item need the hull-scanning narrow phase (narrow_kernel), or is it closed form?
+template <typename T> VK_HD bool item_needs_scan(const Pair &pr, const Shape<T> &B) {
+  return pr.kind == PK_GJK || (pr.kind == PK_PLANE && B.kind == SK_VERTS && B.nvert > 8);
+}
+// Bin of an item, so that the lanes of a warp scan hulls of similar size: plane-hull items and
+// tiny pairs first, then small-core-vs-hull pairs by hull size, then hull-vs-hull by total size.
+template <typename T> VK_HD int item_bin(const Pair &pr, const Shape<T> &A, const Shape<T> &B) {
+  if (pr.kind != PK_GJK) return 0;
+  const int lo = A.nvert < B.nvert ? A.nvert : B.nvert, hi = A.nvert < B.nvert ? B.nvert : A.nvert;
+  if (hi <= 8) return 0;
+  if (lo <= 8) return hi <= 48 ? 1 : (hi <= 64 ? 2 : (hi <= 102 ? 3 : 4));
+  const int nv = lo + hi;
+  return nv <= 130 ? 5 : (nv <= 210 ? 6 : 7);
+}
+
 // ------------------------------------------------------------------------------ counter-based row generator
 // splitmix64 finaliser over (seed, row, joint) -> 24-bit uniform in [0,1)
 VK_HD uint32_t sweep_bits(uint64_t seed, uint64_t row, uint32_t j) {

@@ -69,12 +69,18 @@ struct KArgs {
   long long *recheck_rows;              // rows to re-evaluate whole; capacity >= number of rows
   unsigned long long *recheck_items;    // (row | pair << 44) items to re-evaluate; capacity item_cap
   unsigned long long item_cap;
+  // two-kernel pipeline (broad_kernel -> narrow_kernel): poses and (row, pair) items of the whole batch
+  float *pose8;                         // [row][slot][8]: px py pz qw qx qy qz 0
+  unsigned long long *bin_items;        // NBIN regions: row | pair << 44
+  unsigned long long bin_off[NBIN], bin_capv[NBIN];   // start and capacity of each bin's region
+  uint32_t *row_flags;                  // 1 byte per row (bit 0: queued for whole-row fp64 re-evaluation)
 };
 
 // counters layout
 constexpr int C_TICKET = 0, C_RECHECK = 1, C_RTICKET = 2, C_RITEMS = 3, C_RITICKET = 4;   // per launch
-constexpr int C_ITEMS = 5, C_OVERFLOW = 6, C_UNCERTAIN = 7, C_ROWS = 8, C_TRIPS = 9, C_HIST = 10, C_NCOUNTERS = 20;  // statistics
-constexpr int C_PER_LAUNCH = 5;  // counters [0, C_PER_LAUNCH) are cleared before every launch
+constexpr int C_BIN = 5, C_BTICKET = 13;   // per launch: fill and consumer ticket of each bin
+constexpr int C_ITEMS = 21, C_OVERFLOW = 22, C_UNCERTAIN = 23, C_ROWS = 24, C_TRIPS = 25, C_HIST = 26, C_NCOUNTERS = 36;  // statistics
+constexpr int C_PER_LAUNCH = 21;  // counters [0, C_PER_LAUNCH) are cleared before every launch
 
 // ---------------------------------------------------------------------------- PTX helpers (sm_90+/sm_100a)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -324,3 +324,32 @@ def test_streamed_host_entry_point_matches_device_path():
     lim = eng.valid_configs(big[:100_000], 1)
     col = eng.valid_configs(big[:100_000], 2)
     np.testing.assert_array_equal(lim & col, want[:100_000])
+
+
+def test_single_kernel_and_two_kernel_pipeline_agree(monkeypatch):
+    """The validity path exists as one fused kernel and as a broad-phase + narrow-phase pipeline
+    (large batches); both must give the same mask, edge verdicts and first-bad indices, also when
+    the pipeline's item bins are so small that most items are decided on the spot."""
+    import torch
+
+    model = models.load("franka_scene_with_obstacles")
+    allowed = [("left_finger", "right_finger")]
+    Q = rows(model, 60_000, 31)
+    E0, E1 = rows(model, 1500, 32), rows(model, 1500, 33)
+    results = {}
+    for name, env in (("single", {"MJB_SPLIT": "0"}), ("split", {"MJB_SPLIT": "1"}), ("tiny_bins", {"MJB_SPLIT": "1", "MJB_BIN_CAP": "64"})):
+        for k in ("MJB_SPLIT", "MJB_BIN_CAP"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng = mj.ValidityEngine(model, allowed)     # not the cached engine: the knobs are read at creation
+        ve, fb = eng.valid_edges(E0, E1, 0.05, want_first_bad=True)
+        results[name] = (eng.valid_configs(Q), eng.valid_configs(Q, 2), ve, fb, eng.sweep(5, 100, 40_000).cpu().numpy())
+        eng.close()
+    for name in ("split", "tiny_bins"):
+        for got, want in zip(results[name], results["single"]):
+            np.testing.assert_array_equal(np.asarray(got), np.asarray(want))
+    orc = oracle.Oracle(model, allowed)
+    want, dist, _ = orc.check(Q[:20_000].astype(np.float64), 3, want_dist=True)
+    bad, outside = compare(results["split"][0][:20_000], want, dist)
+    assert outside == 0
