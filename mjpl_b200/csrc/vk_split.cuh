@@ -425,7 +425,8 @@ __global__ void __launch_bounds__(NARROW_THREADS, 2) narrow_kernel(const __grid_
   for (;;) {
     // fill: every lane without an item takes the next one; items of rows that already have a
     // contact are dropped, plane items are decided on the spot -- keep taking until every lane
-    // holds a GJK item or all bins are exhausted
+    // holds a GJK item or all bins are exhausted.  (Refilling only once 8..24 lanes are idle, so
+    // that the fetch code runs with more lanes active, measured 2.5-4.5 % slower.)
 #pragma unroll 1
     for (;;) {
       const unsigned need = __ballot_sync(0xffffffffu, !have);
