@@ -207,6 +207,7 @@ def main():
         eng.valid_configs(q_dev, FLAGS)
     torch.cuda.synchronize()
     eng.reset_stats()
+    eng.kernel_timing(True)   # CUDA events around each kernel of the launch, on the launch stream
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -220,6 +221,7 @@ def main():
         evs.append((e0, e1))
     barrier()
     clocks = sampler.stop()
+    ktime = eng.kernel_timing(False, read=True)
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
     st = eng.stats()
@@ -250,20 +252,26 @@ def main():
             peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
         else:
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-        kernel_ms = total_ms / args.steps / 1.0  # the validity kernel dominates the step (see profiles/)
+        # dominant kernel of the step and its live average duration (CUDA events recorded by the
+        # library around each kernel): validity_kernel, or broad_kernel when the batch ran as the
+        # two-kernel pipeline (broad phase + narrow phase)
+        nl = max(1, ktime["launches"])
+        first_ms, narrow_ms, fp64_ms = ktime["first_ms"] / nl, ktime["narrow_ms"] / nl, ktime["fp64_ms"] / nl
+        kernel_name = "broad_kernel" if ktime["pipeline"] == "broad+narrow" else "validity_kernel"
+        kernel_ms = first_ms if first_ms > 0 else total_ms / args.steps
         achieved = ALG_BYTES_PER_ROW * ROWS_PER_STEP / (kernel_ms * 1e-3) / 1e9
         traffic, fp32 = None, None
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
             prof = json.loads(tf.read_text())
-            traffic = prof.get("validity_kernel_dram_bytes_per_launch")
+            traffic = prof.get(f"{kernel_name}_dram_bytes_per_launch")
             if prof.get("fp32_flop_per_row_executed"):
                 # executed FP32 flops per row from the committed ncu capture x live row rate,
                 # against the nominal CUDA-core peak (148 SM x 128 lanes x 2 x 1.965 GHz)
-                tfl = prof["fp32_flop_per_row_executed"] * ROWS_PER_STEP / (kernel_ms * 1e-3) / 1e12
+                tfl = prof["fp32_flop_per_row_executed"] * ROWS_PER_STEP / (total_ms / args.steps * 1e-3) / 1e12
                 fp32 = {"achieved_tflops": tfl, "peak_tflops_nominal": prof["fp32_peak_tflops_nominal"],
                         "frac": tfl / prof["fp32_peak_tflops_nominal"], "flop_per_row": prof["fp32_flop_per_row_executed"],
-                        "source": "profiles/traffic.json (ncu op counts) x live rows/s"}
+                        "source": "profiles/traffic.json (ncu op counts of the single kernel) x live rows/s of the whole step"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -276,9 +284,12 @@ def main():
                     "d2h_bytes_per_step": int(ROWS_PER_STEP), "api": "ValidityEngine.valid_configs(pinned CPU tensor)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
+                         "kernel_ms": {"dominant": kernel_ms, "narrow_kernel": narrow_ms, "fp64_item_pass": fp64_ms,
+                                       "share_of_step": kernel_ms / (total_ms / args.steps)},
                          "note": "the path is FP32-ALU/latency bound, not HBM bound (37 algorithmic bytes per row); "
-                                 "see DESIGN.md and profiles/ for the pipe-utilisation view"},
+                                 "traffic above the algorithmic bytes is the pose/item scratch the two kernels of the "
+                                 "pipeline hand over (DESIGN.md section 3); see profiles/ for the pipe-utilisation view"},
             "roofline_fp32": fp32,
             "stats": {"valid_fraction": float(mask.float().mean()), "narrow_items_per_row": st["narrow_items"] / max(1, st["rows"]),
                       "fp64_rows_fraction": st["uncertain_rows"] / max(1, st["rows"]),

@@ -204,6 +204,16 @@ int mjb_ik_solve(mjb_model *m, const mjb_ik_spec *spec, const double *d_target_p
                  const double *d_target_quat, const double *d_q_init, int64_t n, double *d_q_out,
                  uint8_t *d_ok, int32_t *d_iters, double *d_err, void *stream);
 
+/*
+ * Per-kernel timing of the validity launches (measurement aid for bench.py; off by default).
+ * enable != 0 switches CUDA-event recording on for later launches (up to 2048 launches between
+ * reads).  If ms3 != NULL the device is synchronised and ms3 receives the summed durations since
+ * the last read: [0] validity_kernel, or broad_kernel when the batch ran as the two-kernel
+ * pipeline, [1] narrow_kernel (0 for the single kernel), [2] the fp64 item pass; *launches = number
+ * of validity launches summed.
+ */
+int mjb_kernel_timing(mjb_model *m, int enable, double *ms3, int64_t *launches);
+
 int mjb_get_stats(mjb_model *m, mjb_stats *out);   /* synchronises the handle's last stream */
 int mjb_reset_stats(mjb_model *m);
 

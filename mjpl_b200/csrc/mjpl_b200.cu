@@ -52,7 +52,9 @@ struct mjb_model {
   // two-kernel pipeline (MJB_SPLIT=1): poses / item bins / row flags of one batch
   bool split = false; int split_tile = 0; size_t split_smem = 0, narrow_smem = 0; int narrow_grid = 0;
   float *d_pose8 = nullptr; unsigned long long *d_bins = nullptr; uint32_t *d_row_flags = nullptr; size_t split_cap = 0;
-  size_t cur_rows = 0, split_min = 0, bin_cap_override = 0; bool use_split = false;   // decided per launch from the row count
+  size_t cur_rows = 0, split_min = 0, bin_cap_override = 0; bool use_split = false;
+  // optional per-kernel timing (mjb_kernel_timing): 4 events per validity launch
+  bool timing = false; std::vector<cudaEvent_t> tev; size_t tev_used = 0;   // decided per launch from the row count
   long long *d_edge_count = nullptr, *d_edge_prefix = nullptr; int *d_first_bad = nullptr; size_t edge_cap = 0;
   void *d_cub = nullptr; size_t cub_bytes = 0;
   double *d_chain_near = nullptr; long long *d_chain_nn = nullptr; size_t chain_cap = 0;
@@ -252,6 +254,7 @@ extern "C" void mjb_model_destroy(mjb_model *m) {
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   if (m->copy_stream) { cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_ready_reset); cudaFree(m->d_rows_ready); }
   if (m->h_progress) cudaFreeHost(m->h_progress);
+  for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
   cudaGetLastError();
   delete m;
 }
@@ -302,6 +305,9 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
   k.recheck_items = (unsigned long long *)(m->d_recheck + m->recheck_cap);
   r.recheck_items = k.recheck_items;
   k.item_cap = r.item_cap = m->recheck_cap;
+  cudaEvent_t *ev = nullptr;
+  if (m->timing && m->tev_used + 4 <= m->tev.size()) { ev = &m->tev[m->tev_used]; m->tev_used += 4; }
+  if (ev) CU(cudaEventRecord(ev[0], st));
   if (m->use_split && (k.flags & F_COLLISION)) {
     // two-kernel pipeline: broad phase writes poses + binned items, narrow phase consumes them
     k.pose8 = m->d_pose8; k.bin_items = m->d_bins; k.row_flags = m->d_row_flags;
@@ -318,6 +324,7 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
       default: broad_kernel<128><<<m->num_sms, 128, m->split_smem, st>>>(k); break;
     }
     CU(cudaGetLastError());
+    if (ev) CU(cudaEventRecord(ev[1], st));
     narrow_kernel<<<m->narrow_grid, NARROW_THREADS, m->narrow_smem, st>>>(k);
     CU(cudaGetLastError());
     m->launches += 2;
@@ -328,13 +335,16 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
       default: validity_kernel<128><<<m->grid, 128, m->smem_bytes, st>>>(k); break;
     }
     CU(cudaGetLastError());
+    if (ev) CU(cudaEventRecord(ev[1], st));
     m->launches++;
   }
+  if (ev) CU(cudaEventRecord(ev[2], st));
   if ((k.flags & F_COLLISION) && !(k.flags & F_NO_RECHECK)) {
     recheck_kernel<<<m->num_sms * 4, 128, 0, st>>>(r);
     CU(cudaGetLastError());
     m->launches++;
   }
+  if (ev) CU(cudaEventRecord(ev[3], st));
   m->last_stream = st;
   return MJB_OK;
 }
@@ -406,6 +416,7 @@ extern "C" int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n,
   if ((size_t)nchunk > m->progress_cap) {
     CU(cudaStreamSynchronize(m->copy_stream));
     if (m->h_progress) cudaFreeHost(m->h_progress);
+  for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
     m->h_progress = nullptr;
     size_t cap = std::max<size_t>((size_t)nchunk, 64);
     CU(cudaMallocHost((void **)&m->h_progress, cap * sizeof(unsigned long long)));
@@ -519,6 +530,30 @@ extern "C" int mjb_sweep_rows(mjb_model *m, uint64_t seed, int64_t row0, int64_t
   CU(cudaGetLastError());
   m->launches++;
   m->last_stream = st;
+  return MJB_OK;
+}
+
+extern "C" int mjb_kernel_timing(mjb_model *m, int enable, double *ms3, int64_t *launches) {
+  if (!m) return fail(MJB_ERR_ARG, "null model");
+  CU(cudaSetDevice(m->device));
+  if (ms3) {
+    CU(cudaDeviceSynchronize());
+    ms3[0] = ms3[1] = ms3[2] = 0.0;
+    for (size_t i = 0; i + 4 <= m->tev_used; i += 4) {
+      float a = 0, b = 0, c = 0;
+      CU(cudaEventElapsedTime(&a, m->tev[i], m->tev[i + 1]));
+      CU(cudaEventElapsedTime(&b, m->tev[i + 1], m->tev[i + 2]));
+      CU(cudaEventElapsedTime(&c, m->tev[i + 2], m->tev[i + 3]));
+      ms3[0] += a; ms3[1] += b; ms3[2] += c;
+    }
+    if (launches) *launches = (int64_t)(m->tev_used / 4);
+    m->tev_used = 0;
+  }
+  m->timing = enable != 0;
+  if (m->timing && m->tev.empty()) {
+    m->tev.resize(4 * 2048);
+    for (auto &e : m->tev) CU(cudaEventCreate(&e));
+  }
   return MJB_OK;
 }
 

@@ -196,6 +196,19 @@ class ValidityEngine:
                 _abi.check(self._L.mjb_sweep_rows(self._h, seed, row0, n, q.data_ptr(), self._stream()))
             return q
 
+    def kernel_timing(self, enable: bool = True, read: bool = False):
+        """Switch per-kernel CUDA-event timing of the validity launches on/off; with ``read`` return
+        ``{"first_ms", "narrow_ms", "fp64_ms", "launches", "pipeline"}`` summed since the last read."""
+        with _torch().cuda.device(self.device):
+            if not read:
+                _abi.check(self._L.mjb_kernel_timing(self._h, int(enable), None, None))
+                return None
+            ms = (C.c_double * 3)()
+            n = C.c_int64(0)
+            _abi.check(self._L.mjb_kernel_timing(self._h, int(enable), ms, C.byref(n)))
+            return {"first_ms": ms[0], "narrow_ms": ms[1], "fp64_ms": ms[2], "launches": int(n.value),
+                    "pipeline": "broad+narrow" if ms[1] > 0 else "single"}
+
     def stats(self) -> dict:
         st = _abi.Stats()
         _abi.check(self._L.mjb_get_stats(self._h, C.byref(st)))
