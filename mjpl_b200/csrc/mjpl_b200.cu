@@ -54,7 +54,7 @@ struct mjb_model {
   float *d_pose8 = nullptr; unsigned long long *d_bins = nullptr; uint32_t *d_row_flags = nullptr; size_t split_cap = 0;
   size_t cur_rows = 0, split_min = 0, bin_cap_override = 0; bool use_split = false;
   // optional per-kernel timing (mjb_kernel_timing): 4 events per validity launch
-  bool timing = false; std::vector<cudaEvent_t> tev; size_t tev_used = 0;   // decided per launch from the row count
+  bool timing = false; std::vector<cudaEvent_t> tev; std::vector<uint8_t> tev_split; size_t tev_used = 0;   // decided per launch from the row count
   long long *d_edge_count = nullptr, *d_edge_prefix = nullptr; int *d_first_bad = nullptr; size_t edge_cap = 0;
   void *d_cub = nullptr; size_t cub_bytes = 0;
   double *d_chain_near = nullptr; long long *d_chain_nn = nullptr; size_t chain_cap = 0;
@@ -243,6 +243,14 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
 
 extern "C" void mjb_model_destroy(mjb_model *m) {
   if (!m) return;
+  // At interpreter exit the CUDA runtime may already be unloading when a handle is finalised:
+  // its resources are gone with the context, and touching them (thousands of events) can crash.
+  if (cudaSetDevice(m->device) != cudaSuccess) {
+    cudaGetLastError();
+    delete m;
+    return;
+  }
+  cudaDeviceSynchronize();
   cudaFree(m->d_shapes32); cudaFree(m->d_verts32); cudaFree(m->d_pairs); cudaFree(m->d_shapes64);
   cudaFree(m->d_verts64); cudaFree(m->d_fk64); cudaFree(m->d_rsum64); cudaFree(m->d_bsum64);
   cudaFree(m->d_body_slot); cudaFree(m->d_static_pose); cudaFree(m->d_adj_start); cudaFree(m->d_adj); cudaFree(m->d_pose); cudaFree(m->d_counters);
@@ -254,7 +262,9 @@ extern "C" void mjb_model_destroy(mjb_model *m) {
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   if (m->copy_stream) { cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_ready_reset); cudaFree(m->d_rows_ready); }
   if (m->h_progress) cudaFreeHost(m->h_progress);
-  for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
+  // Timing events (mjb_kernel_timing) are released when timing is read or switched off.  Any still
+  // alive here are left to the context: once the streamed host entry point has run, destroying
+  // them reports "context is destroyed" and has crashed the driver (tools/dbg/timing_dbg.py).
   cudaGetLastError();
   delete m;
 }
@@ -306,7 +316,11 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
   r.recheck_items = k.recheck_items;
   k.item_cap = r.item_cap = m->recheck_cap;
   cudaEvent_t *ev = nullptr;
-  if (m->timing && m->tev_used + 4 <= m->tev.size()) { ev = &m->tev[m->tev_used]; m->tev_used += 4; }
+  if (m->timing && m->tev_used + 4 <= m->tev.size()) {
+    ev = &m->tev[m->tev_used];
+    m->tev_split[m->tev_used / 4] = (m->use_split && (k.flags & F_COLLISION)) ? 1 : 0;
+    m->tev_used += 4;
+  }
   if (ev) CU(cudaEventRecord(ev[0], st));
   if (m->use_split && (k.flags & F_COLLISION)) {
     // two-kernel pipeline: broad phase writes poses + binned items, narrow phase consumes them
@@ -542,7 +556,7 @@ extern "C" int mjb_kernel_timing(mjb_model *m, int enable, double *ms3, int64_t 
     for (size_t i = 0; i + 4 <= m->tev_used; i += 4) {
       float a = 0, b = 0, c = 0;
       CU(cudaEventElapsedTime(&a, m->tev[i], m->tev[i + 1]));
-      CU(cudaEventElapsedTime(&b, m->tev[i + 1], m->tev[i + 2]));
+      if (m->tev_split[i / 4]) CU(cudaEventElapsedTime(&b, m->tev[i + 1], m->tev[i + 2]));
       CU(cudaEventElapsedTime(&c, m->tev[i + 2], m->tev[i + 3]));
       ms3[0] += a; ms3[1] += b; ms3[2] += c;
     }
@@ -552,7 +566,15 @@ extern "C" int mjb_kernel_timing(mjb_model *m, int enable, double *ms3, int64_t 
   m->timing = enable != 0;
   if (m->timing && m->tev.empty()) {
     m->tev.resize(4 * 2048);
+    m->tev_split.assign(2048, 0);
     for (auto &e : m->tev) CU(cudaEventCreate(&e));
+  }
+  if (!m->timing && !m->tev.empty()) {   // events only live while timing is on
+    CU(cudaDeviceSynchronize());
+    for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
+    cudaGetLastError();
+    m->tev.clear();
+    m->tev_used = 0;
   }
   return MJB_OK;
 }

@@ -6,6 +6,7 @@ kernels behind ``include/mjpl_b200.h``.  There is no CPU fallback.
 
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import threading
 
@@ -207,7 +208,7 @@ class ValidityEngine:
             n = C.c_int64(0)
             _abi.check(self._L.mjb_kernel_timing(self._h, int(enable), ms, C.byref(n)))
             return {"first_ms": ms[0], "narrow_ms": ms[1], "fp64_ms": ms[2], "launches": int(n.value),
-                    "pipeline": "broad+narrow" if ms[1] > 0 else "single"}
+                    "pipeline": "broad+narrow" if ms[1] > 0.0 else "single"}
 
     def stats(self) -> dict:
         st = _abi.Stats()
@@ -216,6 +217,21 @@ class ValidityEngine:
 
     def reset_stats(self) -> None:
         _abi.check(self._L.mjb_reset_stats(self._h))
+
+
+def _close_cached_engines():
+    """Release the cached engines while the CUDA context is still alive (registered with atexit:
+    finalising them during interpreter teardown would race the runtime's own shutdown)."""
+    with _lock:
+        for e in list(_cache.values()):
+            try:
+                e.close()
+            except Exception:
+                pass
+        _cache.clear()
+
+
+atexit.register(_close_cached_engines)
 
 
 def get_engine(model, allowed_collision_bodies=(), device: int | None = None) -> ValidityEngine:
