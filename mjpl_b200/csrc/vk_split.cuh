@@ -366,9 +366,15 @@ __host__ __device__ inline NarrowLayout narrow_layout(int nvert, int nshape, int
   return L;
 }
 
-constexpr int NARROW_THREADS = 256;
+#ifndef VK_NARROW_THREADS
+#define VK_NARROW_THREADS 256
+#endif
+constexpr int NARROW_THREADS = VK_NARROW_THREADS;
+#ifndef VK_NARROW_CTAS
+#define VK_NARROW_CTAS 3   // resident CTAs per SM the register budget is set for (B200, 1M Franka rows: 2 -> 2.91 ms, 3 -> 2.77, 4 -> 2.92)
+#endif
 
-__global__ void __launch_bounds__(NARROW_THREADS, 2) narrow_kernel(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const NarrowLayout L = narrow_layout(a.nvert, a.nshape, a.npair, a.nadj);
   Vtx<float> *s_verts = reinterpret_cast<Vtx<float> *>(smem + L.verts);
