@@ -207,7 +207,8 @@ def main():
         eng.valid_configs(q_dev, FLAGS)
     torch.cuda.synchronize()
     eng.reset_stats()
-    eng.kernel_timing(True)   # CUDA events around each kernel of the launch, on the launch stream
+    if not os.environ.get("BENCH_NO_KERNEL_TIMING"):
+        eng.kernel_timing(True)   # CUDA events around each kernel of the launch, on the launch stream
     sampler = ClockSampler(local)
     barrier()
     sampler.start()

@@ -9,7 +9,7 @@ from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
 SOURCES = [_PKG / "csrc" / "mjpl_b200.cu"]
-HEADERS = [_PKG / "csrc" / n for n in ("vk_core.cuh", "vk_kernels.cuh", "vk_build.h")] + [_PKG.parent / "include" / "mjpl_b200.h"]
+HEADERS = sorted((_PKG / "csrc").glob("*.cuh")) + sorted((_PKG / "csrc").glob("*.h")) + [_PKG.parent / "include" / "mjpl_b200.h"]
 OUT = _PKG / "lib" / "libmjpl_b200.so"
 
 NVCC_FLAGS = [
