@@ -15,6 +15,7 @@ from .constraint import (
     JointLimitConstraint,
     PoseConstraint,
     apply_constraints,
+    apply_constraints_batch,
     obeys_constraints,
     obeys_constraints_batch,
 )
@@ -45,6 +46,7 @@ __all__ = (
     "ValidityEngine",
     "all_joints",
     "apply_constraints",
+    "apply_constraints_batch",
     "cartesian_plan",
     "generate_constrained_trajectory",
     "get_engine",

@@ -53,17 +53,55 @@ def _fusable(constraints):
 
 def obeys_constraints_batch(Q, constraints: list[Constraint]):
     """Batched :func:`obeys_constraints`: ``(n,nq) -> (n,) bool`` (numpy in -> numpy out,
-    tensor in -> tensor out).  Non-projecting built-in constraints on one model are fused into
-    one kernel launch; anything else is AND-ed constraint by constraint."""
+    tensor in -> tensor out).  The built-in non-projecting constraints on one model are fused into
+    one kernel launch (also when other constraints are in the list); anything else is AND-ed
+    constraint by constraint."""
     fused = _fusable(constraints)
     if fused is not None:
         eng, flags = fused
         return eng.valid_configs(Q, flags)
+    builtin = [c for c in constraints if type(c) in (JointLimitConstraint, CollisionConstraint)]
+    rest = [c for c in constraints if type(c) not in (JointLimitConstraint, CollisionConstraint)]
     out = None
-    for c in constraints:
+    if len(builtin) > 1 and _fusable(builtin) is not None:
+        eng, flags = _fusable(builtin)
+        out = eng.valid_configs(Q, flags)
+    else:
+        rest = list(constraints)
+    for c in rest:
         v = c.valid_configs(Q)
         out = v if out is None else (out & v)
     if out is None:
         n = len(Q)
         return np.ones(n, dtype=bool)
     return out
+
+
+def apply_constraints_batch(Q_old: np.ndarray, Q: np.ndarray, constraints: list[Constraint]):
+    """Batched :func:`apply_constraints` -> ``(Q_constrained, ok)``: every constraint is applied in
+    order to the rows that are still alive (a projecting constraint moves them, the others only
+    accept or reject), then the survivors are re-validated against all constraints as one block
+    (reference ``constraint/utils.py:38-43``).  Rows with ``ok == False`` are the ones for which the
+    reference returns ``None``; their output row is unspecified."""
+    Q_old = np.asarray(Q_old, dtype=np.float64)
+    out = np.array(Q, dtype=np.float64, copy=True)
+    ok = np.ones(len(out), dtype=bool)
+    for c in constraints:
+        idx = np.flatnonzero(ok)
+        if not len(idx):
+            break
+        if getattr(c, "projects", False):
+            moved, good = c.apply_batch(Q_old[idx], out[idx])
+            out[idx] = np.asarray(moved, dtype=np.float64)
+            ok[idx] = np.asarray(good, dtype=bool)
+        else:
+            ok[idx] = np.asarray(c.valid_configs(out[idx]), dtype=bool)
+    # Re-validation: a non-projecting constraint that ran after the last projection has already
+    # seen the final rows, so only the constraints up to that projection are checked again (the
+    # answer is the reference's; it re-checks everything, :43).
+    proj = [i for i, c in enumerate(constraints) if getattr(c, "projects", False)]
+    again = constraints[: proj[-1] + 1] if proj else []
+    idx = np.flatnonzero(ok)
+    if len(idx) and again:
+        ok[idx] = np.asarray(obeys_constraints_batch(out[idx], again), dtype=bool)
+    return out, ok

@@ -30,8 +30,14 @@ import time
 import numpy as np
 
 from ..constraint.constraint_interface import Constraint
-from ..constraint.utils import _fusable, obeys_constraints_batch
+from ..constraint.utils import apply_constraints_batch, _fusable, obeys_constraints_batch
 from ..utils import qpos_idx
+
+
+def _row_norms(D: np.ndarray) -> np.ndarray:
+    """Euclidean norm of every row, computed the way ``np.linalg.norm`` does for one vector
+    (``sqrt(x.dot(x))``) so that a batched step is bit-identical to the reference's scalar step."""
+    return np.sqrt(np.array([x.dot(x) for x in D], dtype=np.float64)) if len(D) else np.zeros(0)
 
 
 class _Forest:
@@ -87,7 +93,12 @@ class _Forest:
 
 
 class BatchedRRT:
-    """Lock-step bi-RRT over many (q_init, q_goal) queries; non-projecting constraints only."""
+    """Lock-step bi-RRT over many (q_init, q_goal) queries.
+
+    With non-projecting constraints whole extend chains are validated at once (device driver when
+    the constraints fuse into the engine).  With a projecting constraint (``PoseConstraint``) the
+    reference's step-by-step extend (``planning/utils.py:139-164``) is kept, but every step is
+    taken by all queries together: one projection block and one validity block per step."""
 
     def __init__(self, model, planning_joints: list[str], constraints: list[Constraint],
                  max_planning_time: float = 10.0, epsilon: float = 0.05, seed: int | None = None,
@@ -101,8 +112,6 @@ class BatchedRRT:
             raise ValueError("`epsilon` must be > 0.0")
         if goal_biasing_probability < 0.0 or goal_biasing_probability > 1.0:
             raise ValueError("`goal_biasing_probability` must be within [0.0, 1.0].")
-        if any(getattr(c, "projects", False) for c in constraints):
-            raise ValueError("BatchedRRT supports non-projecting constraints only")
         self.model = model
         self.planning_joints = planning_joints
         self.constraints = constraints
@@ -150,6 +159,35 @@ class BatchedRRT:
         good = np.minimum(good, k)
         last = forest.append_chains(rows, near_idx, chains, good)
         return forest.q[rows, last], last
+
+    # one extend with a projecting constraint: all queries take each step together
+    def _extend_projected(self, forest: _Forest, rows: np.ndarray, targets: np.ndarray):
+        eps = self.epsilon
+        last = forest.nearest(rows, targets)
+        q_old = forest.q[rows, last].copy()
+        alive = np.ones(len(rows), dtype=bool)
+        for _ in range(self.max_chain):
+            alive &= ~np.all(q_old == targets, axis=1)      # reference: `if np.array_equal(q_target, q): return q`
+            idx = np.flatnonzero(alive)
+            if not len(idx):
+                break
+            cur, tgt = q_old[idx], targets[idx]
+            d = tgt - cur
+            dist = _row_norms(d)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                q = np.where((dist <= eps)[:, None], tgt, cur + d * (eps / dist)[:, None])   # _step
+            qn, ok = apply_constraints_batch(cur, q, self.constraints)
+            self.stats["configs_checked"] = self.stats.get("configs_checked", 0) + len(idx)
+            self.stats["launches"] = self.stats.get("launches", 0) + 1
+            # the reference's stop rules (:151-160): no progress, or further from the target than before
+            ok &= _row_norms(qn - cur) >= 1e-8
+            ok &= _row_norms(tgt - qn) <= dist
+            good = idx[ok]
+            if len(good):
+                last[good] = forest.append_chains(rows[good], last[good], qn[ok][:, None, :], np.ones(len(good), dtype=np.int64))
+                q_old[good] = qn[ok]
+            alive[idx[~ok]] = False
+        return q_old, last
 
     def plan(self, q_inits: np.ndarray, q_goals: np.ndarray) -> list[list[np.ndarray]]:
         """``q_inits``, ``q_goals``: (B, nq).  Returns one waypoint list per query (empty on failure)."""
@@ -408,6 +446,7 @@ class BatchedRRT:
         if len(fixed) and not np.allclose(q_inits[:, fixed], q_goals[:, fixed], rtol=0, atol=1e-12):
             raise ValueError("goal configs have values for joints outside of the planner's planning joints "
                              "that don't match q_init")
+        projecting = any(getattr(c, "projects", False) for c in self.constraints)
         paths: list[list[np.ndarray]] = [[] for _ in range(B)]
         direct = np.linalg.norm(q_goals - q_inits, axis=1) <= self.epsilon
         for b in np.flatnonzero(direct):
@@ -439,8 +478,9 @@ class BatchedRRT:
                     t[q_idx] = r.uniform(lo, hi)[q_idx]
                     targets[i] = t
             # ---- extend A towards the samples, then B towards what A reached (connect) ------
-            qa, ia = self._extend(fa, active, targets)
-            qb, ib = self._extend(fb, active, qa)
+            extend = self._extend_projected if projecting else self._extend
+            qa, ia = extend(fa, active, targets)
+            qb, ib = extend(fb, active, qa)
             met = np.all(qa == qb, axis=1)
             for i in np.flatnonzero(met):
                 b = int(active[i])

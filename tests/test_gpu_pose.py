@@ -106,3 +106,56 @@ def test_constrained_rrt_with_pose_constraint():
     po = oracle.PoseOracle(model, "ee_site", ref.translation(), ref.rotation().wxyz, [INF] * 3 + [lim, lim, INF])
     assert all(po.valid_config(q) for q in P)
     assert oracle.Oracle(model, allowed).check(P, 3).all()
+
+
+def _constrained_problem(n_goals, seed=17):
+    """Franka obstacle scene, PoseConstraint(roll, pitch in +-0.1) + limits + collision, home as the
+    start and ``n_goals`` goals obtained by projecting random configurations onto the constraints
+    (examples/franka_constrained_move_to_pose.py:51-95 parameters)."""
+    model = models.load("franka_scene_with_obstacles")
+    allowed = [("left_finger", "right_finger")]
+    joints = [f"joint{i}" for i in range(1, 8)]
+    q_init = model.keyframe("home").qpos.copy()
+    ref = mj.site_pose(model, q_init, "ee_site")
+    lim = (-0.1, 0.1)
+    pose = mj.PoseConstraint(model, "ee_site", ref, roll=lim, pitch=lim, q_step=0.05)
+    cons = [mj.JointLimitConstraint(model), pose, mj.CollisionConstraint(model, allowed)]
+    rng = np.random.default_rng(seed)
+    goals = np.empty((0, model.nq))
+    while len(goals) < n_goals:
+        cand = np.tile(q_init, (4 * n_goals, 1))
+        cand[:, :7] += rng.uniform(-0.8, 0.8, size=(len(cand), 7))
+        pose.q_step = np.inf
+        proj, ok = mj.apply_constraints_batch(np.tile(q_init, (len(cand), 1)), cand, cons)
+        pose.q_step = 0.05
+        ok &= np.linalg.norm(proj - q_init, axis=1) > 0.5
+        goals = np.concatenate([goals, proj[ok]])
+    return model, allowed, joints, q_init, ref, lim, cons, goals[:n_goals]
+
+
+def test_batched_constrained_rrt():
+    """BASELINE configs[3] as a batch: every query takes each projected extend step together with the
+    others.  Paths start and end where they should and every waypoint satisfies all constraints
+    (pose checked with the numpy restatement, collisions with the CPU oracle)."""
+    model, allowed, joints, q_init, ref, lim, cons, goals = _constrained_problem(48)
+    B = len(goals)
+    planner = mj.BatchedRRT(model, joints, cons, max_planning_time=120, epsilon=0.05, seed=17, goal_biasing_probability=0.1)
+    paths = planner.plan(np.tile(q_init, (B, 1)), goals)
+    solved = [b for b in range(B) if paths[b]]
+    assert len(solved) >= 0.9 * B, planner.stats
+    po = oracle.PoseOracle(model, "ee_site", ref.translation(), ref.rotation().wxyz, [INF] * 3 + [lim, lim, INF])
+    orc = oracle.Oracle(model, allowed)
+    for b in solved:
+        P = np.asarray(paths[b])
+        np.testing.assert_array_equal(P[0], q_init)
+        np.testing.assert_array_equal(P[-1], goals[b])
+        assert np.asarray(mj.obeys_constraints_batch(P, cons)).all()
+    for b in solved[:8]:
+        P = np.asarray(paths[b])
+        assert all(po.valid_config(q) for q in P)
+        assert orc.check(P, 3).all()
+    # the same query alone through the reference-style sequential planner gives the same path
+    b = solved[0]
+    want = mj.RRT(model, joints, cons, max_planning_time=120, epsilon=0.05, seed=17 + b, goal_biasing_probability=0.1).plan_to_config(q_init, goals[b])
+    assert len(want) == len(paths[b]) and all(np.array_equal(x, y) for x, y in zip(want, paths[b]))
+    print(f"batched constrained rrt: {len(solved)}/{B} solved in {planner.stats['seconds']:.2f} s, {planner.stats}")

@@ -162,13 +162,44 @@ def bench_poses(nq_queries=1024, time_limit=60.0):
                       "solved": nsolved, "seconds": dt, "queries_per_s": nsolved / dt, "stats": planner.stats}))
 
 
+def bench_constrained(nq_queries=256, time_limit=120.0):
+    """BASELINE config #4 as a batch: PoseConstraint (roll, pitch within +-0.1) + limits + collision,
+    Franka obstacle scene, lock-step projected extends; the sequential planner timed on a few of
+    the same queries beside it."""
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
+    from tests.test_gpu_pose import _constrained_problem
+
+    model, allowed, joints, q_init, ref, lim, cons, goals = _constrained_problem(nq_queries)
+    B = len(goals)
+    planner = mj.BatchedRRT(model, joints, cons, max_planning_time=time_limit, epsilon=0.05, seed=17, goal_biasing_probability=0.1)
+    planner.plan(np.tile(q_init, (4, 1)), goals[:4])
+    t0 = time.perf_counter()
+    paths = planner.plan(np.tile(q_init, (B, 1)), goals)
+    dt = time.perf_counter() - t0
+    solved = [b for b in range(B) if paths[b]]
+    ok = all(np.asarray(mj.obeys_constraints_batch(np.asarray(paths[b]), cons)).all() for b in solved[:64])
+    nseq = 4
+    t1 = time.perf_counter()
+    seq_ok = 0
+    for b in range(nseq):
+        r = mj.RRT(model, joints, cons, max_planning_time=60, epsilon=0.05, seed=17 + b, goal_biasing_probability=0.1)
+        seq_ok += bool(r.plan_to_config(q_init, goals[b]))
+    seq_dt = time.perf_counter() - t1
+    print(json.dumps({"case": "constrained bi-RRT (PoseConstraint + limits + collision), Franka scene_with_obstacles", "queries": B,
+                      "solved": len(solved), "seconds": dt, "plans_per_s": len(solved) / dt, "paths_valid": bool(ok),
+                      "stats": planner.stats,
+                      "sequential_same_engine": {"queries": nseq, "solved": seq_ok, "seconds": seq_dt, "plans_per_s": seq_ok / seq_dt}}))
+
+
 if __name__ == "__main__":
     args = sys.argv[1:]
     nqq = int(args[args.index("--queries") + 1]) if "--queries" in args else 1024
-    which = [a for a in args if a in ("edges", "plans", "poses")] or ["edges", "plans"]
+    which = [a for a in args if a in ("edges", "plans", "poses", "constrained")] or ["edges", "plans"]
     if "edges" in which:
         bench_edges()
     if "plans" in which:
         bench_plans(nqq)
     if "poses" in which:
         bench_poses(nqq)
+    if "constrained" in which:
+        bench_constrained(min(nqq, 1024))
