@@ -35,9 +35,13 @@ from ..utils import qpos_idx
 
 
 def _row_norms(D: np.ndarray) -> np.ndarray:
-    """Euclidean norm of every row, computed the way ``np.linalg.norm`` does for one vector
-    (``sqrt(x.dot(x))``) so that a batched step is bit-identical to the reference's scalar step."""
-    return np.sqrt(np.array([x.dot(x) for x in D], dtype=np.float64)) if len(D) else np.zeros(0)
+    """Euclidean norm of every row.  Small blocks are computed the way ``np.linalg.norm`` does for
+    one vector (``sqrt(x.dot(x))``), so that a batched step is bit-identical to the reference's
+    scalar step (the tests compare whole paths with the sequential planner); large blocks use one
+    vectorised reduction, which can differ from that in the last bit."""
+    if len(D) <= 64:
+        return np.sqrt(np.array([x.dot(x) for x in D], dtype=np.float64)) if len(D) else np.zeros(0)
+    return np.sqrt(np.einsum("ij,ij->i", D, D))
 
 
 class _Forest:
@@ -83,6 +87,15 @@ class _Forest:
             self.count[b] = c + k
             last[i] = c + k - 1
         return last
+
+    def append_one(self, rows, parents, q):
+        """one node per tree (``rows`` are distinct trees); returns the new node indices"""
+        c = self.count[rows].copy()
+        self._grow(int(c.max()) + 1)
+        self.q[rows, c] = q
+        self.parent[rows, c] = parents
+        self.count[rows] = c + 1
+        return c
 
     def path_to_root(self, b: int, idx: int) -> list[np.ndarray]:
         out = []
@@ -184,7 +197,7 @@ class BatchedRRT:
             ok &= _row_norms(tgt - qn) <= dist
             good = idx[ok]
             if len(good):
-                last[good] = forest.append_chains(rows[good], last[good], qn[ok][:, None, :], np.ones(len(good), dtype=np.int64))
+                last[good] = forest.append_one(rows[good], last[good], qn[ok])
                 q_old[good] = qn[ok]
             alive[idx[~ok]] = False
         return q_old, last

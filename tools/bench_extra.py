@@ -202,4 +202,4 @@ if __name__ == "__main__":
     if "poses" in which:
         bench_poses(nqq)
     if "constrained" in which:
-        bench_constrained(min(nqq, 1024))
+        bench_constrained(nqq)
