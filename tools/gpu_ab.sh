@@ -1,5 +1,5 @@
 #!/bin/bash
-# same-box A/B: previous commit's kernel sources (tools/ab_prev) against the working tree
+# same-box A/B: a commit's kernel sources (tools/ab_prev, made by tools/make_ab_prev.sh) against the working tree
 F="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -shared -Xcompiler -fPIC"
 nvcc $F -o /tmp/prev.so tools/ab_prev/mjpl_b200/csrc/mjpl_b200.cu 2>&1 | grep error &
 nvcc $F -o /tmp/cur.so mjpl_b200/csrc/mjpl_b200.cu 2>&1 | grep error &
