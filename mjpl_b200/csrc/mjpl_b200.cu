@@ -184,13 +184,13 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   m->grid = m->num_sms * m->ctas_per_sm;
 
   {  // Two-kernel pipeline (vk_split.cuh) for large batches.  Measured on B200 against the single
-     // kernel: 1M Franka rows 2.93 vs 3.00 ms, 12M UR5e edge waypoints 3.7 vs 5.0 ms; small launches
-     // (the planner's extends, ~10k rows) are faster in one kernel.  MJB_SPLIT=0 never, =1 always,
-     // default: batches of at least MJB_SPLIT_MIN rows (131072).
+     // kernel (tools/split_crossover.py, Franka rows): 4k..128k rows 15-35 % slower, 262k 6 % slower,
+     // 524k 2 % faster, 1M 10 % faster; 12M UR5e edge waypoints 3.7 vs 5.0 ms.  MJB_SPLIT=0 never,
+     // =1 always, default: batches of at least MJB_SPLIT_MIN rows (500000).
     const char *sp = getenv("MJB_SPLIT");
     const char *smin = getenv("MJB_SPLIT_MIN");
     const int mode = sp ? atoi(sp) : -1;
-    m->split_min = mode == 1 ? 0 : (smin ? (size_t)atoll(smin) : (size_t)131072);
+    m->split_min = mode == 1 ? 0 : (smin ? (size_t)atoll(smin) : (size_t)500000);
     const char *bc = getenv("MJB_BIN_CAP");   // testing: tiny bins force the on-the-spot path of full bins
     m->bin_cap_override = bc ? (size_t)atoll(bc) : 0;
     if (mode != 0) {

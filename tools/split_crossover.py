@@ -1,0 +1,33 @@
+"""Raw validity call (rows resident) at several batch sizes, single kernel vs two-kernel pipeline:
+where does the pipeline start to win?  (sets the default of MJB_SPLIT_MIN)"""
+import os, sys, ctypes as C
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np, torch
+import mjpl_b200 as mj
+from mjpl_b200 import models, _abi
+from bench import make_rows, MODEL, ALLOWED
+
+model = models.load(MODEL)
+rows = make_rows(model, 1_000_000)
+L = _abi.lib()
+for n in (4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288):
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["MJB_SPLIT"] = mode
+        eng = mj.ValidityEngine(model, ALLOWED)
+        q = torch.from_numpy(rows[:n]).cuda()
+        out = torch.empty(n, dtype=torch.uint8, device="cuda")
+        def raw():
+            _abi.check(L.mjb_check_configs(eng._h, q.data_ptr(), n, 9, out.data_ptr(), 3, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        for _ in range(10): raw()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(40):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); raw(); e1.record(); ts.append((e0, e1))
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in ts)
+        res[mode] = ms[len(ms) // 2]
+        eng.close()
+    print(f"rows {n:7d}: single {res['0']*1e3:8.1f} us  pipeline {res['1']*1e3:8.1f} us  ratio {res['1']/res['0']:.3f}")
