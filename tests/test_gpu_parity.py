@@ -324,6 +324,9 @@ def test_streamed_host_entry_point_matches_device_path():
     lim = eng.valid_configs(big[:100_000], 1)
     col = eng.valid_configs(big[:100_000], 2)
     np.testing.assert_array_equal(lim & col, want[:100_000])
+    # twice the rows: large enough for the two-kernel pipeline, whose broad phase then polls the copy
+    double = np.concatenate([big, big])
+    np.testing.assert_array_equal(eng.valid_configs(double), np.concatenate([want, want]))
 
 
 def test_single_kernel_and_two_kernel_pipeline_agree(monkeypatch):
