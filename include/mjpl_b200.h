@@ -96,7 +96,9 @@ int mjb_check_configs(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, ui
                       uint32_t flags, void *stream);
 
 /* Same, host buffers: H2D copy, kernels, D2H copy, stream synchronised before returning.
- * This is what a Python caller holding numpy arrays uses (the end-to-end path). */
+ * This is what a Python caller holding numpy arrays uses (the end-to-end path).  Batches of more
+ * than 65536 rows are copied in chunks on a second stream while the (single) validity launch is
+ * already consuming them; pinned host memory makes those copies asynchronous. */
 int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n, uint8_t *h_valid,
                            uint32_t flags);
 
