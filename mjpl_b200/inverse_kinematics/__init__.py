@@ -1,4 +1,6 @@
-from .dls_ik_solver import DLSIKSolver
-from .ik_solver_interface import IKSolver
+"""IK for pose goals: the solver interface and the batched damped-least-squares solver."""
 
-__all__ = ("DLSIKSolver", "IKSolver")
+from .ik_solver_interface import IKSolver  # noqa: I001  (interface first: the solver imports it)
+from .dls_ik_solver import DLSIKSolver
+
+__all__ = ["IKSolver", "DLSIKSolver"]

@@ -1,27 +1,24 @@
-"""Abstract IK solver (reference: ``src/mjpl/inverse_kinematics/ik_solver_interface.py``)."""
+"""Pluggable inverse kinematics (the ``solver=`` argument of ``RRT.plan_to_pose(s)`` and
+``cartesian_plan``).  Mirrors the reference's interface, ``src/mjpl/inverse_kinematics/
+ik_solver_interface.py:7-28``: one method, ``solve_ik``."""
 
 from __future__ import annotations
 
-from abc import ABC, abstractmethod
+import abc
 
 import numpy as np
 
 from ..lie import SE3
 
 
-class IKSolver(ABC):
-    """Abstract base class for an inverse kinematics solver."""
+class IKSolver(abc.ABC):
+    """Anything that can turn a site pose into joint configurations."""
 
-    @abstractmethod
+    @abc.abstractmethod
     def solve_ik(self, pose: SE3, site: str, q_init_guess: np.ndarray | None) -> list[np.ndarray]:
-        """Solve IK.
+        """Configurations that put ``site`` at ``pose``.
 
-        Args:
-            pose: The target pose, in the world frame.
-            site: Name of the site for the target pose (i.e., the target frame).
-            q_init_guess: Initial guess for the joint configuration.
-
-        Returns:
-            A list of joint configurations that satisfy the target pose. An empty list is
-            returned if IK was unable to be solved.
+        ``pose`` is expressed in the world frame; ``q_init_guess`` seeds the search (``None``
+        means the model's default configuration).  The result is empty when no solution was
+        found; every returned configuration is a full ``qpos`` vector.
         """

@@ -1,18 +1,25 @@
-"""Trajectory container and generator interface (reference:
-``src/mjpl/trajectory/trajectory_interface.py``).  The reference's generators wrap Ruckig and
-TOPP-RA, which are not part of the validity path; any object with ``generate_trajectory`` fits."""
+"""What a trajectory is and what produces one.
+
+Same shape as the reference's ``src/mjpl/trajectory/trajectory_interface.py`` so that generators
+written against it plug in unchanged; the reference's own generators wrap Ruckig and TOPP-RA,
+which are third-party libraries outside the validity path.
+"""
 
 from __future__ import annotations
 
-from abc import ABC, abstractmethod
-from dataclasses import dataclass
+import abc
+import dataclasses
 
 import numpy as np
 
 
-@dataclass(frozen=True)
+@dataclasses.dataclass(frozen=True)
 class Trajectory:
-    """Trajectory data: ``n`` states at increments of ``dt`` over ``t = [dt, n*dt]``."""
+    """Sampled joint-space motion.
+
+    ``positions[k]``, ``velocities[k]`` and ``accelerations[k]`` describe the state at time
+    ``(k + 1) * dt``; ``q_init`` is the state at time zero, so ``n`` samples span ``n * dt`` seconds.
+    """
 
     dt: float
     q_init: np.ndarray
@@ -21,9 +28,9 @@ class Trajectory:
     accelerations: list[np.ndarray]
 
 
-class TrajectoryGenerator(ABC):
-    """Abstract base class for generating trajectories."""
+class TrajectoryGenerator(abc.ABC):
+    """Turns a list of waypoints into a :class:`Trajectory`."""
 
-    @abstractmethod
+    @abc.abstractmethod
     def generate_trajectory(self, waypoints: list[np.ndarray]) -> Trajectory | None:
-        """A trajectory that follows ``waypoints``, or None if one cannot be generated."""
+        """The trajectory through ``waypoints``; ``None`` when none can be produced."""
