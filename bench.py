@@ -293,7 +293,9 @@ def main():
                                  "pipeline hand over (DESIGN.md section 3); see profiles/ for the pipe-utilisation view"},
             "roofline_fp32": fp32,
             "stats": {"valid_fraction": float(mask.float().mean()), "narrow_items_per_row": st["narrow_items"] / max(1, st["rows"]),
-                      "fp64_rows_fraction": st["uncertain_rows"] / max(1, st["rows"]),
+                      # single kernel: rows that needed the fp64 pass; pipeline: uncertain (row, pair) items,
+                      # counted before it is known whether another pair already settles the row
+                      "fp64_reevaluated_per_row": st["uncertain_rows"] / max(1, st["rows"]),
                       "queue_overflow_rows": st["queue_overflow"]},
         }
         del out["config"]["model"]
