@@ -52,6 +52,7 @@ def lib():
         L.hs_ik.argtypes = [C.c_void_p, C.POINTER(_abi.IkSpec), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
         L.hs_pair_census.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.hs_bins.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_pair_verdict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -154,3 +155,11 @@ class HostSim:
         out = np.zeros((lib().hs_npair(self._h), 4), np.int64)
         lib().hs_pair_census(self._h, q.ctypes.data, len(q), out.ctypes.data)
         return out
+
+    def bins(self):
+        """(bin_expect[8], calibrated items per row, bin of every pair or -1 for closed-form pairs)"""
+        be = np.zeros(8)
+        tot = C.c_double(0)
+        pb = np.zeros(lib().hs_npair(self._h), np.int32)
+        lib().hs_bins(self._h, be.ctypes.data, C.byref(tot), pb.ctypes.data)
+        return be, tot.value, pb

@@ -291,4 +291,17 @@ void hs_pair_census(Sim *s, const float *q, int64_t n, int64_t *out) {
   }
 }
 
+// calibrated narrow-phase items per row for each bin of the two-kernel pipeline, the total over all
+// pairs, and every pair's bin (-1: closed form, decided in the broad phase)
+void hs_bins(Sim *s, double *bin_expect, double *items_per_row, int32_t *pair_bin) {
+  const auto &H = s->H;
+  for (int b = 0; b < NBIN; b++) bin_expect[b] = H.bin_expect[b];
+  *items_per_row = H.calib_items_per_row;
+  for (size_t p = 0; p < H.pairs.size(); p++) {
+    const Pair &pr = H.pairs[p];
+    const Shape<double> &A = H.shapes[pr.sa], &B = H.shapes[pr.sb];
+    pair_bin[p] = item_needs_scan(pr, B) ? item_bin(pr, A, B) : -1;
+  }
+}
+
 }  // extern "C"

@@ -356,3 +356,31 @@ def test_collision_ruleset_semantics():
         cr.obeys_ruleset(np.zeros((1, 2, 1)))
     with pytest.raises(KeyError):
         CollisionRuleset(m, [("link1", "nope")])
+
+
+def test_pipeline_bins_from_calibration():
+    """Host side of the two-kernel pipeline: every pair that needs hull scans has a bin, closed-form
+    pairs (plane against a box / capsule, capsule against capsule) have none, and the calibrated
+    per-bin item rates that size the bins add up to no more than the calibrated total."""
+    from mjpl_b200 import models
+    from tests.hostsim import HostSim
+
+    m = models.load("franka_scene_with_obstacles")
+    hs = HostSim(m, [("left_finger", "right_finger")])
+    be, total, pb = hs.bins()
+    pairs = hs.pairs()
+    assert len(pb) == len(pairs) == 324
+    assert ((pb >= -1) & (pb < 8)).all()
+    assert (be >= 0).all() and 0.5 < be.sum() <= total + 1e-9
+    mesh = m.geom_type == 7
+    both_mesh = mesh[pairs[:, 0]] & mesh[pairs[:, 1]]
+    assert both_mesh.any() and (pb[both_mesh] >= 5).all()     # hull against hull: the three largest bins
+    one_mesh = mesh[pairs[:, 0]] ^ mesh[pairs[:, 1]]
+    assert ((pb[one_mesh] >= 0) & (pb[one_mesh] <= 4)).all()  # hull against a small core (or the plane)
+    assert 0 < (pb == -1).sum() < 40
+    u = models.load("ur5e_scene")
+    be_u, total_u, pb_u = HostSim(u).bins()
+    caps = u.geom_type == 3
+    pu = HostSim(u).pairs()
+    both_caps = caps[pu[:, 0]] & caps[pu[:, 1]]
+    assert (pb_u[both_caps] == -1).all() and be_u[1:].sum() == 0.0   # UR5e: capsules, a cylinder, a plane
