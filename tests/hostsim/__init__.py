@@ -8,6 +8,7 @@ Not a product path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -25,7 +26,8 @@ def build(force=False):
     newest = max(p.stat().st_mtime for p in srcs)
     if force or not _SO.exists() or _SO.stat().st_mtime < newest:
         subprocess.run(
-            ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-x", "c++",
+            ["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+             *os.environ.get("HOSTSIM_CXXFLAGS", "").split(), "-x", "c++",   # e.g. -DVK_OBB_EDGE_AXES=1 for experiments
              str(_HERE / "hostsim.cpp"), "-o", str(_SO)],
             check=True, capture_output=True, text=True,
         )
