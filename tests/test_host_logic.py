@@ -384,3 +384,28 @@ def test_pipeline_bins_from_calibration():
     pu = HostSim(u).pairs()
     both_caps = caps[pu[:, 0]] & caps[pu[:, 1]]
     assert (pb_u[both_caps] == -1).all() and be_u[1:].sum() == 0.0   # UR5e: capsules, a cylinder, a plane
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): rank 0 prints one JSON
+    line with the contract's keys, other ranks print nothing; no GPU involved."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    cmd = [sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "RANK": "0"})
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "collision-checked configs/sec" and d["unit"] == "configs/s"
+    assert d["higher_is_better"] is True and d["value"] > 1e4 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "configs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
+    other = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env={**os.environ, "RANK": "1"})
+    assert other.returncode == 0 and other.stdout.strip() == ""
