@@ -35,6 +35,12 @@ extern "C" {
 #define MJB_CHECK_COLLISION 2u  /* CollisionConstraint.valid_config   (collision_constraint.py:26-30)  */
 #define MJB_NO_OBB_CULL 4u      /* debugging: skip the OBB mid-phase (results must not change) */
 #define MJB_NO_FP64_RECHECK 8u  /* debugging: leave uncertain rows marked 2 instead of re-evaluating */
+#define MJB_LIMITS_OUTWARD 16u  /* with MJB_CHECK_LIMITS: compare the fp32 row against the limits rounded OUTWARD to
+                                   fp32.  For callers whose rows were fp64 before the cast: such a caller decides the
+                                   limits itself on the fp64 values (joint_limit_constraint.py:19-20 is an fp64
+                                   compare) and ANDs its mask with the result; a row exactly on a limit that fp32
+                                   cannot represent is then not lost to the cast, and rows beyond the limits still
+                                   skip the collision work */
 
 /*
  * Constant tables taken from the MuJoCo model, under MjModel's own field names so that a real

@@ -16,7 +16,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "lib" / "libmjpl_b200.so"
 
 MJB_OK, MJB_ERR_ARG, MJB_ERR_MODEL, MJB_ERR_CUDA = 0, 1, 2, 3
-CHECK_LIMITS, CHECK_COLLISION, NO_OBB_CULL, NO_FP64_RECHECK = 1, 2, 4, 8
+CHECK_LIMITS, CHECK_COLLISION, NO_OBB_CULL, NO_FP64_RECHECK, LIMITS_OUTWARD = 1, 2, 4, 8, 16
 
 _I32P = C.POINTER(C.c_int32)
 _F64P = C.POINTER(C.c_double)

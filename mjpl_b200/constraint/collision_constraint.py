@@ -46,6 +46,8 @@ class CollisionRuleset:
 class CollisionConstraint(Constraint):
     """Constraint that enforces collision rules on a configuration."""
 
+    projects = False   # apply() never moves q: chains of configurations can be validated as one block
+
     def __init__(self, model, allowed_collision_bodies: list[tuple[str, str]] = []) -> None:
         self.model = model
         self.cr = CollisionRuleset(model, allowed_collision_bodies)

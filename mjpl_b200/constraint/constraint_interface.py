@@ -24,9 +24,11 @@ class Constraint(ABC):
     def apply(self, q_old: np.ndarray, q: np.ndarray) -> np.ndarray | None:
         """A configuration derived from ``q`` that obeys the constraint, or ``None``."""
 
-    #: constraints that never change ``q`` in ``apply`` (``q if valid else None``) can be
-    #: evaluated for a whole extend chain at once; projecting constraints set this to False.
-    projects: bool = False
+    #: True (the safe default, and what the reference assumes of every constraint): ``apply`` may
+    #: move ``q``, so planners call it step by step.  A constraint whose ``apply`` is exactly
+    #: ``q if valid_config(q) else None`` sets this to False; whole extend chains can then be
+    #: validated as one block through ``valid_configs``.
+    projects: bool = True
 
     def valid_configs(self, Q) -> np.ndarray:
         """Batched twin of :meth:`valid_config`; default = one scalar call per row."""

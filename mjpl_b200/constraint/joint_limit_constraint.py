@@ -18,6 +18,8 @@ from .constraint_interface import Constraint
 class JointLimitConstraint(Constraint):
     """Constraint that enforces joint limits on a configuration."""
 
+    projects = False   # apply() never moves q: chains of configurations can be validated as one block
+
     def __init__(self, model) -> None:
         self.model = model
         self.lower = model.jnt_range[:, 0]

@@ -90,16 +90,23 @@ def apply_constraints_batch(Q_old: np.ndarray, Q: np.ndarray, constraints: list[
         idx = np.flatnonzero(ok)
         if not len(idx):
             break
-        if getattr(c, "projects", False):
-            moved, good = c.apply_batch(Q_old[idx], out[idx])
-            out[idx] = np.asarray(moved, dtype=np.float64)
-            ok[idx] = np.asarray(good, dtype=bool)
+        if getattr(c, "projects", True):
+            if hasattr(c, "apply_batch"):
+                moved, good = c.apply_batch(Q_old[idx], out[idx])
+                out[idx] = np.asarray(moved, dtype=np.float64)
+                ok[idx] = np.asarray(good, dtype=bool)
+            else:   # a constraint written against the reference interface only: one apply() per row
+                for i in idx:
+                    r = c.apply(Q_old[i], out[i])
+                    ok[i] = r is not None
+                    if r is not None:
+                        out[i] = r
         else:
             ok[idx] = np.asarray(c.valid_configs(out[idx]), dtype=bool)
     # Re-validation: a non-projecting constraint that ran after the last projection has already
     # seen the final rows, so only the constraints up to that projection are checked again (the
     # answer is the reference's; it re-checks everything, :43).
-    proj = [i for i, c in enumerate(constraints) if getattr(c, "projects", False)]
+    proj = [i for i, c in enumerate(constraints) if getattr(c, "projects", True)]
     again = constraints[: proj[-1] + 1] if proj else []
     idx = np.flatnonzero(ok)
     if len(idx) and again:

@@ -63,7 +63,8 @@ struct mjb_model {
   cudaStream_t own_stream = nullptr;
   cudaStream_t copy_stream = nullptr; cudaEvent_t ev_ready_reset = nullptr;   // streamed host entry point
   unsigned long long *d_rows_ready = nullptr, *h_progress = nullptr; size_t progress_cap = 0;
-  cudaStream_t last_stream = nullptr;
+  // per-handle ordering of calls that arrive on different streams (see enter_stream)
+  cudaStream_t last_stream = nullptr; cudaEvent_t ev_last = nullptr; bool have_last = false;
   long long rows_total = 0, launches = 0;
 };
 
@@ -214,6 +215,7 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   CU(cudaMalloc((void **)&m->d_counters, C_NCOUNTERS * sizeof(unsigned long long)));
   CU(cudaMemset(m->d_counters, 0, C_NCOUNTERS * sizeof(unsigned long long)));
   CU(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&m->ev_last, cudaEventDisableTiming));
 
   // constant kernel arguments
   KArgs &k = m->kargs;
@@ -262,9 +264,9 @@ extern "C" void mjb_model_destroy(mjb_model *m) {
   if (m->own_stream) cudaStreamDestroy(m->own_stream);
   if (m->copy_stream) { cudaStreamDestroy(m->copy_stream); cudaEventDestroy(m->ev_ready_reset); cudaFree(m->d_rows_ready); }
   if (m->h_progress) cudaFreeHost(m->h_progress);
-  // Timing events (mjb_kernel_timing) are released when timing is read or switched off.  Any still
-  // alive here are left to the context: once the streamed host entry point has run, destroying
-  // them reports "context is destroyed" and has crashed the driver (tools/dbg/timing_dbg.py).
+  if (m->ev_last) cudaEventDestroy(m->ev_last);
+  for (cudaEvent_t e : m->tev) cudaEventDestroy(e);   // timing events still alive (timing left on)
+  m->tev.clear();
   cudaGetLastError();
   delete m;
 }
@@ -359,7 +361,6 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
     m->launches++;
   }
   if (ev) CU(cudaEventRecord(ev[3], st));
-  m->last_stream = st;
   return MJB_OK;
 }
 
@@ -372,6 +373,22 @@ static int check_common(mjb_model *m, uint32_t flags) {
   return MJB_OK;
 }
 
+// Every call on a handle uses the handle's scratch (counters with the tile ticket, pose arrays, item
+// bins, fp64 work lists, edge prefix sums).  Calls are therefore ordered per handle: each one leaves
+// an event behind on its stream, and a call that arrives on a DIFFERENT stream first makes its stream
+// wait for that event (also before any scratch buffer is grown and the old one freed).  Calls from
+// several host threads still have to be serialised by the caller (mjpl_b200.engine holds a lock).
+static int enter_stream(mjb_model *m, cudaStream_t st) {
+  if (m->have_last && m->last_stream != st) CU(cudaStreamWaitEvent(st, m->ev_last, 0));
+  return MJB_OK;
+}
+static int leave_stream(mjb_model *m, cudaStream_t st) {
+  CU(cudaEventRecord(m->ev_last, st));
+  m->last_stream = st;
+  m->have_last = true;
+  return MJB_OK;
+}
+
 extern "C" int mjb_check_configs(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, uint8_t *d_valid,
                                  uint32_t flags, void *stream) {
   int rc = check_common(m, flags);
@@ -380,13 +397,15 @@ extern "C" int mjb_check_configs(mjb_model *m, const float *d_q, int64_t n, int3
   if (n == 0) return MJB_OK;
   if (!d_q || !d_valid) return fail(MJB_ERR_ARG, "null device pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = enter_stream(m, st))) return rc;
   if ((rc = ensure_recheck(m, (size_t)n, st))) return rc;
   KArgs k = m->kargs;
   k.mode = MODE_DENSE; k.q = d_q; k.ldq = ldq; k.n = n; k.valid = d_valid; k.flags = flags;
   RArgs r = m->rargs;
   r.mode = MODE_DENSE; r.q = d_q; r.ldq = ldq; r.valid = d_valid;
   m->rows_total += n;
-  return launch_validity(m, k, r, st);
+  if ((rc = launch_validity(m, k, r, st))) return rc;
+  return leave_stream(m, st);
 }
 
 // Host buffers in, host mask out.  The rows are copied in chunks on a second stream while ONE
@@ -404,6 +423,7 @@ extern "C" int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n,
   if (!h_q || !h_valid) return fail(MJB_ERR_ARG, "null host pointer");
   const int nq = m->H.nq;
   cudaStream_t st = m->own_stream;
+  if ((rc = enter_stream(m, st))) return rc;
   if ((size_t)n > m->stage_rows) {
     CU(cudaStreamSynchronize(st));
     cudaFree(m->d_stage_q); cudaFree(m->d_stage_v);
@@ -430,24 +450,18 @@ extern "C" int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n,
   if ((size_t)nchunk > m->progress_cap) {
     CU(cudaStreamSynchronize(m->copy_stream));
     if (m->h_progress) cudaFreeHost(m->h_progress);
-  for (cudaEvent_t e : m->tev) cudaEventDestroy(e);
     m->h_progress = nullptr;
     size_t cap = std::max<size_t>((size_t)nchunk, 64);
     CU(cudaMallocHost((void **)&m->h_progress, cap * sizeof(unsigned long long)));
     m->progress_cap = cap;
   }
-  // compute stream: reset the progress word, then launch; the kernel starts polling right away
+  if ((rc = ensure_recheck(m, (size_t)n, st))) return rc;
+  // compute stream: reset the progress word.  Copy stream: every chunk in row order, each followed
+  // by its progress mark.  Only then is the kernel launched -- with every copy already queued, a
+  // launch that blocks (CUDA_LAUNCH_BLOCKING, compute-sanitizer, ncu replay) still sees its rows
+  // arrive, and no error path can leave a kernel polling for rows that will never be sent.
   CU(cudaMemsetAsync(m->d_rows_ready, 0, sizeof(unsigned long long), st));
   CU(cudaEventRecord(m->ev_ready_reset, st));
-  if ((rc = ensure_recheck(m, (size_t)n, st))) return rc;
-  KArgs k = m->kargs;
-  k.mode = MODE_DENSE; k.q = m->d_stage_q; k.ldq = nq; k.n = n; k.valid = m->d_stage_v; k.flags = flags;
-  k.rows_ready = m->d_rows_ready;
-  RArgs r = m->rargs;
-  r.mode = MODE_DENSE; r.q = m->d_stage_q; r.ldq = nq; r.valid = m->d_stage_v;
-  m->rows_total += n;
-  if ((rc = launch_validity(m, k, r, st))) return rc;
-  // copy stream: chunks in row order, each followed by its progress mark
   CU(cudaStreamWaitEvent(m->copy_stream, m->ev_ready_reset, 0));
   for (int64_t c = 0; c < nchunk; c++) {
     const int64_t r0 = c * HOST_CHUNK_ROWS, r1 = std::min<int64_t>(n, r0 + HOST_CHUNK_ROWS);
@@ -456,10 +470,17 @@ extern "C" int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n,
                        cudaMemcpyHostToDevice, m->copy_stream));
     CU(cudaMemcpyAsync(m->d_rows_ready, &m->h_progress[c], sizeof(unsigned long long), cudaMemcpyHostToDevice, m->copy_stream));
   }
+  KArgs k = m->kargs;
+  k.mode = MODE_DENSE; k.q = m->d_stage_q; k.ldq = nq; k.n = n; k.valid = m->d_stage_v; k.flags = flags;
+  k.rows_ready = m->d_rows_ready;
+  RArgs r = m->rargs;
+  r.mode = MODE_DENSE; r.q = m->d_stage_q; r.ldq = nq; r.valid = m->d_stage_v;
+  m->rows_total += n;
+  if ((rc = launch_validity(m, k, r, st))) return rc;
   CU(cudaMemcpyAsync(h_valid, m->d_stage_v, (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   CU(cudaStreamSynchronize(m->copy_stream));
-  return MJB_OK;
+  return leave_stream(m, st);
 }
 
 extern "C" int mjb_fk(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, float *d_xpos, float *d_xquat, void *stream) {
@@ -474,7 +495,6 @@ extern "C" int mjb_fk(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, fl
   fk_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(f);
   CU(cudaGetLastError());
   m->launches++;
-  m->last_stream = st;
   return MJB_OK;
 }
 
@@ -488,6 +508,7 @@ extern "C" int mjb_check_edges(mjb_model *m, const float *d_q0, const float *d_q
   if (ne == 0) return MJB_OK;
   if (!d_q0 || !d_q1 || !d_valid) return fail(MJB_ERR_ARG, "null device pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = enter_stream(m, st))) return rc;
   if ((rc = ensure_edge_buffers(m, (size_t)ne, st))) return rc;
   const int nq = m->H.nq;
   edge_count_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(d_q0, d_q1, ne, nq, ldq, step, m->d_edge_count, m->d_first_bad);
@@ -513,7 +534,7 @@ extern "C" int mjb_check_edges(mjb_model *m, const float *d_q0, const float *d_q
   edge_finalize_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(ne, m->d_first_bad, d_valid, d_first_bad);
   CU(cudaGetLastError());
   m->launches++;
-  return MJB_OK;
+  return leave_stream(m, st);
 }
 
 extern "C" int mjb_check_sweep(mjb_model *m, uint64_t seed, int64_t row0, int64_t n, uint8_t *d_valid, uint32_t flags, void *stream) {
@@ -523,13 +544,15 @@ extern "C" int mjb_check_sweep(mjb_model *m, uint64_t seed, int64_t row0, int64_
   if (n == 0) return MJB_OK;
   if (!d_valid) return fail(MJB_ERR_ARG, "null device pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = enter_stream(m, st))) return rc;
   if ((rc = ensure_recheck(m, (size_t)n, st))) return rc;
   KArgs k = m->kargs;
   k.mode = MODE_SWEEP; k.seed = seed; k.row0 = row0; k.n = n; k.valid = d_valid; k.flags = flags; k.ldq = m->H.nq;
   RArgs r = m->rargs;
   r.mode = MODE_SWEEP; r.seed = seed; r.row0 = row0; r.valid = d_valid;
   m->rows_total += n;
-  return launch_validity(m, k, r, st);
+  if ((rc = launch_validity(m, k, r, st))) return rc;
+  return leave_stream(m, st);
 }
 
 extern "C" int mjb_sweep_rows(mjb_model *m, uint64_t seed, int64_t row0, int64_t n, float *d_q, void *stream) {
@@ -543,7 +566,6 @@ extern "C" int mjb_sweep_rows(mjb_model *m, uint64_t seed, int64_t row0, int64_t
   sweep_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->kargs.fk, seed, row0, n, d_q);
   CU(cudaGetLastError());
   m->launches++;
-  m->last_stream = st;
   return MJB_OK;
 }
 
@@ -652,6 +674,7 @@ extern "C" int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, 
   if (!d_nodes || !d_parent || !d_count || !d_targets || !d_reached || !d_last) return fail(MJB_ERR_ARG, "null device pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int nq = m->H.nq;
+  if ((rc = enter_stream(m, st))) return rc;
   if ((rc = ensure_edge_buffers(m, (size_t)n, st))) return rc;
   if ((size_t)n > m->chain_cap) {
     CU(cudaStreamSynchronize(st));
@@ -689,7 +712,7 @@ extern "C" int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, 
       m->d_counters + C_OVERFLOW);
   CU(cudaGetLastError());
   m->launches += 4;
-  return MJB_OK;
+  return leave_stream(m, st);
 }
 
 // ---- PoseConstraint --------------------------------------------------------------------------------
@@ -715,7 +738,6 @@ static int launch_pose(mjb_model *m, const mjb_pose_spec *spec, const double *d_
   pose_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(a);
   CU(cudaGetLastError());
   m->launches++;
-  m->last_stream = st;
   return MJB_OK;
 }
 
@@ -746,7 +768,6 @@ extern "C" int mjb_ik_solve(mjb_model *m, const mjb_ik_spec *spec, const double 
   ik_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(a);
   CU(cudaGetLastError());
   m->launches++;
-  m->last_stream = st;
   return MJB_OK;
 }
 

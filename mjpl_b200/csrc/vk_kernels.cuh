@@ -30,7 +30,7 @@
 namespace vk {
 
 constexpr int MODE_DENSE = 0, MODE_EDGES = 1, MODE_SWEEP = 2, MODE_CHAINS = 3;
-constexpr uint32_t F_LIMITS = 1u, F_COLLISION = 2u, F_NO_OBB = 4u, F_NO_RECHECK = 8u;
+constexpr uint32_t F_LIMITS = 1u, F_COLLISION = 2u, F_NO_OBB = 4u, F_NO_RECHECK = 8u, F_LIMITS_OUTWARD = 16u;
 #ifndef VK_Q1
 #define VK_Q1 8
 #endif
@@ -177,8 +177,12 @@ __device__ __forceinline__ void edge_row(const float *q0, const float *q1, int l
 // and the target itself when that step covers the remaining distance.  Evaluated in fp64 exactly
 // like chain_append_kernel stores it, so the checked row is the fp32 rounding of the stored node.
 // reference: _constrained_extend / _step (src/mjpl/planning/utils.py:139-185)
+// `lo` / `hi` (optional): joint limits; the return value is the reference's JointLimitConstraint
+// answer for the fp64 chain point itself (joint_limit_constraint.py:19-20), decided BEFORE the point
+// is rounded to fp32 for the collision check.
 template <typename TO>
-__device__ __forceinline__ void chain_point(const double *c0, const double *c1, int nq, double eps, long long e, int k, TO *q) {
+__device__ __forceinline__ bool chain_point(const double *c0, const double *c1, int nq, double eps, long long e, int k, TO *q,
+                                            const double *lo = nullptr, const double *hi = nullptr) {
   double d2 = 0;
   for (int j = 0; j < nq; j++) {
     double d = c1[e * nq + j] - c0[e * nq + j];
@@ -186,12 +190,31 @@ __device__ __forceinline__ void chain_point(const double *c0, const double *c1, 
   }
   const double dist = sqrt(d2);
   const double reach = (double)(k + 1) * eps;
-  if (reach >= dist) {
-    for (int j = 0; j < nq; j++) q[j] = (TO)c1[e * nq + j];
-  } else {
-    const double s = reach / dist;
-    for (int j = 0; j < nq; j++) q[j] = (TO)(c0[e * nq + j] + s * (c1[e * nq + j] - c0[e * nq + j]));
+  const double s = reach >= dist ? 1.0 : reach / dist;
+  bool ok = true;
+  for (int j = 0; j < nq; j++) {
+    const double x = reach >= dist ? c1[e * nq + j] : c0[e * nq + j] + s * (c1[e * nq + j] - c0[e * nq + j]);
+    if (lo) ok = ok && (x >= lo[j]) && (x <= hi[j]);
+    q[j] = (TO)x;
   }
+  return ok;
+}
+
+// JointLimitConstraint on the fp32 row (reference: np.all((q >= lower) & (q <= upper)) in fp64,
+// joint_limit_constraint.py:19-20).  For a caller whose rows ARE fp32 this is the reference's answer
+// for that row.  A caller whose rows were fp64 decides the limits itself on the fp64 values and asks
+// for OUTWARD-rounded limits here, so that a row sitting exactly on a limit that fp32 cannot represent
+// is not thrown away by the cast (the exact mask is AND-ed by the caller: mjpl_b200/engine.py).
+__device__ __forceinline__ bool limits_ok(const float *q, int njnt, const double *lo, const double *hi, bool outward) {
+  bool ok = true;
+#pragma unroll 1
+  for (int j = 0; j < njnt; j++) {
+    const double x = (double)q[j];
+    const double l = outward ? (double)__double2float_rd(lo[j]) : lo[j];
+    const double h = outward ? (double)__double2float_ru(hi[j]) : hi[j];
+    ok = ok && (x >= l) && (x <= h);
+  }
+  return ok;
 }
 
 __device__ __forceinline__ Pose<float> load_pose(const float *ps, int slot, int cfg, int tile) {
@@ -459,20 +482,15 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
         edge_row<float>(a.q0, a.q1, a.ldq, nq, a.step, e_idx, e_k, q);
       } else if (a.mode == MODE_CHAINS) {
         edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
-        chain_point<float>(a.c0, a.c1, nq, a.ceps, e_idx, e_k, q);
+        const bool lim = a.flags & F_LIMITS;
+        lim_ok = chain_point<float>(a.c0, a.c1, nq, a.ceps, e_idx, e_k, q, lim ? a.jnt_lo : nullptr, lim ? a.jnt_hi : nullptr);
       } else if (a.mode == MODE_SWEEP) {
 #pragma unroll 1
         for (int j = 0; j < nq; j++)
           q[j] = sweep_value(a.seed, (uint64_t)(a.row0 + row), (uint32_t)j, a.fk.jnt_lo[j], a.fk.jnt_hi[j]);
       }
-      if (a.flags & F_LIMITS) {
-        // reference: np.all((q >= lower) & (q <= upper)) in fp64 (joint_limit_constraint.py:19-20)
-#pragma unroll 1
-        for (int j = 0; j < a.fk.njnt; j++) {
-          double x = (double)q[j];
-          lim_ok = lim_ok && (x >= a.jnt_lo[j]) && (x <= a.jnt_hi[j]);
-        }
-      }
+      if ((a.flags & F_LIMITS) && a.mode != MODE_CHAINS)
+        lim_ok = limits_ok(q, a.fk.njnt, a.jnt_lo, a.jnt_hi, a.flags & F_LIMITS_OUTWARD);
     }
     const bool do_coll = active && lim_ok && (a.flags & F_COLLISION);
     if (do_coll) {

@@ -204,19 +204,15 @@ __global__ void __launch_bounds__(TILE) broad_kernel(const __grid_constant__ KAr
         edge_row<float>(a.q0, a.q1, a.ldq, nq, a.step, e_idx, e_k, q);
       } else if (a.mode == MODE_CHAINS) {
         edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
-        chain_point<float>(a.c0, a.c1, nq, a.ceps, e_idx, e_k, q);
+        const bool lim = a.flags & F_LIMITS;
+        lim_ok = chain_point<float>(a.c0, a.c1, nq, a.ceps, e_idx, e_k, q, lim ? a.jnt_lo : nullptr, lim ? a.jnt_hi : nullptr);
       } else if (a.mode == MODE_SWEEP) {
 #pragma unroll 1
         for (int j = 0; j < nq; j++)
           q[j] = sweep_value(a.seed, (uint64_t)(a.row0 + row), (uint32_t)j, a.fk.jnt_lo[j], a.fk.jnt_hi[j]);
       }
-      if (a.flags & F_LIMITS) {
-#pragma unroll 1
-        for (int j = 0; j < a.fk.njnt; j++) {
-          double x = (double)q[j];
-          lim_ok = lim_ok && (x >= a.jnt_lo[j]) && (x <= a.jnt_hi[j]);
-        }
-      }
+      if ((a.flags & F_LIMITS) && a.mode != MODE_CHAINS)
+        lim_ok = limits_ok(q, a.fk.njnt, a.jnt_lo, a.jnt_hi, a.flags & F_LIMITS_OUTWARD);
       if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) {
         if (!lim_ok) atomicMin(&a.first_bad[e_idx], e_k);
       } else {

@@ -53,6 +53,12 @@ class ValidityEngine:
         self._h = h
         self._L = L
         self._host_mask = None   # pinned result buffer of the host entry point (grown on demand)
+        # a handle is not re-entrant (its scratch is per handle): host threads are serialised here,
+        # streams are ordered inside the library (csrc/mjpl_b200.cu: enter_stream / leave_stream)
+        self._call_lock = threading.RLock()
+        self._lo = np.ascontiguousarray(model.jnt_range[:, 0], dtype=np.float64)
+        self._hi = np.ascontiguousarray(model.jnt_range[:, 1], dtype=np.float64)
+        self._lim_dev = None
         del keep
 
     def close(self):
@@ -105,22 +111,50 @@ class ValidityEngine:
         return np.stack([g1, g2], axis=1)
 
     # ------------------------------------------------------------------ entry points
+    def _exact_limits(self, Q):
+        """``JointLimitConstraint.valid_config`` for rows that are wider than fp32, in the rows' own
+        precision and container (reference ``joint_limit_constraint.py:19-20``: a closed-interval fp64
+        compare).  The device kernels see the fp32 rounding of such rows, so they are asked for
+        outward-rounded limits (``MJB_LIMITS_OUTWARD``) and this mask settles the rows within one
+        fp32 ulp of a limit.  Returns None for rows that are fp32 (or narrower) already."""
+        torch = _torch()
+        if isinstance(Q, np.ndarray):
+            if Q.dtype != np.float64 or Q.ndim != 2 or Q.shape[1] != self.nq:
+                return None
+            return ((Q >= self._lo) & (Q <= self._hi)).all(axis=1)
+        if torch.is_tensor(Q) and Q.dtype == torch.float64 and Q.ndim == 2 and Q.shape[1] == self.nq:
+            if Q.is_cuda:
+                if self._lim_dev is None or self._lim_dev[0].device != Q.device:
+                    self._lim_dev = (torch.from_numpy(self._lo).to(Q.device), torch.from_numpy(self._hi).to(Q.device))
+                lo, hi = self._lim_dev
+            else:
+                lo, hi = torch.from_numpy(self._lo), torch.from_numpy(self._hi)
+            return ((Q >= lo) & (Q <= hi)).all(dim=1)
+        return None
+
     def valid_configs(self, Q, flags: int = CHECK_LIMITS | CHECK_COLLISION):
         """(n,nq) -> (n,) bool, same container kind as the input (numpy / CPU tensor / CUDA tensor).
 
         Host containers go through ``mjb_check_configs_host``: the rows are copied in chunks while the
         (single) validity launch is already consuming them, so copy and compute overlap.
+        Joint limits of fp64 rows are decided on the fp64 values (see ``_exact_limits``).
         """
         torch = _torch()
-        if isinstance(Q, np.ndarray) or (torch.is_tensor(Q) and not Q.is_cuda):
-            return self._valid_host(Q, flags)
-        with torch.cuda.device(self.device):
-            q, kind = self._rows(Q)
-            n = q.shape[0]
-            out = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
-            if n:
-                _abi.check(self._L.mjb_check_configs(self._h, q.data_ptr(), n, q.stride(0), out.data_ptr(), flags, self._stream()))
-            return self._back(out.bool() if not (flags & _abi.NO_FP64_RECHECK) else out, kind)
+        exact = self._exact_limits(Q) if (flags & CHECK_LIMITS) and not (flags & _abi.NO_FP64_RECHECK) else None
+        if exact is not None:
+            flags |= _abi.LIMITS_OUTWARD
+        with self._call_lock:
+            if isinstance(Q, np.ndarray) or (torch.is_tensor(Q) and not Q.is_cuda):
+                res = self._valid_host(Q, flags)
+            else:
+                with torch.cuda.device(self.device):
+                    q, kind = self._rows(Q)
+                    n = q.shape[0]
+                    out = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
+                    if n:
+                        _abi.check(self._L.mjb_check_configs(self._h, q.data_ptr(), n, q.stride(0), out.data_ptr(), flags, self._stream()))
+                    res = self._back(out.bool() if not (flags & _abi.NO_FP64_RECHECK) else out, kind)
+        return res if exact is None else (res & exact)
 
     def _valid_host(self, Q, flags: int):
         torch = _torch()
@@ -165,7 +199,7 @@ class ValidityEngine:
         if not step > 0.0:
             raise ValueError("`step_dist` must be > 0")
         torch = _torch()
-        with torch.cuda.device(self.device):
+        with self._call_lock, torch.cuda.device(self.device):
             q0, kind = self._rows(Q0)
             q1, _ = self._rows(Q1)
             if q0.shape != q1.shape:
@@ -182,7 +216,7 @@ class ValidityEngine:
     def sweep(self, seed: int, row0: int, n: int, flags: int = CHECK_LIMITS | CHECK_COLLISION, out=None):
         """Validity of device-generated uniform rows [row0, row0+n) -> uint8 CUDA tensor."""
         torch = _torch()
-        with torch.cuda.device(self.device):
+        with self._call_lock, torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty(n, dtype=torch.uint8, device=self.torch_device)
             if n:

@@ -459,7 +459,7 @@ class BatchedRRT:
         if len(fixed) and not np.allclose(q_inits[:, fixed], q_goals[:, fixed], rtol=0, atol=1e-12):
             raise ValueError("goal configs have values for joints outside of the planner's planning joints "
                              "that don't match q_init")
-        projecting = any(getattr(c, "projects", False) for c in self.constraints)
+        projecting = any(getattr(c, "projects", True) for c in self.constraints)
         paths: list[list[np.ndarray]] = [[] for _ in range(B)]
         direct = np.linalg.norm(q_goals - q_inits, axis=1) <= self.epsilon
         for b in np.flatnonzero(direct):

@@ -140,7 +140,7 @@ def _constrained_extend(q_target: np.ndarray, tree: Tree, eps: float, constraint
     configuration that was reached (CBiRRT algorithm 2)."""
     if eps <= 0.0:
         raise ValueError("`max_step_dist` must be > 0.0")
-    if any(getattr(c, "projects", False) for c in constraints):
+    if any(getattr(c, "projects", True) for c in constraints):
         return _constrained_extend_sequential(q_target, tree, eps, constraints, collision_interval_check,
                                               equality_threshold)
     closest = tree.nearest_neighbor(q_target)

@@ -51,7 +51,7 @@ def random_config(model, q_init: np.ndarray, joints: list[str], seed: int | None
     q_idx = qpos_idx(model, joints)
     rng = np.random.default_rng(seed=seed)
     lo, hi = model.jnt_range.T
-    if any(getattr(c, "projects", False) for c in constraints):
+    if any(getattr(c, "projects", True) for c in constraints):
         q = q_init.copy()
         while True:
             q[q_idx] = rng.uniform(lo, hi)[q_idx]

@@ -10,7 +10,7 @@
  * third-party `mujoco` wheel (pyproject.toml:12, "mujoco >= 3", unpinned, not vendored, not
  * installable here: no network, no wheel).  This file restates MuJoCo 3.x's published
  * semantics and is pinned only by the reference's own known-answer
- * tests (tests/test_oracle_known_answers.py lists them with reference file:line) and by
+ * tests (tests/test_oracle.py lists them with reference file:line) and by
  * closed-form analytic cases.  tools/make_golden.py regenerates real-MuJoCo vectors whenever
  * a MuJoCo install is reachable.
  */

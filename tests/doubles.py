@@ -14,6 +14,8 @@ from mjpl_b200.constraint.constraint_interface import Constraint
 
 
 class OracleJointLimitConstraint(Constraint):
+    projects = False
+
     def __init__(self, model):
         self.model = model
         self.orc = oracle.Oracle(model)
@@ -30,6 +32,8 @@ class OracleJointLimitConstraint(Constraint):
 
 
 class OracleCollisionConstraint(Constraint):
+    projects = False
+
     def __init__(self, model, allowed_collision_bodies=()):
         self.model = model
         self.orc = oracle.Oracle(model, allowed_collision_bodies)

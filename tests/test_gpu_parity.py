@@ -356,3 +356,164 @@ def test_single_kernel_and_two_kernel_pipeline_agree(monkeypatch):
     want, dist, _ = orc.check(Q[:20_000].astype(np.float64), 3, want_dist=True)
     bad, outside = compare(results["split"][0][:20_000], want, dist)
     assert outside == 0
+
+
+def _oracle_edges(orc, q0, q1, step, block=8):
+    """``_valid_collision_interval`` semantics for many edges on the fp64 oracle, with the per-edge
+    early exit of the reference loop (planning/utils.py:206-216) done in rounds of ``block``
+    waypoints: -> (valid, first_bad, near_band) where near_band marks edges that have a waypoint
+    within 1e-4 of contact at or before their first failing waypoint."""
+    q0, q1 = q0.astype(np.float64), q1.astype(np.float64)
+    E, nq = q0.shape
+    d = q1 - q0
+    dist = np.linalg.norm(d, axis=1)
+    K = np.maximum(np.ceil(dist / step).astype(np.int64) - 1, 0)
+    fb = np.full(E, -1, dtype=np.int64)
+    near = np.zeros(E, dtype=bool)
+    alive = np.flatnonzero(K > 0)
+    k0 = 0
+    while len(alive):
+        ks = k0 + np.arange(block)
+        real = ks[None, :] < K[alive][:, None]
+        s = (ks[None, :] + 1) * step / dist[alive][:, None]
+        W = q0[alive][:, None, :] + s[:, :, None] * d[alive][:, None, :]
+        v, dd, _ = orc.check(W[real], 2, want_dist=True)
+        ok = np.ones(real.shape, dtype=bool)
+        ok[real] = v
+        close = np.zeros(real.shape, dtype=bool)
+        close[real] = np.abs(dd) < 1e-4
+        first = np.where(ok.all(axis=1), block, np.argmin(ok, axis=1))
+        upto = np.arange(block)[None, :] <= first[:, None]
+        near[alive] |= (close & upto).any(axis=1)
+        bad = first < block
+        fb[alive[bad]] = k0 + first[bad]
+        k0 += block
+        alive = alive[~bad & (K[alive] > k0)]
+    return fb < 0, fb, near
+
+
+def test_full_size_edges_against_oracle():
+    """BASELINE configs[2] at its full size: 100,000 UR5e edges at 0.05 rad against the reference
+    loop restated on the fp64 oracle (same verdict and same first failing waypoint for every edge
+    that has no waypoint near the contact band)."""
+    import os
+    import torch
+
+    model = models.load("ur5e_scene")
+    eng = mj.get_engine(model, [])
+    orc = oracle.Oracle(model)
+    oracle.Oracle.set_threads(len(os.sched_getaffinity(0)))
+    rng = np.random.default_rng(0)
+    E = 100_000
+    q0 = rng.uniform(-3.1415, 3.1415, size=(E, 6)).astype(np.float32)
+    q1 = rng.uniform(-3.1415, 3.1415, size=(E, 6)).astype(np.float32)
+    v, fb = eng.valid_edges(torch.from_numpy(q0).cuda(), torch.from_numpy(q1).cuda(), 0.05, want_first_bad=True)
+    v, fb = v.cpu().numpy(), fb.cpu().numpy()
+    want_v, want_fb, near = _oracle_edges(orc, q0, q1, float(np.float32(0.05)))
+    dis = (v != want_v) | (fb != want_fb)
+    print(f"100k UR5e edges: valid={v.mean():.4f}, disagreements={int(dis.sum())}, edges near the band={int(near.sum())}")
+    assert not (dis & ~near).any()
+    assert 0.05 < v.mean() < 0.5
+
+
+def test_margins_on_the_device():
+    """geom_margin > 0 (reference semantics, SURVEY A.3: a contact exists iff the signed distance is
+    <= max(margin1, margin2)): primitives and the Franka meshes with margins on moving and on
+    world-fixed geoms, both kernel paths, against the oracle."""
+    import copy
+
+    zoo = mjcf.from_xml_string(toys.PRIMITIVE_ARM)
+    zoo.geom_margin = np.where(np.arange(zoo.ngeom) % 2 == 0, 0.015, 0.004)
+    franka = copy.deepcopy(models.load("franka_scene_with_obstacles"))
+    franka.geom_margin = np.where(np.arange(franka.ngeom) % 3 == 0, 0.01, 0.002)
+    for model, allowed, n in ((zoo, [], 50_000), (franka, [("left_finger", "right_finger")], 60_000)):
+        eng = mj.ValidityEngine(model, allowed)
+        orc = oracle.Oracle(model, allowed)
+        base = oracle.Oracle(_no_margin(model), allowed)
+        Q = rows(model, n, 4)
+        want, dist, _ = orc.check(Q.astype(np.float64), 3, want_dist=True)
+        got = eng.valid_configs(Q)
+        nbad, nout = compare(got, want, dist)
+        plain = base.check(Q.astype(np.float64), 3)
+        flipped = int((plain & ~want).sum())
+        print(f"margins: mismatches={nbad} outside band={nout}, rows the margins turn invalid={flipped}")
+        assert nout == 0
+        assert flipped > 50          # the margins matter on these rows
+        big = np.tile(Q, (10, 1))    # large batch: the multi-kernel pipeline
+        assert compare(eng.valid_configs(big), np.tile(want, 10), np.tile(dist, 10))[1] == 0
+        eng.close()
+
+
+def _no_margin(model):
+    import copy
+
+    m = copy.deepcopy(model)
+    m.geom_margin = np.zeros(m.ngeom)
+    return m
+
+
+def test_joint_limits_are_decided_in_the_callers_precision():
+    """A configuration exactly ON a joint limit is valid in the reference
+    (joint_limit_constraint.py:19-20 is a closed-interval fp64 compare), also when the limit is not
+    representable in fp32; one ulp (fp64) beyond it is not."""
+    import torch
+
+    model = models.load("franka_scene")
+    jl, cc = mj.JointLimitConstraint(model), mj.CollisionConstraint(model)
+    lo, hi = model.jnt_range[:, 0].copy(), model.jnt_range[:, 1].copy()
+    home = model.keyframe("home").qpos.copy()
+    assert jl.valid_config(lo) and jl.valid_config(hi)
+    Q = np.repeat(home[None, :], 4 * model.nq, axis=0)
+    want = np.ones(len(Q), dtype=bool)
+    for j in range(model.nq):
+        Q[4 * j, j] = lo[j]
+        Q[4 * j + 1, j] = hi[j]
+        Q[4 * j + 2, j] = np.nextafter(lo[j], -np.inf); want[4 * j + 2] = False
+        Q[4 * j + 3, j] = np.nextafter(hi[j], np.inf); want[4 * j + 3] = False
+    np.testing.assert_array_equal(jl.valid_configs(Q), want)
+    np.testing.assert_array_equal(jl.valid_configs(torch.from_numpy(Q)).numpy(), want)
+    np.testing.assert_array_equal(jl.valid_configs(torch.from_numpy(Q).cuda()).cpu().numpy(), want)
+    # fused with the collision check: limits from the fp64 rows, collision on their fp32 rounding
+    orc = oracle.Oracle(model)
+    fused = mj.obeys_constraints_batch(Q, [jl, cc])
+    np.testing.assert_array_equal(fused, want & orc.check(Q.astype(np.float32).astype(np.float64), 2))
+    # fp32 callers: the row IS fp32, the reference's answer for that row is the fp64 compare of it
+    Q32 = Q.astype(np.float32)
+    np.testing.assert_array_equal(jl.valid_configs(Q32), ((Q32.astype(np.float64) >= lo) & (Q32.astype(np.float64) <= hi)).all(axis=1))
+
+
+def test_kernel_timing_survives_a_large_host_batch():
+    """kernel_timing(True) followed by a host batch that grows the progress table (> 65536 rows)
+    used to record on destroyed events (a stray cudaEventDestroy); the timing must read back."""
+    model = models.load("franka_scene")
+    eng = mj.ValidityEngine(model)
+    Q = rows(model, 200_000, 3)
+    eng.kernel_timing(True)
+    a = eng.valid_configs(Q)
+    t = eng.kernel_timing(False, read=True)
+    assert t["launches"] >= 1 and t["first_ms"] > 0.0
+    np.testing.assert_array_equal(a, eng.valid_configs(Q))
+    eng.close()
+
+
+def test_calls_on_different_streams_are_ordered_per_handle():
+    """Engines are shared by every constraint on a model and use per-handle scratch: a CUDA-tensor
+    call on a side stream followed at once by a host-array call (the handle's own stream) must not
+    overlap on the device."""
+    import torch
+
+    model = models.load("franka_scene_with_obstacles")
+    allowed = [("left_finger", "right_finger")]
+    eng = mj.get_engine(model, allowed)
+    A, B = rows(model, 700_000, 5), rows(model, 90_000, 6)
+    want_a, want_b = eng.valid_configs(A), eng.valid_configs(B)
+    a_dev = torch.from_numpy(A).cuda()
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(5):
+        with torch.cuda.stream(side):
+            got_a = eng.valid_configs(a_dev)          # asynchronous, side stream
+        got_b = eng.valid_configs(B)                  # host path, handle's own stream
+        side.synchronize()
+        np.testing.assert_array_equal(got_b, want_b)
+        np.testing.assert_array_equal(got_a.cpu().numpy(), want_a)

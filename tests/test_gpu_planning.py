@@ -194,3 +194,103 @@ def test_trajectory_revalidation_matches_oracle():
             assert np.abs(dist[lo:hi + 1]).min() < 1e-5
         hits += want >= 0
     assert hits >= 2
+
+
+def test_rrt_extend_matches_the_reference_extend_call_by_call():
+    """``mjb_rrt_extend`` (nearest node + chain + validity + stop rules + append, all on the device)
+    against ``_constrained_extend`` restated on the oracle (reference planning/utils.py:135-164),
+    one call at a time: same nearest node, same number of appended nodes, same appended
+    configurations, same reached configuration -- for every (tree, target) pair whose chain has no
+    row inside the contact band."""
+    import ctypes as C
+    import os
+
+    import torch
+
+    from mjpl_b200 import _abi
+
+    model = models.load("franka_scene_with_obstacles")
+    allowed = [("left_finger", "right_finger")]
+    eng = mj.get_engine(model, allowed)
+    orc = oracle.Oracle(model, allowed)
+    oracle.Oracle.set_threads(len(os.sched_getaffinity(0)))
+    rng = np.random.default_rng(77)
+    nq, B, cap, kcap, eps = model.nq, 10_000, 96, 48, 0.05
+    lo, hi = model.jnt_range[:, 0], model.jnt_range[:, 1]
+    # trees: 1..24 valid nodes each (random valid configurations; parents form a chain)
+    pool = rng.uniform(lo, hi, size=(400_000, nq))
+    pool = pool[orc.check(pool.astype(np.float32).astype(np.float64), 3)]
+    count = rng.integers(1, 25, size=B)
+    nodes = np.full((B, cap, nq), np.inf)
+    parent = np.full((B, cap), -1, dtype=np.int64)
+    take = rng.integers(0, len(pool), size=(B, 24))
+    for k in range(24):
+        has = count > k
+        nodes[has, k] = pool[take[has, k]]
+        parent[has, k] = k - 1
+    # targets: random configurations, some close to a node of the tree, some exactly a node, some out of limits
+    targets = rng.uniform(lo, hi, size=(B, nq))
+    close = rng.random(B) < 0.3
+    targets[close] = nodes[close, 0] + rng.normal(0, 0.04, size=(int(close.sum()), nq))
+    far = rng.random(B) < 0.05
+    targets[far, 0] = hi[0] + 0.2
+    same = rng.random(B) < 0.02
+    targets[same] = nodes[same, 0]
+    dev = eng.torch_device
+    d_nodes, d_parent = torch.from_numpy(nodes).to(dev), torch.from_numpy(parent).to(dev)
+    d_count, d_targets = torch.from_numpy(count.astype(np.int64)).to(dev), torch.from_numpy(targets).to(dev)
+    d_slots = torch.arange(B, dtype=torch.int64, device=dev)
+    reached = torch.empty((B, nq), dtype=torch.float64, device=dev)
+    last = torch.empty(B, dtype=torch.int64, device=dev)
+    _abi.check(_abi.lib().mjb_rrt_extend(eng._h, d_nodes.data_ptr(), d_parent.data_ptr(), d_count.data_ptr(), cap,
+                                         d_slots.data_ptr(), d_targets.data_ptr(), B, eps, kcap, 3, reached.data_ptr(),
+                                         last.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    g_nodes, g_parent, g_count = d_nodes.cpu().numpy(), d_parent.cpu().numpy(), d_count.cpu().numpy()
+    g_reached, g_last = reached.cpu().numpy(), last.cpu().numpy()
+    # ---- the reference's extend on the oracle -----------------------------------------------------
+    d2 = ((nodes[:, :24] - targets[:, None, :]) ** 2).sum(-1)
+    d2[np.arange(24)[None, :] >= count[:, None]] = np.inf
+    nn = np.argmin(d2, axis=1)
+    near = nodes[np.arange(B), nn]
+    delta = targets - near
+    dist = np.linalg.norm(delta, axis=1)
+    K = np.minimum(np.where(dist > 0, np.ceil(dist / eps), 0).astype(np.int64), kcap)
+    ks = np.arange(kcap)
+    real = ks[None, :] < K[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        s = np.minimum((ks[None, :] + 1) * eps / dist[:, None], 1.0)
+    chain = near[:, None, :] + s[:, :, None] * delta[:, None, :]
+    lands = ((ks[None, :] + 1) * eps >= dist[:, None]) & real
+    chain[lands] = np.broadcast_to(targets[:, None, :], chain.shape)[lands]
+    flat = chain[real]
+    lim_ok = ((flat >= lo) & (flat <= hi)).all(axis=1)                   # limits: the fp64 chain point
+    col_ok, cdist, _ = orc.check(flat.astype(np.float32).astype(np.float64), 2, want_dist=True)   # collision: its fp32 rounding
+    ok = np.zeros(real.shape, dtype=bool)
+    ok[real] = lim_ok & col_ok
+    band = np.zeros(real.shape, dtype=bool)
+    band[real] = np.abs(cdist) < 1e-5
+    prev = np.concatenate([near[:, None, :], chain[:, :-1]], axis=1)
+    moved = np.linalg.norm(chain - prev, axis=2) >= 1e-8                 # stop rule of planning/utils.py:153
+    good = ok & moved & real
+    n_ok = np.where(good.all(axis=1), kcap, np.argmin(good, axis=1))
+    n_ok = np.minimum(n_ok, K)
+    in_band = (band & (ks[None, :] <= n_ok[:, None])).any(axis=1)
+    # ---- compare ----------------------------------------------------------------------------------
+    clean = ~in_band
+    appended = g_count - count
+    assert (appended[clean] == n_ok[clean]).all(), int((appended[clean] != n_ok[clean]).sum())
+    want_last = np.where(n_ok > 0, count + n_ok - 1, nn)
+    assert (g_last[clean] == want_last[clean]).all()
+    want_reached = np.where((n_ok > 0)[:, None], chain[np.arange(B), np.maximum(n_ok - 1, 0)], near)
+    np.testing.assert_allclose(g_reached[clean], want_reached[clean], rtol=0, atol=1e-12)
+    for b in np.flatnonzero(clean & (n_ok > 0))[:2000]:
+        k = int(n_ok[b])
+        np.testing.assert_allclose(g_nodes[b, count[b]:count[b] + k], chain[b, :k], rtol=0, atol=1e-12)
+        assert g_parent[b, count[b]] == nn[b]
+        assert (g_parent[b, count[b] + 1:count[b] + k] == np.arange(count[b], count[b] + k - 1)).all()
+    np.testing.assert_array_equal(g_nodes[:, :24][np.arange(24)[None, :] < count[:, None]],
+                                  nodes[:, :24][np.arange(24)[None, :] < count[:, None]])   # old nodes untouched
+    print(f"rrt_extend: {B} calls, mean appended {appended.mean():.2f}, reached the target {int((n_ok == K).sum())}, "
+          f"chains with a row in the band {int(in_band.sum())}")
+    assert (same <= (appended == 0)).all() and appended.mean() > 1.0
