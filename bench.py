@@ -257,9 +257,11 @@ def main():
         # library around each kernel): validity_kernel, or broad_kernel when the batch ran as the
         # two-kernel pipeline (broad phase + narrow phase)
         nl = max(1, ktime["launches"])
-        first_ms, narrow_ms, fp64_ms = ktime["first_ms"] / nl, ktime["narrow_ms"] / nl, ktime["fp64_ms"] / nl
-        kernel_name = "broad_kernel" if ktime["pipeline"] == "broad+narrow" else "validity_kernel"
-        kernel_ms = first_ms if first_ms > 0 else total_ms / args.steps
+        first_ms, mid_ms, narrow_ms, fp64_ms = (ktime[k] / nl for k in ("first_ms", "mid_ms", "narrow_ms", "fp64_ms"))
+        piped = ktime["pipeline"] != "single"
+        per_kernel = {"fk_cull_kernel": first_ms, "mid_kernel": mid_ms, "narrow_kernel": narrow_ms} if piped else {"validity_kernel": first_ms}
+        kernel_name = max(per_kernel, key=per_kernel.get)
+        kernel_ms = per_kernel[kernel_name] if per_kernel[kernel_name] > 0 else total_ms / args.steps
         achieved = ALG_BYTES_PER_ROW * ROWS_PER_STEP / (kernel_ms * 1e-3) / 1e9
         traffic, fp32 = None, None
         tf = ROOT / "profiles" / "traffic.json"
@@ -286,7 +288,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": kernel_name,
-                         "kernel_ms": {"dominant": kernel_ms, "narrow_kernel": narrow_ms, "fp64_item_pass": fp64_ms,
+                         "kernel_ms": {"dominant": kernel_ms, **per_kernel, "fp64_item_pass": fp64_ms,
                                        "share_of_step": kernel_ms / (total_ms / args.steps)},
                          "note": "the path is FP32-ALU/latency bound, not HBM bound (37 algorithmic bytes per row); "
                                  "traffic above the algorithmic bytes is the pose/item scratch the two kernels of the "

@@ -215,12 +215,12 @@ int mjb_ik_solve(mjb_model *m, const mjb_ik_spec *spec, const double *d_target_p
 /*
  * Per-kernel timing of the validity launches (measurement aid for bench.py; off by default).
  * enable != 0 switches CUDA-event recording on for later launches (up to 2048 launches between
- * reads).  If ms3 != NULL the device is synchronised and ms3 receives the summed durations since
- * the last read: [0] validity_kernel, or broad_kernel when the batch ran as the two-kernel
- * pipeline, [1] narrow_kernel (0 for the single kernel), [2] the fp64 item pass; *launches = number
- * of validity launches summed.
+ * reads).  If ms4 != NULL the device is synchronised and ms4 receives the summed durations since
+ * the last read: [0] validity_kernel, or fk_cull_kernel when the batch ran as the multi-kernel
+ * pipeline, [1] mid_kernel, [2] narrow_kernel (both 0 for the single kernel), [3] the fp64 item
+ * pass; *launches = number of validity launches summed.
  */
-int mjb_kernel_timing(mjb_model *m, int enable, double *ms3, int64_t *launches);
+int mjb_kernel_timing(mjb_model *m, int enable, double *ms4, int64_t *launches);
 
 int mjb_get_stats(mjb_model *m, mjb_stats *out);   /* synchronises the handle's last stream */
 int mjb_reset_stats(mjb_model *m);

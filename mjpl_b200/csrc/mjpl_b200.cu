@@ -16,8 +16,11 @@
 #include "vk_core.cuh"
 #include "vk_kernels.cuh"
 #include "vk_split.cuh"
+#include "vk_pipe.cuh"
 
 using namespace vk;
+
+static const size_t TEV = 5;   // timing events per validity launch (mjb_kernel_timing)
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string &msg) { g_err = msg; return code; }
@@ -49,10 +52,12 @@ struct mjb_model {
   float *d_pose = nullptr;
   unsigned long long *d_counters = nullptr;
   long long *d_recheck = nullptr; size_t recheck_cap = 0;
-  // two-kernel pipeline (MJB_SPLIT=1): poses / item bins / row flags of one batch
-  bool split = false; int split_tile = 0; size_t split_smem = 0, narrow_smem = 0; int narrow_grid = 0;
+  // multi-kernel pipeline (vk_pipe.cuh, large batches): poses / level-0 list / item bins / row flags of one batch
+  bool split = false; size_t fk_smem = 0, mid_smem = 0, narrow_smem = 0; int fk_grid = 0, mid_grid = 0, narrow_grid = 0;
   float *d_pose8 = nullptr; unsigned long long *d_bins = nullptr; uint32_t *d_row_flags = nullptr; size_t split_cap = 0;
-  size_t cur_rows = 0, split_min = 0, bin_cap_override = 0; bool use_split = false;
+  unsigned long long *d_l0 = nullptr; size_t l0_cap = 0;
+  GroupPair *d_gpairs = nullptr; StaticGroup *d_sgroups = nullptr; uint16_t *d_gp_member = nullptr;
+  size_t cur_rows = 0, split_min = 0, bin_cap_override = 0, l0_cap_override = 0; bool use_split = false;
   // optional per-kernel timing (mjb_kernel_timing): 4 events per validity launch
   bool timing = false; std::vector<cudaEvent_t> tev; std::vector<uint8_t> tev_split; size_t tev_used = 0;   // decided per launch from the row count
   long long *d_edge_count = nullptr, *d_edge_prefix = nullptr; int *d_first_bad = nullptr; size_t edge_cap = 0;
@@ -105,18 +110,6 @@ template <int TILE> static int try_tile(const vkb::HostModel &H, int max_smem_op
   return occ * TILE;
 }
 
-template <int TILE> static bool try_split(const vkb::HostModel &H, int max_smem_optin, size_t *smem) {
-  BroadLayout L = broad_layout<TILE>((int)H.shapes.size(), (int)H.pairs.size(), H.nmoving_shapes, H.nq);
-  if ((int)L.total > max_smem_optin) return false;
-  if ((int)H.shapes.size() - H.nmoving_shapes > TILE) return false;
-  if (cudaFuncSetAttribute(broad_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  *smem = L.total;
-  return true;
-}
-
 extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   if (!desc || !out) return fail(MJB_ERR_ARG, "null argument");
   *out = nullptr;
@@ -164,6 +157,12 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   }
   if ((rc = upload(&m->d_static_pose, sp))) return bail(rc);
   if ((rc = upload(&m->d_body_slot, H.body_slot))) return bail(rc);
+  {
+    std::vector<uint16_t> mem = H.gp_member; mem.resize(align_up(std::max<size_t>(mem.size(), 1), 8), 0);   // 16-byte units
+    if ((rc = upload(&m->d_gpairs, H.group_pairs))) return bail(rc);
+    if ((rc = upload(&m->d_sgroups, H.static_groups))) return bail(rc);
+    if ((rc = upload(&m->d_gp_member, mem))) return bail(rc);
+  }
   {  // padded to 16-byte multiples: the kernel bulk-copies whole 16-byte units
     std::vector<uint16_t> as = H.adj_start; as.resize(align_up(as.size(), 8), 0);
     std::vector<uint8_t> ad = H.adj; ad.resize(align_up(std::max<size_t>(ad.size(), 1), 16), 0);
@@ -194,21 +193,33 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
     m->split_min = mode == 1 ? 0 : (smin ? (size_t)atoll(smin) : (size_t)500000);
     const char *bc = getenv("MJB_BIN_CAP");   // testing: tiny bins force the on-the-spot path of full bins
     m->bin_cap_override = bc ? (size_t)atoll(bc) : 0;
+    const char *lc = getenv("MJB_L0_CAP");    // testing: a tiny level-0 list forces the whole-row fp64 path
+    m->l0_cap_override = lc ? (size_t)atoll(lc) : 0;
     if (mode != 0) {
-      int st_ = 0;
-      size_t ss = 0;
-      if (try_split<512>(H, optin, &ss)) st_ = 512;
-      else if (try_split<256>(H, optin, &ss)) st_ = 256;
-      else if (try_split<128>(H, optin, &ss)) st_ = 128;
-      NarrowLayout NL = narrow_layout((int)H.verts.size(), (int)H.shapes.size(), (int)H.pairs.size(), (int)H.adj.size());
-      int nocc = 0;
-      if (st_ && (int)NL.total <= optin &&
-          cudaFuncSetAttribute(narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess &&
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nocc, narrow_kernel, NARROW_THREADS, NL.total) == cudaSuccess && nocc >= 1) {
-        m->split = true; m->split_tile = st_; m->split_smem = ss; m->narrow_smem = NL.total; m->narrow_grid = m->num_sms * nocc;
-      } else {
-        cudaGetLastError();
+      const PipeFkLayout FL = pipe_fk_layout((int)H.group_pairs.size(), (int)H.static_groups.size(), H.ngroup_moving, H.nq);
+      const MidLayout ML = mid_layout((int)H.shapes.size(), (int)H.pairs.size(), (int)H.group_pairs.size(), (int)H.gp_member.size());
+      const NarrowLayout NL = narrow_layout((int)H.verts.size(), (int)H.shapes.size(), (int)H.pairs.size(), (int)H.adj.size());
+      int focc = 0, mocc = 0, nocc = 0;
+      const bool dbg = getenv("MJB_DEBUG") != nullptr;
+      auto ok = [&](cudaError_t e, const char *what) {
+        if (e != cudaSuccess && dbg) fprintf(stderr, "[mjb] %s: %s\n", what, cudaGetErrorString(e));
+        if (e != cudaSuccess) cudaGetLastError();
+        return e == cudaSuccess;
+      };
+      if ((int)FL.total <= optin && (int)ML.total <= optin && (int)NL.total <= optin && !H.group_pairs.empty() &&
+          ok(cudaFuncSetAttribute(fk_cull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin), "attr fk_cull_kernel") &&
+          ok(cudaFuncSetAttribute(mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024), "attr mid_kernel") &&
+          ok(cudaFuncSetAttribute(narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin), "attr narrow_kernel") &&
+          ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&focc, fk_cull_kernel, PIPE_FK_THREADS, FL.total), "occupancy fk_cull_kernel") && focc >= 1 &&
+          ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mocc, mid_kernel, MID_THREADS, ML.total), "occupancy mid_kernel") && mocc >= 1 &&
+          ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nocc, narrow_kernel, NARROW_THREADS, NL.total), "occupancy narrow_kernel") && nocc >= 1) {
+        m->split = true;
+        m->fk_smem = FL.total; m->mid_smem = ML.total; m->narrow_smem = NL.total;
+        m->fk_grid = m->num_sms * focc; m->mid_grid = m->num_sms * mocc; m->narrow_grid = m->num_sms * nocc;
       }
+      if (getenv("MJB_DEBUG"))
+        fprintf(stderr, "[mjb] pipeline %s: smem fk %zu mid %zu narrow %zu (optin %d), CTAs/SM fk %d mid %d narrow %d, group pairs %zu\n",
+                m->split ? "on" : "OFF", FL.total, ML.total, NL.total, optin, focc, mocc, nocc, H.group_pairs.size());
     }
   }
   CU(cudaMalloc((void **)&m->d_pose, (size_t)m->grid * std::max(H.nslot, 1) * 7 * m->tile * sizeof(float)));
@@ -231,6 +242,12 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   for (int r = 0; r <= H.nrounds; r++) k.round_start[r] = H.round_start[r];
   for (int r = 0; r < H.nrounds; r++) k.round_gjk[r] = H.round_gjk[r];
   k.pose_scratch = m->d_pose; k.counters = m->d_counters;
+  for (int sl = 0; sl < MAX_BODY; sl++) k.slot_group[sl] = H.slot_group[sl];
+  for (int g = 0; g < H.ngroup_moving; g++) for (int a = 0; a < 3; a++) k.group_c[g][a] = (float)H.group_c[g][a];
+  k.gpairs = m->d_gpairs; k.sgroups = m->d_sgroups; k.gp_member = m->d_gp_member;
+  k.ngpair = (int)H.group_pairs.size(); k.nsgroup = (int)H.static_groups.size(); k.ngroup_moving = H.ngroup_moving;
+  k.nmember = (int)H.gp_member.size();
+  for (int a = 0; a < 3; a++) k.gp_kind_end[a] = H.gp_kind_end[a];
   RArgs &ra = m->rargs;
   memset(&ra, 0, sizeof ra);
   ra.fk = m->d_fk64; ra.shapes = m->d_shapes64; ra.verts = m->d_verts64; ra.pairs = m->d_pairs;
@@ -256,7 +273,8 @@ extern "C" void mjb_model_destroy(mjb_model *m) {
   cudaFree(m->d_shapes32); cudaFree(m->d_verts32); cudaFree(m->d_pairs); cudaFree(m->d_shapes64);
   cudaFree(m->d_verts64); cudaFree(m->d_fk64); cudaFree(m->d_rsum64); cudaFree(m->d_bsum64);
   cudaFree(m->d_body_slot); cudaFree(m->d_static_pose); cudaFree(m->d_adj_start); cudaFree(m->d_adj); cudaFree(m->d_pose); cudaFree(m->d_counters);
-  cudaFree(m->d_pose8); cudaFree(m->d_bins); cudaFree(m->d_row_flags);
+  cudaFree(m->d_pose8); cudaFree(m->d_bins); cudaFree(m->d_row_flags); cudaFree(m->d_l0);
+  cudaFree(m->d_gpairs); cudaFree(m->d_sgroups); cudaFree(m->d_gp_member);
   cudaFree(m->d_recheck); cudaFree(m->d_edge_count); cudaFree(m->d_edge_prefix); cudaFree(m->d_first_bad);
   cudaFree(m->d_cub); cudaFree(m->d_stage_q); cudaFree(m->d_stage_v); cudaFree(m->d_chain_near); cudaFree(m->d_chain_nn);
   if (m->h_pin_q) cudaFreeHost(m->h_pin_q);
@@ -292,9 +310,13 @@ static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st, bool may_s
   m->use_split = may_split && m->split && rows >= m->split_min;
   if (m->use_split && rows > m->split_cap) {
     CU(cudaStreamSynchronize(st));
-    cudaFree(m->d_pose8); cudaFree(m->d_bins); cudaFree(m->d_row_flags);
-    m->d_pose8 = nullptr; m->d_bins = nullptr; m->d_row_flags = nullptr;
+    cudaFree(m->d_pose8); cudaFree(m->d_bins); cudaFree(m->d_row_flags); cudaFree(m->d_l0);
+    m->d_pose8 = nullptr; m->d_bins = nullptr; m->d_row_flags = nullptr; m->d_l0 = nullptr;
     size_t cap = std::max<size_t>(rows, 1 << 16);
+    // level-0 list: 3x the calibrated survivors per row + 4 (uniform rows are what the calibration saw;
+    // rows whose entries do not fit are re-evaluated whole in fp64, so a full list costs speed only)
+    m->l0_cap = (size_t)((3.0 * m->H.calib_l0_per_row + 4.0) * (double)cap) + 4096;
+    CU(cudaMalloc((void **)&m->d_l0, m->l0_cap * sizeof(unsigned long long)));
     CU(cudaMalloc((void **)&m->d_pose8, cap * std::max(m->H.nslot, 1) * 8 * sizeof(float)));
     size_t tot = 0;
     for (int b = 0; b < NBIN; b++) tot += bin_capacity(m->H, b, cap);
@@ -317,15 +339,16 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
   k.recheck_items = (unsigned long long *)(m->d_recheck + m->recheck_cap);
   r.recheck_items = k.recheck_items;
   k.item_cap = r.item_cap = m->recheck_cap;
-  cudaEvent_t *ev = nullptr;
-  if (m->timing && m->tev_used + 4 <= m->tev.size()) {
+  cudaEvent_t *ev = nullptr;   // TEV events per launch: start, after each of up to four kernels
+  const bool pipe = m->use_split && (k.flags & F_COLLISION);
+  if (m->timing && m->tev_used + TEV <= m->tev.size()) {
     ev = &m->tev[m->tev_used];
-    m->tev_split[m->tev_used / 4] = (m->use_split && (k.flags & F_COLLISION)) ? 1 : 0;
-    m->tev_used += 4;
+    m->tev_split[m->tev_used / TEV] = pipe ? 1 : 0;
+    m->tev_used += TEV;
   }
   if (ev) CU(cudaEventRecord(ev[0], st));
-  if (m->use_split && (k.flags & F_COLLISION)) {
-    // two-kernel pipeline: broad phase writes poses + binned items, narrow phase consumes them
+  if (pipe) {
+    // multi-kernel pipeline (vk_pipe.cuh): FK + group cull -> expansion, capsule and OBB culls, bins -> narrow phase
     k.pose8 = m->d_pose8; k.bin_items = m->d_bins; k.row_flags = m->d_row_flags;
     size_t off = 0;
     for (int b = 0; b < NBIN; b++) {
@@ -333,17 +356,18 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
       k.bin_off[b] = off; k.bin_capv[b] = m->bin_cap_override ? std::min(c, m->bin_cap_override) : c;
       off += c;
     }
+    k.l0_items = m->d_l0; k.l0_cap = m->l0_cap_override ? std::min(m->l0_cap, m->l0_cap_override) : m->l0_cap;
     CU(cudaMemsetAsync(m->d_row_flags, 0, align_up(std::min(m->cur_rows, m->split_cap), 4), st));
-    switch (m->split_tile) {
-      case 512: broad_kernel<512><<<m->num_sms, 512, m->split_smem, st>>>(k); break;
-      case 256: broad_kernel<256><<<m->num_sms, 256, m->split_smem, st>>>(k); break;
-      default: broad_kernel<128><<<m->num_sms, 128, m->split_smem, st>>>(k); break;
-    }
+    fk_cull_kernel<<<m->fk_grid, PIPE_FK_THREADS, m->fk_smem, st>>>(k);
     CU(cudaGetLastError());
     if (ev) CU(cudaEventRecord(ev[1], st));
+    mid_kernel<<<m->mid_grid, MID_THREADS, m->mid_smem, st>>>(k);
+    CU(cudaGetLastError());
+    if (ev) CU(cudaEventRecord(ev[2], st));
     narrow_kernel<<<m->narrow_grid, NARROW_THREADS, m->narrow_smem, st>>>(k);
     CU(cudaGetLastError());
-    m->launches += 2;
+    if (ev) CU(cudaEventRecord(ev[3], st));
+    m->launches += 3;
   } else {
     switch (m->tile) {
       case 512: validity_kernel<512><<<m->grid, 512, m->smem_bytes, st>>>(k); break;
@@ -351,16 +375,15 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
       default: validity_kernel<128><<<m->grid, 128, m->smem_bytes, st>>>(k); break;
     }
     CU(cudaGetLastError());
-    if (ev) CU(cudaEventRecord(ev[1], st));
+    if (ev) { CU(cudaEventRecord(ev[1], st)); CU(cudaEventRecord(ev[2], st)); CU(cudaEventRecord(ev[3], st)); }
     m->launches++;
   }
-  if (ev) CU(cudaEventRecord(ev[2], st));
   if ((k.flags & F_COLLISION) && !(k.flags & F_NO_RECHECK)) {
     recheck_kernel<<<m->num_sms * 4, 128, 0, st>>>(r);
     CU(cudaGetLastError());
     m->launches++;
   }
-  if (ev) CU(cudaEventRecord(ev[3], st));
+  if (ev) CU(cudaEventRecord(ev[4], st));
   return MJB_OK;
 }
 
@@ -569,25 +592,25 @@ extern "C" int mjb_sweep_rows(mjb_model *m, uint64_t seed, int64_t row0, int64_t
   return MJB_OK;
 }
 
-extern "C" int mjb_kernel_timing(mjb_model *m, int enable, double *ms3, int64_t *launches) {
+extern "C" int mjb_kernel_timing(mjb_model *m, int enable, double *ms4, int64_t *launches) {
   if (!m) return fail(MJB_ERR_ARG, "null model");
   CU(cudaSetDevice(m->device));
-  if (ms3) {
+  if (ms4) {
     CU(cudaDeviceSynchronize());
-    ms3[0] = ms3[1] = ms3[2] = 0.0;
-    for (size_t i = 0; i + 4 <= m->tev_used; i += 4) {
-      float a = 0, b = 0, c = 0;
-      CU(cudaEventElapsedTime(&a, m->tev[i], m->tev[i + 1]));
-      if (m->tev_split[i / 4]) CU(cudaEventElapsedTime(&b, m->tev[i + 1], m->tev[i + 2]));
-      CU(cudaEventElapsedTime(&c, m->tev[i + 2], m->tev[i + 3]));
-      ms3[0] += a; ms3[1] += b; ms3[2] += c;
+    ms4[0] = ms4[1] = ms4[2] = ms4[3] = 0.0;
+    for (size_t i = 0; i + TEV <= m->tev_used; i += TEV) {
+      for (int k = 0; k < 4; k++) {
+        float t = 0;
+        CU(cudaEventElapsedTime(&t, m->tev[i + k], m->tev[i + k + 1]));
+        ms4[k] += t;
+      }
     }
-    if (launches) *launches = (int64_t)(m->tev_used / 4);
+    if (launches) *launches = (int64_t)(m->tev_used / TEV);
     m->tev_used = 0;
   }
   m->timing = enable != 0;
   if (m->timing && m->tev.empty()) {
-    m->tev.resize(4 * 2048);
+    m->tev.resize(TEV * 2048);
     m->tev_split.assign(2048, 0);
     for (auto &e : m->tev) CU(cudaEventCreate(&e));
   }

@@ -40,6 +40,16 @@ struct HostModel {
   std::vector<Pair> pairs;              // processing order
   std::vector<int> pair_g1, pair_g2;    // MuJoCo geom ids, same order as `pairs`
   std::vector<double> pair_rsum64, pair_bsum64;  // fp64 copies of Pair::rsum / bsum
+  // cull groups (vk_pipe.cuh): moving bodies that carry shapes, and every world-fixed shape by itself
+  int ngroup_moving = 0;
+  int slot_group[MAX_BODY];              // pose slot -> moving group or -1
+  double group_c[MAX_GROUP][3];          // bounding-sphere centre of a moving group, body frame
+  double group_r[MAX_GROUP] = {0};       // its radius (covers the swept radii of the member shapes)
+  std::vector<StaticGroup> static_groups;
+  std::vector<GroupPair> group_pairs;    // sorted by kind, then by moving group
+  std::vector<uint16_t> gp_member;       // pair indices (into `pairs`), grouped by group pair
+  int gp_kind_end[3] = {0, 0, 0};        // group_pairs[0 .. end[0]) spheres, [end[0] .. end[1]) capsules, then planes
+  double calib_l0_per_row = 0, calib_sub_per_row = 0;   // calibrated level-0 survivors / expanded shape pairs per row
   double bin_expect[NBIN] = {0};   // calibrated narrow-phase items per row that land in each bin (vk_split.cuh)
   int nrounds = 0;
   int round_start[MAX_ROUNDS + 1] = {0};  // pair index range of each round
@@ -175,6 +185,93 @@ inline void fit_bounds(Shape<double> &s, const std::vector<Vtx<double>> &verts) 
   }
 }
 
+// distance from point p to the segment a..b
+inline double point_segment_dist(const double *p, const double *a, const double *b) {
+  double ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ap[3] = {p[0] - a[0], p[1] - a[1], p[2] - a[2]};
+  double l2 = ab[0] * ab[0] + ab[1] * ab[1] + ab[2] * ab[2];
+  double t = l2 > 0 ? (ap[0] * ab[0] + ap[1] * ab[1] + ap[2] * ab[2]) / l2 : 0.0;
+  t = t < 0 ? 0 : (t > 1 ? 1 : t);
+  double d[3] = {ap[0] - t * ab[0], ap[1] - t * ab[1], ap[2] - t * ab[2]};
+  return sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+}
+
+// Bounding capsule of a sphere-swept vertex set: axis = principal direction of the vertices (or a
+// given direction), through the centroid or through the mid-point of the perpendicular extent; for a
+// few radius factors the shortest segment that keeps every vertex within that radius; the smallest
+// volume wins.  The radius is finally raised to the largest vertex distance actually found, so the
+// capsule contains the set by construction, whatever the heuristics above did.
+inline void fit_capsule(Shape<double> &s, const std::vector<Vtx<double>> &verts) {
+  const int n = s.nvert;
+  const Vtx<double> *v = verts.data() + s.vadr;
+  if (n == 1) {
+    s.ca[0] = s.cb[0] = v[0].x; s.ca[1] = s.cb[1] = v[0].y; s.ca[2] = s.cb[2] = v[0].z;
+    s.crad = s.radius; s.caplen = 0;
+    return;
+  }
+  double m[3] = {0, 0, 0};
+  for (int i = 0; i < n; i++) { m[0] += v[i].x; m[1] += v[i].y; m[2] += v[i].z; }
+  for (int k = 0; k < 3; k++) m[k] /= n;
+  double C[3][3] = {{0}}, V[3][3];
+  for (int i = 0; i < n; i++) {
+    double d[3] = {v[i].x - m[0], v[i].y - m[1], v[i].z - m[2]};
+    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) C[a][b] += d[a] * d[b];
+  }
+  jacobi3(C, V);
+  int kmax = 0;
+  for (int k = 1; k < 3; k++) if (C[k][k] > C[kmax][kmax]) kmax = k;
+  double u[3] = {V[0][kmax], V[1][kmax], V[2][kmax]};
+  double un = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+  if (!(un > 1e-12)) { u[0] = 1; u[1] = u[2] = 0; un = 1; }
+  for (int k = 0; k < 3; k++) u[k] /= un;
+  // mid-point of the perpendicular extent (AABB of the vertices projected on the plane normal to u)
+  double plo[3] = {1e300, 1e300, 1e300}, phi[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < n; i++) {
+    double d[3] = {v[i].x - m[0], v[i].y - m[1], v[i].z - m[2]};
+    double t = d[0] * u[0] + d[1] * u[1] + d[2] * u[2];
+    for (int k = 0; k < 3; k++) { double pk = d[k] - t * u[k]; plo[k] = std::min(plo[k], pk); phi[k] = std::max(phi[k], pk); }
+  }
+  double best = 1e300;
+  for (int cand = 0; cand < 2; cand++) {
+    double c0[3];
+    for (int k = 0; k < 3; k++) c0[k] = m[k] + (cand ? 0.5 * (plo[k] + phi[k]) : 0.0);
+    std::vector<double> t(n), ri(n);
+    double rmax = 0;
+    for (int i = 0; i < n; i++) {
+      double d[3] = {v[i].x - c0[0], v[i].y - c0[1], v[i].z - c0[2]};
+      t[i] = d[0] * u[0] + d[1] * u[1] + d[2] * u[2];
+      double pr[3] = {d[0] - t[i] * u[0], d[1] - t[i] * u[1], d[2] - t[i] * u[2]};
+      ri[i] = sqrt(pr[0] * pr[0] + pr[1] * pr[1] + pr[2] * pr[2]);
+      rmax = std::max(rmax, ri[i]);
+    }
+    const double scales[6] = {1.0, 1.05, 1.1, 1.2, 1.35, 1.5};
+    for (double sc : scales) {
+      double r = std::max(rmax * sc, 1e-9);
+      double lo = 1e300, hi = -1e300;
+      for (int i = 0; i < n; i++) {
+        double h = sqrt(std::max(r * r - ri[i] * ri[i], 0.0));
+        lo = std::min(lo, t[i] + h); hi = std::max(hi, t[i] - h);
+      }
+      if (lo > hi) lo = hi = 0.5 * (lo + hi);
+      double a[3], b[3];
+      for (int k = 0; k < 3; k++) { a[k] = c0[k] + lo * u[k]; b[k] = c0[k] + hi * u[k]; }
+      for (int i = 0; i < n; i++) { double p[3] = {v[i].x, v[i].y, v[i].z}; r = std::max(r, point_segment_dist(p, a, b)); }
+      double len = hi - lo;
+      double vol = M_PI * r * r * len + 4.0 / 3.0 * M_PI * r * r * r;
+      if (vol < best) {
+        best = vol;
+        for (int k = 0; k < 3; k++) { s.ca[k] = a[k]; s.cb[k] = b[k]; }
+        s.crad = r * (1 + 1e-9) + 1e-12 + s.radius; s.caplen = len;
+      }
+    }
+  }
+  if (s.caplen < 1e-6) {   // degenerate segment: a sphere; re-centre on the segment's mid-point
+    for (int k = 0; k < 3; k++) s.ca[k] = s.cb[k] = 0.5 * (s.ca[k] + s.cb[k]);
+    double r = 0;
+    for (int i = 0; i < n; i++) { double p[3] = {v[i].x, v[i].y, v[i].z}; r = std::max(r, point_segment_dist(p, s.ca, s.cb)); }
+    s.crad = r * (1 + 1e-9) + 1e-12 + s.radius; s.caplen = 0;
+  }
+}
+
 template <typename T> inline FkTables<T> convert_fk(const FkTables<double> &s) {
   FkTables<T> o; memset(&o, 0, sizeof o);
   o.nq = s.nq; o.nbody = s.nbody; o.njnt = s.njnt;
@@ -199,7 +296,157 @@ template <typename T> inline Shape<T> convert_shape(const Shape<double> &s) {
   o.radius = (T)s.radius; o.halflen = (T)s.halflen; o.brad = (T)s.brad;
   for (int k = 0; k < 3; k++) { o.c[k] = (T)s.c[k]; o.ax[k] = (T)s.ax[k]; o.bc[k] = (T)s.bc[k]; o.oc[k] = (T)s.oc[k]; o.ohalf[k] = (T)s.ohalf[k]; }
   for (int k = 0; k < 9; k++) o.orot[k] = (T)s.orot[k];
+  o.group = s.group;
+  for (int k = 0; k < 3; k++) { o.ca[k] = (T)s.ca[k]; o.cb[k] = (T)s.cb[k]; }
+  // rounding the end points can move them by half an ulp: the radius absorbs it
+  o.crad = (T)(s.crad * (1.0 + 2e-7) + (sizeof(T) == 4 ? 1e-6 : 0.0)); o.caplen = (T)s.caplen;
   return o;
+}
+
+// ---- cull groups and group pairs (level 0 of the pipeline's broad phase, vk_pipe.cuh) ---------------
+// A moving body with all its shapes is one group (bounding sphere in the body frame); a world-fixed
+// shape is a group of its own (bounding capsule / plane in the world frame: the reference scenes'
+// obstacles are long thin boxes and capsules, for which a sphere is a useless bound).  Every shape pair
+// belongs to exactly one group pair; a group pair that passes the level-0 test is expanded into its
+// shape pairs, each of which then faces the bounding-capsule test and the OBB test.
+inline bool build_groups(HostModel &H) {
+  const double slack = 1e-4;
+  for (int s = 0; s < MAX_BODY; s++) H.slot_group[s] = -1;
+  H.ngroup_moving = 0;
+  for (int sl = 0; sl < H.nslot; sl++) {
+    if (H.slot_shape_num[sl] == 0) continue;
+    const int g = H.ngroup_moving++;
+    H.slot_group[sl] = g;
+    const int s0 = H.slot_shape_adr[sl], s1 = s0 + H.slot_shape_num[sl];
+    // radius needed at centre c: the farthest vertex (+ swept radius) of any member shape
+    auto radius_at = [&](const double *c) {
+      double r = 0;
+      for (int k = s0; k < s1; k++) {
+        const Shape<double> &sh = H.shapes[k];
+        if (sh.kind == SK_VERTS) {
+          for (int i = 0; i < sh.nvert; i++) {
+            const Vtx<double> &v = H.verts[sh.vadr + i];
+            r = std::max(r, sqrt((v.x - c[0]) * (v.x - c[0]) + (v.y - c[1]) * (v.y - c[1]) + (v.z - c[2]) * (v.z - c[2])) + sh.radius);
+          }
+        } else {
+          r = std::max(r, sqrt((sh.bc[0] - c[0]) * (sh.bc[0] - c[0]) + (sh.bc[1] - c[1]) * (sh.bc[1] - c[1]) + (sh.bc[2] - c[2]) * (sh.bc[2] - c[2])) + sh.brad);
+        }
+      }
+      return r;
+    };
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int k = s0; k < s1; k++)
+      for (int a = 0; a < 3; a++) {
+        lo[a] = std::min(lo[a], H.shapes[k].bc[a] - H.shapes[k].brad);
+        hi[a] = std::max(hi[a], H.shapes[k].bc[a] + H.shapes[k].brad);
+      }
+    double c[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+    double r = radius_at(c);
+    for (int it = 0; it < 300; it++) {   // shrink: small random-free moves along the axes while they help
+      const double step = 0.25 * r / (1 + it * 0.1);
+      bool moved = false;
+      for (int a = 0; a < 3 && !moved; a++)
+        for (int sg = -1; sg <= 1 && !moved; sg += 2) {
+          double c2[3] = {c[0], c[1], c[2]};
+          c2[a] += sg * step;
+          const double r2 = radius_at(c2);
+          if (r2 < r) { r = r2; memcpy(c, c2, sizeof c); moved = true; }
+        }
+    }
+    for (int a = 0; a < 3; a++) H.group_c[g][a] = c[a];
+    H.group_r[g] = r * (1 + 1e-6) + 1e-6;   // covers the fp32 rounding of centre and vertices
+    for (int k = s0; k < s1; k++) H.shapes[k].group = g;
+  }
+  H.static_groups.clear();
+  for (size_t k = (size_t)H.nmoving_shapes; k < H.shapes.size(); k++) {
+    Shape<double> &sh = H.shapes[k];
+    StaticGroup sg; memset(&sg, 0, sizeof sg);
+    if (sh.kind == SK_PLANE) {
+      for (int a = 0; a < 3; a++) { sg.a[a] = (float)sh.c[a]; sg.ab[a] = (float)sh.ax[a]; }
+    } else {
+      double l2 = 0;
+      for (int a = 0; a < 3; a++) { sg.a[a] = (float)sh.ca[a]; sg.ab[a] = (float)(sh.cb[a] - sh.ca[a]); l2 += (double)sg.ab[a] * sg.ab[a]; }
+      sg.inv_len2 = l2 > 1e-12 ? (float)(1.0 / l2) : 0.f;
+      if (!(l2 > 1e-12)) sg.ab[0] = sg.ab[1] = sg.ab[2] = 0.f;
+    }
+    sh.group = H.ngroup_moving + (int)H.static_groups.size();
+    H.static_groups.push_back(sg);
+  }
+  // group pairs
+  struct Key { int kind, ga, gb; };
+  std::vector<Key> keys;
+  std::vector<std::vector<uint16_t>> members;
+  std::vector<double> lims;
+  for (size_t p = 0; p < H.pairs.size(); p++) {
+    const Pair &pr = H.pairs[p];
+    const Shape<double> &A = H.shapes[pr.sa], &B = H.shapes[pr.sb];
+    if (A.slot < 0 && B.slot < 0) { H.err = "a pair of two world-fixed geoms survived the filters"; return false; }
+    const double margin = H.pair_rsum64[p] - (A.kind == SK_VERTS ? A.radius : 0.0) - (B.kind == SK_VERTS ? B.radius : 0.0);
+    Key k;
+    double lim;
+    if (A.slot >= 0 && B.slot >= 0) {
+      k.kind = GK_SPHERE; k.ga = std::min(A.group, B.group); k.gb = std::max(A.group, B.group);
+      lim = H.group_r[A.group] + H.group_r[B.group] + margin + slack;
+    } else {
+      const Shape<double> &M = A.slot >= 0 ? A : B, &S = A.slot >= 0 ? B : A;
+      k.kind = S.kind == SK_PLANE ? GK_PLANE : GK_CAPSULE;
+      k.ga = M.group; k.gb = S.group - H.ngroup_moving;
+      lim = H.group_r[M.group] + (S.kind == SK_PLANE ? 0.0 : S.crad * (1 + 2e-7) + 1e-6) + margin + slack;
+    }
+    size_t idx = 0;
+    for (; idx < keys.size(); idx++) if (keys[idx].kind == k.kind && keys[idx].ga == k.ga && keys[idx].gb == k.gb) break;
+    if (idx == keys.size()) { keys.push_back(k); members.emplace_back(); lims.push_back(lim); }
+    members[idx].push_back((uint16_t)p);
+    lims[idx] = std::max(lims[idx], lim);
+  }
+  std::vector<int> ord(keys.size());
+  for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
+  std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
+    if (keys[x].kind != keys[y].kind) return keys[x].kind < keys[y].kind;
+    if (keys[x].ga != keys[y].ga) return keys[x].ga < keys[y].ga;
+    return keys[x].gb < keys[y].gb;
+  });
+  H.group_pairs.clear(); H.gp_member.clear();
+  H.gp_kind_end[0] = H.gp_kind_end[1] = H.gp_kind_end[2] = 0;
+  for (int i : ord) {
+    GroupPair g; memset(&g, 0, sizeof g);
+    g.ga = (uint16_t)keys[i].ga; g.gb = (uint16_t)keys[i].gb; g.kind = (uint32_t)keys[i].kind;
+    if (H.gp_member.size() + members[i].size() > 65535) { H.err = "too many geom pairs"; return false; }
+    g.first = (uint16_t)H.gp_member.size(); g.n = (uint16_t)members[i].size();
+    g.lim = (float)(lims[i] * (1 + 2e-7));
+    for (uint16_t p : members[i]) H.gp_member.push_back(p);
+    H.group_pairs.push_back(g);
+    for (int k = keys[i].kind; k < 3; k++) H.gp_kind_end[k]++;
+  }
+  if (H.group_pairs.size() > 2047) { H.err = "too many body pairs"; return false; }   // 11 bits in a level-0 queue entry
+  // calibration of the level-0 output (buffer sizing only): the same fp32 test on seeded rows
+  {
+    FkTables<float> fk32 = convert_fk<float>(H.fk);
+    Pose<float> ident; ident.p = mk<float>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+    const int NCAL = 1024;
+    double n0 = 0, nsub = 0;
+    for (int r = 0; r < NCAL; r++) {
+      float q[MAX_JNT];
+      for (int j = 0; j < H.nq; j++) {
+        float lo = (float)H.jnt_lo[j], hi = (float)H.jnt_hi[j];
+        if (!(hi > lo)) { lo = -3.14159f; hi = 3.14159f; }
+        q[j] = sweep_value(0x5eedull, (uint64_t)r, (uint32_t)j, lo, hi);
+      }
+      Pose<float> P[MAX_BODY];
+      V3<float> cen[MAX_GROUP];
+      for (int k = 0; k < H.nslot; k++) {
+        int ps = fk32.body_parent[k];
+        P[k] = fk_body(fk32, k, ps < 0 ? ident : P[ps], q);
+        const int g = H.slot_group[k];
+        if (g >= 0) cen[g] = P[k].p + qrot(P[k].q, mk<float>((float)H.group_c[g][0], (float)H.group_c[g][1], (float)H.group_c[g][2]));
+      }
+      for (const GroupPair &g : H.group_pairs)
+        if (group_pair_near(g, cen[g.ga], g.kind == GK_SPHERE ? cen[g.gb] : cen[g.ga],
+                            g.kind == GK_SPHERE ? nullptr : &H.static_groups[g.gb])) { n0 += 1; nsub += g.n; }
+    }
+    H.calib_l0_per_row = n0 / NCAL; H.calib_sub_per_row = nsub / NCAL;
+  }
+  return true;
 }
 
 inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
@@ -355,7 +602,11 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
       default: H.err = "unsupported geom type"; return false;
     }
     s.nvert = (int)H.verts.size() - s.vadr;
-    if (s.kind == SK_VERTS) fit_bounds(s, H.verts);
+    if (s.kind == SK_VERTS) { fit_bounds(s, H.verts); fit_capsule(s, H.verts); }
+    if (s.kind == SK_CYL) {   // the axis segment swept by the cylinder's radius contains the cylinder
+      for (int k = 0; k < 3; k++) { s.ca[k] = s.c[k] - s.halflen * s.ax[k]; s.cb[k] = s.c[k] + s.halflen * s.ax[k]; }
+      s.crad = s.radius * (1 + 1e-9); s.caplen = 2 * s.halflen;
+    }
     geom_shape[g] = (int)tmp.size();
     tmp.push_back(s);
     tmp_slot.push_back(s.slot);
@@ -452,7 +703,7 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
     }
     H.adj_start[lists.size()] = (uint16_t)H.adj.size();
   }
-  for (auto &sh : H.shapes) sh.pad = 0;
+  for (auto &sh : H.shapes) sh.group = -1;
 
   // ---- pairs in processing order --------------------------------------------------------------------
   struct Tmp { Pair p; int g1, g2; long key; double rsum, bsum; };
@@ -539,7 +790,8 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
     for (size_t p = 0; p < tp.size(); p++) {
       H.calib_sphere_per_row += n_sph[p] / NCAL; H.calib_items_per_row += n_obb[p] / NCAL;
       const Shape<double> &A = H.shapes[tp[p].p.sa], &B = H.shapes[tp[p].p.sb];
-      if (item_needs_scan(tp[p].p, B)) H.bin_expect[item_bin(tp[p].p, A, B)] += n_obb[p] / NCAL;
+      (void)B;
+      H.bin_expect[item_bin(tp[p].p, A, B)] += n_obb[p] / NCAL;   // every surviving item goes to a bin (closed forms: bin 0)
     }
     H.calib_pen_rows /= NCAL;
   }
@@ -615,7 +867,7 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
   }
   H.round_start[H.nrounds] = (int)ord.size();
   if (H.pairs.size() > 60000) { H.err = "too many geom pairs"; return false; }
-  return true;
+  return build_groups(H);
 }
 
 // mjb_pose_spec (caller's view: site in its body frame, reference frame world_T_C) -> PoseSpec

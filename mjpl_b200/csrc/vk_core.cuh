@@ -178,9 +178,12 @@ template <typename T> struct Shape {
   int geom;        // MuJoCo geom id
   int graph;       // 1: hull adjacency available (hill-climbing support), 0: scan all vertices
   uint8_t ext[8];  // graph: local ids of the extreme vertices along +x,-x,+y,-y,+z,-z (start points)
-  int pad;
+  int group;       // cull group of the shape (vk_pipe.cuh): its moving body, or the shape itself if world fixed
+  // bounding capsule (line-swept sphere) in the same frame as the vertices: segment ca..cb, radius
+  // crad (includes the swept radius); caplen == 0 marks a point-like capsule (a sphere)
+  T ca[3], cb[3], crad, caplen;
 };
-static_assert(sizeof(Shape<float>) == 144, "Shape<float> must stay a multiple of 16 bytes (cp.async.bulk granularity)");
+static_assert(sizeof(Shape<float>) == 176, "Shape<float> must stay a multiple of 16 bytes (cp.async.bulk granularity)");
 
 struct Pair {
   uint16_t sa, sb;  // shape indices (sa: plane if any; else the one with more vertices first)
@@ -634,14 +637,104 @@ VK_HD int segseg_item(const Shape<T> &A, const Shape<T> &B, const Vtx<T> *verts,
   return segseg_classify(p1, q1, p2, q2, R);
 }
 
-// the mid-phase cull of one surviving (row, pair): true => certainly no contact
+// ------------------------------------------------------------------------------ bounding-capsule cull
+// squared distance between the segments p1..q1 and p2..q2 (either may be a point): closed form with
+// clamping (exact in exact arithmetic: the clamped coordinate steps below can only decrease the
+// distance of the pair found so far).  The scalar part runs in fp64 whatever T is: for nearly
+// parallel segments `a e - b b` cancels, and in fp32 the pair that comes out can be off by
+// angle x length (4e-4 m measured on unit segments) -- too much for a cull that has to be
+// conservative.  B200 issues fp64 at half the fp32 rate, and this is ~40 flops per shape pair.
+template <typename T>
+VK_HD T segseg_dist2(V3<T> p1, V3<T> q1, V3<T> p2, V3<T> q2) {
+  const V3<double> P1 = mk<double>(p1.x, p1.y, p1.z), P2 = mk<double>(p2.x, p2.y, p2.z);
+  const V3<double> d1 = mk<double>(q1.x, q1.y, q1.z) - P1, d2 = mk<double>(q2.x, q2.y, q2.z) - P2, r = P1 - P2;
+  const double a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
+  const double den = a * e - b * b;
+  double s = den > 1e-14 * a * e ? (b * f - c * e) / den : 0.0;
+  s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
+  double t = e > 1e-30 ? (b * s + f) / e : 0.0;
+  t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+  s = a > 1e-30 ? (b * t - c) / a : 0.0;
+  s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
+  const V3<double> dd = r + d1 * s - d2 * t;
+  return (T)dot(dd, dd);
+}
+
+// true => the bounding capsules of the two shapes are certainly further apart than rsum_core +
+// slack, i.e. the pair cannot be in contact.  `lim` = margin + slack (the capsule radii already
+// include the swept radii).  The clamped closed form above can overestimate the distance of
+// near-parallel segments by rounding only; `slack` (1e-4) is far above that.
+template <typename T>
+VK_HD bool capsule_cull(const Pair &pr, const Shape<T> &A, const Shape<T> &B, const Pose<T> &PA, const Pose<T> &PB, T lim) {
+  const V3<T> b0 = PB.p + qrot(PB.q, mk<T>(B.ca[0], B.ca[1], B.ca[2]));
+  const bool bseg = B.caplen > T(0);
+  const V3<T> b1 = bseg ? PB.p + qrot(PB.q, mk<T>(B.cb[0], B.cb[1], B.cb[2])) : b0;
+  if (pr.kind == PK_PLANE) {
+    const V3<T> n = mk<T>(A.ax[0], A.ax[1], A.ax[2]), c = mk<T>(A.c[0], A.c[1], A.c[2]);
+    const T d = vk_min(dot(n, b0 - c), dot(n, b1 - c));
+    return d > B.crad + lim;
+  }
+  const V3<T> a0 = PA.p + qrot(PA.q, mk<T>(A.ca[0], A.ca[1], A.ca[2]));
+  const bool aseg = A.caplen > T(0);
+  const V3<T> a1 = aseg ? PA.p + qrot(PA.q, mk<T>(A.cb[0], A.cb[1], A.cb[2])) : a0;
+  const T r = A.crad + B.crad + lim;
+  T d2;
+  if (!aseg && !bseg) { const V3<T> d = a0 - b0; d2 = dot(d, d); }
+  else d2 = segseg_dist2(a0, a1, b0, b1);
+  return d2 > r * r;
+}
+
+// the mid-phase cull of one (row, pair) that survived the bounding spheres: true => certainly no
+// contact.  Bounding capsules first (cheap, and tight for the long thin shapes spheres are useless
+// for), then the OBB separating axes for the pairs whose narrow phase is expensive enough (PF_OBB).
 template <typename T>
 VK_HD bool midphase_cull(const Pair &pr, const Shape<T> &A, const Shape<T> &B, const Pose<T> &PA, const Pose<T> &PB,
                          T margin, T slack) {
+  if (pr.kind != PK_SEGSEG && capsule_cull(pr, A, B, PA, PB, margin + slack)) return true;
   if (!(pr.flags & PF_OBB)) return false;
   if (pr.kind == PK_PLANE) return obb_above_plane(A, B, PB, margin + slack);
   Rel<T> rel = relative_pose(PA, PB);
   return obb_disjoint(A, B, rel, margin + slack);
+}
+
+// ------------------------------------------------------------------------------ cull groups (vk_pipe.cuh)
+// Level 0 of the broad phase works on GROUPS: a moving body with all its collision shapes (one
+// bounding sphere in the body frame), or one world-fixed shape (its bounding capsule / plane in the
+// world frame).  A group pair stands for all the shape pairs between its two groups.
+enum GroupPairKind : int { GK_SPHERE = 0, GK_CAPSULE = 1, GK_PLANE = 2 };
+struct GroupPair {
+  uint16_t ga;      // moving group (index into the moving-group table = row of the centre array)
+  uint16_t gb;      // GK_SPHERE: moving group; GK_CAPSULE / GK_PLANE: index into the static table
+  uint16_t first;   // its shape pairs: member[first .. first + n)
+  uint16_t n;
+  float lim;        // radii + largest margin of the member pairs + slack (GK_PLANE: radius + margin + slack)
+  uint32_t kind;
+};
+static_assert(sizeof(GroupPair) == 16, "GroupPair is loaded as one 16-byte word");
+struct StaticGroup {   // world frame
+  float a[3];          // GK_CAPSULE: segment start;   GK_PLANE: a point of the plane
+  float inv_len2;      // GK_CAPSULE: 1 / |ab|^2 (0 for a point)
+  float ab[3];         // GK_CAPSULE: segment vector;  GK_PLANE: unit normal
+  float pad;
+};
+static_assert(sizeof(StaticGroup) == 32, "StaticGroup is loaded as two 16-byte words");
+constexpr int MAX_GROUP = MAX_BODY;
+
+// level-0 test of one group pair: false => no shape pair between the two groups can be in contact.
+// cA: world centre of moving group ga; cB: world centre of moving group gb (GK_SPHERE only);
+// S: the static group (GK_CAPSULE / GK_PLANE).
+VK_HD bool group_pair_near(const GroupPair &g, V3<float> cA, V3<float> cB, const StaticGroup *S) {
+  if (g.kind == GK_SPHERE) {
+    const V3<float> d = cA - cB;
+    return dot(d, d) <= g.lim * g.lim;
+  }
+  const V3<float> e = cA - mk<float>(S->a[0], S->a[1], S->a[2]);
+  const V3<float> ab = mk<float>(S->ab[0], S->ab[1], S->ab[2]);
+  if (g.kind == GK_PLANE) return dot(e, ab) <= g.lim;
+  float t = dot(e, ab) * S->inv_len2;
+  t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+  const V3<float> f = e - ab * t;
+  return dot(f, f) <= g.lim * g.lim;
 }
 
 // ------------------------------------------------------------------------------ narrow phase of one item (scalar)

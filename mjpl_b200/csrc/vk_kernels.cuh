@@ -74,13 +74,22 @@ struct KArgs {
   unsigned long long *bin_items;        // NBIN regions: row | pair << 44
   unsigned long long bin_off[NBIN], bin_capv[NBIN];   // start and capacity of each bin's region
   uint32_t *row_flags;                  // 1 byte per row (bit 0: queued for whole-row fp64 re-evaluation)
+  // cull groups (vk_pipe.cuh)
+  int slot_group[MAX_BODY];             // pose slot -> moving group or -1
+  float group_c[MAX_GROUP][3];          // bounding-sphere centre of a moving group, body frame
+  const GroupPair *gpairs; const StaticGroup *sgroups; const uint16_t *gp_member;
+  int ngpair, nsgroup, ngroup_moving, nmember;
+  int gp_kind_end[3];
+  unsigned long long *l0_items;         // level-0 survivors: row | group pair << 40
+  unsigned long long l0_cap;
 };
 
 // counters layout
 constexpr int C_TICKET = 0, C_RECHECK = 1, C_RTICKET = 2, C_RITEMS = 3, C_RITICKET = 4;   // per launch
 constexpr int C_BIN = 5, C_BTICKET = 13;   // per launch: fill and consumer ticket of each bin
-constexpr int C_ITEMS = 21, C_OVERFLOW = 22, C_UNCERTAIN = 23, C_ROWS = 24, C_TRIPS = 25, C_HIST = 26, C_NCOUNTERS = 36;  // statistics
-constexpr int C_PER_LAUNCH = 21;  // counters [0, C_PER_LAUNCH) are cleared before every launch
+constexpr int C_L0 = 21, C_L0TICKET = 22;  // per launch: fill of the level-0 list (vk_pipe.cuh) and its consumer ticket
+constexpr int C_ITEMS = 23, C_OVERFLOW = 24, C_UNCERTAIN = 25, C_ROWS = 26, C_TRIPS = 27, C_HIST = 28, C_NCOUNTERS = 38;  // statistics
+constexpr int C_PER_LAUNCH = 23;  // counters [0, C_PER_LAUNCH) are cleared before every launch
 
 // ---------------------------------------------------------------------------- PTX helpers (sm_90+/sm_100a)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -593,7 +602,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
             const int r = it & 0xffff;
             const Pair pr = s_pairs[it >> 16];
             keep = !((hit_mask >> r) & 1u);
-            if (keep && use_obb && (pr.flags & PF_OBB)) {
+            if (keep && use_obb) {
               const Shape<float> &A = s_shapes[pr.sa];
               const Shape<float> &B = s_shapes[pr.sb];
               Pose<float> PA = load_pose(pose, A.slot, wrow0 + r, TILE);

@@ -1,0 +1,420 @@
+// vk_pipe.cuh -- the validity path for large batches: a pipeline of small kernels.
+//
+//   fk_cull_kernel  lane = row.  Joint limits, forward kinematics (poses to an L2-resident
+//                   [row][slot][8] array), then LEVEL 0 of the broad phase on cull GROUPS: a moving body
+//                   with all its shapes is one bounding sphere, a world-fixed shape is its bounding
+//                   capsule or plane.  ~120 group tests per row instead of ~320 shape-pair tests, and no
+//                   per-shape state in shared memory: 6.4 KB per warp, <= 64 registers, 32 warps per SM.
+//                   Surviving (row, group pair) entries are staged per warp and flushed to a global list
+//                   with ONE atomic per flush.
+//   mid_kernel      lane = entry / shape pair.  Expands every surviving group pair into its shape pairs,
+//                   culls them with the shapes' bounding CAPSULES (the reference scenes' obstacles are
+//                   long thin boxes and capsules: spheres around them are useless, capsules are tight),
+//                   compacts, culls the survivors with the OBB separating-axis test, and appends what is
+//                   left to the narrow phase's bins (closed-form kinds into the first bin).
+//   narrow_kernel   (vk_split.cuh) persistent lanes over the bins, certified verdicts, fp64 list.
+//
+// Measured on the uniform Franka sweep (scene_with_obstacles, tests/hostsim census): 6.1 group pairs
+// per row survive level 0, they expand to 20 shape pairs, 3.8 survive the capsules, 2.6 the OBBs --
+// against 30 sphere survivors and 7.8 narrow-phase items per row with per-shape bounding spheres.
+// Culls are conservative (slack 1e-4 m, far above fp32 rounding) and never decide a result.
+#pragma once
+
+#include "vk_kernels.cuh"
+#include "vk_split.cuh"
+
+namespace vk {
+
+constexpr int L0_QCAP = 256;          // per-warp staging queue of level-0 survivors (entries)
+constexpr int PIPE_FK_THREADS = 256;  // fk_cull_kernel: 8 warps per CTA, 4 CTAs per SM
+constexpr int MID_THREADS = 256;
+constexpr int MID_Q1CAP = 1024;       // per-warp queue of expanded shape pairs
+constexpr int MID_Q2CAP = 96;         // per-warp queue of capsule survivors waiting for the OBB test
+constexpr int MID_CHUNK = 128;        // level-0 entries a warp claims per ticket
+
+struct PipeFkLayout { size_t gpairs, sgroups, cen, qtile, q0, bars, total; };
+__host__ __device__ inline PipeFkLayout pipe_fk_layout(int ngpair, int nsgroup, int ngroup_moving, int nq) {
+  PipeFkLayout L;
+  const int W = PIPE_FK_THREADS / 32;
+  size_t o = 0;
+  L.gpairs = o; o = align_up(o + (size_t)ngpair * sizeof(GroupPair), 128);
+  L.sgroups = o; o = align_up(o + (size_t)(nsgroup > 0 ? nsgroup : 1) * sizeof(StaticGroup), 128);
+  L.cen = o; o = align_up(o + (size_t)W * (ngroup_moving > 0 ? ngroup_moving : 1) * 3 * 32 * sizeof(float), 128);
+  L.qtile = o; o = align_up(o + (size_t)W * 32 * nq * sizeof(float), 128);
+  L.q0 = o; o = align_up(o + (size_t)W * L0_QCAP * sizeof(uint32_t), 128);
+  L.bars = o; o = align_up(o + 64 + 8 * W, 128);
+  L.total = o;
+  return L;
+}
+
+// rows whose level-0 entries did not fit the global list are re-evaluated whole in fp64 (the list is
+// sized at several times the calibrated average; only degenerate batches get here)
+__device__ __forceinline__ void pipe_row_overflow(const KArgs &a, long long row) {
+  const uint32_t bit = 1u << ((unsigned)(row & 3) * 8u);
+  if (!(atomicOr(&a.row_flags[row >> 2], bit) & bit)) {
+    const unsigned long long s = atomicAdd(&a.counters[C_RECHECK], 1ull);
+    a.recheck_rows[s] = row;
+  }
+}
+
+__global__ void __launch_bounds__(PIPE_FK_THREADS, 4) fk_cull_kernel(const __grid_constant__ KArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int nq = a.fk.nq;
+  const PipeFkLayout L = pipe_fk_layout(a.ngpair, a.nsgroup, a.ngroup_moving, nq);
+  GroupPair *s_gp = reinterpret_cast<GroupPair *>(smem + L.gpairs);
+  StaticGroup *s_sg = reinterpret_cast<StaticGroup *>(smem + L.sgroups);
+  uint64_t *s_bar = reinterpret_cast<uint64_t *>(smem + L.bars);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ngm = a.ngroup_moving > 0 ? a.ngroup_moving : 1;
+  float *cen = reinterpret_cast<float *>(smem + L.cen) + (size_t)warp * ngm * 96;   // [group][xyz][lane]
+  float *wq = reinterpret_cast<float *>(smem + L.qtile) + (size_t)warp * 32 * nq;   // this warp's 32 rows
+  uint32_t *q0 = reinterpret_cast<uint32_t *>(smem + L.q0) + (size_t)warp * L0_QCAP;
+
+  // ---- one-time: group tables -> shared memory through the bulk-copy engine ----------------------
+  const uint32_t bytes_g = (uint32_t)(a.ngpair * sizeof(GroupPair));
+  const uint32_t bytes_s = (uint32_t)(a.nsgroup * sizeof(StaticGroup));
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&s_bar[0], bytes_g + bytes_s);
+    if (bytes_g) bulk_g2s(s_gp, a.gpairs, bytes_g, &s_bar[0]);
+    if (bytes_s) bulk_g2s(s_sg, a.sgroups, bytes_s, &s_bar[0]);
+  }
+  mbar_wait(&s_bar[0], 0);
+  __syncthreads();
+
+  long long nrows = a.n;
+  if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) nrows = a.edge_prefix[a.nedge];
+  const long long ntiles = (nrows + 31) / 32;
+  uint32_t row_parity = 0;
+  const bool dense_bulk = (a.mode == MODE_DENSE) && (a.ldq == nq) && ((reinterpret_cast<uintptr_t>(a.q) & 15) == 0);
+  long long rows_total = 0;
+  uint64_t *wbar = s_bar + 8 + warp;
+  if (lane == 0) mbar_init(wbar, 1);
+  fence_barrier_init();
+  __syncwarp();
+  const unsigned below = (1u << lane) - 1u;
+
+  for (;;) {
+    long long tile = 0;
+    if (lane == 0) tile = (long long)atomicAdd(&a.counters[C_TICKET], 1ull);
+    tile = __shfl_sync(0xffffffffu, tile, 0);
+    if (tile >= ntiles) break;
+    const long long row_base = tile * 32;
+    const int rows_here = (int)((nrows - row_base) < 32 ? (nrows - row_base) : 32);
+    const long long row = row_base + lane;
+    const bool active = lane < rows_here;
+    rows_total += rows_here;
+
+    // ---- P0: the warp's rows -> shared (one TMA bulk copy per tile) ---------------------------------
+    if (a.mode == MODE_DENSE) {
+      if (a.rows_ready) {   // host -> device copy still in flight (mjb_check_configs_host)
+        if (lane == 0) {
+          const unsigned long long need = (unsigned long long)(row_base + rows_here);
+          const long long t0 = clock64();
+          while (ld_acquire_sys(a.rows_ready) < need) {
+            __nanosleep(256);
+            if (clock64() - t0 > 8000000000ll) __trap();
+          }
+        }
+        __syncwarp();
+      }
+      if (dense_bulk && rows_here == 32) {
+        if (lane == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(wbar, (uint32_t)(32 * nq * sizeof(float)));
+          bulk_g2s(wq, a.q + row_base * nq, (uint32_t)(32 * nq * sizeof(float)), wbar);
+        }
+        mbar_wait(wbar, row_parity);
+        row_parity ^= 1;
+      } else {
+        for (int i = lane; i < rows_here * nq; i += 32) {
+          int r = i / nq, j = i - r * nq;
+          wq[i] = a.q[(row_base + r) * a.ldq + j];
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- P1: limits + FK, lane = row; the row's preliminary answer ----------------------------------
+    float *q = wq + lane * nq;
+    long long e_idx = 0;
+    int e_k = 0;
+    bool lim_ok = true;
+    if (active) {
+      if (a.mode == MODE_EDGES) {
+        edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
+        edge_row<float>(a.q0, a.q1, a.ldq, nq, a.step, e_idx, e_k, q);
+      } else if (a.mode == MODE_CHAINS) {
+        edge_lookup(a.edge_prefix, a.nedge, row, e_idx, e_k);
+        const bool lim = a.flags & F_LIMITS;
+        lim_ok = chain_point<float>(a.c0, a.c1, nq, a.ceps, e_idx, e_k, q, lim ? a.jnt_lo : nullptr, lim ? a.jnt_hi : nullptr);
+      } else if (a.mode == MODE_SWEEP) {
+#pragma unroll 1
+        for (int j = 0; j < nq; j++)
+          q[j] = sweep_value(a.seed, (uint64_t)(a.row0 + row), (uint32_t)j, a.fk.jnt_lo[j], a.fk.jnt_hi[j]);
+      }
+      if ((a.flags & F_LIMITS) && a.mode != MODE_CHAINS)
+        lim_ok = limits_ok(q, a.fk.njnt, a.jnt_lo, a.jnt_hi, a.flags & F_LIMITS_OUTWARD);
+      if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) {
+        if (!lim_ok) atomicMin(&a.first_bad[e_idx], e_k);
+      } else {
+        a.valid[row] = lim_ok ? 1 : 0;   // the later kernels can only turn it to 0
+      }
+    }
+    const bool do_coll = active && lim_ok && (a.flags & F_COLLISION);
+    if (__ballot_sync(0xffffffffu, do_coll) == 0) continue;
+    if (do_coll) {
+      Pose<float> prev;
+      prev.p = mk<float>(0, 0, 0); prev.q.w = 1; prev.q.x = prev.q.y = prev.q.z = 0;
+      int prev_slot = -1;
+#pragma unroll 1
+      for (int s = 0; s < a.nslot; s++) {
+        const int ps = a.fk.body_parent[s];
+        Pose<float> P = (ps == prev_slot) ? prev : load_pose8(a.pose8, a.nslot, row, ps);
+        Pose<float> B = fk_body(a.fk, s, P, q);
+        prev = B; prev_slot = s;
+        float4 *b = reinterpret_cast<float4 *>(a.pose8 + ((size_t)row * a.nslot + s) * 8);
+        b[0] = make_float4(B.p.x, B.p.y, B.p.z, B.q.w);
+        b[1] = make_float4(B.q.x, B.q.y, B.q.z, 0.f);
+        const int g = a.slot_group[s];
+        if (g >= 0) {
+          const V3<float> c = B.p + qrot(B.q, mk<float>(a.group_c[g][0], a.group_c[g][1], a.group_c[g][2]));
+          float *cc = cen + g * 96 + lane;
+          cc[0] = c.x; cc[32] = c.y; cc[64] = c.z;
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- level 0: group pairs, lane = row; survivors -> per-warp queue -> global list --------------
+    int n0 = 0;   // warp-uniform queue fill
+    auto flush = [&]() {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&a.counters[C_L0], (unsigned long long)n0);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      for (int i = lane; i < n0; i += 32) {
+        const uint32_t e = q0[i];
+        const unsigned long long r = (unsigned long long)(row_base + (e & 31u));
+        if (base + i < a.l0_cap) a.l0_items[base + i] = r | ((unsigned long long)(e >> 5) << 40);
+        else pipe_row_overflow(a, (long long)r);
+      }
+      n0 = 0;
+      __syncwarp();
+    };
+    auto push = [&](bool s, int p) {
+      const unsigned m = __ballot_sync(0xffffffffu, s);
+      if (m) {
+        if (s) q0[n0 + __popc(m & below)] = (uint32_t)lane | ((uint32_t)p << 5);
+        n0 += __popc(m);
+        if (n0 + 32 > L0_QCAP) { __syncwarp(); flush(); }
+      }
+    };
+    auto centre = [&](int g) { const float *cc = cen + g * 96 + lane; return mk<float>(cc[0], cc[32], cc[64]); };
+    int p = 0;
+    {  // moving sphere against moving sphere (pairs sorted by ga: its centre is fetched once per run)
+      int cached = -1;
+      V3<float> cA = mk<float>(0.f, 0.f, 0.f);
+#pragma unroll 2
+      for (; p < a.gp_kind_end[0]; p++) {
+        const GroupPair g = s_gp[p];
+        if ((int)g.ga != cached) { cached = g.ga; cA = centre(g.ga); }
+        const V3<float> d = cA - centre(g.gb);
+        push(do_coll && dot(d, d) <= g.lim * g.lim, p);
+      }
+    }
+    {  // moving sphere against a world-fixed capsule
+      int cached = -1;
+      V3<float> cA = mk<float>(0.f, 0.f, 0.f);
+#pragma unroll 2
+      for (; p < a.gp_kind_end[1]; p++) {
+        const GroupPair g = s_gp[p];
+        if ((int)g.ga != cached) { cached = g.ga; cA = centre(g.ga); }
+        const StaticGroup S = s_sg[g.gb];
+        const V3<float> e = cA - mk<float>(S.a[0], S.a[1], S.a[2]);
+        const V3<float> ab = mk<float>(S.ab[0], S.ab[1], S.ab[2]);
+        float t = dot(e, ab) * S.inv_len2;
+        t = fminf(fmaxf(t, 0.f), 1.f);
+        const V3<float> f = e - ab * t;
+        push(do_coll && dot(f, f) <= g.lim * g.lim, p);
+      }
+    }
+    for (; p < a.gp_kind_end[2]; p++) {  // moving sphere against a plane
+      const GroupPair g = s_gp[p];
+      const StaticGroup S = s_sg[g.gb];
+      const V3<float> e = centre(g.ga) - mk<float>(S.a[0], S.a[1], S.a[2]);
+      push(do_coll && dot(e, mk<float>(S.ab[0], S.ab[1], S.ab[2])) <= g.lim, p);
+    }
+    __syncwarp();
+    if (n0) flush();
+  }
+  if (lane == 0 && rows_total) atomicAdd(&a.counters[C_ROWS], (unsigned long long)rows_total);
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct MidLayout { size_t shapes, pairs, gpairs, member, q1, q2, total; };
+__host__ __device__ inline MidLayout mid_layout(int nshape, int npair, int ngpair, int nmember) {
+  MidLayout L;
+  const int W = MID_THREADS / 32;
+  size_t o = 0;
+  L.shapes = o; o = align_up(o + (size_t)nshape * sizeof(Shape<float>), 128);
+  L.pairs = o; o = align_up(o + (size_t)npair * sizeof(Pair), 128);
+  L.gpairs = o; o = align_up(o + (size_t)ngpair * sizeof(GroupPair), 128);
+  L.member = o; o = align_up(o + (size_t)nmember * sizeof(uint16_t), 128);
+  L.q1 = o; o = align_up(o + (size_t)W * MID_Q1CAP * sizeof(uint32_t), 128);
+  L.q2 = o; o = align_up(o + (size_t)W * MID_Q2CAP * sizeof(unsigned long long), 128);
+  L.total = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(MID_THREADS, 2) mid_kernel(const __grid_constant__ KArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const MidLayout L = mid_layout(a.nshape, a.npair, a.ngpair, a.nmember);
+  Shape<float> *s_shapes = reinterpret_cast<Shape<float> *>(smem + L.shapes);
+  Pair *s_pairs = reinterpret_cast<Pair *>(smem + L.pairs);
+  GroupPair *s_gp = reinterpret_cast<GroupPair *>(smem + L.gpairs);
+  uint16_t *s_member = reinterpret_cast<uint16_t *>(smem + L.member);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t *q1 = reinterpret_cast<uint32_t *>(smem + L.q1) + (size_t)warp * MID_Q1CAP;
+  unsigned long long *q2 = reinterpret_cast<unsigned long long *>(smem + L.q2) + (size_t)warp * MID_Q2CAP;
+  __shared__ uint64_t s_bar;
+
+  const uint32_t bytes_s = (uint32_t)(a.nshape * sizeof(Shape<float>));
+  const uint32_t bytes_p = (uint32_t)(a.npair * sizeof(Pair));
+  const uint32_t bytes_g = (uint32_t)(a.ngpair * sizeof(GroupPair));
+  const uint32_t bytes_m = (uint32_t)align_up((size_t)a.nmember * sizeof(uint16_t), 16);   // device array is padded
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&s_bar, bytes_s + bytes_p + bytes_g + bytes_m);
+    if (bytes_s) bulk_g2s(s_shapes, a.shapes, bytes_s, &s_bar);
+    if (bytes_p) bulk_g2s(s_pairs, a.pairs, bytes_p, &s_bar);
+    if (bytes_g) bulk_g2s(s_gp, a.gpairs, bytes_g, &s_bar);
+    if (bytes_m) bulk_g2s(s_member, a.gp_member, bytes_m, &s_bar);
+  }
+  mbar_wait(&s_bar, 0);
+  __syncthreads();
+
+  unsigned long long total = a.counters[C_L0];
+  if (total > a.l0_cap) total = a.l0_cap;
+  const bool use_obb = !(a.flags & F_NO_OBB);
+  const float slack = 1e-4f;
+  const unsigned below = (1u << lane) - 1u;
+  long long items_total = 0;
+  int n2 = 0;   // warp-uniform: capsule survivors waiting in q2
+
+  // the OBB cull of the last `count` (<= 32) queued survivors, then the bins (lane = survivor)
+  auto drain = [&](int count) {
+    int bin = -1;
+    unsigned long long it = 0;
+    __syncwarp();
+    if (lane < count) {
+      it = q2[n2 - count + lane];
+      const int ip = (int)(it >> 44);
+      const long long irow = (long long)(it & ((1ull << 44) - 1ull));
+      const Pair pr = s_pairs[ip];
+      const Shape<float> &A = s_shapes[pr.sa];
+      const Shape<float> &B = s_shapes[pr.sb];
+      bool keep = true;
+      if (use_obb && (pr.flags & PF_OBB)) {
+        const Pose<float> PB = load_pose8(a.pose8, a.nslot, irow, B.slot);
+        if (pr.kind == PK_PLANE) {
+          keep = !obb_above_plane(A, B, PB, pr.rsum - swept_radius(B) + slack);
+        } else {
+          const Pose<float> PA = load_pose8(a.pose8, a.nslot, irow, A.slot);
+          keep = !obb_disjoint(A, B, relative_pose(PA, PB), pr.rsum - swept_radius(A) - swept_radius(B) + slack);
+        }
+      }
+      if (keep) bin = item_bin(pr, A, B);
+    }
+    n2 -= count;
+    __syncwarp();
+    unsigned todo = __ballot_sync(0xffffffffu, bin >= 0);
+    while (todo) {
+      const int b = __shfl_sync(0xffffffffu, bin, __ffs(todo) - 1);
+      const unsigned m = __ballot_sync(0xffffffffu, bin == b);
+      unsigned long long base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(&a.counters[C_BIN + b], (unsigned long long)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      if (bin == b) {
+        const unsigned long long idx = base + __popc(m & below);
+        if (idx < a.bin_capv[b]) a.bin_items[a.bin_off[b] + idx] = it;
+        else broad_overflow_item(a, (int)(it >> 44), (long long)(it & ((1ull << 44) - 1ull)));
+        items_total += 1;
+      }
+      todo &= ~m;
+    }
+  };
+
+  for (;;) {
+    unsigned long long chunk = 0;
+    if (lane == 0) chunk = atomicAdd(&a.counters[C_L0TICKET], 1ull);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
+    const unsigned long long c0 = chunk * MID_CHUNK;
+    if (c0 >= total) break;
+#pragma unroll 1
+    for (int sub = 0; sub < MID_CHUNK / 32; sub++) {
+      const unsigned long long ei = c0 + (unsigned long long)sub * 32 + lane;
+      if (c0 + (unsigned long long)sub * 32 >= total) break;
+      // ---- expand: every entry (row, group pair) -> its shape pairs ----------------------------------
+      long long row = 0;
+      int first = 0, n = 0;
+      if (ei < total) {
+        const unsigned long long e = a.l0_items[ei];
+        row = (long long)(e & ((1ull << 40) - 1ull));
+        const GroupPair g = s_gp[(int)(e >> 40)];
+        first = g.first; n = g.n;
+      }
+      int off = n;   // inclusive warp scan of n
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, off, o);
+        if (lane >= o) off += v;
+      }
+      const int T = __shfl_sync(0xffffffffu, off, 31);
+      off -= n;
+      for (int i = 0; i < n; i++)
+        if (off + i < MID_Q1CAP) q1[off + i] = ((uint32_t)lane << 16) | (uint32_t)s_member[first + i];
+      __syncwarp();
+      const int Tq = T < MID_Q1CAP ? T : MID_Q1CAP;
+      // entries whose shape pairs did not fit (T > MID_Q1CAP: never with the shipped models, whose group
+      // pairs have <= 18 members; 32 x 32 = 1024) fall back to whole-row fp64 re-evaluation
+      if (T > MID_Q1CAP && off + n > MID_Q1CAP && n > 0) pipe_row_overflow(a, row);
+      // ---- capsule cull, lane = shape pair of some entry -------------------------------------------------
+#pragma unroll 1
+      for (int s0 = 0; s0 < Tq; s0 += 32) {
+        const int s = s0 + lane;
+        const uint32_t subit = s < Tq ? q1[s] : 0u;
+        const long long irow = __shfl_sync(0xffffffffu, row, (int)(subit >> 16));
+        bool keep = false;
+        const int ip = (int)(subit & 0xffffu);
+        if (s < Tq) {
+          const Pair pr = s_pairs[ip];
+          keep = true;
+          if (use_obb && pr.kind != PK_SEGSEG) {
+            const Shape<float> &A = s_shapes[pr.sa];
+            const Shape<float> &B = s_shapes[pr.sb];
+            const Pose<float> PA = load_pose8(a.pose8, a.nslot, irow, A.slot);
+            const Pose<float> PB = load_pose8(a.pose8, a.nslot, irow, B.slot);
+            keep = !capsule_cull(pr, A, B, PA, PB, pr.rsum - swept_radius(A) - swept_radius(B) + slack);
+          }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (keep) q2[n2 + __popc(m & below)] = (unsigned long long)irow | ((unsigned long long)ip << 44);
+        n2 += __popc(m);
+        __syncwarp();
+        while (n2 >= 32) drain(32);   // keeps n2 + 32 <= MID_Q2CAP for the next push
+      }
+    }
+  }
+  while (n2 > 0) drain(n2 < 32 ? n2 : 32);
+  if (items_total) atomicAdd(&a.counters[C_ITEMS], (unsigned long long)items_total);
+}
+
+}  // namespace vk

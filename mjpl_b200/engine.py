@@ -233,16 +233,17 @@ class ValidityEngine:
 
     def kernel_timing(self, enable: bool = True, read: bool = False):
         """Switch per-kernel CUDA-event timing of the validity launches on/off; with ``read`` return
-        ``{"first_ms", "narrow_ms", "fp64_ms", "launches", "pipeline"}`` summed since the last read."""
+        ``{"first_ms", "mid_ms", "narrow_ms", "fp64_ms", "launches", "pipeline"}`` summed since the last
+        read (``first`` = ``validity_kernel``, or ``fk_cull_kernel`` of the multi-kernel pipeline)."""
         with _torch().cuda.device(self.device):
             if not read:
                 _abi.check(self._L.mjb_kernel_timing(self._h, int(enable), None, None))
                 return None
-            ms = (C.c_double * 3)()
+            ms = (C.c_double * 4)()
             n = C.c_int64(0)
             _abi.check(self._L.mjb_kernel_timing(self._h, int(enable), ms, C.byref(n)))
-            return {"first_ms": ms[0], "narrow_ms": ms[1], "fp64_ms": ms[2], "launches": int(n.value),
-                    "pipeline": "broad+narrow" if ms[1] > 0.0 else "single"}
+            return {"first_ms": ms[0], "mid_ms": ms[1], "narrow_ms": ms[2], "fp64_ms": ms[3], "launches": int(n.value),
+                    "pipeline": "fk_cull+mid+narrow" if ms[2] > 0.0 else "single"}
 
     def stats(self) -> dict:
         st = _abi.Stats()

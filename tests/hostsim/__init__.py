@@ -56,6 +56,11 @@ def lib():
         L.hs_pair_census.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.hs_bins.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_pair_verdict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.hs_check_pipe.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.hs_bounds_check.argtypes = [C.c_void_p]
+        L.hs_bounds_check.restype = C.c_double
+        L.hs_segseg_check.argtypes = [C.c_int, C.c_uint64]
+        L.hs_segseg_check.restype = C.c_double
         _lib = L
     return _lib
 
@@ -103,6 +108,19 @@ class HostSim:
         d['gjk_iters_by_verdict'] = stats[44:47].tolist()
         d['vertex_evals'] = int(stats[47])
         return valid, d
+
+    def check_pipe(self, q, flags=3):
+        """validity through the pipeline's culling order (group level -> capsule -> OBB -> narrow), no
+        early exit -> (valid, {level0, expanded, capsule, items, contacts})"""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.model.nq)
+        valid = np.zeros(len(q), np.uint8)
+        stats = np.zeros(8, np.int64)
+        lib().hs_check_pipe(self._h, q.ctypes.data, len(q), flags, valid.ctypes.data, stats.ctypes.data)
+        return valid, dict(zip("level0 expanded capsule items contacts".split(), stats[:5].tolist()))
+
+    def bounds_check(self):
+        """largest distance by which a vertex sticks out of its bounding capsule / group sphere (<= 0: contained)"""
+        return lib().hs_bounds_check(self._h)
 
     def pair_verdict(self, q, g1, g2, fp64=False):
         """(verdict, iterations) of one geom pair: 0 separated, 1 contact, 2 uncertain."""
@@ -159,9 +177,14 @@ class HostSim:
         return out
 
     def bins(self):
-        """(bin_expect[8], calibrated items per row, bin of every pair or -1 for closed-form pairs)"""
+        """(bin_expect[8], calibrated items per row, bin of every pair)"""
         be = np.zeros(8)
         tot = C.c_double(0)
         pb = np.zeros(lib().hs_npair(self._h), np.int32)
         lib().hs_bins(self._h, be.ctypes.data, C.byref(tot), pb.ctypes.data)
         return be, tot.value, pb
+
+
+def segseg_check(ncase=20000, seed=3):
+    """largest overestimate of the fp32 segment-segment distance against an fp64 search"""
+    return lib().hs_segseg_check(ncase, seed)

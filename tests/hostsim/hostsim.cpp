@@ -291,8 +291,8 @@ void hs_pair_census(Sim *s, const float *q, int64_t n, int64_t *out) {
   }
 }
 
-// calibrated narrow-phase items per row for each bin of the two-kernel pipeline, the total over all
-// pairs, and every pair's bin (-1: closed form, decided in the broad phase)
+// calibrated narrow-phase items per row for each bin of the multi-kernel pipeline, the total over all
+// pairs, and every pair's bin
 void hs_bins(Sim *s, double *bin_expect, double *items_per_row, int32_t *pair_bin) {
   const auto &H = s->H;
   for (int b = 0; b < NBIN; b++) bin_expect[b] = H.bin_expect[b];
@@ -300,8 +300,121 @@ void hs_bins(Sim *s, double *bin_expect, double *items_per_row, int32_t *pair_bi
   for (size_t p = 0; p < H.pairs.size(); p++) {
     const Pair &pr = H.pairs[p];
     const Shape<double> &A = H.shapes[pr.sa], &B = H.shapes[pr.sb];
-    pair_bin[p] = item_needs_scan(pr, B) ? item_bin(pr, A, B) : -1;
+    (void)B;
+    pair_bin[p] = item_bin(pr, A, B);   // closed-form kinds share bin 0 with the smallest scans
   }
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+// The pipeline's culling order (vk_pipe.cuh): level-0 group test -> expansion into shape pairs ->
+// bounding-capsule cull -> OBB cull -> narrow phase.  fp32, no early exit; fp64 re-evaluation of
+// uncertain rows as in hs_check.  stats: [0] level-0 survivors, [1] expanded shape pairs,
+// [2] capsule survivors, [3] OBB survivors (narrow items), [4] contacts
+extern "C" void hs_check_pipe(Sim *s, const float *q, int64_t n, uint32_t flags, uint8_t *valid, int64_t *stats) {
+  const auto &H = s->H;
+  Pose<float> P[MAX_BODY], ident;
+  ident.p = mk<float>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  const float slack = 1e-4f;
+  for (int64_t r = 0; r < n; r++) {
+    const float *qr = q + r * H.nq;
+    bool ok = true;
+    if (flags & 1u)
+      for (int j = 0; j < H.njnt; j++) ok = ok && ((double)qr[j] >= H.jnt_lo[j]) && ((double)qr[j] <= H.jnt_hi[j]);
+    int out = ok ? 1 : 0;
+    if (ok && (flags & 2u)) {
+      V3<float> cen[MAX_GROUP];
+      for (int k = 0; k < H.nslot; k++) {
+        int ps = s->fk32.body_parent[k];
+        P[k] = fk_body(s->fk32, k, ps < 0 ? ident : P[ps], qr);
+        const int g = H.slot_group[k];
+        if (g >= 0) cen[g] = P[k].p + qrot(P[k].q, mk<float>((float)H.group_c[g][0], (float)H.group_c[g][1], (float)H.group_c[g][2]));
+      }
+      bool pen = false, unc = false;
+      for (const GroupPair &g : H.group_pairs) {
+        if (!group_pair_near(g, cen[g.ga], g.kind == GK_SPHERE ? cen[g.gb] : cen[g.ga],
+                             g.kind == GK_SPHERE ? nullptr : &H.static_groups[g.gb])) continue;
+        stats[0]++;
+        for (int i = 0; i < g.n; i++) {
+          const int p = H.gp_member[g.first + i];
+          const Pair pr = H.pairs[p];
+          const Shape<float> &A = s->s32[pr.sa], &B = s->s32[pr.sb];
+          const Pose<float> &PA = A.slot < 0 ? ident : P[A.slot];
+          const Pose<float> &PB = B.slot < 0 ? ident : P[B.slot];
+          stats[1]++;
+          const float margin = pr.rsum - swept_radius(A) - swept_radius(B);
+          if (capsule_cull(pr, A, B, PA, PB, margin + slack)) continue;
+          stats[2]++;
+          if (midphase_cull(pr, A, B, PA, PB, margin, slack)) continue;
+          stats[3]++;
+          int v = narrow_item<float>(pr.kind, A, B, s->v32.data(), PA, PB, pr.rsum);
+          if (v == V_PEN) { pen = true; stats[4]++; }
+          if (v == V_UNC) unc = true;
+        }
+      }
+      int v = pen ? 1 : (unc ? 2 : 0);
+      if (v == 2) v = row_verdict<double>(H, H.fk, H.shapes.data(), H.verts.data(), qr, false, nullptr) != 0 ? 1 : 0;
+      out = v == 0 ? 1 : 0;
+    }
+    valid[r] = (uint8_t)out;
+  }
+}
+
+// every vertex of every shape lies inside the shape's bounding capsule and inside its group's bounding
+// sphere (fp32 tables, as the device sees them): returns the largest violation (<= 0 means contained)
+extern "C" double hs_bounds_check(Sim *s) {
+  const auto &H = s->H;
+  double worst = -1e300;
+  for (size_t k = 0; k < s->s32.size(); k++) {
+    const Shape<float> &sh = s->s32[k];
+    if (sh.kind != SK_VERTS) continue;
+    for (int i = 0; i < sh.nvert; i++) {
+      const Vtx<float> &v = s->v32[sh.vadr + i];
+      double p[3] = {v.x, v.y, v.z}, a[3] = {sh.ca[0], sh.ca[1], sh.ca[2]}, b[3] = {sh.cb[0], sh.cb[1], sh.cb[2]};
+      worst = std::max(worst, vkb::point_segment_dist(p, a, b) + (double)sh.radius - (double)sh.crad);
+      if (sh.slot >= 0) {
+        const int g = sh.group;
+        double d = sqrt((p[0] - (float)H.group_c[g][0]) * (p[0] - (float)H.group_c[g][0]) + (p[1] - (float)H.group_c[g][1]) * (p[1] - (float)H.group_c[g][1]) +
+                        (p[2] - (float)H.group_c[g][2]) * (p[2] - (float)H.group_c[g][2]));
+        worst = std::max(worst, d + (double)sh.radius - H.group_r[g]);
+      }
+    }
+  }
+  return worst;
+}
+
+// segseg_dist2 in fp32 against a brute-force fp64 minimum over a fine grid: returns the largest
+// overestimate of the DISTANCE (the cull needs estimate <= truth + slack)
+extern "C" double hs_segseg_check(int ncase, uint64_t seed) {
+  double worst = 0;
+  for (int c = 0; c < ncase; c++) {
+    float x[12];
+    for (int k = 0; k < 12; k++) x[k] = sweep_value(seed, c, k, -1.f, 1.f);
+    V3<float> p1 = mk<float>(x[0], x[1], x[2]), q1 = mk<float>(x[3], x[4], x[5]), p2 = mk<float>(x[6], x[7], x[8]), q2 = mk<float>(x[9], x[10], x[11]);
+    const int kind = c % 6;
+    if (kind == 1) q2 = p2 + (q1 - p1) * 0.7f;                                   // parallel
+    if (kind == 2) { q2 = p2 + (q1 - p1) * 0.7f; q2.x += 1e-4f * x[9]; }          // nearly parallel
+    if (kind == 3) q1 = p1;                                                      // point vs segment
+    if (kind == 4) { q1 = p1 + (q1 - p1) * 0.05f; q2 = p2 + (q2 - p2) * 0.05f; }  // short segments
+    if (kind == 5) { p2 = p1 + (p2 - p1) * 0.01f; q2 = p2 + (q1 - p1) * 0.5f; q2.y += 3e-3f * x[10]; }  // close, nearly parallel
+    const double est = sqrt((double)segseg_dist2(p1, q1, p2, q2));
+    // brute force: the distance is convex in (s, t); nested ternary search in fp64
+    auto dist = [&](double sA, double tB) {
+      double d[3] = {(p1.x + sA * ((double)q1.x - p1.x)) - (p2.x + tB * ((double)q2.x - p2.x)),
+                     (p1.y + sA * ((double)q1.y - p1.y)) - (p2.y + tB * ((double)q2.y - p2.y)),
+                     (p1.z + sA * ((double)q1.z - p1.z)) - (p2.z + tB * ((double)q2.z - p2.z))};
+      return sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    };
+    auto best_t = [&](double sA) {
+      double lo = 0, hi = 1;
+      for (int it = 0; it < 100; it++) { double m1 = lo + (hi - lo) / 3, m2 = hi - (hi - lo) / 3; if (dist(sA, m1) < dist(sA, m2)) hi = m2; else lo = m1; }
+      return dist(sA, 0.5 * (lo + hi));
+    };
+    double lo = 0, hi = 1;
+    for (int it = 0; it < 100; it++) { double m1 = lo + (hi - lo) / 3, m2 = hi - (hi - lo) / 3; if (best_t(m1) < best_t(m2)) hi = m2; else lo = m1; }
+    const double truth = best_t(0.5 * (lo + hi));
+    worst = std::max(worst, est - truth);
+  }
+  return worst;
+}

@@ -359,9 +359,9 @@ def test_collision_ruleset_semantics():
 
 
 def test_pipeline_bins_from_calibration():
-    """Host side of the two-kernel pipeline: every pair that needs hull scans has a bin, closed-form
-    pairs (plane against a box / capsule, capsule against capsule) have none, and the calibrated
-    per-bin item rates that size the bins add up to no more than the calibrated total."""
+    """Host side of the multi-kernel pipeline: every pair has a bin (closed-form pairs -- plane against
+    a box / capsule, capsule against capsule -- share bin 0 with the smallest hull scans), and the
+    calibrated per-bin item rates that size the bins add up to the calibrated total."""
     from mjpl_b200 import models
     from tests.hostsim import HostSim
 
@@ -370,20 +370,46 @@ def test_pipeline_bins_from_calibration():
     be, total, pb = hs.bins()
     pairs = hs.pairs()
     assert len(pb) == len(pairs) == 324
-    assert ((pb >= -1) & (pb < 8)).all()
-    assert (be >= 0).all() and 0.5 < be.sum() <= total + 1e-9
+    assert ((pb >= 0) & (pb < 8)).all()
+    assert (be >= 0).all() and 0.5 < be.sum() and abs(be.sum() - total) < 1e-9
     mesh = m.geom_type == 7
     both_mesh = mesh[pairs[:, 0]] & mesh[pairs[:, 1]]
     assert both_mesh.any() and (pb[both_mesh] >= 5).all()     # hull against hull: the three largest bins
     one_mesh = mesh[pairs[:, 0]] ^ mesh[pairs[:, 1]]
     assert ((pb[one_mesh] >= 0) & (pb[one_mesh] <= 4)).all()  # hull against a small core (or the plane)
-    assert 0 < (pb == -1).sum() < 40
     u = models.load("ur5e_scene")
     be_u, total_u, pb_u = HostSim(u).bins()
-    caps = u.geom_type == 3
-    pu = HostSim(u).pairs()
-    both_caps = caps[pu[:, 0]] & caps[pu[:, 1]]
-    assert (pb_u[both_caps] == -1).all() and be_u[1:].sum() == 0.0   # UR5e: capsules, a cylinder, a plane
+    assert (pb_u == 0).all() and be_u[1:].sum() == 0.0        # UR5e: capsules, a cylinder, a plane
+
+
+def test_bounding_capsules_and_cull_groups_are_conservative():
+    """Level 0 (group spheres / world-fixed capsules), the bounding-capsule cull and the OBB cull of the
+    pipeline only ever remove pairs that cannot be in contact: every vertex lies inside its shape's
+    capsule and its group's sphere, the fp32 segment-segment distance never overestimates by more than
+    rounding, and the culled evaluation gives the oracle's answer on every row outside the band."""
+    import oracle
+    from mjpl_b200 import mjcf, models
+    from tests import hostsim, toy_models as toys
+    from tests.hostsim import HostSim
+
+    assert hostsim.segseg_check(30000) < 1e-6
+    zoo = mjcf.from_xml_string(toys.PRIMITIVE_ARM)
+    zoo.geom_margin = np.where(np.arange(zoo.ngeom) % 2 == 0, 0.015, 0.004)   # margins widen the culls too
+    cases = [(models.load("franka_scene_with_obstacles"), [("left_finger", "right_finger")], 6000),
+             (models.load("franka_scene"), [], 4000), (models.load("ur5e_scene"), [], 4000),
+             (mjcf.from_xml_string(toys.PRIMITIVE_ARM), [], 6000), (zoo, [], 6000)]
+    for m, allowed, n in cases:
+        hs = HostSim(m, allowed)
+        assert hs.bounds_check() <= 0.0
+        rng = np.random.default_rng(8)
+        Q = rng.uniform(m.jnt_range[:, 0], m.jnt_range[:, 1], size=(n, m.nq)).astype(np.float32)
+        got, st = hs.check_pipe(Q)
+        assert st["level0"] >= st["capsule"] >= st["items"] >= st["contacts"] > 0
+        assert st["expanded"] >= st["capsule"]
+        want, dist, _ = oracle.Oracle(m, allowed).check(Q.astype(np.float64), 3, want_dist=True)
+        bad = got.astype(bool) != want
+        assert not (bad & (np.abs(dist) >= 1e-5)).any()
+        np.testing.assert_array_equal(got, hs.check(Q)[0])   # same answer as the per-pair sphere + mid-phase order
 
 
 def test_bench_reference_arm_contract():
