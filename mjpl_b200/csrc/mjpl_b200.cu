@@ -183,14 +183,15 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   if (best < 0) return bail(fail(MJB_ERR_MODEL, "model tables do not fit in shared memory"));
   m->grid = m->num_sms * m->ctas_per_sm;
 
-  {  // Two-kernel pipeline (vk_split.cuh) for large batches.  Measured on B200 against the single
-     // kernel (tools/split_crossover.py, Franka rows): 4k..128k rows 15-35 % slower, 262k 6 % slower,
-     // 524k 2 % faster, 1M 10 % faster; 12M UR5e edge waypoints 3.7 vs 5.0 ms.  MJB_SPLIT=0 never,
-     // =1 always, default: batches of at least MJB_SPLIT_MIN rows (500000).
+  {  // Multi-kernel pipeline (vk_pipe.cuh) for large batches.  Measured on B200 against the single
+     // kernel (tools/split_crossover.py, Franka rows, raw call): 1k..64k rows 1.5-1.9x slower (five
+     // launches and three persistent grids that each stage their tables cost ~0.2 ms before the first
+     // row), 131k rows 7 % slower, 262k 24 % faster, 524k 31 % faster, 1M 43 % faster.  MJB_SPLIT=0
+     // never, =1 always, default: batches of at least MJB_SPLIT_MIN rows (200000).
     const char *sp = getenv("MJB_SPLIT");
     const char *smin = getenv("MJB_SPLIT_MIN");
     const int mode = sp ? atoi(sp) : -1;
-    m->split_min = mode == 1 ? 0 : (smin ? (size_t)atoll(smin) : (size_t)500000);
+    m->split_min = mode == 1 ? 0 : (smin ? (size_t)atoll(smin) : (size_t)200000);
     const char *bc = getenv("MJB_BIN_CAP");   // testing: tiny bins force the on-the-spot path of full bins
     m->bin_cap_override = bc ? (size_t)atoll(bc) : 0;
     const char *lc = getenv("MJB_L0_CAP");    // testing: a tiny level-0 list forces the whole-row fp64 path

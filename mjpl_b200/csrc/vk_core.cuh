@@ -643,44 +643,60 @@ VK_HD int segseg_item(const Shape<T> &A, const Shape<T> &B, const Vtx<T> *verts,
 // distance of the pair found so far).  The scalar part runs in fp64 whatever T is: for nearly
 // parallel segments `a e - b b` cancels, and in fp32 the pair that comes out can be off by
 // angle x length (4e-4 m measured on unit segments) -- too much for a cull that has to be
-// conservative.  B200 issues fp64 at half the fp32 rate, and this is ~40 flops per shape pair.
+// conservative.  B200 issues fp64 at half the fp32 rate, and this is ~35 flops per shape pair.
+// inv_a / inv_e: 1 / |q1-p1|^2 and 1 / |q2-p2|^2 (0 for a point).  The three quotients are products
+// with fp32-accurate reciprocals: the parameters s, t only need to be feasible and near the optimum
+// (a relative error of 1e-7 in them moves the distance by 1e-7 x length), it is the cancellation in
+// numerator and denominator that needs the wide format.
+VK_HD float vk_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
 template <typename T>
-VK_HD T segseg_dist2(V3<T> p1, V3<T> q1, V3<T> p2, V3<T> q2) {
+VK_HD T segseg_dist2(V3<T> p1, V3<T> q1, T inv_a, V3<T> p2, V3<T> q2, T inv_e) {
   const V3<double> P1 = mk<double>(p1.x, p1.y, p1.z), P2 = mk<double>(p2.x, p2.y, p2.z);
   const V3<double> d1 = mk<double>(q1.x, q1.y, q1.z) - P1, d2 = mk<double>(q2.x, q2.y, q2.z) - P2, r = P1 - P2;
   const double a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
   const double den = a * e - b * b;
-  double s = den > 1e-14 * a * e ? (b * f - c * e) / den : 0.0;
+  double s = den > 1e-14 * a * e ? (b * f - c * e) * (double)vk_rcp((float)den) : 0.0;
   s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
-  double t = e > 1e-30 ? (b * s + f) / e : 0.0;
+  double t = (b * s + f) * (double)inv_e;
   t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
-  s = a > 1e-30 ? (b * t - c) / a : 0.0;
+  s = (b * t - c) * (double)inv_a;
   s = s < 0.0 ? 0.0 : (s > 1.0 ? 1.0 : s);
   const V3<double> dd = r + d1 * s - d2 * t;
   return (T)dot(dd, dd);
 }
+template <typename T> VK_HD T segseg_dist2(V3<T> p1, V3<T> q1, V3<T> p2, V3<T> q2) {
+  const V3<T> d1 = q1 - p1, d2 = q2 - p2;
+  const T a = dot(d1, d1), e = dot(d2, d2);
+  return segseg_dist2(p1, q1, a > T(1e-30) ? T(1) / a : T(0), p2, q2, e > T(1e-30) ? T(1) / e : T(0));
+}
 
 // true => the bounding capsules of the two shapes are certainly further apart than rsum_core +
 // slack, i.e. the pair cannot be in contact.  `lim` = margin + slack (the capsule radii already
-// include the swept radii).  The clamped closed form above can overestimate the distance of
-// near-parallel segments by rounding only; `slack` (1e-4) is far above that.
+// include the swept radii).  World-fixed shapes (slot < 0) carry world-frame capsules: no transform.
 template <typename T>
 VK_HD bool capsule_cull(const Pair &pr, const Shape<T> &A, const Shape<T> &B, const Pose<T> &PA, const Pose<T> &PB, T lim) {
-  const V3<T> b0 = PB.p + qrot(PB.q, mk<T>(B.ca[0], B.ca[1], B.ca[2]));
-  const bool bseg = B.caplen > T(0);
-  const V3<T> b1 = bseg ? PB.p + qrot(PB.q, mk<T>(B.cb[0], B.cb[1], B.cb[2])) : b0;
+  const bool bseg = B.caplen > T(0), bmov = B.slot >= 0;
+  V3<T> b0 = mk<T>(B.ca[0], B.ca[1], B.ca[2]), b1 = mk<T>(B.cb[0], B.cb[1], B.cb[2]);
+  if (bmov) { b0 = PB.p + qrot(PB.q, b0); b1 = bseg ? PB.p + qrot(PB.q, b1) : b0; }
   if (pr.kind == PK_PLANE) {
     const V3<T> n = mk<T>(A.ax[0], A.ax[1], A.ax[2]), c = mk<T>(A.c[0], A.c[1], A.c[2]);
     const T d = vk_min(dot(n, b0 - c), dot(n, b1 - c));
     return d > B.crad + lim;
   }
-  const V3<T> a0 = PA.p + qrot(PA.q, mk<T>(A.ca[0], A.ca[1], A.ca[2]));
-  const bool aseg = A.caplen > T(0);
-  const V3<T> a1 = aseg ? PA.p + qrot(PA.q, mk<T>(A.cb[0], A.cb[1], A.cb[2])) : a0;
+  const bool aseg = A.caplen > T(0), amov = A.slot >= 0;
+  V3<T> a0 = mk<T>(A.ca[0], A.ca[1], A.ca[2]), a1 = mk<T>(A.cb[0], A.cb[1], A.cb[2]);
+  if (amov) { a0 = PA.p + qrot(PA.q, a0); a1 = aseg ? PA.p + qrot(PA.q, a1) : a0; }
   const T r = A.crad + B.crad + lim;
   T d2;
   if (!aseg && !bseg) { const V3<T> d = a0 - b0; d2 = dot(d, d); }
-  else d2 = segseg_dist2(a0, a1, b0, b1);
+  else d2 = segseg_dist2(a0, a1, aseg ? (T)vk_rcp((float)(A.caplen * A.caplen)) : T(0), b0, b1,
+                         bseg ? (T)vk_rcp((float)(B.caplen * B.caplen)) : T(0));
   return d2 > r * r;
 }
 

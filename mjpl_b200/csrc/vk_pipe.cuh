@@ -28,9 +28,18 @@ namespace vk {
 constexpr int L0_QCAP = 256;          // per-warp staging queue of level-0 survivors (entries)
 constexpr int PIPE_FK_THREADS = 256;  // fk_cull_kernel: 8 warps per CTA, 4 CTAs per SM
 constexpr int MID_THREADS = 256;
+#ifndef VK_MID_CTAS
+#define VK_MID_CTAS 2
+#endif
+constexpr int MID_CTAS = VK_MID_CTAS;      // resident CTAs per SM the register budget is set for
 constexpr int MID_Q1CAP = 1024;       // per-warp queue of expanded shape pairs
 constexpr int MID_Q2CAP = 96;         // per-warp queue of capsule survivors waiting for the OBB test
-constexpr int MID_CHUNK = 128;        // level-0 entries a warp claims per ticket
+constexpr int MID_CHUNK = 256;        // level-0 entries a warp claims per ticket
+#ifndef VK_MID_STAGE
+#define VK_MID_STAGE 32
+#endif
+static_assert(VK_MID_STAGE >= 32, "a drain batch can put 32 items into one bin");
+constexpr int MID_STAGE = VK_MID_STAGE;         // per-warp, per-bin staging of narrow-phase items (entries)
 
 struct PipeFkLayout { size_t gpairs, sgroups, cen, qtile, q0, bars, total; };
 __host__ __device__ inline PipeFkLayout pipe_fk_layout(int ngpair, int nsgroup, int ngroup_moving, int nq) {
@@ -255,7 +264,7 @@ __global__ void __launch_bounds__(PIPE_FK_THREADS, 4) fk_cull_kernel(const __gri
 }
 
 // ---------------------------------------------------------------------------------------------------
-struct MidLayout { size_t shapes, pairs, gpairs, member, q1, q2, total; };
+struct MidLayout { size_t shapes, pairs, gpairs, member, q1, q2, stage, stage_cnt, total; };
 __host__ __device__ inline MidLayout mid_layout(int nshape, int npair, int ngpair, int nmember) {
   MidLayout L;
   const int W = MID_THREADS / 32;
@@ -266,11 +275,77 @@ __host__ __device__ inline MidLayout mid_layout(int nshape, int npair, int ngpai
   L.member = o; o = align_up(o + (size_t)nmember * sizeof(uint16_t), 128);
   L.q1 = o; o = align_up(o + (size_t)W * MID_Q1CAP * sizeof(uint32_t), 128);
   L.q2 = o; o = align_up(o + (size_t)W * MID_Q2CAP * sizeof(unsigned long long), 128);
+  L.stage = o; o = align_up(o + (size_t)W * NBIN * MID_STAGE * sizeof(unsigned long long), 128);
+  L.stage_cnt = o; o = align_up(o + (size_t)W * NBIN * sizeof(int), 128);
   L.total = o;
   return L;
 }
 
-__global__ void __launch_bounds__(MID_THREADS, 2) mid_kernel(const __grid_constant__ KArgs a) {
+// The OBB cull of the last `count` (<= 32) survivors queued in q2, then the bins (lane = survivor).
+// Out of line: it is called from two places of mid_kernel and must not be duplicated there.
+// one warp's staged items of bin b -> the global bin (a full bin: decided on the spot, see vk_split.cuh)
+__device__ __forceinline__ void mid_flush_bin(const KArgs &a, const unsigned long long *stage, int c, int b) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == 0) base = atomicAdd(&a.counters[C_BIN + b], (unsigned long long)c);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int i = lane; i < c; i += 32) {
+    const unsigned long long it = stage[b * MID_STAGE + i];
+    if (base + i < a.bin_capv[b]) a.bin_items[a.bin_off[b] + base + i] = it;
+    else broad_overflow_item(a, (int)(it >> 44), (long long)(it & ((1ull << 44) - 1ull)));
+  }
+  __syncwarp();
+}
+
+__device__ __noinline__ int mid_drain(const KArgs &a, const Shape<float> *s_shapes, const Pair *s_pairs,
+                                      const unsigned long long *q2, int n2, int count, unsigned long long *stage, int *stage_cnt) {
+  const int lane = threadIdx.x & 31;
+  const bool use_obb = !(a.flags & F_NO_OBB);
+  const float slack = 1e-4f;
+  const unsigned below = (1u << lane) - 1u;
+  int items = 0;
+  int bin = -1;
+  unsigned long long it = 0;
+  __syncwarp();
+  if (lane < count) {
+    it = q2[n2 - count + lane];
+    const int ip = (int)(it >> 44);
+    const long long irow = (long long)(it & ((1ull << 44) - 1ull));
+    const Pair pr = s_pairs[ip];
+    const Shape<float> &A = s_shapes[pr.sa];
+    const Shape<float> &B = s_shapes[pr.sb];
+    bool keep = true;
+    if (use_obb && (pr.flags & PF_OBB)) {
+      const Pose<float> PB = load_pose8(a.pose8, a.nslot, irow, B.slot);
+      if (pr.kind == PK_PLANE) {
+        keep = !obb_above_plane(A, B, PB, pr.rsum - swept_radius(B) + slack);
+      } else {
+        const Pose<float> PA = load_pose8(a.pose8, a.nslot, irow, A.slot);
+        keep = !obb_disjoint(A, B, relative_pose(PA, PB), pr.rsum - swept_radius(A) - swept_radius(B) + slack);
+      }
+    }
+    if (keep) bin = item_bin(pr, A, B);
+  }
+  __syncwarp();
+  // Survivors are staged per warp and per bin in shared memory; a bin's stage goes to the global bin
+  // with ONE atomic when it is full (every warp of the grid appends to the same eight counters).
+  unsigned todo = __ballot_sync(0xffffffffu, bin >= 0);
+  while (todo) {
+    const int b = __shfl_sync(0xffffffffu, bin, __ffs(todo) - 1);
+    const unsigned m = __ballot_sync(0xffffffffu, bin == b);
+    int c = stage_cnt[b];
+    __syncwarp();
+    if (c + __popc(m) > MID_STAGE) { mid_flush_bin(a, stage, c, b); c = 0; }
+    if (bin == b) { stage[b * MID_STAGE + c + __popc(m & below)] = it; items += 1; }
+    __syncwarp();
+    if (lane == 0) stage_cnt[b] = c + __popc(m);
+    __syncwarp();
+    todo &= ~m;
+  }
+  return items;
+}
+
+__global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const MidLayout L = mid_layout(a.nshape, a.npair, a.ngpair, a.nmember);
   Shape<float> *s_shapes = reinterpret_cast<Shape<float> *>(smem + L.shapes);
@@ -280,6 +355,9 @@ __global__ void __launch_bounds__(MID_THREADS, 2) mid_kernel(const __grid_consta
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t *q1 = reinterpret_cast<uint32_t *>(smem + L.q1) + (size_t)warp * MID_Q1CAP;
   unsigned long long *q2 = reinterpret_cast<unsigned long long *>(smem + L.q2) + (size_t)warp * MID_Q2CAP;
+  unsigned long long *stage = reinterpret_cast<unsigned long long *>(smem + L.stage) + (size_t)warp * NBIN * MID_STAGE;
+  int *stage_cnt = reinterpret_cast<int *>(smem + L.stage_cnt) + warp * NBIN;
+  if (lane < NBIN) stage_cnt[lane] = 0;
   __shared__ uint64_t s_bar;
 
   const uint32_t bytes_s = (uint32_t)(a.nshape * sizeof(Shape<float>));
@@ -309,66 +387,42 @@ __global__ void __launch_bounds__(MID_THREADS, 2) mid_kernel(const __grid_consta
   long long items_total = 0;
   int n2 = 0;   // warp-uniform: capsule survivors waiting in q2
 
-  // the OBB cull of the last `count` (<= 32) queued survivors, then the bins (lane = survivor)
-  auto drain = [&](int count) {
-    int bin = -1;
-    unsigned long long it = 0;
-    __syncwarp();
-    if (lane < count) {
-      it = q2[n2 - count + lane];
-      const int ip = (int)(it >> 44);
-      const long long irow = (long long)(it & ((1ull << 44) - 1ull));
-      const Pair pr = s_pairs[ip];
-      const Shape<float> &A = s_shapes[pr.sa];
-      const Shape<float> &B = s_shapes[pr.sb];
-      bool keep = true;
-      if (use_obb && (pr.flags & PF_OBB)) {
-        const Pose<float> PB = load_pose8(a.pose8, a.nslot, irow, B.slot);
-        if (pr.kind == PK_PLANE) {
-          keep = !obb_above_plane(A, B, PB, pr.rsum - swept_radius(B) + slack);
-        } else {
-          const Pose<float> PA = load_pose8(a.pose8, a.nslot, irow, A.slot);
-          keep = !obb_disjoint(A, B, relative_pose(PA, PB), pr.rsum - swept_radius(A) - swept_radius(B) + slack);
-        }
-      }
-      if (keep) bin = item_bin(pr, A, B);
-    }
-    n2 -= count;
-    __syncwarp();
-    unsigned todo = __ballot_sync(0xffffffffu, bin >= 0);
-    while (todo) {
-      const int b = __shfl_sync(0xffffffffu, bin, __ffs(todo) - 1);
-      const unsigned m = __ballot_sync(0xffffffffu, bin == b);
-      unsigned long long base = 0;
-      if (lane == __ffs(m) - 1) base = atomicAdd(&a.counters[C_BIN + b], (unsigned long long)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-      if (bin == b) {
-        const unsigned long long idx = base + __popc(m & below);
-        if (idx < a.bin_capv[b]) a.bin_items[a.bin_off[b] + idx] = it;
-        else broad_overflow_item(a, (int)(it >> 44), (long long)(it & ((1ull << 44) - 1ull)));
-        items_total += 1;
-      }
-      todo &= ~m;
-    }
-  };
-
-  for (;;) {
+  // The level-0 list is consumed in batches of 32 entries (lane = entry), a warp claiming MID_CHUNK
+  // entries per ticket.  Everything with a long latency is issued ONE BATCH AHEAD: the next batch's
+  // entries are loaded (and the next chunk's ticket claimed) while the current batch is processed, and
+  // the pose blocks of the next batch's rows are prefetched into L1 -- the kernel was bound by exactly
+  // these dependent global loads (ncu: 35 % of the stall samples on the long scoreboard).
+  const size_t pose_row_bytes = (size_t)a.nslot * 8 * sizeof(float);
+  auto claim = [&]() {
     unsigned long long chunk = 0;
     if (lane == 0) chunk = atomicAdd(&a.counters[C_L0TICKET], 1ull);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    const unsigned long long c0 = chunk * MID_CHUNK;
-    if (c0 >= total) break;
-#pragma unroll 1
-    for (int sub = 0; sub < MID_CHUNK / 32; sub++) {
-      const unsigned long long ei = c0 + (unsigned long long)sub * 32 + lane;
-      if (c0 + (unsigned long long)sub * 32 >= total) break;
+    return __shfl_sync(0xffffffffu, chunk, 0) * MID_CHUNK;
+  };
+  auto load_entry = [&](unsigned long long pos) {   // entry of this lane in the batch starting at pos (or ~0)
+    const unsigned long long ei = pos + lane;
+    unsigned long long e = ~0ull;
+    if (pos < total && ei < total) {
+      e = a.l0_items[ei];
+      const char *pb = reinterpret_cast<const char *>(a.pose8) + (size_t)(e & ((1ull << 40) - 1ull)) * pose_row_bytes;
+      for (size_t o = 0; o < pose_row_bytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + o));
+    }
+    return e;
+  };
+  unsigned long long pos = claim(), chunk_end = pos + MID_CHUNK;
+  unsigned long long e_next = load_entry(pos);
+  while (pos < total) {
+    const unsigned long long e_cur = e_next;
+    // the batch after this one: same chunk, or the first batch of a freshly claimed chunk
+    unsigned long long pos_next = pos + 32;
+    if (pos_next >= chunk_end || pos_next >= total) { pos_next = claim(); chunk_end = pos_next + MID_CHUNK; }
+    e_next = load_entry(pos_next);
+    {
       // ---- expand: every entry (row, group pair) -> its shape pairs ----------------------------------
       long long row = 0;
       int first = 0, n = 0;
-      if (ei < total) {
-        const unsigned long long e = a.l0_items[ei];
-        row = (long long)(e & ((1ull << 40) - 1ull));
-        const GroupPair g = s_gp[(int)(e >> 40)];
+      if (e_cur != ~0ull) {
+        row = (long long)(e_cur & ((1ull << 40) - 1ull));
+        const GroupPair g = s_gp[(int)(e_cur >> 40)];
         first = g.first; n = g.n;
       }
       int off = n;   // inclusive warp scan of n
@@ -409,11 +463,14 @@ __global__ void __launch_bounds__(MID_THREADS, 2) mid_kernel(const __grid_consta
         if (keep) q2[n2 + __popc(m & below)] = (unsigned long long)irow | ((unsigned long long)ip << 44);
         n2 += __popc(m);
         __syncwarp();
-        while (n2 >= 32) drain(32);   // keeps n2 + 32 <= MID_Q2CAP for the next push
+        while (n2 >= 32) { items_total += mid_drain(a, s_shapes, s_pairs, q2, n2, 32, stage, stage_cnt); n2 -= 32; }   // keeps n2 + 32 <= MID_Q2CAP
       }
     }
+    pos = pos_next;
   }
-  while (n2 > 0) drain(n2 < 32 ? n2 : 32);
+  while (n2 > 0) { const int c = n2 < 32 ? n2 : 32; items_total += mid_drain(a, s_shapes, s_pairs, q2, n2, c, stage, stage_cnt); n2 -= c; }
+  __syncwarp();
+  for (int b = 0; b < NBIN; b++) { const int c = stage_cnt[b]; if (c) mid_flush_bin(a, stage, c, b); }
   if (items_total) atomicAdd(&a.counters[C_ITEMS], (unsigned long long)items_total);
 }
 

@@ -95,6 +95,10 @@ __host__ __device__ inline NarrowLayout narrow_layout(int nvert, int nshape, int
 #define VK_NARROW_THREADS 256
 #endif
 constexpr int NARROW_THREADS = VK_NARROW_THREADS;
+#ifndef VK_NARROW_CLAIM
+#define VK_NARROW_CLAIM 64
+#endif
+constexpr int NARROW_CLAIM = VK_NARROW_CLAIM;   // items a warp claims per ticket
 #ifndef VK_NARROW_CTAS
 #define VK_NARROW_CTAS 3   // resident CTAs per SM the register budget is set for (B200, 1M Franka rows: 2 -> 2.91 ms, 3 -> 2.77, 4 -> 2.92)
 #endif
@@ -152,6 +156,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
   unsigned long long count = 0;
   const unsigned long long *items = a.bin_items;
   bool more = false;  // warp-uniform: the current bin may still hold unclaimed items
+  unsigned long long blk_next = 0, blk_end = 0;   // warp-uniform: the block of items this warp has claimed
 #pragma unroll 1
   for (;;) {
     // fill: every lane without an item takes the next one; items of rows that already have a
@@ -168,15 +173,29 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
         if (count > a.bin_capv[b]) count = a.bin_capv[b];
         items = a.bin_items + a.bin_off[b];
         more = count > 0;
+        blk_next = blk_end = 0;
         continue;
       }
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(&a.counters[C_BTICKET + b], (unsigned long long)__popc(need));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (base + __popc(need) >= count) more = false;
+      // Items are claimed in blocks of NARROW_CLAIM per warp (one atomic per block, not per refill:
+      // every warp of the grid hits the same ticket word, and a same-address atomic with a return
+      // value is served at well under one per nanosecond -- at one ticket per refill the whole kernel
+      // ran at the speed of that one word).  A block is private to the warp until it is used up.
+      if (blk_next >= blk_end) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&a.counters[C_BTICKET + b], (unsigned long long)NARROW_CLAIM);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) { more = false; continue; }
+        blk_next = base;
+        blk_end = base + NARROW_CLAIM < count ? base + NARROW_CLAIM : count;
+      }
+      const unsigned long long left = blk_end - blk_next;
+      const unsigned take = (unsigned long long)__popc(need) < left ? (unsigned)__popc(need) : (unsigned)left;
+      const unsigned rank = __popc(need & ((1u << lane) - 1u));
+      const unsigned long long idx = blk_next + rank;
+      blk_next += take;
+      if (blk_next >= blk_end && blk_end >= count) more = false;   // that was the bin's last block
       if (!have) {
-        const unsigned long long idx = base + __popc(need & ((1u << lane) - 1u));
-        if (idx < count) {
+        if (rank < take) {
           const unsigned long long it = items[idx];
           row = (long long)(it & ((1ull << 44) - 1ull));
           pidx = (int)(it >> 44);

@@ -29,7 +29,7 @@ ia, it, ism = shdr.index("Instructions Executed"), shdr.index("Thread Instructio
 ino, iw = shdr.index("stall_no_inst"), shdr.index("stall_wait")
 tot = sum(int(r[ia]) for r in data); tots = sum(int(r[ism]) for r in data); totthr = sum(int(r[it]) for r in data)
 print(f"total warp-inst {tot} avg thr {totthr/tot:.2f} samples {tots} no_inst {sum(int(r[ino]) for r in data)/tots*100:.1f}% wait {sum(int(r[iw]) for r in data)/tots*100:.1f}%")
-files = {n: (Path("/root/repo/mjpl_b200/csrc")/n).read_text().split("\n") for n in ("vk_kernels.cuh","vk_core.cuh","vk_split.cuh")}
+files = {n: (Path("/root/repo/mjpl_b200/csrc")/n).read_text().split("\n") for n in ("vk_kernels.cuh","vk_core.cuh","vk_split.cuh","vk_pipe.cuh")}
 for title, idx in (("outermost", 1), ("innermost", 0)):
     agg = collections.defaultdict(lambda: [0, 0, 0, 0])
     for r, ii in zip(data, insts):

@@ -11,7 +11,7 @@ from bench import make_rows, MODEL, ALLOWED
 model = models.load(MODEL)
 rows = make_rows(model, 1_000_000)
 L = _abi.lib()
-for n in (4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288):
+for n in (1024, 4096, 8192, 16384, 32768, 65536, 131072, 262144, 524288):
     res = {}
     for mode in ("0", "1"):
         os.environ["MJB_SPLIT"] = mode
