@@ -222,6 +222,14 @@ int mjb_ik_solve(mjb_model *m, const mjb_ik_spec *spec, const double *d_target_p
  */
 int mjb_kernel_timing(mjb_model *m, int enable, double *ms4, int64_t *launches);
 
+/*
+ * Measured FP32 FMA throughput of the current device in TFLOP/s (2 flops per FMA): the roofline
+ * denominator for this path, which is bound by the CUDA cores and not by HBM or tensor cores
+ * (BASELINE.md section 2 asks for a measured figure).  Runs ~25 ms; *ms_out (optional) = duration
+ * of the best pass.
+ */
+int mjb_fma_peak(double *tflops, double *ms_out);
+
 int mjb_get_stats(mjb_model *m, mjb_stats *out);   /* synchronises the handle's last stream */
 int mjb_reset_stats(mjb_model *m);
 

@@ -120,7 +120,7 @@ EXPORTS = (
     "mjb_last_error mjb_device_count mjb_model_create mjb_model_destroy mjb_model_npair "
     "mjb_model_pairs mjb_check_configs mjb_check_configs_host mjb_fk mjb_check_edges "
     "mjb_check_sweep mjb_sweep_rows mjb_get_stats mjb_reset_stats mjb_nearest_batch mjb_rrt_extend mjb_pose_valid mjb_pose_project mjb_site_pose "
-    "mjb_ik_solve mjb_kernel_timing"
+    "mjb_ik_solve mjb_kernel_timing mjb_fma_peak"
 ).split()
 
 
@@ -158,6 +158,7 @@ def lib():
     L.mjb_pose_project.argtypes = [vp, C.POINTER(PoseSpec), vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp]
     L.mjb_ik_solve.argtypes = [vp, C.POINTER(IkSpec), vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp]
     L.mjb_kernel_timing.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.mjb_fma_peak.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.mjb_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.mjb_reset_stats.argtypes = [vp]
     for n in EXPORTS:

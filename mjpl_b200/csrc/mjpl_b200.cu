@@ -816,3 +816,47 @@ extern "C" int mjb_site_pose(mjb_model *m, int32_t site_bodyid, const double *si
   m->launches++;
   return MJB_OK;
 }
+
+// ---- FP32 FMA throughput of the device (roofline denominator) ---------------
+// Every thread runs 8 independent FFMA chains; nothing else is in the loop, so the kernel runs at the
+// FMA pipes' issue rate.  The result is written out so the compiler cannot drop the chains.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, float a, float b) {
+  float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" int mjb_fma_peak(double *tflops, double *ms_out) {
+  if (!tflops) return fail(MJB_ERR_ARG, "null argument");
+  int dev = 0, sms = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int ctas = sms * 8, threads = 256, iters = 4096;
+  float *out = nullptr;
+  CU(cudaMalloc((void **)&out, (size_t)ctas * threads * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 1e30;
+  for (int rep = 0; rep < 5; rep++) {   // first pass warms up; best of the rest
+    CU(cudaEventRecord(e0, 0));
+    fma_peak_kernel<<<ctas, threads>>>(out, iters, 0.999f, 1e-3f);
+    CU(cudaEventRecord(e1, 0));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  CU(cudaGetLastError());
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  const double flops = 2.0 * 128.0 * (double)iters * (double)ctas * (double)threads;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms_out) *ms_out = best;
+  return MJB_OK;
+}

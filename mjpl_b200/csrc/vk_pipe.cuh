@@ -393,10 +393,14 @@ __global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid
   // the pose blocks of the next batch's rows are prefetched into L1 -- the kernel was bound by exactly
   // these dependent global loads (ncu: 35 % of the stall samples on the long scoreboard).
   const size_t pose_row_bytes = (size_t)a.nslot * 8 * sizeof(float);
+  // entries per ticket: MID_CHUNK for large lists, fewer (a multiple of 32) when the list would otherwise
+  // be shared out among a handful of warps (small batches run as long as their busiest warp)
+  unsigned long long chunk_size = total / ((unsigned long long)gridDim.x * (MID_THREADS / 32)) / 32 * 32;
+  chunk_size = chunk_size < 32 ? 32 : (chunk_size > MID_CHUNK ? MID_CHUNK : chunk_size);
   auto claim = [&]() {
     unsigned long long chunk = 0;
     if (lane == 0) chunk = atomicAdd(&a.counters[C_L0TICKET], 1ull);
-    return __shfl_sync(0xffffffffu, chunk, 0) * MID_CHUNK;
+    return __shfl_sync(0xffffffffu, chunk, 0) * chunk_size;
   };
   auto load_entry = [&](unsigned long long pos) {   // entry of this lane in the batch starting at pos (or ~0)
     const unsigned long long ei = pos + lane;
@@ -408,13 +412,13 @@ __global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid
     }
     return e;
   };
-  unsigned long long pos = claim(), chunk_end = pos + MID_CHUNK;
+  unsigned long long pos = claim(), chunk_end = pos + chunk_size;
   unsigned long long e_next = load_entry(pos);
   while (pos < total) {
     const unsigned long long e_cur = e_next;
     // the batch after this one: same chunk, or the first batch of a freshly claimed chunk
     unsigned long long pos_next = pos + 32;
-    if (pos_next >= chunk_end || pos_next >= total) { pos_next = claim(); chunk_end = pos_next + MID_CHUNK; }
+    if (pos_next >= chunk_end || pos_next >= total) { pos_next = claim(); chunk_end = pos_next + chunk_size; }
     e_next = load_entry(pos_next);
     {
       // ---- expand: every entry (row, group pair) -> its shape pairs ----------------------------------

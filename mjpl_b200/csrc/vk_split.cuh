@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
   unsigned long long count = 0;
   const unsigned long long *items = a.bin_items;
   bool more = false;  // warp-uniform: the current bin may still hold unclaimed items
-  unsigned long long blk_next = 0, blk_end = 0;   // warp-uniform: the block of items this warp has claimed
+  unsigned long long blk_next = 0, blk_end = 0, claim = 1;   // warp-uniform: the block of items this warp has claimed, block size
 #pragma unroll 1
   for (;;) {
     // fill: every lane without an item takes the next one; items of rows that already have a
@@ -174,6 +174,10 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
         items = a.bin_items + a.bin_off[b];
         more = count > 0;
         blk_next = blk_end = 0;
+        // block size: NARROW_CLAIM for large bins, smaller when the bin would otherwise be shared out
+        // among a handful of warps (small batches: the launch then runs as long as its busiest warp)
+        claim = count / ((unsigned long long)gridDim.x * (NARROW_THREADS / 32));
+        claim = claim < 1 ? 1 : (claim > NARROW_CLAIM ? NARROW_CLAIM : claim);
         continue;
       }
       // Items are claimed in blocks of NARROW_CLAIM per warp (one atomic per block, not per refill:
@@ -182,11 +186,11 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
       // ran at the speed of that one word).  A block is private to the warp until it is used up.
       if (blk_next >= blk_end) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&a.counters[C_BTICKET + b], (unsigned long long)NARROW_CLAIM);
+        if (lane == 0) base = atomicAdd(&a.counters[C_BTICKET + b], claim);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= count) { more = false; continue; }
         blk_next = base;
-        blk_end = base + NARROW_CLAIM < count ? base + NARROW_CLAIM : count;
+        blk_end = base + claim < count ? base + claim : count;
       }
       const unsigned long long left = blk_end - blk_next;
       const unsigned take = (unsigned long long)__popc(need) < left ? (unsigned)__popc(need) : (unsigned)left;

@@ -287,6 +287,17 @@ def get_engine(model, allowed_collision_bodies=(), device: int | None = None) ->
         return e
 
 
+def fma_peak(device: int | None = None) -> dict:
+    """Measured FP32 FMA throughput of a GPU (``mjb_fma_peak``): ``{"tflops", "ms"}``."""
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise EngineUnavailable("no CUDA device")
+    t, ms = C.c_double(0), C.c_double(0)
+    with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+        _abi.check(_abi.lib().mjb_fma_peak(C.byref(t), C.byref(ms)))
+    return {"tflops": t.value, "ms": ms.value}
+
+
 def sweep_rows_host(model, seed: int, row0: int, n: int) -> np.ndarray:
     """numpy mirror of the device row generator (``vk::sweep_value``), bit-identical in fp32."""
     lo = model.jnt_range[:, 0].astype(np.float32)

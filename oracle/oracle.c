@@ -11,10 +11,12 @@
  * region GJK + full EPA here; signed-volume GJK with certified bounds there) so that the
  * two implementations fail independently.
  */
+#define _GNU_SOURCE
 #include "oracle.h"
 
 #include <math.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -859,8 +861,26 @@ int orc_check(const orc_model *m, const double *q, int64_t n, uint32_t flags, ui
   int nt = g_threads;
   if (n < 2 * CHUNK) nt = 1;
   if (nt == 1) { check_worker(&job); return 0; }
+  /* one worker per core, PINNED (north star: "reference path timed on the box's own host cores ...
+   * threads pinned"): worker t runs on the t-th core of the calling thread's affinity mask */
   pthread_t th[256];
-  for (int t = 0; t < nt; t++) pthread_create(&th[t], NULL, check_worker, &job);
+  cpu_set_t allowed;
+  int cores[256], ncores = 0;
+  if (sched_getaffinity(0, sizeof allowed, &allowed) == 0)
+    for (int c = 0; c < CPU_SETSIZE && ncores < 256; c++)
+      if (CPU_ISSET(c, &allowed)) cores[ncores++] = c;
+  for (int t = 0; t < nt; t++) {
+    pthread_attr_t at;
+    pthread_attr_init(&at);
+    if (ncores > 0) {
+      cpu_set_t one;
+      CPU_ZERO(&one);
+      CPU_SET(cores[t % ncores], &one);
+      pthread_attr_setaffinity_np(&at, sizeof one, &one);
+    }
+    if (pthread_create(&th[t], &at, check_worker, &job) != 0) pthread_create(&th[t], NULL, check_worker, &job);
+    pthread_attr_destroy(&at);
+  }
   for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
   return 0;
 }
