@@ -344,7 +344,7 @@ def plan_leg(model, eng, rank, world, dist, torch):
     lo, hi = (len(goals) * rank) // world, (len(goals) * (rank + 1)) // world
     mine = goals[lo:hi]
     planner = mj.BatchedRRT(model, PLAN_JOINTS, c, max_planning_time=60.0, epsilon=0.05, seed=rank, goal_biasing_probability=0.1,
-                            max_active=4096, max_iterations_per_query=2000)
+                            max_active=4096, max_iterations_per_query=2000, sync_every=32)
     planner.plan(np.tile(q_init, (8, 1)), mine[:8])   # warm-up (allocator, kernels)
     torch.cuda.synchronize()
     if world > 1:

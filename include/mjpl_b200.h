@@ -158,6 +158,35 @@ int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, int64_t *d_
                    const int64_t *d_slots, const double *d_targets, int64_t n, double eps,
                    int32_t kcap, uint32_t flags, double *d_reached, int64_t *d_last, void *stream);
 
+/* Same, with a per-query mask: queries with d_active[i] == 0 (or with NaN targets) build no chain and
+ * append nothing (their d_reached is the nearest node).  d_active may be NULL (all active). */
+int mjb_rrt_extend_masked(mjb_model *m, double *d_nodes, int64_t *d_parent, int64_t *d_count, int64_t cap,
+                          const int64_t *d_slots, const double *d_targets, const uint8_t *d_active, int64_t n,
+                          double eps, int32_t kcap, uint32_t flags, double *d_reached, int64_t *d_last, void *stream);
+
+/*
+ * The rest of one iteration of RRT.plan_to_configs (src/mjpl/planning/rrt.py:195-235) for S queries held
+ * in S slots, with all planner state on the device so that whole iterations can be enqueued -- or
+ * captured into a CUDA graph and replayed -- without a host round trip:
+ *   mjb_rrt_sample  the sampling step (:206-215): with probability goal_bias the other tree's root
+ *                   (q_goal, or q_init when the trees are swapped), else q_init with the planning
+ *                   joints (d_plan_mask) drawn uniformly in [lo, hi]; counter-based random stream keyed
+ *                   by (seed, slot, iteration).  Slots with d_active == 0 get NaN targets.
+ *   mjb_rrt_meet    the connection test (:217-229): slots whose two extends reached the same
+ *                   configuration record their connecting nodes (d_res_start / d_res_goal: node index in
+ *                   the start / goal tree) and are retired; slots older than max_age iterations are
+ *                   retired unsolved; the iteration counter advances (the trees swap roles, :231-235).
+ * d_counters (int64[8], zero-initialised by the caller): [0] iteration, [1] solved, [2] gave up,
+ * [3] active slots after the last iteration, [4] scratch.  The parity of [0] is `swapped`: on odd
+ * iterations the caller extends the goal tree first and passes (qa, ia) of the goal tree.
+ */
+int mjb_rrt_sample(uint64_t seed, const int64_t *d_counters, int64_t nslots, int32_t nq, const double *d_q_init,
+                   const double *d_q_goal, const uint8_t *d_plan_mask, const double *d_lo, const double *d_hi,
+                   double goal_bias, const uint8_t *d_active, double *d_targets, void *stream);
+int mjb_rrt_meet(int64_t nslots, int32_t nq, const double *d_qa, const double *d_qb, const int64_t *d_ia,
+                 const int64_t *d_ib, int64_t max_age, uint8_t *d_active, int64_t *d_age, int64_t *d_res_start,
+                 int64_t *d_res_goal, int64_t *d_counters, void *stream);
+
 /*
  * PoseConstraint (src/mjpl/constraint/pose_constraint.py:11-171): a site must stay inside a box
  * of translations and roll/pitch/yaw expressed in a constraint frame.  fp64, rows (n,nq) of

@@ -57,7 +57,7 @@ struct mjb_model {
   float *d_pose8 = nullptr; unsigned long long *d_bins = nullptr; uint32_t *d_row_flags = nullptr; size_t split_cap = 0;
   unsigned long long *d_l0 = nullptr; size_t l0_cap = 0;
   GroupPair *d_gpairs = nullptr; StaticGroup *d_sgroups = nullptr; uint16_t *d_gp_member = nullptr;
-  size_t cur_rows = 0, split_min = 0, bin_cap_override = 0, l0_cap_override = 0; bool use_split = false;
+  size_t cur_rows = 0, cur_rows_hint = 0, grp_small_rows = 0, split_min = 0, bin_cap_override = 0, l0_cap_override = 0; bool use_split = false;
   // optional per-kernel timing (mjb_kernel_timing): 4 events per validity launch
   bool timing = false; std::vector<cudaEvent_t> tev; std::vector<uint8_t> tev_split; size_t tev_used = 0;   // decided per launch from the row count
   long long *d_edge_count = nullptr, *d_edge_prefix = nullptr; int *d_first_bad = nullptr; size_t edge_cap = 0;
@@ -96,12 +96,13 @@ template <int TILE> static int try_tile(const vkb::HostModel &H, int max_smem_op
   if ((int)H.shapes.size() - H.nmoving_shapes > TILE) return -1;  // static centres share one [xyz][TILE] block
   // the attribute is per kernel function, shared by every handle in the process: always ask for
   // the device maximum so that handles with different table sizes can coexist
-  if (cudaFuncSetAttribute(validity_kernel<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) {
+  if (cudaFuncSetAttribute(validity_kernel<TILE, GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess ||
+      cudaFuncSetAttribute(validity_kernel<TILE, GRP_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem_optin) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }
   int occ = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, validity_kernel<TILE>, TILE, L.total) != cudaSuccess || occ < 1) {
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, validity_kernel<TILE, GRP>, TILE, L.total) != cudaSuccess || occ < 1) {
     cudaGetLastError();
     return -1;
   }
@@ -194,6 +195,10 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
     m->split_min = mode == 1 ? 0 : (smin ? (size_t)atoll(smin) : (size_t)200000);
     const char *bc = getenv("MJB_BIN_CAP");   // testing: tiny bins force the on-the-spot path of full bins
     m->bin_cap_override = bc ? (size_t)atoll(bc) : 0;
+    // launches of at most this many rows use the GRP_SMALL-lanes-per-item instance of validity_kernel.  B200, Franka rows, raw
+    // call (tools/grp_crossover.py): 1k rows 132 -> 121 us, 8k 149 -> 130, 16k 183 -> 175, 32k 210 -> 228, 131k 439 -> 550.
+    const char *gr = getenv("MJB_GRP_ROWS");
+    m->grp_small_rows = gr ? (size_t)atoll(gr) : (size_t)12288;
     const char *lc = getenv("MJB_L0_CAP");    // testing: a tiny level-0 list forces the whole-row fp64 path
     m->l0_cap_override = lc ? (size_t)atoll(lc) : 0;
     if (mode != 0) {
@@ -306,8 +311,9 @@ static size_t bin_capacity(const vkb::HostModel &H, int b, size_t rows) {
   return (size_t)((2.0 * H.bin_expect[b] + 0.25) * (double)rows) + 1024;
 }
 
-static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st, bool may_split = true) {
+static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st, bool may_split = true, size_t rows_hint = 0) {
   m->cur_rows = rows;
+  m->cur_rows_hint = rows_hint ? rows_hint : rows;   // expected rows when `rows` is only a worst case (chains)
   m->use_split = may_split && m->split && rows >= m->split_min;
   if (m->use_split && rows > m->split_cap) {
     CU(cudaStreamSynchronize(st));
@@ -370,10 +376,12 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
     if (ev) CU(cudaEventRecord(ev[3], st));
     m->launches += 3;
   } else {
+    // small launches (the planner's extends): the instance whose narrow phase puts GRP_SMALL lanes on one item
+    const bool small = m->cur_rows_hint <= m->grp_small_rows;
     switch (m->tile) {
-      case 512: validity_kernel<512><<<m->grid, 512, m->smem_bytes, st>>>(k); break;
-      case 256: validity_kernel<256><<<m->grid, 256, m->smem_bytes, st>>>(k); break;
-      default: validity_kernel<128><<<m->grid, 128, m->smem_bytes, st>>>(k); break;
+      case 512: if (small) validity_kernel<512, GRP_SMALL><<<m->grid, 512, m->smem_bytes, st>>>(k); else validity_kernel<512, GRP><<<m->grid, 512, m->smem_bytes, st>>>(k); break;
+      case 256: if (small) validity_kernel<256, GRP_SMALL><<<m->grid, 256, m->smem_bytes, st>>>(k); else validity_kernel<256, GRP><<<m->grid, 256, m->smem_bytes, st>>>(k); break;
+      default: if (small) validity_kernel<128, GRP_SMALL><<<m->grid, 128, m->smem_bytes, st>>>(k); else validity_kernel<128, GRP><<<m->grid, 128, m->smem_bytes, st>>>(k); break;
     }
     CU(cudaGetLastError());
     if (ev) { CU(cudaEventRecord(ev[1], st)); CU(cudaEventRecord(ev[2], st)); CU(cudaEventRecord(ev[3], st)); }
@@ -402,11 +410,21 @@ static int check_common(mjb_model *m, uint32_t flags) {
 // an event behind on its stream, and a call that arrives on a DIFFERENT stream first makes its stream
 // wait for that event (also before any scratch buffer is grown and the old one freed).  Calls from
 // several host threads still have to be serialised by the caller (mjpl_b200.engine holds a lock).
+// While `st` is being captured into a CUDA graph (the planner replays whole iterations as graphs) no
+// cross-stream event is waited for or left behind: the graph's own edges order the work, and the
+// caller keeps other calls on the handle away until its replays are done.
+static bool capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); return false; }
+  return cs != cudaStreamCaptureStatusNone;
+}
 static int enter_stream(mjb_model *m, cudaStream_t st) {
+  if (capturing(st)) return MJB_OK;
   if (m->have_last && m->last_stream != st) CU(cudaStreamWaitEvent(st, m->ev_last, 0));
   return MJB_OK;
 }
 static int leave_stream(mjb_model *m, cudaStream_t st) {
+  if (capturing(st)) return MJB_OK;
   CU(cudaEventRecord(m->ev_last, st));
   m->last_stream = st;
   m->have_last = true;
@@ -689,6 +707,13 @@ static int ensure_edge_buffers(mjb_model *m, size_t ne, cudaStream_t st) {
 extern "C" int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, int64_t *d_count, int64_t cap,
                               const int64_t *d_slots, const double *d_targets, int64_t n, double eps, int32_t kcap,
                               uint32_t flags, double *d_reached, int64_t *d_last, void *stream) {
+  return mjb_rrt_extend_masked(m, d_nodes, d_parent, d_count, cap, d_slots, d_targets, nullptr, n, eps, kcap, flags, d_reached,
+                               d_last, stream);
+}
+
+extern "C" int mjb_rrt_extend_masked(mjb_model *m, double *d_nodes, int64_t *d_parent, int64_t *d_count, int64_t cap,
+                                     const int64_t *d_slots, const double *d_targets, const uint8_t *d_active, int64_t n,
+                                     double eps, int32_t kcap, uint32_t flags, double *d_reached, int64_t *d_last, void *stream) {
   int rc = check_common(m, flags);
   if (rc) return rc;
   // reference: ValueError("`max_step_dist` must be > 0.0") (src/mjpl/planning/utils.py:179-180)
@@ -710,13 +735,14 @@ extern "C" int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, 
     m->chain_cap = c;
   }
   // worst case, no host read-back; the actual chains are short, so always the single kernel
-  if ((rc = ensure_recheck(m, (size_t)n * (size_t)kcap, st, false))) return rc;
+  // (expected rows: ~24 chain steps per query on the Franka scenes; only picks the kernel instance)
+  if ((rc = ensure_recheck(m, (size_t)n * (size_t)kcap, st, false, (size_t)n * 24))) return rc;
   // 1. nearest node of every query's tree   2. chain lengths + prefix sums
   nearest_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_count,
                                                                   (const long long *)d_slots, d_targets, (long long)n, m->d_chain_nn);
   chain_setup_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_slots, m->d_chain_nn,
                                                                  d_targets, (long long)n, eps, kcap, m->d_chain_near, m->d_edge_count,
-                                                                 m->d_first_bad);
+                                                                 m->d_first_bad, d_active);
   CU(cudaGetLastError());
   CU(cudaMemsetAsync(m->d_edge_count + n, 0, sizeof(long long), st));
   size_t tb = m->cub_bytes;
@@ -858,5 +884,39 @@ extern "C" int mjb_fma_peak(double *tflops, double *ms_out) {
   const double flops = 2.0 * 128.0 * (double)iters * (double)ctas * (double)threads;
   *tflops = flops / (best * 1e-3) / 1e12;
   if (ms_out) *ms_out = best;
+  return MJB_OK;
+}
+
+// ---- bi-RRT iteration helpers (device-resident planner state; mjpl_b200/planning/batched_rrt.py) ----
+extern "C" int mjb_rrt_sample(uint64_t seed, const int64_t *d_counters, int64_t nslots, int32_t nq, const double *d_q_init,
+                              const double *d_q_goal, const uint8_t *d_plan_mask, const double *d_lo, const double *d_hi,
+                              double goal_bias, const uint8_t *d_active, double *d_targets, void *stream) {
+  if (nslots < 0 || nq < 1 || nq > MAX_JNT) return fail(MJB_ERR_ARG, "bad nslots / nq");
+  // reference: ValueError("`goal_biasing_probability` must be within [0.0, 1.0].") (src/mjpl/planning/rrt.py:57-58)
+  if (!(goal_bias >= 0.0 && goal_bias <= 1.0)) return fail(MJB_ERR_ARG, "`goal_biasing_probability` must be within [0.0, 1.0].");
+  if (nslots == 0) return MJB_OK;
+  if (!d_counters || !d_q_init || !d_q_goal || !d_plan_mask || !d_lo || !d_hi || !d_active || !d_targets)
+    return fail(MJB_ERR_ARG, "null device pointer");
+  rrt_sample_kernel<<<(unsigned)((nslots + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      seed, (const long long *)d_counters, (long long)nslots, nq, d_q_init, d_q_goal, d_plan_mask, d_lo, d_hi, goal_bias, d_active,
+      d_targets);
+  CU(cudaGetLastError());
+  return MJB_OK;
+}
+
+extern "C" int mjb_rrt_meet(int64_t nslots, int32_t nq, const double *d_qa, const double *d_qb, const int64_t *d_ia,
+                            const int64_t *d_ib, int64_t max_age, uint8_t *d_active, int64_t *d_age, int64_t *d_res_start,
+                            int64_t *d_res_goal, int64_t *d_counters, void *stream) {
+  if (nslots < 0 || nq < 1) return fail(MJB_ERR_ARG, "bad nslots / nq");
+  if (nslots == 0) return MJB_OK;
+  if (!d_qa || !d_qb || !d_ia || !d_ib || !d_active || !d_age || !d_res_start || !d_res_goal || !d_counters)
+    return fail(MJB_ERR_ARG, "null device pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  rrt_meet_kernel<<<(unsigned)((nslots + 127) / 128), 128, 0, st>>>((long long)nslots, nq, d_qa, d_qb, (const long long *)d_ia,
+                                                                    (const long long *)d_ib, (long long)max_age, d_active,
+                                                                    (long long *)d_age, (long long *)d_res_start,
+                                                                    (long long *)d_res_goal, (long long *)d_counters);
+  rrt_advance_kernel<<<1, 1, 0, st>>>((long long *)d_counters);
+  CU(cudaGetLastError());
   return MJB_OK;
 }

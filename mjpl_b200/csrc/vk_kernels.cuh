@@ -291,9 +291,15 @@ __device__ __forceinline__ void warp_push(bool want, uint32_t item, uint32_t *qu
 #endif
 #define VK_PRAGMA(x) _Pragma(#x)
 #define VK_UNROLL(n) VK_PRAGMA(unroll n)
-constexpr int GRP = VK_GRP;
+constexpr int GRP = VK_GRP;           // lanes per item of the large-batch instance of validity_kernel
+#ifndef VK_GRP_SMALL
+#define VK_GRP_SMALL 8
+#endif
+constexpr int GRP_SMALL = VK_GRP_SMALL;  // ... of the small-batch instance: an item's hull scans are split over 8 lanes, which
+                                         // shortens the dependent chain a small launch waits for (planner extends)
 
 // `warm` carries the last support vertex of this shape within one GJK run (-1 = cold start).
+template <int G>
 __device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const Vtx<float> *__restrict__ verts,
                                                   const uint16_t *__restrict__ adjs, const uint8_t *__restrict__ adj,
                                                   V3<float> d, int gl, unsigned gmask, int &warm) {
@@ -310,14 +316,14 @@ __device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const 
       int cj = bi;
       float cb = best;
       const int e1 = as[bi + 1];
-      for (int e = as[bi] + gl; e < e1; e += GRP) {
+      for (int e = as[bi] + gl; e < e1; e += G) {
         const int j = adj[e];
         const Vtx<float> p = v[j];
         const float t = p.x * d.x + p.y * d.y + p.z * d.z;
         if (t > cb) { cb = t; cj = j; }
       }
 #pragma unroll
-      for (int o = GRP / 2; o > 0; o >>= 1) {
+      for (int o = G / 2; o > 0; o >>= 1) {
         const float ob = __shfl_xor_sync(gmask, cb, o);
         const int oj = __shfl_xor_sync(gmask, cj, o);
         const bool take = (ob > cb) || (ob == cb && oj < cj);
@@ -333,7 +339,7 @@ __device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const 
     const int n = s.nvert;
     float best = -3.0e38f;
     VK_UNROLL(VK_SCAN_UNROLL)
-    for (int i = gl; i < n; i += GRP) {
+    for (int i = gl; i < n; i += G) {
       const Vtx<float> p = v[i];
       const float t = p.x * d.x + p.y * d.y + p.z * d.z;
       const bool g = t > best;
@@ -341,7 +347,7 @@ __device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const 
       bi = g ? i : bi;
     }
 #pragma unroll
-    for (int o = GRP / 2; o > 0; o >>= 1) {
+    for (int o = G / 2; o > 0; o >>= 1) {
       const float ob = __shfl_xor_sync(gmask, best, o);
       const int oi = __shfl_xor_sync(gmask, bi, o);
       const bool take = (ob > best) || (ob == best && oi < bi);
@@ -353,7 +359,7 @@ __device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const 
   return mk<float>(w.x, w.y, w.z);
 }
 
-template <int TILE>
+template <int TILE, int G>
 __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int nq = a.fk.nq;
@@ -548,8 +554,8 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
     int wa = -1, wb = -1;  // warm-start vertices of the current item's two shapes
     bool have = false;
     s_unc[tid] = 0;
-    const int gl = lane & (GRP - 1);
-    const unsigned gmask = ((1u << GRP) - 1u) << (lane & ~(GRP - 1));
+    const int gl = lane & (G - 1);
+    const unsigned gmask = ((1u << G) - 1u) << (lane & ~(G - 1));
 #pragma unroll 1
     for (int rd = 0; rd < a.nrounds && (coll_mask & ~hit_mask); rd++) {
       int p = a.round_start[rd];
@@ -630,10 +636,10 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
 #pragma unroll 1
           for (;;) {
             const unsigned need = __ballot_sync(0xffffffffu, !have);   // group-uniform bits
-            if (head >= n2 && (need == 0xffffffffu || (!drain && __popc(~need) <= VK_SUSPEND * GRP))) break;
+            if (head >= n2 && (need == 0xffffffffu || (!drain && __popc(~need) <= VK_SUSPEND * G))) break;
             unsigned hb = 0, ub = 0;
             if (!have) {
-              const int i = head + __popc(need & ((1u << (lane & ~(GRP - 1))) - 1u)) / GRP;
+              const int i = head + __popc(need & ((1u << (lane & ~(G - 1))) - 1u)) / G;
               if (i < n2) {
                 const uint32_t it = q2[i];
                 r = it & 0xffff;
@@ -655,29 +661,29 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
                     if (pr.kind == PK_PLANE) {
                       const Shape<float> &Bs = *SB;
                       int cold = -1;
-                      v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, cold); });
+                      v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support<G>(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, cold); });
                     } else {
                       v = segseg_item(*SA, *SB, s_verts, PA, PB, R);
                     }
                     if (v == V_PEN) hb = 1u << r;
-                    else if (v == V_UNC) { ub = 1u << r; if (!(a.flags & F_NO_RECHECK)) note_uncertain(a.counters, a.recheck_items, a.item_cap, row_base + r, pidx, s_unc + wrow0 + r); }
+                    else if (v == V_UNC) { ub = 1u << r; if (!(a.flags & F_NO_RECHECK) && gl == 0) note_uncertain(a.counters, a.recheck_items, a.item_cap, row_base + r, pidx, s_unc + wrow0 + r); }
                   }
                 }
               }
             }
-            head += __popc(need) / GRP;
+            head += __popc(need) / G;
 #ifdef VK_STATS
-            { const int nb = __popc(__ballot_sync(0xffffffffu, have)) / GRP; st_trips++; st_busy += nb;
+            { const int nb = __popc(__ballot_sync(0xffffffffu, have)) / G; st_trips++; st_busy += nb;
               const int bin = nb <= 4 ? 0 : (nb <= 8 ? 1 : (nb <= 16 ? 2 : 3)); st_hist[bin]++; st_histb[bin] += nb; }
 #endif
             if (have) {
               const Shape<float> &As = *SA, &Bs = *SB;
               const int v = gjk_step_impl(
-                  gs, rel, R, [&](V3<float> d) { return group_support(As, s_verts, s_adjs, s_adj, d, gl, gmask, wa); },
-                  [&](V3<float> d) { return group_support(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, wb); });
+                  gs, rel, R, [&](V3<float> d) { return group_support<G>(As, s_verts, s_adjs, s_adj, d, gl, gmask, wa); },
+                  [&](V3<float> d) { return group_support<G>(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, wb); });
               if (v >= 0) {
                 if (v == V_PEN) hb = 1u << r;
-                else if (v == V_UNC) { ub = 1u << r; if (!(a.flags & F_NO_RECHECK)) note_uncertain(a.counters, a.recheck_items, a.item_cap, row_base + r, pidx, s_unc + wrow0 + r); }
+                else if (v == V_UNC) { ub = 1u << r; if (!(a.flags & F_NO_RECHECK) && gl == 0) note_uncertain(a.counters, a.recheck_items, a.item_cap, row_base + r, pidx, s_unc + wrow0 + r); }
                 have = false;
               }
             }
@@ -1039,7 +1045,7 @@ __global__ void __launch_bounds__(64) ik_kernel(const IkArgs a) {
 // near[i] = nodes[slot_i][nn[i]]; chain length K = min(ceil(|target-near|/eps), kcap) (0 if equal)
 __global__ void chain_setup_kernel(const double *nodes, long long cap, int nq, const long long *slots, const long long *nn,
                                    const double *targets, long long n, double eps, int kcap, double *near, long long *count,
-                                   int *first_bad) {
+                                   int *first_bad, const uint8_t *active) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long slot = slots ? slots[i] : i;
@@ -1052,8 +1058,9 @@ __global__ void chain_setup_kernel(const double *nodes, long long cap, int nq, c
     d2 += d * d;
   }
   const double dist = sqrt(d2);
-  long long k = dist > 0 ? (long long)ceil(dist / eps) : 0;
+  long long k = dist > 0 ? (long long)ceil(dist / eps) : 0;   // NaN targets: no chain
   if (k > kcap) k = kcap;
+  if (active && !active[i]) k = 0;                            // masked query: no chain, nothing appended
   count[i] = k;
   first_bad[i] = 0x7fffffff;
 }
@@ -1142,6 +1149,79 @@ __global__ void __launch_bounds__(128) nearest_kernel(const double *nodes, long 
     if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
   }
   if (lane == 0) out[w] = bi;
+}
+
+// ---------------------------------------------------------------------------- bi-RRT iteration on the device
+// Sampling step of RRT.plan_to_configs for S queries at once (reference: src/mjpl/planning/rrt.py:206-215):
+// with probability goal_bias the target is the other tree's root (the goal, or q_init once the trees
+// have been swapped), otherwise q_init with the planning joints drawn uniformly within the joint
+// limits.  The random stream is counter based (slot, iteration, joint), so a CUDA graph of iterations
+// replays without host-side state; the iteration counter lives on the device (counters[0]) and its
+// parity is the reference's `swapped` flag.  Masked (finished) slots get NaN targets.
+__global__ void rrt_sample_kernel(unsigned long long seed, const long long *counters, long long nslots, int nq,
+                                  const double *q_init, const double *q_goal, const uint8_t *plan_mask, const double *lo,
+                                  const double *hi, double goal_bias, const uint8_t *active, double *targets) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nslots) return;
+  const unsigned long long it = (unsigned long long)counters[0];
+  const bool swapped = it & 1ull;
+  double *t = targets + s * nq;
+  if (!active[s]) {
+    for (int j = 0; j < nq; j++) t[j] = __longlong_as_double(0x7ff8000000000000ll);
+    return;
+  }
+  const unsigned long long key = seed + 0xD1B54A32D192ED03ull * (it + 1ull);
+  const double u = (double)sweep_bits(key, (uint64_t)s, 63u) * (1.0 / 16777216.0);
+  if (u <= goal_bias) {
+    const double *src = (swapped ? q_init : q_goal) + s * nq;
+    for (int j = 0; j < nq; j++) t[j] = src[j];
+    return;
+  }
+  for (int j = 0; j < nq; j++) {
+    double v = q_init[s * nq + j];
+    if (plan_mask[j]) {
+      const double r = ((double)sweep_bits(key, (uint64_t)s, (uint32_t)(2 * j)) * 16777216.0 + (double)sweep_bits(key, (uint64_t)s, (uint32_t)(2 * j + 1))) *
+                       (1.0 / 281474976710656.0);   // 48 random bits in [0, 1)
+      v = lo[j] + r * (hi[j] - lo[j]);
+    }
+    t[j] = v;
+  }
+}
+
+// End of one iteration (rrt.py:217-235): a query whose two extends reached the same configuration is
+// solved -- the connecting node of each tree is recorded and the slot is retired; a query that has
+// used up its iteration budget is retired unsolved.  Advances the iteration counter.
+// counters: [0] iteration, [1] solved, [2] gave up, [3] still active after this iteration.
+__global__ void rrt_meet_kernel(long long nslots, int nq, const double *qa, const double *qb, const long long *ia, const long long *ib,
+                                long long max_age, uint8_t *active, long long *age, long long *res_start, long long *res_goal,
+                                long long *counters) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool swapped = counters[0] & 1ll;
+  int still = 0;
+  if (s < nslots && active[s]) {
+    bool met = true;
+    for (int j = 0; j < nq; j++) met = met && (qa[s * nq + j] == qb[s * nq + j]);
+    age[s] += 1;
+    if (met) {
+      res_start[s] = swapped ? ib[s] : ia[s];
+      res_goal[s] = swapped ? ia[s] : ib[s];
+      active[s] = 0;
+      atomicAdd((unsigned long long *)&counters[1], 1ull);
+    } else if (age[s] >= max_age) {
+      active[s] = 0;
+      atomicAdd((unsigned long long *)&counters[2], 1ull);
+    } else {
+      still = 1;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, still);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd((unsigned long long *)&counters[4], (unsigned long long)__popc(m));
+}
+// one thread, after rrt_meet_kernel: iteration += 1, active count of this iteration published
+__global__ void rrt_advance_kernel(long long *counters) {
+  counters[0] += 1;
+  counters[3] = counters[4];
+  counters[4] = 0;
 }
 
 }  // namespace vk

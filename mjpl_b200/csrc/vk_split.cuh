@@ -136,7 +136,6 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
   mbar_wait(&s_bar[0], 0);
   __syncthreads();
 
-  static_assert(GRP == 1, "narrow_kernel assigns one lane per item");
   const bool by_row = !(a.mode == MODE_EDGES || a.mode == MODE_CHAINS);  // the output mask doubles as the early-exit flag
   const int gl = 0;
   const unsigned gmask = 1u << lane;
@@ -220,7 +219,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
               if (pr.kind == PK_PLANE) {
                 const Shape<float> &Bs = *SB;
                 int cold = -1;
-                v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, cold); });
+                v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support<1>(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, cold); });
               } else {
                 v = segseg_item(*SA, *SB, s_verts, PA, PB, R);
               }
@@ -238,8 +237,8 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
     if (have) {
       const Shape<float> &As = *SA, &Bs = *SB;
       const int v = gjk_step_impl(
-          gs, rel, R, [&](V3<float> d) { return group_support(As, s_verts, s_adjs, s_adj, d, gl, gmask, wa); },
-          [&](V3<float> d) { return group_support(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, wb); });
+          gs, rel, R, [&](V3<float> d) { return group_support<1>(As, s_verts, s_adjs, s_adj, d, gl, gmask, wa); },
+          [&](V3<float> d) { return group_support<1>(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, wb); });
       if (v >= 0) {
         if (v == V_PEN) mark_contact(a, row);
         else if (v == V_UNC) mark_uncertain(a, row, pidx);

@@ -116,7 +116,8 @@ class BatchedRRT:
     def __init__(self, model, planning_joints: list[str], constraints: list[Constraint],
                  max_planning_time: float = 10.0, epsilon: float = 0.05, seed: int | None = None,
                  goal_biasing_probability: float = 0.05, max_iterations: int = 1000000,
-                 max_chain: int = 512, max_active: int = 4096, max_iterations_per_query: int = 3000) -> None:
+                 max_chain: int = 512, max_active: int = 4096, max_iterations_per_query: int = 3000,
+                 sync_every: int = 8, use_cuda_graph: bool = True) -> None:
         if not planning_joints:
             raise ValueError("`planning_joints` cannot be empty.")
         if max_planning_time <= 0.0:
@@ -136,6 +137,8 @@ class BatchedRRT:
         self.max_chain = max_chain
         self.max_active = max_active                              # slots of the device driver
         self.max_iterations_per_query = max_iterations_per_query  # a query that exceeds it returns []
+        self.sync_every = sync_every            # device driver: iterations enqueued between two looks of the host
+        self.use_cuda_graph = use_cuda_graph    # device driver: replay iteration pairs as a CUDA graph
         self.stats: dict = {}
 
     # one extend for a set of queries: returns reached configs and node indices
@@ -236,20 +239,20 @@ class BatchedRRT:
 
     # ------------------------------------------------------------------ device driver
     def _plan_device(self, q_inits, q_goals, eng, flags):
-        import ctypes as C
-
+        """All planner state lives in HBM and whole iterations are enqueued without a host round trip:
+        sampling (``mjb_rrt_sample``), the two extends (``mjb_rrt_extend_masked``: nearest node, chain,
+        validity, stop rules, append) and the connection test (``mjb_rrt_meet``) only read and write
+        device memory, and an even + odd iteration pair is captured ONCE into a CUDA graph that is then
+        replayed; the host looks at a four-word status every ``sync_every`` iterations (how many queries
+        are still active, how full the trees are).  Queries are processed in waves of ``max_active``."""
         import torch
 
-        from .. import _abi
-
-        dev, f64 = eng.torch_device, torch.float64
-        L = _abi.lib()
+        dev = eng.torch_device
         B, nq = q_inits.shape
-        eps = float(self.epsilon)
         with torch.cuda.device(eng.device):
             QI = torch.from_numpy(q_inits).to(dev)
             QG = torch.from_numpy(q_goals).to(dev)
-            ok = eng.valid_configs(torch.cat([QI, QG]).float(), flags)
+            ok = eng.valid_configs(torch.cat([QI, QG]), flags)
             if not bool(ok[:B].all()):
                 raise ValueError("q_init is not a valid configuration")
             if not bool(ok[B:].all()):
@@ -260,190 +263,192 @@ class BatchedRRT:
             if fixed and not np.allclose(q_inits[:, fixed], q_goals[:, fixed], rtol=0, atol=1e-12):
                 raise ValueError("goal configs have values for joints outside of the planner's planning joints "
                                  "that don't match q_init")
-            plan_mask = torch.zeros(nq, dtype=torch.bool, device=dev)
-            plan_mask[q_idx] = True
-            lo = torch.from_numpy(np.ascontiguousarray(self.model.jnt_range[:, 0])).to(dev)
-            hi = torch.from_numpy(np.ascontiguousarray(self.model.jnt_range[:, 1])).to(dev)
-            gen = torch.Generator(device=dev)
-            if self.seed is not None:
-                gen.manual_seed(int(self.seed))
-
-            class Forest:
-                def __init__(self, roots, cap=1024):
-                    self.cap = cap
-                    self.q = torch.full((B, cap, nq), float("inf"), dtype=f64, device=dev)
-                    self.parent = torch.full((B, cap), -1, dtype=torch.int64, device=dev)
-                    self.count = torch.ones(B, dtype=torch.int64, device=dev)
-                    self.q[:, 0] = roots
-                    self.hi = 1  # host-side upper bound of count.max()
-
-                def reserve(self, extra):
-                    if self.hi + extra <= self.cap:
-                        return
-                    new = max(self.hi + extra, 2 * self.cap)
-                    q = torch.full((B, new, nq), float("inf"), dtype=f64, device=dev)
-                    q[:, : self.cap] = self.q
-                    p = torch.full((B, new), -1, dtype=torch.int64, device=dev)
-                    p[:, : self.cap] = self.parent
-                    self.q, self.parent, self.cap = q, p, new
-
-                def nearest(self, act, targets):
-                    out = torch.empty(len(act), dtype=torch.int64, device=dev)
-                    t = targets.contiguous()
-                    _abi.check(L.mjb_nearest_batch(self.q.data_ptr(), self.cap, nq, self.count.data_ptr(), act.data_ptr(),
-                                                   t.data_ptr(), len(act), out.data_ptr(),
-                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-                    return out
-
-            kcap = int(self.max_chain)
-            eng.reset_stats()
-
-            def extend(F, act, targets):
-                """One ``_constrained_extend`` per active slot, entirely on the device
-                (``mjb_rrt_extend``: nearest node, chain, validity, stop rules, append)."""
-                n = len(act)
-                F.reserve(kcap)
-                reached = torch.empty((n, nq), dtype=f64, device=dev)
-                last = torch.empty(n, dtype=torch.int64, device=dev)
-                t = targets.contiguous()
-                _abi.check(L.mjb_rrt_extend(eng._h, F.q.data_ptr(), F.parent.data_ptr(), F.count.data_ptr(), F.cap,
-                                            act.data_ptr(), t.data_ptr(), n, eps, kcap, flags, reached.data_ptr(),
-                                            last.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-                F.hi += kcap  # upper bound until the next exact refresh
-                self.stats["launches"] += 1
-                return reached, last
-
-            direct = torch.linalg.vector_norm(QG - QI, dim=1) <= eps
+            direct = np.linalg.norm(q_goals - q_inits, axis=1) <= self.epsilon
             paths: list[list[np.ndarray]] = [[] for _ in range(B)]
-            for b in direct.nonzero(as_tuple=True)[0].tolist():
+            for b in np.flatnonzero(direct):
                 paths[b] = [q_inits[b].copy(), q_goals[b].copy()]
-            pending = (~direct).nonzero(as_tuple=True)[0].cpu().numpy().tolist()[::-1]  # pop() takes the lowest id
-            # ---- continuous batching: S slots, each holding one query's two trees; a slot whose
-            # query is solved (or out of budget) is handed to the next pending query at once, so
-            # the long tail of hard queries never idles the rest of the batch.
-            S = min(len(pending), int(self.max_active)) if pending else 0
-            self.stats = {"iterations": 0, "configs_checked": 0, "launches": 0, "driver": "device", "slots": S,
-                          "gave_up": 0}
+            pending = np.flatnonzero(~direct)
+            S = int(min(len(pending), int(self.max_active)))
+            self.stats = {"iterations": 0, "configs_checked": 0, "launches": 0, "driver": "device", "slots": S, "gave_up": 0,
+                          "graph_replays": 0, "host_syncs": 0, "waves": 0, "chains_clipped_at_capacity": 0}
+            eng.reset_stats()
             t0 = time.time()
-            it = 0
-            if S:
-                slot_query = torch.full((S,), -1, dtype=torch.int64, device=dev)
-                slot_age = torch.zeros(S, dtype=torch.int64, device=dev)
-                first = [pending.pop() for _ in range(S)]
-                slot_query[:] = torch.tensor(first, device=dev)
-                SQI, SQG = QI[slot_query].clone(), QG[slot_query].clone()   # per-slot endpoints
-                B_forest = S
-
-                class SlotForest(Forest):
-                    def __init__(self, roots):
-                        self.cap = 1024
-                        self.q = torch.full((B_forest, self.cap, nq), float("inf"), dtype=f64, device=dev)
-                        self.parent = torch.full((B_forest, self.cap), -1, dtype=torch.int64, device=dev)
-                        self.count = torch.ones(B_forest, dtype=torch.int64, device=dev)
-                        self.q[:, 0] = roots
-                        self.hi = 1
-
-                    def reserve(self, extra):
-                        if self.hi + extra <= self.cap:
-                            return
-                        new = max(self.hi + extra, 2 * self.cap)
-                        q = torch.full((B_forest, new, nq), float("inf"), dtype=f64, device=dev)
-                        q[:, : self.cap] = self.q
-                        p = torch.full((B_forest, new), -1, dtype=torch.int64, device=dev)
-                        p[:, : self.cap] = self.parent
-                        self.q, self.parent, self.cap = q, p, new
-
-                start, goal = SlotForest(SQI), SlotForest(SQG)
-                live = torch.arange(S, device=dev)       # slots that hold a query
-                swapped = False
-                while len(live) and it < self.max_iterations and time.time() - t0 < self.max_planning_time:
-                    it += 1
-                    n = len(live)
-                    fa, fb = (goal, start) if swapped else (start, goal)
-                    u = torch.rand(n, generator=gen, device=dev, dtype=f64)
-                    rnd = lo[None, :] + (hi - lo)[None, :] * torch.rand((n, nq), generator=gen, device=dev, dtype=f64)
-                    qi_a = SQI[live]
-                    targets = torch.where(plan_mask[None, :], rnd, qi_a)
-                    bias = (u <= self.goal_biasing_probability)[:, None]
-                    targets = torch.where(bias, qi_a if swapped else SQG[live], targets)
-                    qa, ia = extend(fa, live, targets)
-                    qb, ib = extend(fb, live, qa)
-                    slot_age[live] += 1
-                    met = (qa == qb).all(dim=1)
-                    done = met | (slot_age[live] >= self.max_iterations_per_query)
-                    # the only host read-back of the iteration: any slot finished? + exact tree sizes
-                    info = torch.stack([done.any().to(torch.int64), start.count.max(), goal.count.max()]).cpu()
-                    start.hi, goal.hi = int(info[1]), int(info[2])
-                    if bool(info[0]):
-                        di = done.nonzero(as_tuple=True)[0]
-                        dslots = live[di]
-                        dmet = met[di].cpu().numpy()
-                        dq = slot_query[dslots].cpu().numpy()
-                        s_idx, g_idx = (ib, ia) if swapped else (ia, ib)
-                        ds, dg = s_idx[di].cpu().numpy(), g_idx[di].cpu().numpy()
-                        hi_s = int(start.count[dslots].max())
-                        hi_g = int(goal.count[dslots].max())
-                        sp = start.parent[dslots, :hi_s].cpu().numpy()
-                        gp = goal.parent[dslots, :hi_g].cpu().numpy()
-                        want_s, want_g, who = [], [], []
-                        for k in range(len(di)):
-                            if not dmet[k]:
-                                self.stats["gave_up"] += 1
-                                continue
-                            a, si = [], int(ds[k])
-                            while si >= 0:
-                                a.append(si)
-                                si = int(sp[k, si])
-                            g, gi = [], int(dg[k])
-                            while gi >= 0:
-                                g.append(gi)
-                                gi = int(gp[k, gi])
-                            want_s.append((int(dslots[k]), a[::-1]))
-                            want_g.append((int(dslots[k]), g))
-                            who.append(int(dq[k]))
-
-                        def gather(F, lists):
-                            if not lists:
-                                return []
-                            bb = np.concatenate([np.full(len(ix), sl) for sl, ix in lists])
-                            ii = np.concatenate([np.asarray(ix) for _, ix in lists])
-                            rows = F.q[torch.from_numpy(bb).to(dev), torch.from_numpy(ii).to(dev)].cpu().numpy()
-                            out, o = [], 0
-                            for _, ix in lists:
-                                out.append(rows[o : o + len(ix)])
-                                o += len(ix)
-                            return out
-
-                        for qid, ps, pg in zip(who, gather(start, want_s), gather(goal, want_g)):
-                            ps, pg = list(ps), list(pg)
-                            if np.array_equal(ps[-1], pg[0]):
-                                ps.pop()
-                            paths[qid] = ps + pg
-                        # hand the freed slots to pending queries (or retire them)
-                        refill = [pending.pop() for _ in range(min(len(pending), len(dslots)))]
-                        nr = len(refill)
-                        if nr:
-                            rs = dslots[:nr]
-                            rq = torch.tensor(refill, device=dev)
-                            slot_query[rs] = rq
-                            SQI[rs], SQG[rs] = QI[rq], QG[rq]
-                            for F, roots in ((start, QI[rq]), (goal, QG[rq])):
-                                F.q[rs, 0] = roots
-                                F.count[rs] = 1
-                                F.parent[rs, 0] = -1
-                            slot_age[rs] = 0
-                        if nr < len(dslots):
-                            keep = torch.ones(n, dtype=torch.bool, device=dev)
-                            keep[di[nr:]] = False
-                            live = live[keep]
-                    swapped = not swapped
-            self.stats["iterations"] = it
+            for w0 in range(0, len(pending), max(S, 1)):
+                ids = pending[w0:w0 + S]
+                left = self.max_planning_time - (time.time() - t0)
+                if left <= 0:
+                    break
+                for qid, path in zip(ids, self._run_wave(eng, flags, QI[ids], QG[ids], left, wave=w0)):
+                    paths[int(qid)] = path
+                self.stats["waves"] += 1
             self.stats["solved"] = int(sum(1 for p in paths if p))
             self.stats["seconds"] = time.time() - t0
             est = eng.stats()
             self.stats["configs_checked"] = est["rows"]
             self.stats["chains_clipped_at_capacity"] = est["queue_overflow"]
             return paths
+
+    def _run_wave(self, eng, flags, QI, QG, time_left, wave=0):
+        """One wave of queries, one slot each (see ``_plan_device``) -> list of paths (``[]`` = unsolved)."""
+        import ctypes as C
+
+        import torch
+
+        from .. import _abi
+
+        L = _abi.lib()
+        dev, f64, i64 = eng.torch_device, torch.float64, torch.int64
+        S, nq = QI.shape
+        eps, kcap = float(self.epsilon), int(self.max_chain)
+        q_idx = qpos_idx(self.model, self.planning_joints)
+        plan_mask = torch.zeros(nq, dtype=torch.uint8, device=dev)
+        plan_mask[q_idx] = 1
+        lo = torch.from_numpy(np.ascontiguousarray(self.model.jnt_range[:, 0], dtype=np.float64)).to(dev)
+        hi = torch.from_numpy(np.ascontiguousarray(self.model.jnt_range[:, 1], dtype=np.float64)).to(dev)
+        # the longest chain an extend can build: the diameter of the sampled box over epsilon
+        span = float(np.linalg.norm((self.model.jnt_range[:, 1] - self.model.jnt_range[:, 0])[q_idx]))
+        chain_max = int(min(kcap, np.ceil(span / eps) + 1))
+        pairs_per_sync = max(1, int(self.sync_every) // 2)
+        headroom = 2 * pairs_per_sync * chain_max + 1      # nodes one tree can gain between two looks of the host
+        seed = int(self.seed if self.seed is not None else np.random.SeedSequence().entropy % (1 << 62)) + 7919 * int(wave)
+
+        class Forest:
+            def __init__(self, roots, cap):
+                self.cap = cap
+                self.q = torch.empty((S, cap, nq), dtype=f64, device=dev)
+                self.parent = torch.full((S, cap), -1, dtype=i64, device=dev)
+                self.count = torch.ones(S, dtype=i64, device=dev)
+                self.q[:, 0] = roots
+
+            def grow(self, cap):
+                q = torch.empty((S, cap, nq), dtype=f64, device=dev)
+                q[:, : self.cap] = self.q
+                p = torch.full((S, cap), -1, dtype=i64, device=dev)
+                p[:, : self.cap] = self.parent
+                self.q, self.parent, self.cap = q, p, cap
+
+        cap0 = 1 << int(np.ceil(np.log2(max(2 * headroom, 1024))))
+        start, goal = Forest(QI, cap0), Forest(QG, cap0)
+        QI, QG = QI.contiguous(), QG.contiguous()
+        active = torch.ones(S, dtype=torch.uint8, device=dev)
+        age = torch.zeros(S, dtype=i64, device=dev)
+        res_s = torch.full((S,), -1, dtype=i64, device=dev)
+        res_g = torch.full((S,), -1, dtype=i64, device=dev)
+        counters = torch.zeros(8, dtype=i64, device=dev)
+        counters[3] = S
+        slots = torch.arange(S, dtype=i64, device=dev)
+        targets = torch.empty((S, nq), dtype=f64, device=dev)
+        qa, qb = torch.empty_like(targets), torch.empty_like(targets)
+        ia, ib = torch.empty(S, dtype=i64, device=dev), torch.empty(S, dtype=i64, device=dev)
+        status = torch.empty(4, dtype=i64, device=dev)
+
+        def stream():
+            return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def extend(F, tgt, reached, last):
+            _abi.check(L.mjb_rrt_extend_masked(eng._h, F.q.data_ptr(), F.parent.data_ptr(), F.count.data_ptr(), F.cap,
+                                               slots.data_ptr(), tgt.data_ptr(), active.data_ptr(), S, eps, kcap, flags,
+                                               reached.data_ptr(), last.data_ptr(), stream()))
+
+        def half(fa, fb):
+            _abi.check(L.mjb_rrt_sample(seed, counters.data_ptr(), S, nq, QI.data_ptr(), QG.data_ptr(), plan_mask.data_ptr(),
+                                        lo.data_ptr(), hi.data_ptr(), float(self.goal_biasing_probability), active.data_ptr(),
+                                        targets.data_ptr(), stream()))
+            extend(fa, targets, qa, ia)
+            extend(fb, qa, qb, ib)
+            _abi.check(L.mjb_rrt_meet(S, nq, qa.data_ptr(), qb.data_ptr(), ia.data_ptr(), ib.data_ptr(),
+                                      int(self.max_iterations_per_query), active.data_ptr(), age.data_ptr(), res_s.data_ptr(),
+                                      res_g.data_ptr(), counters.data_ptr(), stream()))
+
+        def pair():            # an even and an odd iteration: the trees swap roles (rrt.py:231-235)
+            half(start, goal)
+            half(goal, start)
+
+        def look():            # the host's only read-back: iteration, active slots, fullest trees
+            status[0], status[1] = counters[0], counters[3]
+            status[2], status[3] = start.count.max(), goal.count.max()
+            self.stats["host_syncs"] += 1
+            return [int(x) for x in status.cpu()]
+
+        side = torch.cuda.Stream(device=dev)
+        graph = None
+
+        def capture():
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                pair()
+            return g
+
+        with eng._call_lock:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                pair()             # eager once: the library grows its scratch here, never inside a capture
+            side.synchronize()
+            try:
+                graph = capture() if self.use_cuda_graph else None
+            except Exception:      # capture not possible (e.g. a profiler that forbids it): enqueue eagerly
+                graph = None
+            t0 = time.time()
+            while True:
+                it, n_active, hs, hg = look()
+                if n_active == 0 or it >= self.max_iterations or time.time() - t0 >= time_left:
+                    break
+                need = max(hs, hg) + headroom
+                if need > start.cap:
+                    new_cap = 1 << int(np.ceil(np.log2(need + headroom)))
+                    start.grow(new_cap); goal.grow(new_cap)
+                    graph = capture() if (graph is not None) else None
+                if graph is not None:
+                    for _ in range(pairs_per_sync):
+                        graph.replay()
+                    self.stats["graph_replays"] += pairs_per_sync
+                else:
+                    with torch.cuda.stream(side):
+                        for _ in range(pairs_per_sync):
+                            pair()
+                    side.synchronize()
+            torch.cuda.current_stream().wait_stream(side)
+            it, n_active, hs, hg = look()
+            self.stats["iterations"] = max(self.stats["iterations"], it)
+            self.stats["gave_up"] += int(counters[2])
+            # ---- paths of the solved slots: walk the parent links of both trees on the device ----------
+            out: list[list[np.ndarray]] = [[] for _ in range(S)]
+            solved = (res_s >= 0).nonzero(as_tuple=True)[0]
+            if len(solved):
+                def walk(F, first):
+                    """-> (depth, n) node indices from `first` towards the root, -1 past the root"""
+                    idx, cols = first.clone(), []
+                    while True:
+                        cols.append(idx)
+                        nxt = torch.where(idx >= 0, F.parent[solved, idx.clamp(min=0)], idx)
+                        if len(cols) % 32 == 0 and not bool((nxt >= 0).any()):
+                            break
+                        if len(cols) > F.cap:
+                            break
+                        idx = nxt
+                    return torch.stack(cols)
+
+                def rows_of(F, steps):
+                    valid = steps >= 0
+                    sl = solved[None, :].expand_as(steps)[valid]
+                    return F.q[sl, steps[valid]].cpu().numpy(), valid.cpu().numpy()
+
+                ws, wg = walk(start, res_s[solved]), walk(goal, res_g[solved])
+                rs, vs = rows_of(start, ws)
+                rg, vg = rows_of(goal, wg)
+                # rows come depth-major: split them back per query
+                def per_query(rows, valid):
+                    order = np.argsort(np.nonzero(valid)[1], kind="stable")   # group by query, depth order kept
+                    counts = valid.sum(axis=0)
+                    return np.split(rows[order], np.cumsum(counts)[:-1])
+
+                for k, ps, pg in zip(solved.cpu().numpy(), per_query(rs, vs), per_query(rg, vg)):
+                    a = list(ps[::-1])          # root of the start tree -> connecting node
+                    g = list(pg)                # connecting node -> root of the goal tree
+                    if np.array_equal(a[-1], g[0]):
+                        a.pop()
+                    out[int(k)] = a + g
+            return out
 
     # ------------------------------------------------------------------ host driver
     def _plan_host(self, q_inits, q_goals):
