@@ -154,13 +154,62 @@ def _constrained_extend(q_target: np.ndarray, tree: Tree, eps: float, constraint
     return last.q
 
 
+def _extend_blocks(starts: list[np.ndarray], targets: list[np.ndarray], eps: float, constraints: list[Constraint],
+                   collision_interval_check, equality_threshold: float = 1e-8) -> list[np.ndarray]:
+    """``_extend_block`` for many independent (start, target) pairs at once: every chain is generated
+    up front, ALL rows of ALL chains are validated by one ``obeys_constraints_batch`` call (one fused
+    kernel launch), and the stop rules of the reference (``planning/utils.py:151-160``) cut each chain
+    at its first failing row.  Interval checks, when asked for, are one more batched call over the
+    edges of the surviving prefixes."""
+    chains = [_chain(a, b, eps) for a, b in zip(starts, targets)]
+    sizes = [len(c) for c in chains]
+    nq = len(np.asarray(starts[0]))
+    flat = np.concatenate(chains, axis=0) if sum(sizes) else np.empty((0, nq))
+    ok_flat = np.asarray(obeys_constraints_batch(flat, constraints)).astype(bool) if len(flat) else np.zeros(0, dtype=bool)
+    out, prevs, keep, o = [], [], [], 0
+    for a, c, k in zip(starts, chains, sizes):
+        ok = ok_flat[o:o + k].copy()
+        o += k
+        prev = np.concatenate([np.asarray(a, dtype=np.float64)[None, :], c[:-1]], axis=0) if k else c
+        if k:
+            ok &= np.linalg.norm(c - prev, axis=1) >= equality_threshold
+        n_ok = k if ok.all() else int(np.argmin(ok))
+        prevs.append(prev)
+        keep.append(n_ok)
+    if collision_interval_check is not None and sum(keep):
+        step_dist, cc = collision_interval_check
+        e0 = np.concatenate([p[:n] for p, n in zip(prevs, keep)], axis=0)
+        e1 = np.concatenate([c[:n] for c, n in zip(chains, keep)], axis=0)
+        iv = _valid_intervals(e0, e1, step_dist, cc)
+        o = 0
+        for i, n in enumerate(keep):
+            seg = iv[o:o + n]
+            o += n
+            if n and not seg.all():
+                keep[i] = int(np.argmin(seg))
+    for c, n in zip(chains, keep):
+        out.append(c[:n])
+    return out
+
+
 def smooth_path(waypoints: list[np.ndarray], constraints: list[Constraint],
                 collision_interval_check: tuple[float, CollisionConstraint] | None = None,
                 eps: float = 0.05, num_tries: int = 100, seed: int | None = None,
                 sparse: bool = False) -> list[np.ndarray]:
-    """Shortcut smoothing (CBiRRT algorithm 3): ``num_tries`` times pick two waypoints and
-    replace the sub-path by a direct constrained connection when that is shorter.  The random
-    stream (two ``rng.integers`` per try) is the reference's."""
+    """Shortcut smoothing (CBiRRT algorithm 3; reference ``src/mjpl/planning/utils.py:9-87``).
+
+    The reference runs ``num_tries`` tries one after the other: two ``rng.integers`` draws pick a
+    sub-path, a constrained extend tries to connect its ends directly, and the sub-path is replaced
+    when the connection exists and is shorter.  A try changes nothing unless it is accepted, so here
+    ALL remaining tries are evaluated speculatively against the current path -- their draws are taken
+    from the reference's random stream in order, and every candidate connection goes into ONE batched
+    validity call -- and the first try that the reference would accept is applied; the random stream
+    is rewound to just after that try and the rest is speculated again on the new path.  The result is
+    the reference's, waypoint for waypoint, for the same seed.  Every accepted shortcut ends a round
+    (the draws after it depend on the new path), so the number of validity launches is the number of
+    accepted shortcuts plus the rounds without one; the speculation depth adapts (4 tries, doubling
+    after a round without an accepted shortcut, halving after one with).  A projecting constraint makes a
+    connection depend on its own intermediate results, so those are evaluated one try at a time."""
     if not waypoints:
         raise ValueError("`waypoints` cannot be empty.")
     if eps <= 0.0:
@@ -168,23 +217,63 @@ def smooth_path(waypoints: list[np.ndarray], constraints: list[Constraint],
     if num_tries <= 0:
         raise ValueError("`num_tries` must be > 0.")
 
-    smoothed = waypoints
+    projecting = any(getattr(c, "projects", True) for c in constraints)
+    smoothed = list(waypoints)
     rng = np.random.default_rng(seed=seed)
-    for _ in range(num_tries):
-        start = rng.integers(0, len(smoothed) - 1)
-        end = rng.integers(start + 1, len(smoothed))
-        tree = Tree(Node(smoothed[start]))
-        q_reached = _constrained_extend(smoothed[end], tree, eps, constraints, collision_interval_check)
-        if not np.array_equal(q_reached, smoothed[end]):
+    done = 0
+    smooth_path.last_launches = 0    # introspection for tests / benches: batched validity rounds of the last call
+    depth = 4                        # tries speculated per round: doubles after a round without an accepted
+    while done < num_tries:          # shortcut, halves after one with (rows past an accepted try are wasted work)
+        # speculate: the draws of the next tries, assuming none before them is accepted
+        lookahead = 1 if projecting else min(depth, num_tries - done)
+        draws, states = [], []
+        for _ in range(lookahead):
+            start = int(rng.integers(0, len(smoothed) - 1))
+            end = int(rng.integers(start + 1, len(smoothed)))
+            draws.append((start, end))
+            states.append(rng.bit_generator.state)
+        if projecting:
+            start, end = draws[0]
+            tree = Tree(Node(smoothed[start]))
+            reached = _constrained_extend(smoothed[end], tree, eps, constraints, collision_interval_check)
+            segs = [None]
+            if np.array_equal(reached, smoothed[end]):
+                seg = [n.q for n in tree.get_path(tree.nearest_neighbor(reached))]
+                seg.reverse()               # get_path runs node -> root
+                segs = [seg]
+        else:
+            blocks = _extend_blocks([smoothed[s] for s, _ in draws], [smoothed[e] for _, e in draws], eps, constraints,
+                                    collision_interval_check)
+            segs = []
+            for (s, e), rows in zip(draws, blocks):
+                tgt = np.asarray(smoothed[e], dtype=np.float64)
+                if np.array_equal(smoothed[s], tgt):
+                    segs.append([smoothed[s]])            # the extend returns at once: already there
+                elif len(rows) and np.array_equal(rows[-1], tgt):
+                    segs.append([smoothed[s]] + list(rows))
+                else:
+                    segs.append(None)
+        smooth_path.last_launches += 1
+        accepted = None
+        for k, ((start, end), seg) in enumerate(zip(draws, segs)):
+            # (the reference measures the new segment in tree order, end -> start: planning/utils.py:70-73;
+            #  summed in that order so that a tie in exact arithmetic rounds the way it does there)
+            if seg is not None and path_length(seg[::-1]) < path_length(smoothed[start:end + 1]):
+                accepted = k
+                break
+        if accepted is None:
+            done += lookahead
+            depth = min(2 * depth, 64)
             continue
-        end_node = tree.nearest_neighbor(q_reached)
-        segment = [n.q for n in tree.get_path(end_node)]
-        if path_length(segment) < path_length(smoothed[start : end + 1]):
-            if sparse:
-                smoothed = smoothed[: start + 1] + smoothed[end:]
-            else:
-                segment.reverse()  # get_path runs node -> root
-                smoothed = smoothed[:start] + segment[:-1] + smoothed[end:]
+        depth = max(depth // 2, 2)
+        start, end = draws[accepted]
+        seg = segs[accepted]
+        if sparse:
+            smoothed = smoothed[:start + 1] + smoothed[end:]
+        else:
+            smoothed = smoothed[:start] + seg[:-1] + smoothed[end:]
+        rng.bit_generator.state = states[accepted]     # the stream continues right after the accepted try
+        done += accepted + 1
     return smoothed
 
 

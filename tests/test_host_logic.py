@@ -199,6 +199,63 @@ def test_smooth_path_around_obstacle():
         assert mj.obeys_constraints(wp, c)
 
 
+def _smooth_path_one_try_at_a_time(waypoints, constraints, interval, eps, num_tries, seed, sparse):
+    """The reference's loop (src/mjpl/planning/utils.py:53-85) as it is written there: the checker for the
+    speculative implementation."""
+    from mjpl_b200.planning.tree import Node, Tree
+    from mjpl_b200.planning.utils import _constrained_extend
+
+    smoothed = waypoints
+    rng = np.random.default_rng(seed=seed)
+    for _ in range(num_tries):
+        start = rng.integers(0, len(smoothed) - 1)
+        end = rng.integers(start + 1, len(smoothed))
+        tree = Tree(Node(smoothed[start]))
+        q_reached = _constrained_extend(smoothed[end], tree, eps, constraints, interval)
+        if not np.array_equal(q_reached, smoothed[end]):
+            continue
+        segment = [n.q for n in tree.get_path(tree.nearest_neighbor(q_reached))]
+        if path_length(segment) < path_length(smoothed[start:end + 1]):
+            if sparse:
+                smoothed = smoothed[:start + 1] + smoothed[end:]
+            else:
+                segment.reverse()
+                smoothed = smoothed[:start] + segment[:-1] + smoothed[end:]
+    return smoothed
+
+
+def test_speculative_smooth_path_equals_the_reference_loop():
+    """All remaining tries are evaluated against the current path in one batched validity call and the
+    first one the reference would accept is applied: same waypoints as the try-by-try loop for every
+    seed, in far fewer validity rounds than tries."""
+    from mjpl_b200.planning.rrt import RRT
+
+    model = models.load("two_dof_ball")
+    c = cons(model)
+    wps = [np.array(p) for p in [[0.0, 0.0], [0.25, 0.0], [0.25, 1.5], [0.5, 1.5], [1.0, 1.5], [1.0, 0.0], [1.0, 0.0]]]
+    cases = [(wps, c, None, 0.1)]
+    ur = models.load("ur5e_scene")
+    cu = cons(ur)
+    q0 = ur.keyframe("home").qpos.copy()
+    q1 = mj.random_config(ur, q0, mj.all_joints(ur), 3, cu)
+    path = RRT(ur, mj.all_joints(ur), cu, max_planning_time=30, epsilon=0.1, seed=3).plan_to_config(q0, q1)
+    assert path
+    cases.append((path, cu, None, 0.1))
+    cases.append((path, cu, (0.05, cu[1]), 0.1))          # with interval checks
+    rounds = []
+    for way, constraints, interval, eps in cases:
+        for seed in (0, 5, 42):
+            for sparse in (False, True):
+                want = _smooth_path_one_try_at_a_time(list(way), constraints, interval, eps, 60, seed, sparse)
+                got = smooth_path(list(way), constraints, interval, eps=eps, num_tries=60, seed=seed, sparse=sparse)
+                assert len(got) == len(want)
+                for a, b in zip(got, want):
+                    np.testing.assert_array_equal(a, b)
+                rounds.append(smooth_path.last_launches)
+    print('validity rounds for 60 tries:', rounds)
+    assert max(rounds) <= 50 and np.mean(rounds) <= 30, rounds     # 60 tries each; every accepted shortcut ends a round
+
+
 def test_smooth_path_invalid_args():
     with pytest.raises(ValueError, match="waypoints"):
         smooth_path([], [])
