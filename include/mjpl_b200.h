@@ -215,6 +215,49 @@ int mjb_pose_project(mjb_model *m, const mjb_pose_spec *spec, const double *d_q_
                      uint8_t *d_ok, int32_t *d_iters, void *stream);
 
 /*
+ * CBiRRT with a projecting constraint (BASELINE configs[3]): RRT.plan_to_configs
+ * (src/mjpl/planning/rrt.py:195-235) over the step-by-step _constrained_extend
+ * (src/mjpl/planning/utils.py:139-164) for S queries held in S slots, all state on the device.  The
+ * slots advance asynchronously: one call = one TICK = every slot takes one projected step of the
+ * extend it is in (propose `_step`, joint limits of the proposal, PoseConstraint.apply, collision
+ * check of the projected row, the reference's stop rules, append), or sets up its next extend (sample
+ * / nearest node), or runs its connection test.  Nothing returns to the host; the caller looks at
+ * d_counters every few ticks.  Arrays are device pointers owned by the caller:
+ *   nodes[k] (S,cap,nq) fp64, parent[k] (S,cap), count[k] (S): k = 0 start trees (root q_init, count 1),
+ *   k = 1 goal trees (root q_goal); phase (S) int32 zero-initialised; swapped (S); age (S);
+ *   target, tip, qa, cand, proj (S,nq) fp64 scratch; cand32 (S,nq) fp32; last, ia (S);
+ *   proj_ok, valid, stepping (S) bytes; res_start / res_goal (S) = -1 until the slot's query is solved
+ *   (then: connecting node in the start / goal tree); counters int64[8] zero-initialised:
+ *   [0] ticks, [1] solved, [2] gave up (max_age iterations), [3] slots not yet retired after the last
+ *   tick, [4] scratch, [5] appends refused because a tree was at capacity.
+ */
+typedef struct mjb_cbirrt_state {
+  int64_t nslots, cap;
+  int32_t nq, check_limits_before;   /* a JointLimitConstraint precedes the PoseConstraint in the list */
+  double eps, goal_bias;
+  uint64_t seed;
+  int64_t max_age;
+  const double *q_init, *q_goal;
+  const uint8_t *plan_mask;
+  const double *lo, *hi;
+  double *nodes[2];
+  int64_t *parent[2], *count[2];
+  int32_t *phase;
+  uint8_t *swapped;
+  int64_t *age;
+  double *target, *tip, *qa;
+  int64_t *last, *ia;
+  double *cand;
+  float *cand32;
+  double *proj;
+  uint8_t *proj_ok, *valid, *stepping;
+  int64_t *res_start, *res_goal, *counters;
+} mjb_cbirrt_state;
+
+int mjb_cbirrt_tick(mjb_model *m, const mjb_cbirrt_state *state, const mjb_pose_spec *pose, int32_t pose_max_iters,
+                    uint32_t flags, void *stream);
+
+/*
  * IKSolver.solve_ik (src/mjpl/inverse_kinematics/ik_solver_interface.py:11-28) for n (target,
  * initial guess) rows at once; replaces the per-attempt iteration loop of the stock solver
  * (mink_ik_solver.py:93-108: iterate until |position error| <= pos_tolerance and |orientation

@@ -70,6 +70,20 @@ class IkSpec(C.Structure):
                 ("iterations", C.c_int32)]
 
 
+class CbirrtState(C.Structure):
+    """``mjb_cbirrt_state``: device pointers of the tick-based constrained planner"""
+
+    _fields_ = [("nslots", C.c_int64), ("cap", C.c_int64), ("nq", C.c_int32), ("check_limits_before", C.c_int32),
+                ("eps", C.c_double), ("goal_bias", C.c_double), ("seed", C.c_uint64), ("max_age", C.c_int64),
+                ("q_init", C.c_void_p), ("q_goal", C.c_void_p), ("plan_mask", C.c_void_p), ("lo", C.c_void_p), ("hi", C.c_void_p),
+                ("nodes", C.c_void_p * 2), ("parent", C.c_void_p * 2), ("count", C.c_void_p * 2),
+                ("phase", C.c_void_p), ("swapped", C.c_void_p), ("age", C.c_void_p),
+                ("target", C.c_void_p), ("tip", C.c_void_p), ("qa", C.c_void_p), ("last", C.c_void_p), ("ia", C.c_void_p),
+                ("cand", C.c_void_p), ("cand32", C.c_void_p), ("proj", C.c_void_p),
+                ("proj_ok", C.c_void_p), ("valid", C.c_void_p), ("stepping", C.c_void_p),
+                ("res_start", C.c_void_p), ("res_goal", C.c_void_p), ("counters", C.c_void_p)]
+
+
 class EngineUnavailable(RuntimeError):
     """The CUDA engine cannot run here (library not built, or no GPU).  Never caught internally."""
 
@@ -120,7 +134,7 @@ EXPORTS = (
     "mjb_last_error mjb_device_count mjb_model_create mjb_model_destroy mjb_model_npair "
     "mjb_model_pairs mjb_check_configs mjb_check_configs_host mjb_fk mjb_check_edges "
     "mjb_check_sweep mjb_sweep_rows mjb_get_stats mjb_reset_stats mjb_nearest_batch mjb_rrt_extend mjb_pose_valid mjb_pose_project mjb_site_pose "
-    "mjb_ik_solve mjb_kernel_timing mjb_fma_peak mjb_rrt_extend_masked mjb_rrt_sample mjb_rrt_meet"
+    "mjb_ik_solve mjb_kernel_timing mjb_fma_peak mjb_rrt_extend_masked mjb_rrt_sample mjb_rrt_meet mjb_cbirrt_tick"
 ).split()
 
 
@@ -156,6 +170,7 @@ def lib():
     L.mjb_rrt_extend_masked.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int64, C.c_double, C.c_int32, C.c_uint32, vp, vp, vp]
     L.mjb_rrt_sample.argtypes = [C.c_uint64, vp, C.c_int64, C.c_int32, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp]
     L.mjb_rrt_meet.argtypes = [C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp]
+    L.mjb_cbirrt_tick.argtypes = [vp, C.POINTER(CbirrtState), C.POINTER(PoseSpec), C.c_int32, C.c_uint32, vp]
     L.mjb_site_pose.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, C.c_int64, vp, vp, vp]
     L.mjb_pose_valid.argtypes = [vp, C.POINTER(PoseSpec), vp, C.c_int64, vp, vp]
     L.mjb_pose_project.argtypes = [vp, C.POINTER(PoseSpec), vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp]

@@ -773,7 +773,7 @@ static int fill_pose_spec(mjb_model *m, const mjb_pose_spec *in, PoseSpec &sp) {
 }
 
 static int launch_pose(mjb_model *m, const mjb_pose_spec *spec, const double *d_q_old, const double *d_q, int64_t n, int project,
-                       int32_t max_iters, double *d_q_out, uint8_t *d_ok, int32_t *d_iters, void *stream) {
+                       int32_t max_iters, double *d_q_out, uint8_t *d_ok, int32_t *d_iters, void *stream, const uint8_t *d_mask = nullptr) {
   int rc = check_common(m, MJB_CHECK_LIMITS);
   if (rc) return rc;
   if (n < 0) return fail(MJB_ERR_ARG, "bad n");
@@ -783,7 +783,7 @@ static int launch_pose(mjb_model *m, const mjb_pose_spec *spec, const double *d_
   if (n == 0) return MJB_OK;
   if (!d_q || !d_ok || (project && (!d_q_old || !d_q_out))) return fail(MJB_ERR_ARG, "null device pointer");
   a.fk = m->d_fk64; a.nslot = m->H.nslot; a.q_old = d_q_old; a.q = d_q; a.n = n; a.project = project;
-  a.max_iters = max_iters > 0 ? max_iters : 1000; a.q_out = d_q_out; a.ok = d_ok; a.iters = d_iters;
+  a.max_iters = max_iters > 0 ? max_iters : 1000; a.q_out = d_q_out; a.ok = d_ok; a.iters = d_iters; a.mask = d_mask;
   cudaStream_t st = (cudaStream_t)stream;
   pose_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(a);
   CU(cudaGetLastError());
@@ -918,5 +918,52 @@ extern "C" int mjb_rrt_meet(int64_t nslots, int32_t nq, const double *d_qa, cons
                                                                     (long long *)d_res_goal, (long long *)d_counters);
   rrt_advance_kernel<<<1, 1, 0, st>>>((long long *)d_counters);
   CU(cudaGetLastError());
+  return MJB_OK;
+}
+
+// ---- CBiRRT with a projecting constraint: one tick for every slot (vk_kernels.cuh: TickState) ----------
+extern "C" int mjb_cbirrt_tick(mjb_model *m, const mjb_cbirrt_state *cs, const mjb_pose_spec *pose, int32_t pose_max_iters,
+                               uint32_t flags, void *stream) {
+  if (!m || !cs || !pose) return fail(MJB_ERR_ARG, "null argument");
+  if (cs->nq != m->H.nq || cs->nslots < 0 || cs->cap < 2) return fail(MJB_ERR_ARG, "bad nq / nslots / cap");
+  // reference: ValueError texts of RRT.__init__ (src/mjpl/planning/rrt.py:53-58)
+  if (!(cs->eps > 0.0)) return fail(MJB_ERR_ARG, "`epsilon` must be > 0.0");
+  if (!(cs->goal_bias >= 0.0 && cs->goal_bias <= 1.0)) return fail(MJB_ERR_ARG, "`goal_biasing_probability` must be within [0.0, 1.0].");
+  if (cs->nslots == 0) return MJB_OK;
+  TickState t;
+  memset(&t, 0, sizeof t);
+  t.nslots = cs->nslots; t.cap = cs->cap; t.nq = cs->nq; t.eps = cs->eps; t.goal_bias = cs->goal_bias; t.seed = cs->seed;
+  t.max_age = cs->max_age; t.check_limits_before = cs->check_limits_before;
+  t.q_init = cs->q_init; t.q_goal = cs->q_goal; t.plan_mask = cs->plan_mask; t.lo = cs->lo; t.hi = cs->hi;
+  for (int k = 0; k < 2; k++) { t.nodes[k] = cs->nodes[k]; t.parent[k] = (long long *)cs->parent[k]; t.count[k] = (long long *)cs->count[k]; }
+  t.phase = cs->phase; t.swapped = cs->swapped; t.age = (long long *)cs->age;
+  t.target = cs->target; t.tip = cs->tip; t.qa = cs->qa; t.last = (long long *)cs->last; t.ia = (long long *)cs->ia;
+  t.cand = cs->cand; t.cand32 = cs->cand32; t.proj = cs->proj; t.proj_ok = cs->proj_ok; t.valid = cs->valid; t.stepping = cs->stepping;
+  t.res_start = (long long *)cs->res_start; t.res_goal = (long long *)cs->res_goal; t.counters = (long long *)cs->counters;
+  const void *need[] = {t.q_init, t.q_goal, t.plan_mask, t.lo, t.hi, t.nodes[0], t.nodes[1], t.parent[0], t.parent[1], t.count[0],
+                        t.count[1], t.phase, t.swapped, t.age, t.target, t.tip, t.qa, t.last, t.ia, t.cand, t.cand32, t.proj,
+                        t.proj_ok, t.valid, t.stepping, t.res_start, t.res_goal, t.counters};
+  for (const void *p : need) if (!p) return fail(MJB_ERR_ARG, "null device pointer in mjb_cbirrt_state");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long S = cs->nslots;
+  tick_begin_kernel<<<(unsigned)((S * 32 + 127) / 128), 128, 0, st>>>(t);
+  CU(cudaGetLastError());
+  // the projecting constraint's apply() for the slots that proposed a step (pose_constraint.py:78-91)
+  int rc = launch_pose(m, pose, t.tip, t.cand, S, 1, pose_max_iters, t.proj, t.proj_ok, nullptr, stream, t.stepping);
+  if (rc) return rc;
+  tick_rows_kernel<<<(unsigned)((S * cs->nq + 255) / 256), 256, 0, st>>>(t);
+  CU(cudaGetLastError());
+  // the constraints after it, and the re-validation of apply_constraints (constraint/utils.py:38-43): the
+  // projection has enforced the joint limits and the pose in fp64; what is left is the collision check
+  if (flags & MJB_CHECK_COLLISION) {
+    rc = mjb_check_configs(m, t.cand32, S, cs->nq, t.valid, MJB_CHECK_COLLISION, stream);
+    if (rc) return rc;
+  } else {
+    CU(cudaMemsetAsync(t.valid, 1, (size_t)S, st));
+  }
+  tick_end_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(t);
+  tick_advance_kernel<<<1, 1, 0, st>>>(t.counters);
+  CU(cudaGetLastError());
+  m->launches += 5;
   return MJB_OK;
 }

@@ -990,6 +990,7 @@ struct PoseArgs {
   double *q_out;                // (n,nq) projected rows (project) -- untouched rows when !ok
   uint8_t *ok;                  // valid / projection succeeded
   int *iters;                   // optional
+  const uint8_t *mask;          // optional: only rows with mask[row] == 1 are evaluated (others: ok = 0)
 };
 
 __global__ void __launch_bounds__(64) pose_kernel(const PoseArgs a) {
@@ -997,6 +998,7 @@ __global__ void __launch_bounds__(64) pose_kernel(const PoseArgs a) {
   if (row >= a.n) return;
   const FkTables<double> &fk = *a.fk;
   const int nq = fk.nq;
+  if (a.mask && a.mask[row] != 1) { a.ok[row] = 0; return; }
   double q[MAX_JNT];
   for (int j = 0; j < nq; j++) q[j] = a.q[row * nq + j];
   if (!a.project) {
@@ -1219,6 +1221,185 @@ __global__ void rrt_meet_kernel(long long nslots, int nq, const double *qa, cons
 }
 // one thread, after rrt_meet_kernel: iteration += 1, active count of this iteration published
 __global__ void rrt_advance_kernel(long long *counters) {
+  counters[0] += 1;
+  counters[3] = counters[4];
+  counters[4] = 0;
+}
+
+// ---------------------------------------------------------------------------- CBiRRT with a projecting constraint: ticks
+// RRT.plan_to_configs (reference: src/mjpl/planning/rrt.py:195-235) with the step-by-step
+// _constrained_extend (planning/utils.py:139-164) that a projecting constraint needs, for S queries
+// that advance ASYNCHRONOUSLY: every slot is a small state machine, and one TICK moves every slot by
+// one projected step of whatever extend it is in (or sets up its next extend).  No slot waits for the
+// longest chain of another one, and nothing returns to the host in between.
+//   phase 0  start of an iteration: sample a target, nearest node of tree A      -> 1
+//   phase 1  stepping in tree A            (extend ended: remember q_a)            -> 2
+//   phase 2  nearest node of tree B to q_a                                        -> 3
+//   phase 3  stepping in tree B            (extend ended: connection test; swap)   -> 0 / 4
+//   phase 4  retired (solved, or out of iterations)
+// tick_begin (one warp per slot): setups and the proposal of one step (`_step`, and the non-projecting
+// constraints that come before the projecting one see the unprojected configuration: joint limits).
+// The projection (pose_kernel, masked) and the validity launch on the projected rows follow; tick_end
+// (one thread per slot) applies the reference's stop rules (:151-160), appends, and moves the phase.
+struct TickState {
+  long long nslots, cap;
+  int nq;
+  double eps, goal_bias;
+  unsigned long long seed;
+  long long max_age;
+  int check_limits_before;            // a JointLimitConstraint precedes the projecting constraint
+  const double *q_init, *q_goal;      // (S,nq)
+  const uint8_t *plan_mask;           // (nq)
+  const double *lo, *hi;              // (nq)
+  double *nodes[2]; long long *parent[2]; long long *count[2];   // [0] start trees, [1] goal trees: (S,cap,nq) (S,cap) (S)
+  int *phase; uint8_t *swapped; long long *age;
+  double *target, *tip, *qa; long long *last, *ia;
+  double *cand; float *cand32; double *proj; uint8_t *proj_ok, *valid, *stepping;
+  long long *res_start, *res_goal;
+  long long *counters;                // [0] ticks, [1] solved, [2] gave up, [3] slots not yet retired, [4] scratch, [5] trees at capacity
+};
+
+__global__ void __launch_bounds__(128) tick_begin_kernel(const TickState t) {
+  const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= t.nslots) return;
+  const int nq = t.nq;
+  int ph = t.phase[s];
+  if (ph == 4) { if (lane == 0) t.stepping[s] = 0; return; }
+  const int A = t.swapped[s] ? 1 : 0;
+  double *tgt = t.target + s * nq, *tip = t.tip + s * nq;
+  if (ph == 0 || ph == 2) {
+    // ---- set up an extend: the target, then Tree.nearest_neighbor (tree.py:57-66) with the warp
+    if (ph == 0) {
+      if (lane == 0) {
+        const unsigned long long key = t.seed + 0xD1B54A32D192ED03ull * ((unsigned long long)t.age[s] + 1ull);
+        const double u = (double)sweep_bits(key, (uint64_t)s, 63u) * (1.0 / 16777216.0);
+        const double *src = (A ? t.q_init : t.q_goal) + s * nq;   // the other tree's root (rrt.py:207-212)
+        for (int j = 0; j < nq; j++) {
+          double v = src[j];
+          if (!(u <= t.goal_bias)) {
+            v = t.q_init[s * nq + j];
+            if (t.plan_mask[j]) {
+              const double r = ((double)sweep_bits(key, (uint64_t)s, (uint32_t)(2 * j)) * 16777216.0 +
+                                (double)sweep_bits(key, (uint64_t)s, (uint32_t)(2 * j + 1))) * (1.0 / 281474976710656.0);
+              v = t.lo[j] + r * (t.hi[j] - t.lo[j]);
+            }
+          }
+          tgt[j] = v;
+        }
+      }
+    } else if (lane < nq) {
+      tgt[lane] = t.qa[s * nq + lane];
+    }
+    __syncwarp();
+    const int T = ph == 0 ? A : 1 - A;
+    const double *base = t.nodes[T] + s * t.cap * nq;
+    const long long cnt = t.count[T][s];
+    double best = 1.0e300;
+    long long bi = 0;
+    for (long long i = lane; i < cnt; i += 32) {
+      double d2 = 0;
+      for (int j = 0; j < nq; j++) { const double d = base[i * nq + j] - tgt[j]; d2 += d * d; }
+      if (d2 < best) { best = d2; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane < nq) tip[lane] = base[bi * nq + lane];
+    if (lane == 0) t.last[s] = bi;
+    ph += 1;
+    __syncwarp();
+  }
+  // ---- propose one step (ph is 1 or 3): _step (planning/utils.py:167-185), target reached => extend over
+  if (lane == 0) {
+    bool same = true;
+    double d2 = 0;
+    for (int j = 0; j < nq; j++) { const double d = tgt[j] - tip[j]; same = same && (tgt[j] == tip[j]); d2 += d * d; }
+    int st = 2;   // extend ends without a step
+    if (!same) {
+      const double dist = sqrt(d2);
+      bool lim = true;
+      for (int j = 0; j < nq; j++) {
+        const double x = dist <= t.eps ? tgt[j] : tip[j] + (tgt[j] - tip[j]) * (t.eps / dist);
+        t.cand[s * nq + j] = x;
+        lim = lim && (x >= t.lo[j]) && (x <= t.hi[j]);
+      }
+      st = (!t.check_limits_before || lim) ? 1 : 2;
+    }
+    t.stepping[s] = (uint8_t)st;
+    t.phase[s] = ph;
+  }
+}
+
+// projected rows of the stepping slots -> fp32 rows for the validity launch (other slots keep a copy
+// of their tip: a configuration that is already known to be valid)
+__global__ void tick_rows_kernel(const TickState t) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.nslots * t.nq) return;
+  const long long s = i / t.nq;
+  t.cand32[i] = (float)((t.stepping[s] == 1 && t.proj_ok[s]) ? t.proj[i] : t.tip[i]);
+}
+
+__global__ void tick_end_kernel(const TickState t) {
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int alive = 0;
+  if (s < t.nslots && t.phase[s] != 4) {
+    const int nq = t.nq;
+    const int ph = t.phase[s], st = t.stepping[s];
+    const int A = t.swapped[s] ? 1 : 0, T = ph == 1 ? A : 1 - A;
+    double *tip = t.tip + s * nq;
+    const double *tgt = t.target + s * nq, *pr = t.proj + s * nq;
+    bool ended = st == 2;
+    if (st == 1) {
+      double moved = 0, dnew = 0, dold = 0;
+      for (int j = 0; j < nq; j++) {
+        moved += (pr[j] - tip[j]) * (pr[j] - tip[j]);
+        dnew += (tgt[j] - pr[j]) * (tgt[j] - pr[j]);
+        dold += (tgt[j] - tip[j]) * (tgt[j] - tip[j]);
+      }
+      // planning/utils.py:151-160: constraints failed, no progress, or further from the target than before
+      bool ok = t.proj_ok[s] && t.valid[s] && sqrt(moved) >= 1e-8 && sqrt(dnew) <= sqrt(dold);
+      const long long idx = t.count[T][s];
+      if (ok && idx >= t.cap) { ok = false; atomicAdd((unsigned long long *)&t.counters[5], 1ull); }
+      if (ok) {
+        double *dst = t.nodes[T] + (s * t.cap + idx) * nq;
+        for (int j = 0; j < nq; j++) { dst[j] = pr[j]; tip[j] = pr[j]; }
+        t.parent[T][s * t.cap + idx] = t.last[s];
+        t.count[T][s] = idx + 1;
+        t.last[s] = idx;
+      } else {
+        ended = true;
+      }
+    }
+    alive = 1;
+    if (ended) {
+      if (ph == 1) {
+        for (int j = 0; j < nq; j++) t.qa[s * nq + j] = tip[j];
+        t.ia[s] = t.last[s];
+        t.phase[s] = 2;
+      } else {
+        bool met = true;
+        for (int j = 0; j < nq; j++) met = met && (tip[j] == t.qa[s * nq + j]);
+        if (met) {   // rrt.py:223-229
+          t.res_start[s] = A ? t.last[s] : t.ia[s];
+          t.res_goal[s] = A ? t.ia[s] : t.last[s];
+          t.phase[s] = 4; alive = 0;
+          atomicAdd((unsigned long long *)&t.counters[1], 1ull);
+        } else {
+          t.swapped[s] ^= 1;
+          t.age[s] += 1;
+          if (t.age[s] >= t.max_age) { t.phase[s] = 4; alive = 0; atomicAdd((unsigned long long *)&t.counters[2], 1ull); }
+          else t.phase[s] = 0;
+        }
+      }
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, alive);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd((unsigned long long *)&t.counters[4], (unsigned long long)__popc(m));
+}
+__global__ void tick_advance_kernel(long long *counters) {
   counters[0] += 1;
   counters[3] = counters[4];
   counters[4] = 0;

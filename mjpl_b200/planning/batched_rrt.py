@@ -117,7 +117,7 @@ class BatchedRRT:
                  max_planning_time: float = 10.0, epsilon: float = 0.05, seed: int | None = None,
                  goal_biasing_probability: float = 0.05, max_iterations: int = 1000000,
                  max_chain: int = 512, max_active: int = 4096, max_iterations_per_query: int = 3000,
-                 sync_every: int = 8, use_cuda_graph: bool = True) -> None:
+                 sync_every: int = 8, use_cuda_graph: bool = True, device_projection: bool = True) -> None:
         if not planning_joints:
             raise ValueError("`planning_joints` cannot be empty.")
         if max_planning_time <= 0.0:
@@ -139,6 +139,8 @@ class BatchedRRT:
         self.max_iterations_per_query = max_iterations_per_query  # a query that exceeds it returns []
         self.sync_every = sync_every            # device driver: iterations enqueued between two looks of the host
         self.use_cuda_graph = use_cuda_graph    # device driver: replay iteration pairs as a CUDA graph
+        self.device_projection = device_projection  # projecting constraint: device ticks (False: lock-step host driver,
+        #                                             one random stream per query as in the sequential planner)
         self.stats: dict = {}
 
     # one extend for a set of queries: returns reached configs and node indices
@@ -214,7 +216,36 @@ class BatchedRRT:
         fused = _fusable(self.constraints)
         if fused is not None:
             return self._plan_device(q_inits, q_goals, *fused)
+        proj = self._projected_on_device() if self.device_projection else None
+        if proj is not None:
+            return self._plan_device_projected(q_inits, q_goals, *proj)
         return self._plan_host(q_inits, q_goals)
+
+    def _projected_on_device(self):
+        """``[JointLimitConstraint?, PoseConstraint, CollisionConstraint?]`` on one model, the collision
+        constraint (if any) AFTER the pose constraint, so that it sees the projected configuration just as
+        the final re-validation does: that list runs as device ticks (``mjb_cbirrt_tick``).  Returns
+        ``(engine, pose_constraint, flags, limits_before)`` or None (any other list: the host driver)."""
+        from ..constraint.collision_constraint import CollisionConstraint
+        from ..constraint.joint_limit_constraint import JointLimitConstraint
+        from ..constraint.pose_constraint import PoseConstraint
+
+        pose, coll, limits_before, seen_pose = None, None, False, False
+        for c in self.constraints:
+            if type(c) is PoseConstraint and pose is None:
+                pose, seen_pose = c, True
+            elif type(c) is JointLimitConstraint:
+                limits_before = limits_before or not seen_pose
+            elif type(c) is CollisionConstraint and coll is None and seen_pose:
+                coll = c
+            else:
+                return None
+            if c.model is not self.model:
+                return None
+        if pose is None:
+            return None
+        eng = coll.engine if coll is not None else pose.engine
+        return eng, pose, (2 if coll is not None else 0), limits_before
 
     def plan_to_poses(self, q_inits: np.ndarray, poses, site: str, solver=None) -> list[list[np.ndarray]]:
         """One pose goal per query (the reference's ``RRT.plan_to_pose``, rrt.py:69-139, for a block of
@@ -449,6 +480,176 @@ class BatchedRRT:
                         a.pop()
                     out[int(k)] = a + g
             return out
+
+    # ------------------------------------------------------------------ device driver, projecting constraint
+    def _plan_device_projected(self, q_inits, q_goals, eng, pose, flags, limits_before):
+        """BASELINE configs[3] on the device: every query is a small state machine in HBM and one
+        ``mjb_cbirrt_tick`` advances ALL of them by one projected extend step (or one setup); ticks are
+        captured into a CUDA graph and replayed, the host reads a status word every ``sync_every`` ticks.
+        Same algorithm per query as the sequential planner (sampling distribution, step-by-step extend
+        with projection, stop rules, connection test, swap); the random stream is counter based."""
+        import ctypes as C
+
+        import torch
+
+        from .. import _abi
+        from ..constraint.utils import obeys_constraints_batch as _obeys
+
+        L = _abi.lib()
+        dev, f64, i64 = eng.torch_device, torch.float64, torch.int64
+        B, nq = q_inits.shape
+        ok = np.asarray(_obeys(np.concatenate([q_inits, q_goals]), self.constraints)).astype(bool)
+        if not ok[:B].all():
+            raise ValueError("q_init is not a valid configuration")
+        if not ok[B:].all():
+            bad = q_goals[np.flatnonzero(~ok[B:])[0]]
+            raise ValueError(f"The following goal config is not a valid configuration: {bad}")
+        q_idx = qpos_idx(self.model, self.planning_joints)
+        fixed = [i for i in range(nq) if i not in set(q_idx)]
+        if fixed and not np.allclose(q_inits[:, fixed], q_goals[:, fixed], rtol=0, atol=1e-12):
+            raise ValueError("goal configs have values for joints outside of the planner's planning joints "
+                             "that don't match q_init")
+        paths: list[list[np.ndarray]] = [[] for _ in range(B)]
+        direct = np.linalg.norm(q_goals - q_inits, axis=1) <= self.epsilon
+        for b in np.flatnonzero(direct):
+            paths[b] = [q_inits[b].copy(), q_goals[b].copy()]
+        ids = np.flatnonzero(~direct)
+        S = len(ids)
+        self.stats = {"iterations": 0, "ticks": 0, "configs_checked": 0, "launches": 0, "driver": "device ticks", "slots": S,
+                      "gave_up": 0, "host_syncs": 0, "appends_refused_at_capacity": 0}
+        t0 = time.time()
+        if S == 0:
+            self.stats.update(solved=int(direct.sum()), seconds=0.0)
+            return paths
+        with torch.cuda.device(eng.device), eng._call_lock:
+            QI = torch.from_numpy(np.ascontiguousarray(q_inits[ids])).to(dev)
+            QG = torch.from_numpy(np.ascontiguousarray(q_goals[ids])).to(dev)
+            cap = 2048
+            plan_mask = torch.zeros(nq, dtype=torch.uint8, device=dev)
+            plan_mask[q_idx] = 1
+            lo = torch.from_numpy(np.ascontiguousarray(self.model.jnt_range[:, 0], dtype=np.float64)).to(dev)
+            hi = torch.from_numpy(np.ascontiguousarray(self.model.jnt_range[:, 1], dtype=np.float64)).to(dev)
+            T = {}
+
+            def alloc(cap):
+                old = dict(T)
+                for k, roots in ((0, QI), (1, QG)):
+                    T[f"nodes{k}"] = torch.empty((S, cap, nq), dtype=f64, device=dev)
+                    T[f"parent{k}"] = torch.full((S, cap), -1, dtype=i64, device=dev)
+                    if old:
+                        oc = old[f"nodes{k}"].shape[1]
+                        T[f"nodes{k}"][:, :oc] = old[f"nodes{k}"]
+                        T[f"parent{k}"][:, :oc] = old[f"parent{k}"]
+                    else:
+                        T[f"nodes{k}"][:, 0] = roots
+                        T[f"count{k}"] = torch.ones(S, dtype=i64, device=dev)
+
+            alloc(cap)
+            z = lambda *shape, dt=f64: torch.zeros(shape, dtype=dt, device=dev)
+            bufs = {"phase": z(S, dt=torch.int32), "swapped": z(S, dt=torch.uint8), "age": z(S, dt=i64),
+                    "target": z(S, nq), "tip": z(S, nq), "qa": z(S, nq), "last": z(S, dt=i64), "ia": z(S, dt=i64),
+                    "cand": z(S, nq), "cand32": z(S, nq, dt=torch.float32), "proj": z(S, nq),
+                    "proj_ok": z(S, dt=torch.uint8), "valid": z(S, dt=torch.uint8), "stepping": z(S, dt=torch.uint8),
+                    "res_start": torch.full((S,), -1, dtype=i64, device=dev), "res_goal": torch.full((S,), -1, dtype=i64, device=dev),
+                    "counters": z(8, dt=i64)}
+            bufs["counters"][3] = S
+            spec = pose._spec()
+
+            def make_state(cap):
+                st = _abi.CbirrtState()
+                st.nslots, st.cap, st.nq, st.check_limits_before = S, cap, nq, int(limits_before)
+                st.eps, st.goal_bias = float(self.epsilon), float(self.goal_biasing_probability)
+                st.seed = int(self.seed if self.seed is not None else np.random.SeedSequence().entropy % (1 << 62))
+                st.max_age = int(self.max_iterations_per_query)
+                st.q_init, st.q_goal, st.plan_mask, st.lo, st.hi = (x.data_ptr() for x in (QI, QG, plan_mask, lo, hi))
+                for k in (0, 1):
+                    st.nodes[k], st.parent[k], st.count[k] = (T[f"{n}{k}"].data_ptr() for n in ("nodes", "parent", "count"))
+                for name, tns in bufs.items():
+                    setattr(st, name, tns.data_ptr())
+                return st
+
+            state = make_state(cap)
+
+            def tick():
+                _abi.check(L.mjb_cbirrt_tick(eng._h, C.byref(state), C.byref(spec), int(pose.max_iterations), flags,
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+            ticks_per_sync = max(1, int(self.sync_every))
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                tick()             # eager once: the library grows its scratch here, never inside a capture
+            side.synchronize()
+
+            def capture():
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(ticks_per_sync):
+                        tick()
+                return g
+
+            try:
+                graph = capture() if self.use_cuda_graph else None
+            except Exception:
+                graph = None
+            status = torch.empty(4, dtype=i64, device=dev)
+            while True:
+                status[0], status[1] = bufs["counters"][0], bufs["counters"][3]
+                status[2], status[3] = T["count0"].max(), T["count1"].max()
+                nt, n_alive, c0, c1 = (int(x) for x in status.cpu())
+                self.stats["host_syncs"] += 1
+                if n_alive == 0 or time.time() - t0 >= self.max_planning_time:
+                    break
+                if max(c0, c1) + ticks_per_sync + 1 > cap:   # a tree can gain one node per tick
+                    cap *= 2
+                    alloc(cap)
+                    state = make_state(cap)
+                    graph = capture() if graph is not None else None
+                if graph is not None:
+                    graph.replay()
+                else:
+                    with torch.cuda.stream(side):
+                        for _ in range(ticks_per_sync):
+                            tick()
+                    side.synchronize()
+            torch.cuda.current_stream().wait_stream(side)
+            cnt = bufs["counters"].cpu().numpy()
+            self.stats.update(ticks=int(cnt[0]), gave_up=int(cnt[2]), appends_refused_at_capacity=int(cnt[5]),
+                              iterations=int(bufs["age"].max()))
+            res_s, res_g = bufs["res_start"], bufs["res_goal"]
+            solved = (res_s >= 0).nonzero(as_tuple=True)[0]
+            if len(solved):
+                par0 = T["parent0"][solved, : int(T["count0"].max())].cpu().numpy()
+                par1 = T["parent1"][solved, : int(T["count1"].max())].cpu().numpy()
+                rs, rg, sl = res_s[solved].cpu().numpy(), res_g[solved].cpu().numpy(), solved.cpu().numpy()
+                want = []
+                for k in range(len(sl)):
+                    a, i = [], int(rs[k])
+                    while i >= 0:
+                        a.append(i)
+                        i = int(par0[k, i])
+                    g, i = [], int(rg[k])
+                    while i >= 0:
+                        g.append(i)
+                        i = int(par1[k, i])
+                    want.append((a[::-1], g))
+                rows_s = torch.from_numpy(np.concatenate([np.full(len(a), s_) for s_, (a, _) in zip(sl, want)])).to(dev)
+                idx_s = torch.from_numpy(np.concatenate([np.asarray(a) for a, _ in want])).to(dev)
+                rows_g = torch.from_numpy(np.concatenate([np.full(len(g), s_) for s_, (_, g) in zip(sl, want)])).to(dev)
+                idx_g = torch.from_numpy(np.concatenate([np.asarray(g) for _, g in want])).to(dev)
+                Ps, Pg = T["nodes0"][rows_s, idx_s].cpu().numpy(), T["nodes1"][rows_g, idx_g].cpu().numpy()
+                o_s = o_g = 0
+                for s_, (a, g) in zip(sl, want):
+                    ps, pg = list(Ps[o_s:o_s + len(a)]), list(Pg[o_g:o_g + len(g)])
+                    o_s += len(a); o_g += len(g)
+                    if np.array_equal(ps[-1], pg[0]):
+                        ps.pop()
+                    paths[int(ids[s_])] = ps + pg
+        self.stats["solved"] = int(sum(1 for p in paths if p))
+        self.stats["seconds"] = time.time() - t0
+        est = eng.stats()
+        self.stats["configs_checked"] = est["rows"]
+        return paths
 
     # ------------------------------------------------------------------ host driver
     def _plan_host(self, q_inits, q_goals):

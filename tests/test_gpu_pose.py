@@ -133,16 +133,7 @@ def _constrained_problem(n_goals, seed=17):
     return model, allowed, joints, q_init, ref, lim, cons, goals[:n_goals]
 
 
-def test_batched_constrained_rrt():
-    """BASELINE configs[3] as a batch: every query takes each projected extend step together with the
-    others.  Paths start and end where they should and every waypoint satisfies all constraints
-    (pose checked with the numpy restatement, collisions with the CPU oracle)."""
-    model, allowed, joints, q_init, ref, lim, cons, goals = _constrained_problem(48)
-    B = len(goals)
-    planner = mj.BatchedRRT(model, joints, cons, max_planning_time=120, epsilon=0.05, seed=17, goal_biasing_probability=0.1)
-    paths = planner.plan(np.tile(q_init, (B, 1)), goals)
-    solved = [b for b in range(B) if paths[b]]
-    assert len(solved) >= 0.9 * B, planner.stats
+def _check_constrained_paths(model, allowed, ref, lim, cons, q_init, goals, paths, solved):
     po = oracle.PoseOracle(model, "ee_site", ref.translation(), ref.rotation().wxyz, [INF] * 3 + [lim, lim, INF])
     orc = oracle.Oracle(model, allowed)
     for b in solved:
@@ -150,12 +141,56 @@ def test_batched_constrained_rrt():
         np.testing.assert_array_equal(P[0], q_init)
         np.testing.assert_array_equal(P[-1], goals[b])
         assert np.asarray(mj.obeys_constraints_batch(P, cons)).all()
+        assert (np.linalg.norm(np.diff(P, axis=0), axis=1) <= 2 * 0.05 + 1e-9).all()   # a projected step moves at most 2 q_step
     for b in solved[:8]:
         P = np.asarray(paths[b])
         assert all(po.valid_config(q) for q in P)
         assert orc.check(P, 3).all()
-    # the same query alone through the reference-style sequential planner gives the same path
+
+
+def test_batched_constrained_rrt():
+    """BASELINE configs[3] as a batch, lock-step host driver: every query takes each projected extend
+    step together with the others.  Paths start and end where they should, every waypoint satisfies all
+    constraints (pose checked with the numpy restatement, collisions with the CPU oracle), and a query
+    gives the same path as it does alone through the sequential planner."""
+    model, allowed, joints, q_init, ref, lim, cons, goals = _constrained_problem(48)
+    B = len(goals)
+    planner = mj.BatchedRRT(model, joints, cons, max_planning_time=120, epsilon=0.05, seed=17, goal_biasing_probability=0.1,
+                            device_projection=False)
+    paths = planner.plan(np.tile(q_init, (B, 1)), goals)
+    solved = [b for b in range(B) if paths[b]]
+    assert len(solved) >= 0.9 * B, planner.stats
+    _check_constrained_paths(model, allowed, ref, lim, cons, q_init, goals, paths, solved)
     b = solved[0]
     want = mj.RRT(model, joints, cons, max_planning_time=120, epsilon=0.05, seed=17 + b, goal_biasing_probability=0.1).plan_to_config(q_init, goals[b])
     assert len(want) == len(paths[b]) and all(np.array_equal(x, y) for x, y in zip(want, paths[b]))
-    print(f"batched constrained rrt: {len(solved)}/{B} solved in {planner.stats['seconds']:.2f} s, {planner.stats}")
+    print(f"batched constrained rrt (host lock-step): {len(solved)}/{B} solved in {planner.stats['seconds']:.2f} s, {planner.stats}")
+
+
+def test_constrained_rrt_device_ticks():
+    """BASELINE configs[3] with all planner state on the device (mjb_cbirrt_tick): asynchronous slots,
+    one projected step per tick, ticks replayed as a CUDA graph.  Same acceptance test as the host
+    driver: start / goal, every waypoint valid under all constraints (numpy pose restatement + CPU
+    oracle), steps bounded; also without a graph and without the collision constraint."""
+    model, allowed, joints, q_init, ref, lim, cons, goals = _constrained_problem(256)
+    B = len(goals)
+    planner = mj.BatchedRRT(model, joints, cons, max_planning_time=120, epsilon=0.05, seed=17, goal_biasing_probability=0.1)
+    paths = planner.plan(np.tile(q_init, (B, 1)), goals)
+    assert planner.stats["driver"] == "device ticks"
+    solved = [b for b in range(B) if paths[b]]
+    print(f"constrained rrt (device ticks): {len(solved)}/{B} solved in {planner.stats['seconds']:.2f} s, {planner.stats}")
+    assert len(solved) >= 0.9 * B, planner.stats
+    assert planner.stats["appends_refused_at_capacity"] == 0
+    _check_constrained_paths(model, allowed, ref, lim, cons, q_init, goals, paths, solved)
+    eager = mj.BatchedRRT(model, joints, cons, max_planning_time=120, epsilon=0.05, seed=17, goal_biasing_probability=0.1,
+                          use_cuda_graph=False)
+    p2 = eager.plan(np.tile(q_init, (32, 1)), goals[:32])
+    for a, b in zip(p2, paths[:32]):     # same counter-based random stream, same arithmetic: same paths
+        assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+    no_coll = [cons[0], cons[1]]
+    p3 = mj.BatchedRRT(model, joints, no_coll, max_planning_time=60, epsilon=0.05, seed=3, goal_biasing_probability=0.1).plan(
+        np.tile(q_init, (16, 1)), goals[:16])
+    assert sum(1 for p in p3 if p) >= 14
+    for p in p3:
+        if p:
+            assert np.asarray(mj.obeys_constraints_batch(np.asarray(p), no_coll)).all()
