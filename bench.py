@@ -416,12 +416,27 @@ def sweep_leg(eng, rank, world, dist, torch):
         gathered_bytes = int(allm.numel())
     e2.record()
     torch.cuda.synchronize()
+    # band accounting on the device (mjb_min_distance, fp64 signed distance): rows of this shard's first block
+    # whose distance to contact lies within 1e-5 -- the only rows on which a checker may legitimately disagree
+    nb = min(2_000_000, hi - lo)
+    qb = eng.sweep_rows(2024, lo, nb)
+    tb = time.perf_counter()
+    sd, _ = eng.min_distance(qb)
+    torch.cuda.synchronize()
+    tb = time.perf_counter() - tb
+    mb = eng.sweep(2024, lo, nb, flags=2)
+    in_band = (sd.abs() < 1e-5)
+    band = torch.tensor([float(in_band.sum()), float(((mb != 0) != (sd > 0))[~in_band].sum()), float(nb)], dtype=torch.float64, device="cuda")
     t = torch.tensor([e0.elapsed_time(e1), e1.elapsed_time(e2)], dtype=torch.float64, device="cuda")
     nv = nvalid.to(torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(nv, op=dist.ReduceOp.SUM)
-    return {"rows": SWEEP_ROWS, "seconds": float(t[0]) * 1e-3, "configs_per_s": SWEEP_ROWS / (float(t[0]) * 1e-3),
+        dist.all_reduce(band, op=dist.ReduceOp.SUM)
+    return {"rows": SWEEP_ROWS, "band": {"sample_rows": int(band[2]), "rows_within_1e-5_of_contact": int(band[0]),
+                                         "collision_mask_vs_sign_of_distance_mismatches_outside_band": int(band[1]),
+                                         "min_distance_rows_per_s_per_gpu": nb / tb,
+                                         "what": "mjb_min_distance (fp64 GJK / EPA signed distance) on the first 2M rows of every shard"}, "seconds": float(t[0]) * 1e-3, "configs_per_s": SWEEP_ROWS / (float(t[0]) * 1e-3),
             "valid_fraction": float(nv) / SWEEP_ROWS, "mask_gather_ms": float(t[1]), "gathered_bytes": gathered_bytes,
             "what": "mjb_check_sweep in 8M-row blocks over this rank's shard of the global row range, masks bit-packed on the "
                     "device, packed shards all-gathered with NCCL (all_gather_into_tensor)" if world > 1 else

@@ -114,6 +114,21 @@ int mjb_fk(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, float *d_xpos
            void *stream);
 
 /*
+ * Signed distance to contact of every row, for band accounting (the north star counts the rows whose
+ * reference signed distance lies within 1e-5 of the margin): d_dist[i] = min over the static pair list
+ * of (signed distance of the pair - its margin), i.e. the row is in contact iff d_dist[i] <= 0 (SURVEY
+ * A.3); d_pair[i] (optional) = index of the arg-min pair in mjb_model_pairs order.  fp64 throughout
+ * (rows are read as fp32, the precision the validity kernels see): FK, closed forms for plane and
+ * capsule pairs, GJK run to convergence for convex pairs and an expanding-polytope depth when the
+ * cores intersect.  Capped: values above far_cap are reported as far_cap with pair -1 (far_cap <= 0:
+ * MJB_DIST_FAR_DEFAULT), penetration deeper than MJB_DEPTH_CAP as -MJB_DEPTH_CAP.
+ */
+#define MJB_DIST_FAR_DEFAULT 0.01
+#define MJB_DEPTH_CAP 1e-3
+int mjb_min_distance(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, double far_cap, double *d_dist,
+                     int32_t *d_pair, void *stream);
+
+/*
  * Edge validation: _valid_collision_interval(start, end, step, constraint)
  * (src/mjpl/planning/utils.py:188-216) for ne edges at once.  Interior waypoints
  * q0 + k*step*(q1-q0)/|q1-q0|, k = 1..K, K = ceil(|q1-q0|/step)-1, are generated on the device;

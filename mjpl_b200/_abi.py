@@ -134,7 +134,7 @@ EXPORTS = (
     "mjb_last_error mjb_device_count mjb_model_create mjb_model_destroy mjb_model_npair "
     "mjb_model_pairs mjb_check_configs mjb_check_configs_host mjb_fk mjb_check_edges "
     "mjb_check_sweep mjb_sweep_rows mjb_get_stats mjb_reset_stats mjb_nearest_batch mjb_rrt_extend mjb_pose_valid mjb_pose_project mjb_site_pose "
-    "mjb_ik_solve mjb_kernel_timing mjb_fma_peak mjb_rrt_extend_masked mjb_rrt_sample mjb_rrt_meet mjb_cbirrt_tick"
+    "mjb_ik_solve mjb_kernel_timing mjb_fma_peak mjb_rrt_extend_masked mjb_rrt_sample mjb_rrt_meet mjb_cbirrt_tick mjb_min_distance"
 ).split()
 
 
@@ -171,6 +171,7 @@ def lib():
     L.mjb_rrt_sample.argtypes = [C.c_uint64, vp, C.c_int64, C.c_int32, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp]
     L.mjb_rrt_meet.argtypes = [C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp]
     L.mjb_cbirrt_tick.argtypes = [vp, C.POINTER(CbirrtState), C.POINTER(PoseSpec), C.c_int32, C.c_uint32, vp]
+    L.mjb_min_distance.argtypes = [vp, f32p, C.c_int64, C.c_int32, C.c_double, vp, vp, vp]
     L.mjb_site_pose.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), vp, C.c_int64, vp, vp, vp]
     L.mjb_pose_valid.argtypes = [vp, C.POINTER(PoseSpec), vp, C.c_int64, vp, vp]
     L.mjb_pose_project.argtypes = [vp, C.POINTER(PoseSpec), vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp]

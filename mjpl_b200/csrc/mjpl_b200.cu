@@ -967,3 +967,24 @@ extern "C" int mjb_cbirrt_tick(mjb_model *m, const mjb_cbirrt_state *cs, const m
   m->launches += 5;
   return MJB_OK;
 }
+
+// ---- signed distance per row --------------------------------------------------------------------------
+extern "C" int mjb_min_distance(mjb_model *m, const float *d_q, int64_t n, int32_t ldq, double far_cap, double *d_dist,
+                                int32_t *d_pair, void *stream) {
+  int rc = check_common(m, MJB_CHECK_COLLISION);
+  if (rc) return rc;
+  if (n < 0 || ldq < m->H.nq) return fail(MJB_ERR_ARG, "bad n / ldq");
+  if (n == 0) return MJB_OK;
+  if (!d_q || !d_dist) return fail(MJB_ERR_ARG, "null device pointer");
+  MArgs a;
+  memset(&a, 0, sizeof a);
+  a.fk = m->d_fk64; a.shapes = m->d_shapes64; a.verts = m->d_verts64; a.pairs = m->d_pairs; a.pair_rsum = m->d_rsum64;
+  a.npair = (int)m->H.pairs.size(); a.nslot = m->H.nslot;
+  a.q = d_q; a.ldq = ldq; a.n = n;
+  a.far_cap = far_cap > 0.0 ? far_cap : MJB_DIST_FAR_DEFAULT; a.depth_cap = MJB_DEPTH_CAP;
+  a.dist = d_dist; a.pair = d_pair;
+  min_distance_kernel<<<(unsigned)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(a);
+  CU(cudaGetLastError());
+  m->launches++;
+  return MJB_OK;
+}

@@ -1151,6 +1151,225 @@ VK_HD bool ik_row(const FkTables<double> &fk, int nslot, const IkSpec &spec, con
   return ok;
 }
 
+// ------------------------------------------------------------------------------ signed distance (band accounting)
+// mjb_min_distance: the signed distance of a pair, not just its three-way verdict.  fp64 only (it is
+// an accounting pass over rows near the contact band, not the hot path).
+//   cores apart          : GJK run to convergence, distance = |v| - R
+//   cores intersecting   : expanding-polytope depth of the origin inside A - B, distance = -depth - R,
+//                          stopped as soon as the depth is certified >= depth_cap
+// Supports are plain scans of the vertex tables (support_shape).
+constexpr int EPA_MAXV = 40, EPA_MAXF = 96;
+
+struct EpaFace { double n[3], d; uint8_t v[3], alive; };
+
+VK_HD bool epa_make_face(const V3<double> *P, V3<double> inner, int a, int b, int c, EpaFace &f) {
+  V3<double> n = cross(P[b] - P[a], P[c] - P[a]);
+  const double len = vk_sqrt(dot(n, n));
+  if (!(len > 1e-300)) return false;
+  n = n * (1.0 / len);
+  f.v[0] = (uint8_t)a; f.v[1] = (uint8_t)b; f.v[2] = (uint8_t)c;
+  if (dot(n, P[a] - inner) < 0) { n = -n; f.v[1] = (uint8_t)c; f.v[2] = (uint8_t)b; }   // outward
+  f.n[0] = n.x; f.n[1] = n.y; f.n[2] = n.z;
+  f.d = dot(n, P[a]);
+  f.alive = 1;
+  return true;
+}
+
+// support point of A - B along d (A frame)
+template <typename SupA, typename SupB>
+VK_HD V3<double> mink_support(const Rel<double> &rel, V3<double> d, SupA supA, SupB supB) {
+  return supA(d) - (mul(rel.R, supB(mulT(rel.R, -d))) + rel.t);
+}
+
+// depth of the origin inside A - B, given the (possibly degenerate) simplex GJK ended with
+template <typename SupA, typename SupB>
+VK_HD double epa_depth(const GjkState<double> &gs, const Rel<double> &rel, double depth_cap, SupA supA, SupB supB) {
+  V3<double> P[EPA_MAXV];
+  int np = gs.n < 1 ? 1 : gs.n;
+  P[0] = gs.p0; P[1] = gs.p1; P[2] = gs.p2; P[3] = gs.p3;
+  const double tiny = 1e-10;
+  if (np == 1) {   // grow a point into a segment
+    const V3<double> AX[6] = {mk<double>(1, 0, 0), mk<double>(-1, 0, 0), mk<double>(0, 1, 0), mk<double>(0, -1, 0), mk<double>(0, 0, 1), mk<double>(0, 0, -1)};
+    for (int k = 0; k < 6 && np == 1; k++) {
+      const V3<double> w = mink_support(rel, AX[k], supA, supB);
+      const V3<double> dd = w - P[0];
+      if (vk_sqrt(dot(dd, dd)) > tiny) P[np++] = w;
+    }
+    if (np == 1) return 0.0;
+  }
+  if (np == 2) {   // ... a segment into a triangle: search directions around the edge
+    const V3<double> e = P[1] - P[0];
+    const double el = vk_sqrt(dot(e, e));
+    const V3<double> u = e * (1.0 / el);
+    const V3<double> ax = vk_abs(u.x) <= vk_abs(u.y) && vk_abs(u.x) <= vk_abs(u.z) ? mk<double>(1, 0, 0)
+                          : (vk_abs(u.y) <= vk_abs(u.z) ? mk<double>(0, 1, 0) : mk<double>(0, 0, 1));
+    V3<double> d1 = cross(u, ax);
+    d1 = d1 * (1.0 / vk_sqrt(dot(d1, d1)));
+    const V3<double> d2 = cross(u, d1);
+    for (int k = 0; k < 6 && np == 2; k++) {
+      const double ang = k * 1.0471975511965976;
+      const V3<double> dir = d1 * cos(ang) + d2 * sin(ang);
+      const V3<double> w = mink_support(rel, dir, supA, supB);
+      const V3<double> cr = cross(e, w - P[0]);
+      if (vk_sqrt(dot(cr, cr)) > tiny * el) P[np++] = w;
+    }
+    if (np == 2) return 0.0;
+  }
+  if (np == 3) {   // ... a triangle into a tetrahedron
+    V3<double> n = cross(P[1] - P[0], P[2] - P[0]);
+    const double len = vk_sqrt(dot(n, n));
+    if (!(len > 1e-300)) return 0.0;
+    n = n * (1.0 / len);
+    const V3<double> w1 = mink_support(rel, n, supA, supB), w2 = mink_support(rel, -n, supA, supB);
+    const double h1 = vk_abs(dot(w1 - P[0], n)), h2 = vk_abs(dot(w2 - P[0], n));
+    if (h1 < tiny && h2 < tiny) return 0.0;
+    P[np++] = h1 >= h2 ? w1 : w2;
+  }
+  const V3<double> inner = (P[0] + P[1] + P[2] + P[3]) * 0.25;
+  EpaFace F[EPA_MAXF];
+  int nf = 0;
+  const int T[4][3] = {{0, 1, 2}, {0, 1, 3}, {0, 2, 3}, {1, 2, 3}};
+  for (int f = 0; f < 4; f++)
+    if (epa_make_face(P, inner, T[f][0], T[f][1], T[f][2], F[nf])) nf++;
+  if (nf < 4) return 0.0;
+  double lower = 0;
+  for (int it = 0; it < 64; it++) {
+    int bf = -1;
+    double bd = 1e300;
+    for (int f = 0; f < nf; f++)
+      if (F[f].alive && F[f].d < bd) { bd = F[f].d; bf = f; }
+    if (bf < 0) break;
+    lower = bd > 0 ? bd : 0;
+    if (lower >= depth_cap) return lower;
+    const V3<double> fn = mk<double>(F[bf].n[0], F[bf].n[1], F[bf].n[2]);
+    const V3<double> w = mink_support(rel, fn, supA, supB);
+    const double h = dot(w, fn);
+    if (h - bd < 1e-10 || np >= EPA_MAXV) return h > 0 ? h : 0;
+    P[np] = w;
+    // remove the faces w can see, collect the horizon edges
+    uint8_t E[EPA_MAXF][2];
+    int ne = 0;
+    for (int f = 0; f < nf; f++) {
+      if (!F[f].alive) continue;
+      const V3<double> nn = mk<double>(F[f].n[0], F[f].n[1], F[f].n[2]);
+      if (dot(nn, w - P[F[f].v[0]]) > 1e-14) {
+        F[f].alive = 0;
+        for (int e = 0; e < 3; e++) {
+          const uint8_t a = F[f].v[e], b = F[f].v[(e + 1) % 3];
+          int found = -1;
+          for (int k = 0; k < ne; k++)
+            if (E[k][0] == b && E[k][1] == a) { found = k; break; }
+          if (found >= 0) { E[found][0] = E[ne - 1][0]; E[found][1] = E[ne - 1][1]; ne--; }
+          else if (ne < EPA_MAXF) { E[ne][0] = a; E[ne][1] = b; ne++; }
+        }
+      }
+    }
+    if (ne == 0) return h > 0 ? h : 0;
+    for (int k = 0; k < ne; k++) {
+      int slot = -1;
+      for (int f = 0; f < nf; f++)
+        if (!F[f].alive) { slot = f; break; }
+      if (slot < 0) { if (nf >= EPA_MAXF) return lower; slot = nf++; }
+      if (!epa_make_face(P, inner, E[k][0], E[k][1], np, F[slot])) F[slot].alive = 0;
+    }
+    np++;
+  }
+  return lower;
+}
+
+// signed distance of the cores of A and B (swept radii and margin NOT subtracted): > 0 apart, < 0 = -depth
+template <typename SupA, typename SupB>
+VK_HD double gjk_signed_distance(const Shape<double> &A, const Shape<double> &B, const Rel<double> &rel, double depth_cap,
+                                 SupA supA, SupB supB) {
+  GjkState<double> s;
+  gjk_init(s, A, B, rel);
+  for (int it = 0; it < 96; it++) {
+    const V3<double> v = s.v;
+    const V3<double> w = mink_support(rel, -v, supA, supB);
+    const double vv = dot(v, v), vw = dot(v, w);
+    if (s.n > 0 && (vv - vw) <= 1e-13 * vv) return vk_sqrt(vv);   // converged: |v| is the distance
+    double l0 = 0, l1 = 0, l2 = 0, l3 = 0;
+    bool inside = false;
+    if (s.n == 0) { s.p0 = w; l0 = 1; }
+    else if (s.n == 1) { s.p1 = w; solve1(s.p0, s.p1, l0, l1); }
+    else if (s.n == 2) { s.p2 = w; solve2(s.p0, s.p1, s.p2, l0, l1, l2); }
+    else { s.p3 = w; inside = solve3(s.p0, s.p1, s.p2, s.p3, l0, l1, l2, l3); }
+    if (inside) { s.n = 4; return -epa_depth(s, rel, depth_cap, supA, supB); }
+    const V3<double> nv = s.p0 * l0 + s.p1 * l1 + s.p2 * l2 + s.p3 * l3;
+    s.v = nv;
+    bool k0 = l0 > 0, k1 = l1 > 0, k2 = l2 > 0, k3 = l3 > 0;
+    { bool c = !k0 && k1; cswap(c, s.p0, s.p1); cswap(c, k0, k1); }
+    { bool c = !k1 && k2; cswap(c, s.p1, s.p2); cswap(c, k1, k2); }
+    { bool c = !k2 && k3; cswap(c, s.p2, s.p3); cswap(c, k2, k3); }
+    { bool c = !k0 && k1; cswap(c, s.p0, s.p1); cswap(c, k0, k1); }
+    { bool c = !k1 && k2; cswap(c, s.p1, s.p2); cswap(c, k1, k2); }
+    { bool c = !k0 && k1; cswap(c, s.p0, s.p1); cswap(c, k0, k1); }
+    s.n = int(k0) + int(k1) + int(k2) + int(k3);
+    if (!(dot(nv, nv) > 1e-26)) return -epa_depth(s, rel, depth_cap, supA, supB);   // cores touch: depth from the simplex
+    if (s.n == 4) return -epa_depth(s, rel, depth_cap, supA, supB);
+  }
+  return vk_sqrt(dot(s.v, s.v));
+}
+
+// signed distance of one pair minus the margin (rsum = swept radii + margin), clamped below at -depth_cap
+VK_HD double pair_signed_distance(const Pair &pr, const Shape<double> &A, const Shape<double> &B, const Vtx<double> *verts,
+                                  const Pose<double> &PA, const Pose<double> &PB, double rsum, double depth_cap) {
+  double d;
+  if (pr.kind == PK_PLANE) {
+    const V3<double> n = mk<double>(A.ax[0], A.ax[1], A.ax[2]), c = mk<double>(A.c[0], A.c[1], A.c[2]);
+    if (B.kind == SK_CYL) {
+      const V3<double> ax = qrot(PB.q, mk<double>(B.ax[0], B.ax[1], B.ax[2]));
+      const V3<double> cb = PB.p + qrot(PB.q, mk<double>(B.c[0], B.c[1], B.c[2]));
+      const double na = dot(n, ax), rad = 1.0 - na * na;
+      d = dot(n, cb - c) - vk_abs(na) * B.halflen - B.radius * vk_sqrt(rad > 0 ? rad : 0.0);
+    } else {
+      const V3<double> sp = support_verts(verts + B.vadr, B.nvert, -qrot(qconj(PB.q), n));
+      d = dot(n, PB.p + qrot(PB.q, sp) - c);
+    }
+    d -= rsum;
+  } else if (pr.kind == PK_SEGSEG) {
+    const Vtx<double> a0 = verts[A.vadr], a1 = verts[A.vadr + A.nvert - 1], b0 = verts[B.vadr], b1 = verts[B.vadr + B.nvert - 1];
+    const V3<double> p1 = PA.p + qrot(PA.q, mk<double>(a0.x, a0.y, a0.z)), q1 = PA.p + qrot(PA.q, mk<double>(a1.x, a1.y, a1.z));
+    const V3<double> p2 = PB.p + qrot(PB.q, mk<double>(b0.x, b0.y, b0.z)), q2 = PB.p + qrot(PB.q, mk<double>(b1.x, b1.y, b1.z));
+    d = vk_sqrt(segseg_dist2(p1, q1, p2, q2)) - rsum;
+  } else {
+    if (rsum >= depth_cap) {   // sphere-swept pair: a core distance of 0 is already deeper than the cap
+      // fall through to the general routine, the clamp below takes care of it
+    }
+    const Rel<double> rel = relative_pose(PA, PB);
+    d = gjk_signed_distance(A, B, rel, depth_cap + rsum, [&](V3<double> dir) { return support_shape(A, verts, dir); },
+                            [&](V3<double> dir) { return support_shape(B, verts, dir); }) - rsum;
+  }
+  return d < -depth_cap ? -depth_cap : d;
+}
+
+// min over the static pair list of (signed distance - margin) for one row, fp64.  Pairs whose bounding
+// capsules are further apart than the best distance so far cannot improve it and are skipped; the
+// result is capped at far_cap from above (pair = -1: nothing closer than that) and at -depth_cap from
+// below.  Reference semantics of the quantity: SURVEY A.3 (contact iff signed distance <= margin).
+VK_HD void row_min_distance(const FkTables<double> &fk, int nslot, const Shape<double> *shapes, const Vtx<double> *verts,
+                            const Pair *pairs, const double *pair_rsum, int npair, const double *q, double far_cap,
+                            double depth_cap, double &best, int &bestp) {
+  Pose<double> P[MAX_BODY], ident;
+  ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  for (int s = 0; s < nslot; s++) {
+    const int ps = fk.body_parent[s];
+    P[s] = fk_body(fk, s, ps < 0 ? ident : P[ps], q);
+  }
+  best = far_cap; bestp = -1;
+  for (int p = 0; p < npair; p++) {
+    const Pair pr = pairs[p];
+    const Shape<double> &A = shapes[pr.sa], &B = shapes[pr.sb];
+    const Pose<double> &PA = A.slot < 0 ? ident : P[A.slot];
+    const Pose<double> &PB = B.slot < 0 ? ident : P[B.slot];
+    const double rsum = pair_rsum[p];
+    const double margin = rsum - swept_radius(A) - swept_radius(B);
+    if (capsule_cull(pr, A, B, PA, PB, margin + best)) continue;   // lower bound of the signed distance > best
+    const double d = pair_signed_distance(pr, A, B, verts, PA, PB, rsum, depth_cap);
+    if (d < best) { best = d; bestp = p; }
+  }
+}
+
 // ------------------------------------------------------------------------------ two-kernel pipeline: item bins
 // (shared by the device kernels in vk_split.cuh and the host-side capacity estimate in vk_build.h)
 constexpr int NBIN = 8;

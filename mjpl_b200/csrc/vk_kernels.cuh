@@ -1153,6 +1153,31 @@ __global__ void __launch_bounds__(128) nearest_kernel(const double *nodes, long 
   if (lane == 0) out[w] = bi;
 }
 
+// ---------------------------------------------------------------------------- signed distance per row (band accounting)
+struct MArgs {
+  const FkTables<double> *fk;
+  const Shape<double> *shapes;
+  const Vtx<double> *verts;
+  const Pair *pairs;
+  const double *pair_rsum;
+  int npair, nslot;
+  const float *q; int ldq; long long n;
+  double far_cap, depth_cap;
+  double *dist; int *pair;
+};
+__global__ void __launch_bounds__(64) min_distance_kernel(const MArgs a) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= a.n) return;
+  const FkTables<double> &fk = *a.fk;
+  double q[MAX_JNT];
+  for (int j = 0; j < fk.nq; j++) q[j] = (double)a.q[row * a.ldq + j];
+  double best;
+  int bestp;
+  row_min_distance(fk, a.nslot, a.shapes, a.verts, a.pairs, a.pair_rsum, a.npair, q, a.far_cap, a.depth_cap, best, bestp);
+  a.dist[row] = best;
+  if (a.pair) a.pair[row] = bestp;
+}
+
 // ---------------------------------------------------------------------------- bi-RRT iteration on the device
 // Sampling step of RRT.plan_to_configs for S queries at once (reference: src/mjpl/planning/rrt.py:206-215):
 // with probability goal_bias the target is the other tree's root (the goal, or q_init once the trees

@@ -193,6 +193,21 @@ class ValidityEngine:
                 _abi.check(self._L.mjb_fk(self._h, q.data_ptr(), n, q.stride(0), xpos.data_ptr(), xquat.data_ptr(), self._stream()))
             return self._back(xpos, kind), self._back(xquat, kind)
 
+    def min_distance(self, Q, far_cap: float = 0.0):
+        """Signed distance to contact of every row (``mjb_min_distance``, fp64) -> ``(dist (n,) float64,
+        pair (n,) int32)``, same container kind as the input.  ``dist <= 0`` iff the row is in contact;
+        values are capped at ``far_cap`` (default 0.01 m, pair -1) and at -0.001 m."""
+        torch = _torch()
+        with self._call_lock, torch.cuda.device(self.device):
+            q, kind = self._rows(Q)
+            n = q.shape[0]
+            dist = torch.empty(n, dtype=torch.float64, device=self.torch_device)
+            pair = torch.empty(n, dtype=torch.int32, device=self.torch_device)
+            if n:
+                _abi.check(self._L.mjb_min_distance(self._h, q.data_ptr(), n, q.stride(0), float(far_cap), dist.data_ptr(),
+                                                    pair.data_ptr(), self._stream()))
+            return self._back(dist, kind), self._back(pair, kind)
+
     def valid_edges(self, Q0, Q1, step: float, flags: int = CHECK_COLLISION, want_first_bad: bool = False):
         """``_valid_collision_interval`` for many edges: interior waypoints only, early exit."""
         # reference: raise ValueError("`step_dist` must be > 0") (planning/utils.py:203-204)

@@ -521,6 +521,7 @@ class BatchedRRT:
         if S == 0:
             self.stats.update(solved=int(direct.sum()), seconds=0.0)
             return paths
+        eng.reset_stats()
         with torch.cuda.device(eng.device), eng._call_lock:
             QI = torch.from_numpy(np.ascontiguousarray(q_inits[ids])).to(dev)
             QG = torch.from_numpy(np.ascontiguousarray(q_goals[ids])).to(dev)

@@ -57,6 +57,7 @@ def lib():
         L.hs_bins.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_pair_verdict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.hs_check_pipe.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.hs_min_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
         L.hs_bounds_check.argtypes = [C.c_void_p]
         L.hs_bounds_check.restype = C.c_double
         L.hs_segseg_check.argtypes = [C.c_int, C.c_uint64]
@@ -117,6 +118,13 @@ class HostSim:
         stats = np.zeros(8, np.int64)
         lib().hs_check_pipe(self._h, q.ctypes.data, len(q), flags, valid.ctypes.data, stats.ctypes.data)
         return valid, dict(zip("level0 expanded capsule items contacts".split(), stats[:5].tolist()))
+
+    def min_distance(self, q, far_cap=0.01):
+        """signed distance to contact per row through the fp64 core -> (dist, pair index)"""
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.model.nq)
+        dist = np.zeros(len(q)); pair = np.zeros(len(q), np.int32)
+        lib().hs_min_distance(self._h, q.ctypes.data, len(q), far_cap, dist.ctypes.data, pair.ctypes.data)
+        return dist, pair
 
     def bounds_check(self):
         """largest distance by which a vertex sticks out of its bounding capsule / group sphere (<= 0: contained)"""

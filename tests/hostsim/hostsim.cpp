@@ -418,3 +418,16 @@ extern "C" double hs_segseg_check(int ncase, uint64_t seed) {
   }
   return worst;
 }
+
+// mjb_min_distance's per-row routine on the CPU (fp64 core): dist (n), pair (n)
+extern "C" void hs_min_distance(Sim *s, const float *q, int64_t n, double far_cap, double *dist, int32_t *pair) {
+  const auto &H = s->H;
+  for (int64_t r = 0; r < n; r++) {
+    double row[MAX_JNT];
+    for (int j = 0; j < H.nq; j++) row[j] = (double)q[r * H.nq + j];
+    double best; int bp;
+    row_min_distance(H.fk, H.nslot, H.shapes.data(), H.verts.data(), H.pairs.data(), H.pair_rsum64.data(), (int)H.pairs.size(), row,
+                     far_cap, 1e-3, best, bp);
+    dist[r] = best; pair[r] = bp;
+  }
+}

@@ -518,3 +518,30 @@ def test_calls_on_different_streams_are_ordered_per_handle():
         side.synchronize()
         np.testing.assert_array_equal(got_b, want_b)
         np.testing.assert_array_equal(got_a.cpu().numpy(), want_a)
+
+
+def test_min_distance_on_device_and_band_accounting():
+    """mjb_min_distance (fp64 signed distance + arg-min pair per row): equal to the oracle's signed
+    distance wherever that is exact, contact iff dist <= 0 exactly as the validity kernels decide it,
+    and the in-band rows it counts are the only rows on which validity may differ from the oracle."""
+    import torch
+
+    for mname, allowed, n in (("franka_scene_with_obstacles", [("left_finger", "right_finger")], 200_000), ("ur5e_scene", [], 100_000)):
+        model = models.load(mname)
+        eng = mj.get_engine(model, allowed)
+        orc = oracle.Oracle(model, allowed)
+        oracle.Oracle.set_threads(8)
+        Q = rows(model, n, 13)
+        dist, pair = eng.min_distance(torch.from_numpy(Q).cuda())
+        dist, pair = dist.cpu().numpy(), pair.cpu().numpy()
+        want, od, _ = orc.check(Q.astype(np.float64), 2, want_dist=True)
+        exact = np.minimum(dist, od) < 1e-3
+        err = float(np.abs(dist - od)[exact].max())
+        got = eng.valid_configs(Q, 2)
+        band = np.abs(dist) < BAND
+        print(f"{mname}: max |dist - oracle| = {err:.2e} on {int(exact.sum())} rows, rows in the 1e-5 band: {int(band.sum())}")
+        assert err < 1e-9
+        assert ((dist <= 0) == (od <= 0)).all()
+        assert not ((got != (dist > 0)) & ~band).any()      # validity == (dist > 0) outside the band
+        assert not ((got != want) & ~band).any()
+        assert ((pair >= 0) == (dist < 0.01)).all() and pair.max() < len(eng.pairs())

@@ -469,6 +469,30 @@ def test_bounding_capsules_and_cull_groups_are_conservative():
         np.testing.assert_array_equal(got, hs.check(Q)[0])   # same answer as the per-pair sphere + mid-phase order
 
 
+def test_min_distance_core_matches_oracle():
+    """mjb_min_distance's fp64 routine (GJK to convergence, expanding-polytope depth, closed forms, capsule
+    pruning) against the oracle's signed distance: equal to 1e-9 wherever the oracle's own value is exact
+    (it only evaluates pairs within 1 mm of its bounding spheres), same sign everywhere."""
+    import oracle
+    from mjpl_b200 import mjcf, models
+    from tests import toy_models as toys
+    from tests.hostsim import HostSim
+
+    zoo = mjcf.from_xml_string(toys.PRIMITIVE_ARM)
+    zoo_m = mjcf.from_xml_string(toys.PRIMITIVE_ARM)
+    zoo_m.geom_margin = np.where(np.arange(zoo_m.ngeom) % 2 == 0, 0.015, 0.004)
+    for m, allowed, n in ((models.load("franka_scene_with_obstacles"), [("left_finger", "right_finger")], 1500),
+                          (models.load("ur5e_scene"), [], 4000), (zoo, [], 4000), (zoo_m, [], 4000)):
+        rng = np.random.default_rng(5)
+        Q = rng.uniform(m.jnt_range[:, 0], m.jnt_range[:, 1], size=(n, m.nq)).astype(np.float32)
+        d, p = HostSim(m, allowed).min_distance(Q, 0.01)
+        _, od, _ = oracle.Oracle(m, allowed).check(Q.astype(np.float64), 2, want_dist=True)
+        assert ((d <= 0) == (od <= 0)).all()
+        exact = np.minimum(d, od) < 1e-3
+        assert exact.sum() > 100 and np.abs(d - od)[exact].max() < 1e-9
+        assert (d <= 0.01).all() and (d >= -1e-3).all() and ((p >= 0) == (d < 0.01)).all()
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): rank 0 prints one JSON
     line with the contract's keys, other ranks print nothing; no GPU involved."""
