@@ -17,6 +17,7 @@
 #include "vk_kernels.cuh"
 #include "vk_split.cuh"
 #include "vk_pipe.cuh"
+#include "vk_row.cuh"
 
 using namespace vk;
 
@@ -56,6 +57,7 @@ struct mjb_model {
   bool split = false; size_t fk_smem = 0, mid_smem = 0, narrow_smem = 0; int fk_grid = 0, mid_grid = 0, narrow_grid = 0;
   float *d_pose8 = nullptr; unsigned long long *d_bins = nullptr; uint32_t *d_row_flags = nullptr; size_t split_cap = 0;
   unsigned long long *d_l0 = nullptr; size_t l0_cap = 0;
+  bool rowk = false; size_t rowk_smem = 0; int rowk_grid = 0; long long rowk_rows = 0;   // one-warp-per-row kernel for small launches
   GroupPair *d_gpairs = nullptr; StaticGroup *d_sgroups = nullptr; uint16_t *d_gp_member = nullptr;
   size_t cur_rows = 0, cur_rows_hint = 0, grp_small_rows = 0, split_min = 0, bin_cap_override = 0, l0_cap_override = 0; bool use_split = false;
   // optional per-kernel timing (mjb_kernel_timing): 4 events per validity launch
@@ -228,6 +230,21 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
                 m->split ? "on" : "OFF", FL.total, ML.total, NL.total, optin, focc, mocc, nocc, H.group_pairs.size());
     }
   }
+  {  // small launches: one warp per row (vk_row.cuh)
+    const RowLayout RL = row_layout((int)H.verts.size(), (int)H.shapes.size(), (int)H.pairs.size(), (int)H.group_pairs.size(),
+                                    (int)H.static_groups.size(), (int)H.gp_member.size(), (int)H.adj.size(), H.nslot, H.ngroup_moving, H.nq);
+    int rocc = 0;
+    const char *rk = getenv("MJB_ROWK_ROWS");   // launches of at most this many rows take row_kernel (0: never)
+    m->rowk_rows = rk ? atoll(rk) : 6144;   // B200, Franka rows, raw call (tools/rowk_crossover.py): 64 rows 101 -> 39 us, 1k 121 -> 49, 4k 128 -> 72, 8k 130 -> 121, 16k 183 -> 244
+    if (m->rowk_rows > 0 && (int)RL.total <= optin && !H.group_pairs.empty() && H.pairs.size() <= 65535 &&
+        cudaFuncSetAttribute(row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rocc, row_kernel, ROWK_THREADS, RL.total) == cudaSuccess && rocc >= 1) {
+      m->rowk = true; m->rowk_smem = RL.total; m->rowk_grid = m->num_sms * rocc;
+    } else {
+      cudaGetLastError();
+    }
+    if (getenv("MJB_DEBUG")) fprintf(stderr, "[mjb] row kernel %s: smem %zu, CTAs/SM %d, up to %lld rows\n", m->rowk ? "on" : "OFF", RL.total, rocc, m->rowk_rows);
+  }
   CU(cudaMalloc((void **)&m->d_pose, (size_t)m->grid * std::max(H.nslot, 1) * 7 * m->tile * sizeof(float)));
   CU(cudaMalloc((void **)&m->d_counters, C_NCOUNTERS * sizeof(unsigned long long)));
   CU(cudaMemset(m->d_counters, 0, C_NCOUNTERS * sizeof(unsigned long long)));
@@ -376,8 +393,20 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
     if (ev) CU(cudaEventRecord(ev[3], st));
     m->launches += 3;
   } else {
-    // small launches (the planner's extends): the instance whose narrow phase puts GRP_SMALL lanes on one item
+    // small launches: one warp per row.  Dense / sweep launches know their size here; for edges and chains
+    // only the device does: both kernels are enqueued and the one out of its regime returns at once.
+    const bool device_count = k.mode == MODE_EDGES || k.mode == MODE_CHAINS;
+    const bool rowk_only = m->rowk && !device_count && (long long)m->cur_rows <= m->rowk_rows;
+    k.rowk_max = (m->rowk && device_count) ? m->rowk_rows : -1;
+    if (rowk_only || (m->rowk && device_count)) {
+      const long long want = device_count ? (long long)m->rowk_grid : std::min<long long>(m->rowk_grid, ((long long)m->cur_rows + 7) / 8);
+      row_kernel<<<(unsigned)std::max<long long>(want, 1), ROWK_THREADS, m->rowk_smem, st>>>(k);
+      CU(cudaGetLastError());
+      m->launches++;
+    }
+    // (the planner's extends): the instance whose narrow phase puts GRP_SMALL lanes on one item
     const bool small = m->cur_rows_hint <= m->grp_small_rows;
+    if (!rowk_only)
     switch (m->tile) {
       case 512: if (small) validity_kernel<512, GRP_SMALL><<<m->grid, 512, m->smem_bytes, st>>>(k); else validity_kernel<512, GRP><<<m->grid, 512, m->smem_bytes, st>>>(k); break;
       case 256: if (small) validity_kernel<256, GRP_SMALL><<<m->grid, 256, m->smem_bytes, st>>>(k); else validity_kernel<256, GRP><<<m->grid, 256, m->smem_bytes, st>>>(k); break;
@@ -739,7 +768,7 @@ extern "C" int mjb_rrt_extend_masked(mjb_model *m, double *d_nodes, int64_t *d_p
   if ((rc = ensure_recheck(m, (size_t)n * (size_t)kcap, st, false, (size_t)n * 24))) return rc;
   // 1. nearest node of every query's tree   2. chain lengths + prefix sums
   nearest_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_count,
-                                                                  (const long long *)d_slots, d_targets, (long long)n, m->d_chain_nn);
+                                                                  (const long long *)d_slots, d_targets, (long long)n, m->d_chain_nn, d_active);
   chain_setup_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_slots, m->d_chain_nn,
                                                                  d_targets, (long long)n, eps, kcap, m->d_chain_near, m->d_edge_count,
                                                                  m->d_first_bad, d_active);

@@ -82,6 +82,9 @@ struct KArgs {
   int gp_kind_end[3];
   unsigned long long *l0_items;         // level-0 survivors: row | group pair << 40
   unsigned long long l0_cap;
+  // small launches (vk_row.cuh): row_kernel takes launches of at most rowk_max rows, validity_kernel the rest
+  // (both are enqueued when only the device knows the row count; -1: no such dispatch)
+  long long rowk_max;
 };
 
 // counters layout
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int wrow0 = tid & ~31;  // first row (within the tile) owned by this warp
+  if (a.rowk_max >= 0 && (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) && a.edge_prefix[a.nedge] <= a.rowk_max) return;   // row_kernel's launch
   uint32_t *q1 = reinterpret_cast<uint32_t *>(smem + L.queue1) + (tid >> 5) * Q1CAP;  // sphere-cull survivors
   uint32_t *q2 = reinterpret_cast<uint32_t *>(smem + L.queue2) + (tid >> 5) * Q2CAP;  // narrow-phase items
   float *pose = a.pose_scratch + (size_t)blockIdx.x * a.nslot * 7 * TILE;
@@ -1127,10 +1131,11 @@ __global__ void chain_append_kernel(double *nodes, long long *parent, long long 
 // +inf sink root of the reference's goal tree) can never win.
 __global__ void __launch_bounds__(128) nearest_kernel(const double *nodes, long long cap, int nq, const long long *count,
                                                       const long long *rows, const double *targets, long long n,
-                                                      long long *out) {
+                                                      long long *out, const uint8_t *active = nullptr) {
   const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= n) return;
+  if (active && !active[w]) { if (lane == 0) out[w] = 0; return; }   // masked query: no scan (its chain is empty anyway)
   const long long tree = rows ? rows[w] : w;
   const double *base = nodes + tree * cap * nq;
   const double *t = targets + w * nq;
