@@ -59,6 +59,7 @@ struct mjb_model {
   unsigned long long *d_l0 = nullptr; size_t l0_cap = 0;
   bool rowk = false; size_t rowk_smem = 0; int rowk_grid = 0; long long rowk_rows = 0;   // one-warp-per-row kernel for small launches
   GroupPair *d_gpairs = nullptr; StaticGroup *d_sgroups = nullptr; uint16_t *d_gp_member = nullptr;
+  uint32_t *d_smap_cells = nullptr; uint8_t *d_smap_ids = nullptr;
   size_t cur_rows = 0, cur_rows_hint = 0, grp_small_rows = 0, split_min = 0, bin_cap_override = 0, l0_cap_override = 0; bool use_split = false;
   // optional per-kernel timing (mjb_kernel_timing): 4 events per validity launch
   bool timing = false; std::vector<cudaEvent_t> tev; std::vector<uint8_t> tev_split; size_t tev_used = 0;   // decided per launch from the row count
@@ -166,6 +167,10 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
     if ((rc = upload(&m->d_sgroups, H.static_groups))) return bail(rc);
     if ((rc = upload(&m->d_gp_member, mem))) return bail(rc);
   }
+  if (!H.smap_cells.empty() && !(getenv("MJB_SMAP") && atoi(getenv("MJB_SMAP")) == 0)) {   // MJB_SMAP=0: scan all vertices (A/B, tests)
+    if ((rc = upload(&m->d_smap_cells, H.smap_cells))) return bail(rc);
+    if ((rc = upload(&m->d_smap_ids, H.smap_ids))) return bail(rc);
+  }
   {  // padded to 16-byte multiples: the kernel bulk-copies whole 16-byte units
     std::vector<uint16_t> as = H.adj_start; as.resize(align_up(as.size(), 8), 0);
     std::vector<uint8_t> ad = H.adj; ad.resize(align_up(std::max<size_t>(ad.size(), 1), 16), 0);
@@ -268,6 +273,7 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   for (int sl = 0; sl < MAX_BODY; sl++) k.slot_group[sl] = H.slot_group[sl];
   for (int g = 0; g < H.ngroup_moving; g++) for (int a = 0; a < 3; a++) k.group_c[g][a] = (float)H.group_c[g][a];
   k.gpairs = m->d_gpairs; k.sgroups = m->d_sgroups; k.gp_member = m->d_gp_member;
+  k.smap_cells = m->d_smap_cells; k.smap_ids = m->d_smap_ids;
   k.ngpair = (int)H.group_pairs.size(); k.nsgroup = (int)H.static_groups.size(); k.ngroup_moving = H.ngroup_moving;
   k.nmember = (int)H.gp_member.size();
   for (int a = 0; a < 3; a++) k.gp_kind_end[a] = H.gp_kind_end[a];
@@ -297,7 +303,7 @@ extern "C" void mjb_model_destroy(mjb_model *m) {
   cudaFree(m->d_verts64); cudaFree(m->d_fk64); cudaFree(m->d_rsum64); cudaFree(m->d_bsum64);
   cudaFree(m->d_body_slot); cudaFree(m->d_static_pose); cudaFree(m->d_adj_start); cudaFree(m->d_adj); cudaFree(m->d_pose); cudaFree(m->d_counters);
   cudaFree(m->d_pose8); cudaFree(m->d_bins); cudaFree(m->d_row_flags); cudaFree(m->d_l0);
-  cudaFree(m->d_gpairs); cudaFree(m->d_sgroups); cudaFree(m->d_gp_member);
+  cudaFree(m->d_gpairs); cudaFree(m->d_sgroups); cudaFree(m->d_gp_member); cudaFree(m->d_smap_cells); cudaFree(m->d_smap_ids);
   cudaFree(m->d_recheck); cudaFree(m->d_edge_count); cudaFree(m->d_edge_prefix); cudaFree(m->d_first_bad);
   cudaFree(m->d_cub); cudaFree(m->d_stage_q); cudaFree(m->d_stage_v); cudaFree(m->d_chain_near); cudaFree(m->d_chain_nn);
   if (m->h_pin_q) cudaFreeHost(m->h_pin_q);

@@ -40,6 +40,9 @@ struct HostModel {
   std::vector<Pair> pairs;              // processing order
   std::vector<int> pair_g1, pair_g2;    // MuJoCo geom ids, same order as `pairs`
   std::vector<double> pair_rsum64, pair_bsum64;  // fp64 copies of Pair::rsum / bsum
+  // support maps (vk_core.cuh): per hull 6 x R x R cells (offset << 8 | count) and the candidate vertex ids
+  std::vector<uint32_t> smap_cells;
+  std::vector<uint8_t> smap_ids;
   // cull groups (vk_pipe.cuh): moving bodies that carry shapes, and every world-fixed shape by itself
   int ngroup_moving = 0;
   int slot_group[MAX_BODY];              // pose slot -> moving group or -1
@@ -300,6 +303,7 @@ template <typename T> inline Shape<T> convert_shape(const Shape<double> &s) {
   for (int k = 0; k < 3; k++) { o.ca[k] = (T)s.ca[k]; o.cb[k] = (T)s.cb[k]; }
   // rounding the end points can move them by half an ulp: the radius absorbs it
   o.crad = (T)(s.crad * (1.0 + 2e-7) + (sizeof(T) == 4 ? 1e-6 : 0.0)); o.caplen = (T)s.caplen;
+  o.map = s.map;
   return o;
 }
 
@@ -703,7 +707,52 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
     }
     H.adj_start[lists.size()] = (uint16_t)H.adj.size();
   }
-  for (auto &sh : H.shapes) sh.group = -1;
+  for (auto &sh : H.shapes) { sh.group = -1; sh.map = -1; }
+  // ---- support maps for the larger hulls (see vk_core.cuh for the superset argument) --------------
+  {
+    const char *sm = getenv("MJB_SMAP_MIN");
+    const int smap_min = sm ? atoi(sm) : 24;   // hulls with fewer vertices are scanned
+    for (auto &sh : H.shapes) {
+      if (sh.kind != SK_VERTS || sh.nvert < smap_min || sh.nvert > 255) continue;
+      if (H.smap_ids.size() > (1u << 23)) break;
+      const Vtx<double> *v = H.verts.data() + sh.vadr;
+      const int R = SMAP_R;
+      sh.map = (int)H.smap_cells.size();
+      for (int f = 0; f < 6; f++) {
+        const int k = f / 2;
+        const double sg = (f % 2) ? -1.0 : 1.0;
+        for (int iu = 0; iu < R; iu++)
+          for (int iv = 0; iv < R; iv++) {
+            auto dir = [&](double u, double w) {
+              double d[3];
+              d[k] = sg; d[(k + 1) % 3] = u; d[(k + 2) % 3] = w;
+              const double n = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+              return mk<double>(d[0] / n, d[1] / n, d[2] / n);
+            };
+            const double u0 = -1 + 2.0 * iu / R, u1 = -1 + 2.0 * (iu + 1) / R, w0 = -1 + 2.0 * iv / R, w1 = -1 + 2.0 * (iv + 1) / R;
+            const V3<double> c = dir(0.5 * (u0 + u1), 0.5 * (w0 + w1));
+            double delta = 0;
+            for (int a = 0; a < 2; a++)
+              for (int b = 0; b < 2; b++) {
+                const V3<double> q = dir(a ? u1 : u0, b ? w1 : w0) - c;
+                delta = std::max(delta, sqrt(dot(q, q)));
+              }
+            delta = delta * 1.02 + 1e-6;
+            int best = 0; double hb = -1e300;
+            for (int i = 0; i < sh.nvert; i++) { const double h = v[i].x * c.x + v[i].y * c.y + v[i].z * c.z; if (h > hb) { hb = h; best = i; } }
+            std::vector<uint8_t> cand;
+            for (int i = 0; i < sh.nvert; i++) {
+              const double h = v[i].x * c.x + v[i].y * c.y + v[i].z * c.z;
+              const double dx = v[i].x - v[best].x, dy = v[i].y - v[best].y, dz = v[i].z - v[best].z;
+              if (hb - h <= sqrt(dx * dx + dy * dy + dz * dz) * delta + 1e-9) cand.push_back((uint8_t)i);
+            }
+            const uint32_t word = (uint32_t)(H.smap_ids.size() << 8) | (uint32_t)cand.size();   // <= 255 vertices per mapped hull
+            H.smap_ids.insert(H.smap_ids.end(), cand.begin(), cand.end());
+            H.smap_cells.push_back(word);
+          }
+      }
+    }
+  }
 
   // ---- pairs in processing order --------------------------------------------------------------------
   struct Tmp { Pair p; int g1, g2; long key; double rsum, bsum; };

@@ -182,8 +182,10 @@ template <typename T> struct Shape {
   // bounding capsule (line-swept sphere) in the same frame as the vertices: segment ca..cb, radius
   // crad (includes the swept radius); caplen == 0 marks a point-like capsule (a sphere)
   T ca[3], cb[3], crad, caplen;
+  int map;         // support map of the hull (first cell in the cell table), -1: scan all vertices
+  int pad3[3];
 };
-static_assert(sizeof(Shape<float>) == 176, "Shape<float> must stay a multiple of 16 bytes (cp.async.bulk granularity)");
+static_assert(sizeof(Shape<float>) == 192, "Shape<float> must stay a multiple of 16 bytes (cp.async.bulk granularity)");
 
 struct Pair {
   uint16_t sa, sb;  // shape indices (sa: plane if any; else the one with more vertices first)
@@ -362,6 +364,56 @@ VK_HD V3<T> support_verts(const Vtx<T> *__restrict__ v, int n, V3<T> d) {
     bp.x = g ? p.x : bp.x; bp.y = g ? p.y : bp.y; bp.z = g ? p.z : bp.z;
   }
   return bp;
+}
+
+// ------------------------------------------------------------------------------ support maps
+// A hull's support function max_v v.d is piecewise constant in the direction d.  The unit sphere of
+// directions is cut into 6 x SMAP_R x SMAP_R cube-map cells; for every cell the host lists the vertices
+// that can be the support for SOME direction of the cell, so a query reads one cell and scans its
+// few candidates (6 on average for the Franka links at SMAP_R = 8) instead of all 41-152 vertices.
+// The list is a rigorous superset: with c the cell's centre direction, u0 = support(c) and
+// delta = max |d - c| over the unit directions d of the cell, a vertex v that is the support for such
+// a d satisfies v.d >= u0.d, hence (u0 - v).c <= (u0 - v).(c - d) <= |u0 - v| delta.  Every v that
+// passes this test (with delta inflated by 2 %: a direction rounded into the neighbouring cell is
+// still covered) is listed.  The value returned is therefore the same as a full scan's, up to the
+// rounding of the dot products that the certification tolerance already covers.
+constexpr int SMAP_R = 8;
+constexpr int SMAP_CELLS = 6 * SMAP_R * SMAP_R;
+template <typename T> VK_HD int smap_cell(V3<T> d) {
+  const T ax = vk_abs(d.x), ay = vk_abs(d.y), az = vk_abs(d.z);
+  int k; T m, u, v;
+  if (ax >= ay && ax >= az) { k = 0; m = d.x; u = d.y; v = d.z; }
+  else if (ay >= az) { k = 1; m = d.y; u = d.z; v = d.x; }
+  else { k = 2; m = d.z; u = d.x; v = d.y; }
+  const T am = vk_abs(m);
+  if (!(am > T(0))) return -1;
+  const T inv = T(1) / am;
+  int iu = (int)((u * inv + T(1)) * T(SMAP_R / 2)), iv = (int)((v * inv + T(1)) * T(SMAP_R / 2));
+  iu = iu < 0 ? 0 : (iu > SMAP_R - 1 ? SMAP_R - 1 : iu);
+  iv = iv < 0 ? 0 : (iv > SMAP_R - 1 ? SMAP_R - 1 : iv);
+  return ((2 * k + (m < T(0) ? 1 : 0)) * SMAP_R + iu) * SMAP_R + iv;
+}
+// support vertex through the map (cells: offset << 8 | count into ids; ids: local vertex numbers)
+template <typename T>
+VK_HD int support_mapped(const Vtx<T> *__restrict__ v, int nvert, const uint32_t *__restrict__ cells, const uint8_t *__restrict__ ids, V3<T> d) {
+  const int c = smap_cell(d);
+  int bi = 0;
+  if (c < 0) {
+    T best = v[0].x * d.x + v[0].y * d.y + v[0].z * d.z;
+    for (int i = 1; i < nvert; i++) { const T t = v[i].x * d.x + v[i].y * d.y + v[i].z * d.z; if (t > best) { best = t; bi = i; } }
+    return bi;
+  }
+  const uint32_t e = cells[c];
+  const uint8_t *id = ids + (e >> 8);
+  const int n = (int)(e & 255u);
+  bi = id[0];
+  T best = v[bi].x * d.x + v[bi].y * d.y + v[bi].z * d.z;
+  for (int k = 1; k < n; k++) {
+    const int i = id[k];
+    const T t = v[i].x * d.x + v[i].y * d.y + v[i].z * d.z;
+    if (t > best) { best = t; bi = i; }
+  }
+  return bi;
 }
 
 // Hill-climbing support on the hull's vertex graph: from `start`, move to the best strictly

@@ -85,6 +85,8 @@ struct KArgs {
   // small launches (vk_row.cuh): row_kernel takes launches of at most rowk_max rows, validity_kernel the rest
   // (both are enqueued when only the device knows the row count; -1: no such dispatch)
   long long rowk_max;
+  // support maps (vk_core.cuh): global memory, read through L1
+  const uint32_t *smap_cells; const uint8_t *smap_ids;
 };
 
 // counters layout
@@ -305,11 +307,15 @@ constexpr int GRP_SMALL = VK_GRP_SMALL;  // ... of the small-batch instance: an 
 template <int G>
 __device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const Vtx<float> *__restrict__ verts,
                                                   const uint16_t *__restrict__ adjs, const uint8_t *__restrict__ adj,
-                                                  V3<float> d, int gl, unsigned gmask, int &warm) {
+                                                  V3<float> d, int gl, unsigned gmask, int &warm,
+                                                  const uint32_t *__restrict__ smap_cells = nullptr, const uint8_t *__restrict__ smap_ids = nullptr) {
   if (s.kind == SK_CYL) return support_cyl(s, d);
   const Vtx<float> *__restrict__ v = verts + s.vadr;
   int bi = 0;
-  if (s.graph) {
+  if (smap_cells && s.map >= 0) {
+    // support map: one cell, a handful of candidate vertices (every lane of a group reads the same ones)
+    bi = support_mapped(v, s.nvert, smap_cells + s.map, smap_ids, d);
+  } else if (s.graph) {
     // hill-climbing on the hull graph; the lanes of the group split each neighbour list
     const uint16_t *__restrict__ as = adjs + s.vadr;
     bi = warm >= 0 ? warm : hill_start(s, d);

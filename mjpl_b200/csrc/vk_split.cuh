@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
               if (pr.kind == PK_PLANE) {
                 const Shape<float> &Bs = *SB;
                 int cold = -1;
-                v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support<1>(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, cold); });
+                v = plane_classify(*SA, Bs, PB, R, [&](V3<float> d) { return group_support<1>(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, cold, a.smap_cells, a.smap_ids); });
               } else {
                 v = segseg_item(*SA, *SB, s_verts, PA, PB, R);
               }
@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
     if (have) {
       const Shape<float> &As = *SA, &Bs = *SB;
       const int v = gjk_step_impl(
-          gs, rel, R, [&](V3<float> d) { return group_support<1>(As, s_verts, s_adjs, s_adj, d, gl, gmask, wa); },
-          [&](V3<float> d) { return group_support<1>(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, wb); });
+          gs, rel, R, [&](V3<float> d) { return group_support<1>(As, s_verts, s_adjs, s_adj, d, gl, gmask, wa, a.smap_cells, a.smap_ids); },
+          [&](V3<float> d) { return group_support<1>(Bs, s_verts, s_adjs, s_adj, d, gl, gmask, wb, a.smap_cells, a.smap_ids); });
       if (v >= 0) {
         if (v == V_PEN) mark_contact(a, row);
         else if (v == V_UNC) mark_uncertain(a, row, pidx);

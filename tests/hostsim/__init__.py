@@ -58,6 +58,7 @@ def lib():
         L.hs_pair_verdict.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.hs_check_pipe.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p]
         L.hs_min_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
+        L.hs_smap_check.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
         L.hs_bounds_check.argtypes = [C.c_void_p]
         L.hs_bounds_check.restype = C.c_double
         L.hs_segseg_check.argtypes = [C.c_int, C.c_uint64]
@@ -125,6 +126,12 @@ class HostSim:
         dist = np.zeros(len(q)); pair = np.zeros(len(q), np.int32)
         lib().hs_min_distance(self._h, q.ctypes.data, len(q), far_cap, dist.ctypes.data, pair.ctypes.data)
         return dist, pair
+
+    def smap_check(self, ndir=4000, seed=2):
+        """support maps vs full scans -> (mapped shapes, largest shortfall of the mapped support value, mean candidates per query)"""
+        worst, avg = C.c_double(0), C.c_double(0)
+        n = lib().hs_smap_check(self._h, ndir, seed, C.byref(worst), C.byref(avg))
+        return n, worst.value, avg.value
 
     def bounds_check(self):
         """largest distance by which a vertex sticks out of its bounding capsule / group sphere (<= 0: contained)"""

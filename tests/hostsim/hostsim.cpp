@@ -431,3 +431,34 @@ extern "C" void hs_min_distance(Sim *s, const float *q, int64_t n, double far_ca
     dist[r] = best; pair[r] = bp;
   }
 }
+
+// support maps: for every mapped hull and `ndir` directions (random, near-axis, near cell borders) the
+// mapped support VALUE against the full scan's, in fp32 as the device computes it.  Returns the number
+// of mapped shapes; *worst = largest shortfall of the mapped value (0 = always the same maximum);
+// *avg_candidates = mean candidates scanned per query.
+extern "C" int hs_smap_check(Sim *s, int ndir, uint64_t seed, double *worst, double *avg_candidates) {
+  const auto &H = s->H;
+  int nmapped = 0;
+  long long cand = 0, queries = 0;
+  *worst = 0;
+  for (size_t k = 0; k < H.shapes.size(); k++) {
+    const Shape<float> &sh = s->s32[k];
+    if (sh.kind != SK_VERTS || sh.map < 0) continue;
+    nmapped++;
+    const Vtx<float> *v = s->v32.data() + sh.vadr;
+    for (int i = 0; i < ndir; i++) {
+      V3<float> d = mk<float>(sweep_value(seed, i, 0, -1.f, 1.f), sweep_value(seed, i, 1, -1.f, 1.f), sweep_value(seed, i, 2, -1.f, 1.f));
+      if (i % 4 == 1) { d.x *= 1e-4f; }                                       // near an axis plane
+      if (i % 4 == 2) { d.y = d.x * (1.f + 1e-6f * (float)(i % 7 - 3)); }       // near a face boundary of the cube map
+      if (i % 4 == 3) { const float q = 0.25f * (float)(i % 9 - 4); d.x = 1.f; d.y = q + 1e-7f * (float)(i % 5 - 2); }  // on cell borders
+      const int c = smap_cell(d);
+      if (c >= 0) { cand += (long long)(H.smap_cells[sh.map + c] & 255u); queries++; }
+      const int bi = support_mapped(v, sh.nvert, H.smap_cells.data() + sh.map, H.smap_ids.data(), d);
+      const V3<float> full = support_verts(v, sh.nvert, d);
+      const double gap = (double)dot(full, d) - (double)(v[bi].x * d.x + v[bi].y * d.y + v[bi].z * d.z);
+      if (gap > *worst) *worst = gap;
+    }
+  }
+  *avg_candidates = queries ? (double)cand / (double)queries : 0.0;
+  return nmapped;
+}

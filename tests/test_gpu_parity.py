@@ -340,9 +340,11 @@ def test_single_kernel_and_two_kernel_pipeline_agree(monkeypatch):
     Q = rows(model, 60_000, 31)
     E0, E1 = rows(model, 1500, 32), rows(model, 1500, 33)
     results = {}
-    for name, env in (("single", {"MJB_SPLIT": "0"}), ("split", {"MJB_SPLIT": "1"}), ("tiny_bins", {"MJB_SPLIT": "1", "MJB_BIN_CAP": "64"}),
-                      ("tiny_l0", {"MJB_SPLIT": "1", "MJB_L0_CAP": "5000"})):   # level-0 list overflows: whole rows go to fp64
-        for k in ("MJB_SPLIT", "MJB_BIN_CAP", "MJB_L0_CAP"):
+    for name, env in (("single", {"MJB_SPLIT": "0", "MJB_ROWK_ROWS": "0"}), ("split", {"MJB_SPLIT": "1"}), ("tiny_bins", {"MJB_SPLIT": "1", "MJB_BIN_CAP": "64"}),
+                      ("tiny_l0", {"MJB_SPLIT": "1", "MJB_L0_CAP": "5000"}),    # level-0 list overflows: whole rows go to fp64
+                      ("no_maps", {"MJB_SPLIT": "1", "MJB_SMAP": "0"}),         # narrow phase scans whole hulls instead of support maps
+                      ("row_kernel", {"MJB_SPLIT": "0", "MJB_ROWK_ROWS": "100000000"})):   # one warp per row for every launch
+        for k in ("MJB_SPLIT", "MJB_BIN_CAP", "MJB_L0_CAP", "MJB_SMAP", "MJB_ROWK_ROWS"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
@@ -350,7 +352,7 @@ def test_single_kernel_and_two_kernel_pipeline_agree(monkeypatch):
         ve, fb = eng.valid_edges(E0, E1, 0.05, want_first_bad=True)
         results[name] = (eng.valid_configs(Q), eng.valid_configs(Q, 2), ve, fb, eng.sweep(5, 100, 40_000).cpu().numpy())
         eng.close()
-    for name in ("split", "tiny_bins", "tiny_l0"):
+    for name in ("split", "tiny_bins", "tiny_l0", "no_maps", "row_kernel"):
         for got, want in zip(results[name], results["single"]):
             np.testing.assert_array_equal(np.asarray(got), np.asarray(want))
     orc = oracle.Oracle(model, allowed)
