@@ -270,7 +270,7 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
   for (int r = 0; r <= H.nrounds; r++) k.round_start[r] = H.round_start[r];
   for (int r = 0; r < H.nrounds; r++) k.round_gjk[r] = H.round_gjk[r];
   k.pose_scratch = m->d_pose; k.counters = m->d_counters;
-  for (int sl = 0; sl < MAX_BODY; sl++) k.slot_group[sl] = H.slot_group[sl];
+  for (int sl = 0; sl < MAX_BODY; sl++) { k.slot_group_adr[sl] = H.slot_group_adr[sl]; k.slot_group_num[sl] = H.slot_group_num[sl]; }
   for (int g = 0; g < H.ngroup_moving; g++) for (int a = 0; a < 3; a++) k.group_c[g][a] = (float)H.group_c[g][a];
   k.gpairs = m->d_gpairs; k.sgroups = m->d_sgroups; k.gp_member = m->d_gp_member;
   k.smap_cells = m->d_smap_cells; k.smap_ids = m->d_smap_ids;

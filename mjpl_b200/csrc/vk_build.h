@@ -45,7 +45,7 @@ struct HostModel {
   std::vector<uint8_t> smap_ids;
   // cull groups (vk_pipe.cuh): moving bodies that carry shapes, and every world-fixed shape by itself
   int ngroup_moving = 0;
-  int slot_group[MAX_BODY];              // pose slot -> moving group or -1
+  int slot_group_adr[MAX_BODY], slot_group_num[MAX_BODY];   // pose slot -> its moving groups (usually one; none if it carries no shape)
   double group_c[MAX_GROUP][3];          // bounding-sphere centre of a moving group, body frame
   double group_r[MAX_GROUP] = {0};       // its radius (covers the swept radii of the member shapes)
   std::vector<StaticGroup> static_groups;
@@ -315,28 +315,25 @@ template <typename T> inline Shape<T> convert_shape(const Shape<double> &s) {
 // shape pairs, each of which then faces the bounding-capsule test and the OBB test.
 inline bool build_groups(HostModel &H) {
   const double slack = 1e-4;
-  for (int s = 0; s < MAX_BODY; s++) H.slot_group[s] = -1;
+  for (int s = 0; s < MAX_BODY; s++) { H.slot_group_adr[s] = 0; H.slot_group_num[s] = 0; }
   H.ngroup_moving = 0;
-  for (int sl = 0; sl < H.nslot; sl++) {
-    if (H.slot_shape_num[sl] == 0) continue;
-    const int g = H.ngroup_moving++;
-    H.slot_group[sl] = g;
-    const int s0 = H.slot_shape_adr[sl], s1 = s0 + H.slot_shape_num[sl];
-    // radius needed at centre c: the farthest vertex (+ swept radius) of any member shape
-    auto radius_at = [&](const double *c) {
-      double r = 0;
+  // bounding sphere of the shapes [s0, s1) (all on one body): centre by a shrinking axis search, radius =
+  // farthest vertex (+ swept radius) of any member
+  auto fit_group = [&](int s0, int s1, double *c, double &r) {
+    auto radius_at = [&](const double *cc) {
+      double rr = 0;
       for (int k = s0; k < s1; k++) {
         const Shape<double> &sh = H.shapes[k];
         if (sh.kind == SK_VERTS) {
           for (int i = 0; i < sh.nvert; i++) {
             const Vtx<double> &v = H.verts[sh.vadr + i];
-            r = std::max(r, sqrt((v.x - c[0]) * (v.x - c[0]) + (v.y - c[1]) * (v.y - c[1]) + (v.z - c[2]) * (v.z - c[2])) + sh.radius);
+            rr = std::max(rr, sqrt((v.x - cc[0]) * (v.x - cc[0]) + (v.y - cc[1]) * (v.y - cc[1]) + (v.z - cc[2]) * (v.z - cc[2])) + sh.radius);
           }
         } else {
-          r = std::max(r, sqrt((sh.bc[0] - c[0]) * (sh.bc[0] - c[0]) + (sh.bc[1] - c[1]) * (sh.bc[1] - c[1]) + (sh.bc[2] - c[2]) * (sh.bc[2] - c[2])) + sh.brad);
+          rr = std::max(rr, sqrt((sh.bc[0] - cc[0]) * (sh.bc[0] - cc[0]) + (sh.bc[1] - cc[1]) * (sh.bc[1] - cc[1]) + (sh.bc[2] - cc[2]) * (sh.bc[2] - cc[2])) + sh.brad);
         }
       }
-      return r;
+      return rr;
     };
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int k = s0; k < s1; k++)
@@ -344,9 +341,9 @@ inline bool build_groups(HostModel &H) {
         lo[a] = std::min(lo[a], H.shapes[k].bc[a] - H.shapes[k].brad);
         hi[a] = std::max(hi[a], H.shapes[k].bc[a] + H.shapes[k].brad);
       }
-    double c[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
-    double r = radius_at(c);
-    for (int it = 0; it < 300; it++) {   // shrink: small random-free moves along the axes while they help
+    for (int a = 0; a < 3; a++) c[a] = 0.5 * (lo[a] + hi[a]);
+    r = radius_at(c);
+    for (int it = 0; it < 300; it++) {   // shrink: moves along the axes while they help
       const double step = 0.25 * r / (1 + it * 0.1);
       bool moved = false;
       for (int a = 0; a < 3 && !moved; a++)
@@ -354,12 +351,32 @@ inline bool build_groups(HostModel &H) {
           double c2[3] = {c[0], c[1], c[2]};
           c2[a] += sg * step;
           const double r2 = radius_at(c2);
-          if (r2 < r) { r = r2; memcpy(c, c2, sizeof c); moved = true; }
+          if (r2 < r) { r = r2; memcpy(c, c2, sizeof(double) * 3); moved = true; }
         }
     }
-    for (int a = 0; a < 3; a++) H.group_c[g][a] = c[a];
-    H.group_r[g] = r * (1 + 1e-6) + 1e-6;   // covers the fp32 rounding of centre and vertices
-    for (int k = s0; k < s1; k++) H.shapes[k].group = g;
+  };
+  for (int sl = 0; sl < H.nslot; sl++) {
+    if (H.slot_shape_num[sl] == 0) continue;
+    const int s0 = H.slot_shape_adr[sl], s1 = s0 + H.slot_shape_num[sl];
+    double c[3], r;
+    fit_group(s0, s1, c, r);
+    // A body whose shapes are spread out (Franka link5: three meshes along the link, union sphere 0.17 m
+    // against 0.08-0.10 m for the members) makes a useless group: its pairs survive level 0 all the time
+    // and each survival expands into every member pair.  Such a body gets one group per shape instead.
+    double rmax = 0;
+    for (int k = s0; k < s1; k++) rmax = std::max(rmax, H.shapes[k].brad);
+    const bool split = (s1 - s0) > 1 && r > 1.4 * rmax && H.ngroup_moving + (s1 - s0) <= MAX_GROUP;
+    H.slot_group_adr[sl] = H.ngroup_moving;
+    for (int k0 = s0; k0 < s1; k0 = split ? k0 + 1 : s1) {
+      const int k1 = split ? k0 + 1 : s1;
+      if (split) fit_group(k0, k1, c, r);
+      if (H.ngroup_moving >= MAX_GROUP) { H.err = "too many cull groups"; return false; }
+      const int g = H.ngroup_moving++;
+      H.slot_group_num[sl]++;
+      for (int a = 0; a < 3; a++) H.group_c[g][a] = c[a];
+      H.group_r[g] = r * (1 + 1e-6) + 1e-6;   // covers the fp32 rounding of centre and vertices
+      for (int k = k0; k < k1; k++) H.shapes[k].group = g;
+    }
   }
   H.static_groups.clear();
   for (size_t k = (size_t)H.nmoving_shapes; k < H.shapes.size(); k++) {
@@ -441,8 +458,8 @@ inline bool build_groups(HostModel &H) {
       for (int k = 0; k < H.nslot; k++) {
         int ps = fk32.body_parent[k];
         P[k] = fk_body(fk32, k, ps < 0 ? ident : P[ps], q);
-        const int g = H.slot_group[k];
-        if (g >= 0) cen[g] = P[k].p + qrot(P[k].q, mk<float>((float)H.group_c[g][0], (float)H.group_c[g][1], (float)H.group_c[g][2]));
+        for (int g = H.slot_group_adr[k]; g < H.slot_group_adr[k] + H.slot_group_num[k]; g++)
+          cen[g] = P[k].p + qrot(P[k].q, mk<float>((float)H.group_c[g][0], (float)H.group_c[g][1], (float)H.group_c[g][2]));
       }
       for (const GroupPair &g : H.group_pairs)
         if (group_pair_near(g, cen[g.ga], g.kind == GK_SPHERE ? cen[g.gb] : cen[g.ga],

@@ -75,7 +75,7 @@ struct KArgs {
   unsigned long long bin_off[NBIN], bin_capv[NBIN];   // start and capacity of each bin's region
   uint32_t *row_flags;                  // 1 byte per row (bit 0: queued for whole-row fp64 re-evaluation)
   // cull groups (vk_pipe.cuh)
-  int slot_group[MAX_BODY];             // pose slot -> moving group or -1
+  int slot_group_adr[MAX_BODY], slot_group_num[MAX_BODY];   // pose slot -> its moving groups
   float group_c[MAX_GROUP][3];          // bounding-sphere centre of a moving group, body frame
   const GroupPair *gpairs; const StaticGroup *sgroups; const uint16_t *gp_member;
   int ngpair, nsgroup, ngroup_moving, nmember;

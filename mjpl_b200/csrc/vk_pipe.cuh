@@ -189,8 +189,7 @@ __global__ void __launch_bounds__(PIPE_FK_THREADS, 4) fk_cull_kernel(const __gri
         float4 *b = reinterpret_cast<float4 *>(a.pose8 + ((size_t)row * a.nslot + s) * 8);
         b[0] = make_float4(B.p.x, B.p.y, B.p.z, B.q.w);
         b[1] = make_float4(B.q.x, B.q.y, B.q.z, 0.f);
-        const int g = a.slot_group[s];
-        if (g >= 0) {
+        for (int g = a.slot_group_adr[s]; g < a.slot_group_adr[s] + a.slot_group_num[s]; g++) {
           const V3<float> c = B.p + qrot(B.q, mk<float>(a.group_c[g][0], a.group_c[g][1], a.group_c[g][2]));
           float *cc = cen + g * 96 + lane;
           cc[0] = c.x; cc[32] = c.y; cc[64] = c.z;

@@ -152,8 +152,7 @@ __global__ void __launch_bounds__(ROWK_THREADS, 2) row_kernel(const __grid_const
           prev = B; prev_slot = s;
           float *b = wpose + s * 8;
           b[0] = B.p.x; b[1] = B.p.y; b[2] = B.p.z; b[3] = B.q.w; b[4] = B.q.x; b[5] = B.q.y; b[6] = B.q.z;
-          const int g = a.slot_group[s];
-          if (g >= 0) {
+          for (int g = a.slot_group_adr[s]; g < a.slot_group_adr[s] + a.slot_group_num[s]; g++) {
             const V3<float> c = B.p + qrot(B.q, mk<float>(a.group_c[g][0], a.group_c[g][1], a.group_c[g][2]));
             wcen[g * 4] = c.x; wcen[g * 4 + 1] = c.y; wcen[g * 4 + 2] = c.z;
           }

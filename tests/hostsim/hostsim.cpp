@@ -328,8 +328,8 @@ extern "C" void hs_check_pipe(Sim *s, const float *q, int64_t n, uint32_t flags,
       for (int k = 0; k < H.nslot; k++) {
         int ps = s->fk32.body_parent[k];
         P[k] = fk_body(s->fk32, k, ps < 0 ? ident : P[ps], qr);
-        const int g = H.slot_group[k];
-        if (g >= 0) cen[g] = P[k].p + qrot(P[k].q, mk<float>((float)H.group_c[g][0], (float)H.group_c[g][1], (float)H.group_c[g][2]));
+        for (int g = H.slot_group_adr[k]; g < H.slot_group_adr[k] + H.slot_group_num[k]; g++)
+          cen[g] = P[k].p + qrot(P[k].q, mk<float>((float)H.group_c[g][0], (float)H.group_c[g][1], (float)H.group_c[g][2]));
       }
       bool pen = false, unc = false;
       for (const GroupPair &g : H.group_pairs) {
@@ -461,4 +461,42 @@ extern "C" int hs_smap_check(Sim *s, int ndir, uint64_t seed, double *worst, dou
   }
   *avg_candidates = queries ? (double)cand / (double)queries : 0.0;
   return nmapped;
+}
+
+// per group pair (level 0 of the pipeline): how often it survives on the given rows, its kind and its number of
+// member shape pairs, and how many of its members then survive the capsule and the OBB culls: out[g*5 + {0..4}] =
+// survivals, members, capsule survivors, OBB survivors, kind
+extern "C" int hs_group_census(Sim *s, const float *q, int64_t n, int64_t *out, int32_t *ga, int32_t *gb) {
+  const auto &H = s->H;
+  Pose<float> P[MAX_BODY], ident;
+  ident.p = mk<float>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
+  const float slack = 1e-4f;
+  for (size_t g = 0; g < H.group_pairs.size(); g++) { out[g * 5 + 1] = H.group_pairs[g].n; out[g * 5 + 4] = H.group_pairs[g].kind; ga[g] = H.group_pairs[g].ga; gb[g] = H.group_pairs[g].gb; }
+  for (int64_t r = 0; r < n; r++) {
+    const float *qr = q + r * H.nq;
+    V3<float> cen[MAX_GROUP];
+    for (int k = 0; k < H.nslot; k++) {
+      int ps = s->fk32.body_parent[k];
+      P[k] = fk_body(s->fk32, k, ps < 0 ? ident : P[ps], qr);
+        for (int g = H.slot_group_adr[k]; g < H.slot_group_adr[k] + H.slot_group_num[k]; g++)
+          cen[g] = P[k].p + qrot(P[k].q, mk<float>((float)H.group_c[g][0], (float)H.group_c[g][1], (float)H.group_c[g][2]));
+    }
+    for (size_t gi = 0; gi < H.group_pairs.size(); gi++) {
+      const GroupPair &g = H.group_pairs[gi];
+      if (!group_pair_near(g, cen[g.ga], g.kind == GK_SPHERE ? cen[g.gb] : cen[g.ga], g.kind == GK_SPHERE ? nullptr : &H.static_groups[g.gb])) continue;
+      out[gi * 5 + 0]++;
+      for (int i = 0; i < g.n; i++) {
+        const Pair pr = H.pairs[H.gp_member[g.first + i]];
+        const Shape<float> &A = s->s32[pr.sa], &B = s->s32[pr.sb];
+        const Pose<float> &PA = A.slot < 0 ? ident : P[A.slot];
+        const Pose<float> &PB = B.slot < 0 ? ident : P[B.slot];
+        const float margin = pr.rsum - swept_radius(A) - swept_radius(B);
+        if (pr.kind != PK_SEGSEG && capsule_cull(pr, A, B, PA, PB, margin + slack)) continue;
+        out[gi * 5 + 2]++;
+        if ((pr.flags & PF_OBB) && midphase_cull(pr, A, B, PA, PB, margin, slack)) continue;
+        out[gi * 5 + 3]++;
+      }
+    }
+  }
+  return (int)H.group_pairs.size();
 }
