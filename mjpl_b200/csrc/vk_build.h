@@ -19,6 +19,12 @@
 
 namespace vkb {
 
+#ifndef VK_HILL
+#define VK_HILL_HOST 0
+#else
+#define VK_HILL_HOST VK_HILL
+#endif
+
 using namespace vk;
 
 enum { G_PLANE = 0, G_HFIELD = 1, G_SPHERE = 2, G_CAPSULE = 3, G_ELLIPSOID = 4, G_CYLINDER = 5, G_BOX = 6, G_MESH = 7 };
@@ -671,6 +677,7 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
     std::vector<std::vector<uint8_t>> lists(H.verts.size());
     for (auto &sh : H.shapes) {
       sh.graph = 0;
+      if (!VK_HILL_HOST) continue;
       if (sh.kind != SK_VERTS || d->geom_type[sh.geom] != G_MESH || !d->mesh_graph || !d->mesh_graphadr) continue;
       const int id = d->geom_dataid[sh.geom];
       const int ga = d->mesh_graphadr[id];

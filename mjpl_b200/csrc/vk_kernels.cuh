@@ -273,6 +273,9 @@ __device__ __forceinline__ void warp_push(bool want, uint32_t item, uint32_t *qu
 #ifndef VK_GRP
 #define VK_GRP 1
 #endif
+#ifndef VK_HILL
+#define VK_HILL 0   // hill-climbing support queries on the hull graph: compiled out (slower than scanning on hulls of <= 152
+#endif              // vertices, superseded by the support maps, and its code costs instruction-cache misses in every kernel)
 #ifndef VK_SCAN_UNROLL
 #define VK_SCAN_UNROLL 4
 #endif
@@ -304,7 +307,7 @@ constexpr int GRP_SMALL = VK_GRP_SMALL;  // ... of the small-batch instance: an 
                                          // shortens the dependent chain a small launch waits for (planner extends)
 
 // `warm` carries the last support vertex of this shape within one GJK run (-1 = cold start).
-template <int G>
+template <int G, bool HILL = (VK_HILL != 0)>
 __device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const Vtx<float> *__restrict__ verts,
                                                   const uint16_t *__restrict__ adjs, const uint8_t *__restrict__ adj,
                                                   V3<float> d, int gl, unsigned gmask, int &warm,
@@ -315,7 +318,7 @@ __device__ __forceinline__ V3<float> group_support(const Shape<float> &s, const 
   if (smap_cells && s.map >= 0) {
     // support map: one cell, a handful of candidate vertices (every lane of a group reads the same ones)
     bi = support_mapped(v, s.nvert, smap_cells + s.map, smap_ids, d);
-  } else if (s.graph) {
+  } else if (HILL && s.graph) {
     // hill-climbing on the hull graph; the lanes of the group split each neighbour list
     const uint16_t *__restrict__ as = adjs + s.vadr;
     bi = warm >= 0 ? warm : hill_start(s, d);

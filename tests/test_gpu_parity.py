@@ -235,6 +235,7 @@ def test_full_size_sweep_properties():
     assert st["uncertain_rows"] < 0.05 * st["rows"]
 
 
+@pytest.mark.skip(reason="hill-climbing support is compiled out (VK_HILL=0): slower than scanning on these hulls, superseded by support maps")
 def test_hill_climbing_support_path_on_device(monkeypatch):
     """The hull-graph (hill-climbing) support query is switched on only for large hulls; force it
     on for the Franka meshes and require the same parity."""
