@@ -30,6 +30,9 @@ using namespace vk;
 enum { G_PLANE = 0, G_HFIELD = 1, G_SPHERE = 2, G_CAPSULE = 3, G_ELLIPSOID = 4, G_CYLINDER = 5, G_BOX = 6, G_MESH = 7 };
 enum { J_FREE = 0, J_BALL = 1, J_SLIDE = 2, J_HINGE = 3 };
 
+// direction grid of a hull for the inscribed-radius bound below
+struct HullDirs { std::vector<V3<double>> c0, u0; std::vector<double> delta; };
+
 struct HostModel {
   int nq = 0, nbody = 0, njnt = 0, ngeom = 0, nslot = 0;
   FkTables<double> fk;                  // indexed by SLOT (moving bodies only)
@@ -49,6 +52,8 @@ struct HostModel {
   // support maps (vk_core.cuh): per hull 6 x R x R cells (offset << 8 | count) and the candidate vertex ids
   std::vector<uint32_t> smap_cells;
   std::vector<uint8_t> smap_ids;
+  std::vector<struct HullDirs> hull_dirs;   // per shape, build time only (inner shapes); cleared by build_groups
+  double group_rin_any[MAX_GROUP] = {0};    // census only: largest inner ball of a member shape around the group centre
   // cull groups (vk_pipe.cuh): moving bodies that carry shapes, and every world-fixed shape by itself
   int ngroup_moving = 0;
   int slot_group_adr[MAX_BODY], slot_group_num[MAX_BODY];   // pose slot -> its moving groups (usually one; none if it carries no shape)
@@ -281,6 +286,139 @@ inline void fit_capsule(Shape<double> &s, const std::vector<Vtx<double>> &verts)
   }
 }
 
+
+// ---- inner shapes: the certain-contact shortcut ------------------------------------------------------
+// A ball B(c, r) lies inside the hull of the vertices iff h(d) - c.d >= r for every unit direction d
+// (h = support function).  The directions are covered by the cells of a cube map (centre c0, every
+// direction of the cell within delta of c0, u0 = a support vertex for c0); for d in the cell
+//   h(d) - c.d >= (u0 - c).d >= (u0 - c).c0 - |u0 - c| delta,
+// so the minimum of the right-hand side over the cells is a rigorous lower bound of the inscribed radius
+// around c.  It is concave in c (a minimum of concave functions), which the searches below rely on.
+inline void hull_dirs_build(const Vtx<double> *v, int n, HullDirs &D, int R = 32) {
+  D.c0.clear(); D.u0.clear(); D.delta.clear();
+  for (int f = 0; f < 6; f++) {
+    const int k = f / 2;
+    const double sg = (f % 2) ? -1.0 : 1.0;
+    for (int iu = 0; iu < R; iu++)
+      for (int iv = 0; iv < R; iv++) {
+        auto dir = [&](double u, double w) {
+          double d[3];
+          d[k] = sg; d[(k + 1) % 3] = u; d[(k + 2) % 3] = w;
+          const double nn = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+          return mk<double>(d[0] / nn, d[1] / nn, d[2] / nn);
+        };
+        const double u0 = -1 + 2.0 * iu / R, u1 = -1 + 2.0 * (iu + 1) / R, w0 = -1 + 2.0 * iv / R, w1 = -1 + 2.0 * (iv + 1) / R;
+        const V3<double> c = dir(0.5 * (u0 + u1), 0.5 * (w0 + w1));
+        double delta = 0;
+        for (int a = 0; a < 2; a++)
+          for (int b = 0; b < 2; b++) {
+            const V3<double> q = dir(a ? u1 : u0, b ? w1 : w0) - c;
+            delta = std::max(delta, sqrt(dot(q, q)));
+          }
+        int best = 0; double hb = -1e300;
+        for (int i = 0; i < n; i++) { const double h = v[i].x * c.x + v[i].y * c.y + v[i].z * c.z; if (h > hb) { hb = h; best = i; } }
+        D.c0.push_back(c); D.u0.push_back(mk<double>(v[best].x, v[best].y, v[best].z)); D.delta.push_back(delta * 1.02 + 1e-6);
+      }
+  }
+}
+inline double inscribed_radius(const HullDirs &D, V3<double> c) {
+  double r = 1e300;
+  for (size_t i = 0; i < D.c0.size(); i++) {
+    const V3<double> w = D.u0[i] - c;
+    r = std::min(r, dot(w, D.c0[i]) - sqrt(dot(w, w)) * D.delta[i]);
+  }
+  return r;
+}
+// radius of the largest ball around c (shape frame) known to lie inside the shape; <= 0: none
+inline double inner_ball(const Shape<double> &s, const std::vector<Vtx<double>> &verts, const HullDirs *D, V3<double> c) {
+  if (s.kind == SK_CYL) {
+    const V3<double> e = c - mk<double>(s.c[0], s.c[1], s.c[2]), ax = mk<double>(s.ax[0], s.ax[1], s.ax[2]);
+    const double t = dot(e, ax);
+    const V3<double> pr = e - ax * t;
+    return std::min(s.radius - sqrt(dot(pr, pr)), s.halflen - fabs(t));
+  }
+  if (s.kind != SK_VERTS) return -1;
+  const Vtx<double> *v = verts.data() + s.vadr;
+  if (s.nvert <= 2) {
+    const double p[3] = {c.x, c.y, c.z}, a[3] = {v[0].x, v[0].y, v[0].z};
+    const double b[3] = {v[s.nvert - 1].x, v[s.nvert - 1].y, v[s.nvert - 1].z};
+    return s.radius - point_segment_dist(p, a, b);
+  }
+  if (!D || D->c0.empty()) return -1;
+  const double r = inscribed_radius(*D, c);
+  return r >= 0 ? r + s.radius : -1;
+}
+// the longest sub-segment m +- t u (0 <= t <= tmax) on which inner_ball >= target (bisection; inner_ball is concave)
+template <typename F> inline double inner_extent(F ball, V3<double> m, V3<double> u, double tmax, double target, bool symmetric, int sign) {
+  auto ok = [&](double t) {
+    if (symmetric) return ball(m + u * t) >= target && ball(m - u * t) >= target;
+    return ball(m + u * (sign * t)) >= target;
+  };
+  if (ok(tmax)) return tmax;
+  double lo = 0, hi = tmax;
+  for (int it = 0; it < 14; it++) { const double mid = 0.5 * (lo + hi); if (ok(mid)) lo = mid; else hi = mid; }
+  return lo;
+}
+// Inner capsule of a shape: centre of a large inscribed ball (pattern search from a few candidates), then for a
+// few radius factors the longest segment along the bounding capsule's axis; the largest volume wins.
+inline void fit_inner(Shape<double> &s, const std::vector<Vtx<double>> &verts, HullDirs &D) {
+  for (int k = 0; k < 3; k++) s.ia[k] = s.ib[k] = 0;
+  s.irad = 0;
+  if (s.kind == SK_CYL) {
+    const double r = std::min(s.radius, s.halflen), h = std::max(s.halflen - r, 0.0);
+    for (int k = 0; k < 3; k++) { s.ia[k] = s.c[k] - h * s.ax[k]; s.ib[k] = s.c[k] + h * s.ax[k]; }
+    s.irad = r;
+    return;
+  }
+  if (s.kind != SK_VERTS) return;
+  const Vtx<double> *v = verts.data() + s.vadr;
+  if (s.nvert <= 2) {
+    s.ia[0] = v[0].x; s.ia[1] = v[0].y; s.ia[2] = v[0].z;
+    s.ib[0] = v[s.nvert - 1].x; s.ib[1] = v[s.nvert - 1].y; s.ib[2] = v[s.nvert - 1].z;
+    s.irad = s.radius;
+    return;
+  }
+  hull_dirs_build(v, s.nvert, D);
+  auto ball = [&](V3<double> c) { return inner_ball(s, verts, &D, c); };
+  V3<double> cen = mk<double>(0, 0, 0), lo = mk<double>(1e300, 1e300, 1e300), hi = mk<double>(-1e300, -1e300, -1e300);
+  for (int i = 0; i < s.nvert; i++) {
+    cen = cen + mk<double>(v[i].x, v[i].y, v[i].z) * (1.0 / s.nvert);
+    lo.x = std::min(lo.x, v[i].x); lo.y = std::min(lo.y, v[i].y); lo.z = std::min(lo.z, v[i].z);
+    hi.x = std::max(hi.x, v[i].x); hi.y = std::max(hi.y, v[i].y); hi.z = std::max(hi.z, v[i].z);
+  }
+  const V3<double> cand[4] = {cen, (lo + hi) * 0.5, mk<double>(s.bc[0], s.bc[1], s.bc[2]),
+                              (mk<double>(s.ca[0], s.ca[1], s.ca[2]) + mk<double>(s.cb[0], s.cb[1], s.cb[2])) * 0.5};
+  V3<double> c = cand[0];
+  double r = -1e300;
+  for (const V3<double> &cc : cand) { const double rr = ball(cc); if (rr > r) { r = rr; c = cc; } }
+  double step = 0.25 * sqrt(dot(hi - lo, hi - lo));
+  for (int it = 0; it < 16; it++, step *= 0.6) {
+    for (int a = 0; a < 3; a++)
+      for (int sg = -1; sg <= 1; sg += 2) {
+        V3<double> c2 = c;
+        (a == 0 ? c2.x : (a == 1 ? c2.y : c2.z)) += sg * step;
+        const double r2 = ball(c2);
+        if (r2 > r) { r = r2; c = c2; }
+      }
+  }
+  if (!(r > 0)) return;
+  V3<double> a0 = c, b0 = c;
+  double best = 4.0 / 3.0 * M_PI * r * r * r, rbest = r;
+  if (s.caplen > 1e-9) {
+    const V3<double> u = (mk<double>(s.cb[0], s.cb[1], s.cb[2]) - mk<double>(s.ca[0], s.ca[1], s.ca[2])) * (1.0 / s.caplen);
+    const double fac[4] = {0.95, 0.85, 0.7, 0.55};
+    for (double f : fac) {
+      const double rr = f * r;
+      const double tp = inner_extent(ball, c, u, s.caplen, rr, false, +1), tm = inner_extent(ball, c, u, s.caplen, rr, false, -1);
+      const double vol = M_PI * rr * rr * (tp + tm) + 4.0 / 3.0 * M_PI * rr * rr * rr;
+      if (vol > best) { best = vol; rbest = rr; a0 = c - u * tm; b0 = c + u * tp; }
+    }
+  }
+  s.ia[0] = a0.x; s.ia[1] = a0.y; s.ia[2] = a0.z;
+  s.ib[0] = b0.x; s.ib[1] = b0.y; s.ib[2] = b0.z;
+  s.irad = rbest;
+}
+
 template <typename T> inline FkTables<T> convert_fk(const FkTables<double> &s) {
   FkTables<T> o; memset(&o, 0, sizeof o);
   o.nq = s.nq; o.nbody = s.nbody; o.njnt = s.njnt;
@@ -310,6 +448,9 @@ template <typename T> inline Shape<T> convert_shape(const Shape<double> &s) {
   // rounding the end points can move them by half an ulp: the radius absorbs it
   o.crad = (T)(s.crad * (1.0 + 2e-7) + (sizeof(T) == 4 ? 1e-6 : 0.0)); o.caplen = (T)s.caplen;
   o.map = s.map;
+  // inner capsule: rounding moves the end points by half an ulp, the radius gives that up (and a little more)
+  for (int k = 0; k < 3; k++) { o.ia[k] = (T)s.ia[k]; o.ib[k] = (T)s.ib[k]; }
+  o.irad = s.irad > 0 ? (T)(s.irad * (1.0 - 2e-7) - (sizeof(T) == 4 ? 1e-6 : 0.0)) : (T)0;
   return o;
 }
 
@@ -385,6 +526,7 @@ inline bool build_groups(HostModel &H) {
     }
   }
   H.static_groups.clear();
+  std::vector<double> tube_r(H.shapes.size(), 0.0);
   for (size_t k = (size_t)H.nmoving_shapes; k < H.shapes.size(); k++) {
     Shape<double> &sh = H.shapes[k];
     StaticGroup sg; memset(&sg, 0, sizeof sg);
@@ -396,35 +538,76 @@ inline bool build_groups(HostModel &H) {
       sg.inv_len2 = l2 > 1e-12 ? (float)(1.0 / l2) : 0.f;
       if (!(l2 > 1e-12)) sg.ab[0] = sg.ab[1] = sg.ab[2] = 0.f;
     }
+    // inner tube: a piece of the bounding capsule's segment, symmetric about its mid-point, and a radius such
+    // that the swept piece lies inside the shape
+    sg.th = -1.f;
+    tube_r[k] = 0;
+    if (sh.kind != SK_PLANE && sh.irad > 0) {
+      const HullDirs *D = k < H.hull_dirs.size() ? &H.hull_dirs[k] : nullptr;
+      auto ball = [&](V3<double> c) { return inner_ball(sh, H.verts, D, c); };
+      const V3<double> ca = mk<double>(sh.ca[0], sh.ca[1], sh.ca[2]), cb = mk<double>(sh.cb[0], sh.cb[1], sh.cb[2]);
+      const V3<double> m = (ca + cb) * 0.5;
+      const double rm = ball(m);
+      if (rm > 0) {
+        if (!(sh.caplen > 1e-9)) { sg.th = 1.f; tube_r[k] = rm; }
+        else {
+          const V3<double> u = (cb - ca) * (1.0 / sh.caplen);
+          double best = -1;
+          const double fac[5] = {0.98, 0.9, 0.75, 0.6, 0.45};
+          for (double f : fac) {
+            const double t = inner_extent(ball, m, u, 0.5 * sh.caplen, f * rm, true, 0);
+            const double vol = M_PI * f * rm * f * rm * 2 * t + 4.0 / 3.0 * M_PI * f * rm * f * rm * f * rm;
+            if (vol > best) { best = vol; tube_r[k] = f * rm; sg.th = (float)(t / sh.caplen * (1 - 1e-6)); }
+          }
+        }
+      }
+    }
     sh.group = H.ngroup_moving + (int)H.static_groups.size();
     H.static_groups.push_back(sg);
+  }
+  // inner ball of every moving shape around ITS GROUP'S centre (the point level 0 knows in the world frame)
+  std::vector<double> gin(H.shapes.size(), 0.0);
+  for (int g = 0; g < MAX_GROUP; g++) H.group_rin_any[g] = 0;
+  for (int k = 0; k < H.nmoving_shapes; k++) {
+    const Shape<double> &sh = H.shapes[k];
+    if (sh.group < 0 || !(sh.irad > 0)) continue;
+    const int g = sh.group;
+    gin[k] = inner_ball(sh, H.verts, (size_t)k < H.hull_dirs.size() ? &H.hull_dirs[k] : nullptr,
+                        mk<double>(H.group_c[g][0], H.group_c[g][1], H.group_c[g][2]));
+    H.group_rin_any[g] = std::max(H.group_rin_any[g], gin[k]);
   }
   // group pairs
   struct Key { int kind, ga, gb; };
   std::vector<Key> keys;
   std::vector<std::vector<uint16_t>> members;
-  std::vector<double> lims;
+  std::vector<double> lims, lims_in;
+  const double inner_safety = 1e-5;   // fp32 forward kinematics and centres: a few 1e-6 at arm's length
   for (size_t p = 0; p < H.pairs.size(); p++) {
     const Pair &pr = H.pairs[p];
     const Shape<double> &A = H.shapes[pr.sa], &B = H.shapes[pr.sb];
     if (A.slot < 0 && B.slot < 0) { H.err = "a pair of two world-fixed geoms survived the filters"; return false; }
     const double margin = H.pair_rsum64[p] - (A.kind == SK_VERTS ? A.radius : 0.0) - (B.kind == SK_VERTS ? B.radius : 0.0);
     Key k;
-    double lim;
+    double lim, lim_in = -1e30;   // lim_in: the pair's inner balls / tube around the centres level 0 uses
     if (A.slot >= 0 && B.slot >= 0) {
       k.kind = GK_SPHERE; k.ga = std::min(A.group, B.group); k.gb = std::max(A.group, B.group);
       lim = H.group_r[A.group] + H.group_r[B.group] + margin + slack;
+      if (gin[pr.sa] > 0 && gin[pr.sb] > 0) lim_in = gin[pr.sa] + gin[pr.sb] - inner_safety;
     } else {
       const Shape<double> &M = A.slot >= 0 ? A : B, &S = A.slot >= 0 ? B : A;
+      const int im = A.slot >= 0 ? pr.sa : pr.sb, is = A.slot >= 0 ? pr.sb : pr.sa;
       k.kind = S.kind == SK_PLANE ? GK_PLANE : GK_CAPSULE;
       k.ga = M.group; k.gb = S.group - H.ngroup_moving;
       lim = H.group_r[M.group] + (S.kind == SK_PLANE ? 0.0 : S.crad * (1 + 2e-7) + 1e-6) + margin + slack;
+      if (S.kind == SK_PLANE) { if (gin[im] > inner_safety) lim_in = gin[im] - inner_safety; }
+      else if (gin[im] > 0 && tube_r[is] > 0) lim_in = gin[im] + tube_r[is] - inner_safety;
     }
     size_t idx = 0;
     for (; idx < keys.size(); idx++) if (keys[idx].kind == k.kind && keys[idx].ga == k.ga && keys[idx].gb == k.gb) break;
-    if (idx == keys.size()) { keys.push_back(k); members.emplace_back(); lims.push_back(lim); }
+    if (idx == keys.size()) { keys.push_back(k); members.emplace_back(); lims.push_back(lim); lims_in.push_back(lim_in); }
     members[idx].push_back((uint16_t)p);
     lims[idx] = std::max(lims[idx], lim);
+    lims_in[idx] = std::max(lims_in[idx], lim_in);
   }
   std::vector<int> ord(keys.size());
   for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
@@ -437,10 +620,14 @@ inline bool build_groups(HostModel &H) {
   H.gp_kind_end[0] = H.gp_kind_end[1] = H.gp_kind_end[2] = 0;
   for (int i : ord) {
     GroupPair g; memset(&g, 0, sizeof g);
-    g.ga = (uint16_t)keys[i].ga; g.gb = (uint16_t)keys[i].gb; g.kind = (uint32_t)keys[i].kind;
+    g.ga = (uint16_t)keys[i].ga; g.gb = (uint16_t)keys[i].gb; g.kind = (uint8_t)keys[i].kind;
     if (H.gp_member.size() + members[i].size() > 65535) { H.err = "too many geom pairs"; return false; }
-    g.first = (uint16_t)H.gp_member.size(); g.n = (uint16_t)members[i].size();
+    if (members[i].size() > 255) { H.err = "too many geom pairs between two bodies"; return false; }
+    g.first = (uint16_t)H.gp_member.size(); g.n = (uint8_t)members[i].size();
     g.lim = (float)(lims[i] * (1 + 2e-7));
+    // sphere / capsule kinds compare squares: "none" is 0 there; the plane kind compares the signed height
+    const bool none = !(lims_in[i] > 0) || getenv("MJB_NO_INNER0");
+    g.lim_in = none ? (keys[i].kind == GK_PLANE ? -1e30f : 0.f) : (float)(lims_in[i] * (1 - 2e-7));
     for (uint16_t p : members[i]) H.gp_member.push_back(p);
     H.group_pairs.push_back(g);
     for (int k = keys[i].kind; k < 3; k++) H.gp_kind_end[k]++;
@@ -473,6 +660,7 @@ inline bool build_groups(HostModel &H) {
     }
     H.calib_l0_per_row = n0 / NCAL; H.calib_sub_per_row = nsub / NCAL;
   }
+  H.hull_dirs.clear(); H.hull_dirs.shrink_to_fit();
   return true;
 }
 
@@ -574,6 +762,7 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
   std::vector<int> geom_shape(d->ngeom, -1);
   std::vector<Shape<double>> tmp;
   std::vector<int> tmp_slot;
+  std::vector<HullDirs> tmp_dirs;
   auto make_shape = [&](int g) -> bool {
     if (geom_shape[g] >= 0) return true;
     Shape<double> s; memset(&s, 0, sizeof s);
@@ -634,6 +823,8 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
       for (int k = 0; k < 3; k++) { s.ca[k] = s.c[k] - s.halflen * s.ax[k]; s.cb[k] = s.c[k] + s.halflen * s.ax[k]; }
       s.crad = s.radius * (1 + 1e-9); s.caplen = 2 * s.halflen;
     }
+    tmp_dirs.emplace_back();
+    if (!getenv("MJB_NO_INNER")) fit_inner(s, H.verts, tmp_dirs.back());
     geom_shape[g] = (int)tmp.size();
     tmp.push_back(s);
     tmp_slot.push_back(s.slot);
@@ -655,6 +846,7 @@ inline bool build_host_model(const mjb_model_desc *d, HostModel &H) {
     newidx[order[i]] = (int)i;
     const Shape<double> &s = tmp[order[i]];
     H.shapes.push_back(s);
+    H.hull_dirs.push_back(std::move(tmp_dirs[order[i]]));
     if (s.slot >= 0) {
       if (H.slot_shape_num[s.slot] == 0) H.slot_shape_adr[s.slot] = (int)i;
       H.slot_shape_num[s.slot]++;

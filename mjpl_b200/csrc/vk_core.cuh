@@ -183,9 +183,11 @@ template <typename T> struct Shape {
   // crad (includes the swept radius); caplen == 0 marks a point-like capsule (a sphere)
   T ca[3], cb[3], crad, caplen;
   int map;         // support map of the hull (first cell in the cell table), -1: scan all vertices
-  int pad3[3];
+  // inner capsule: segment ia..ib swept by irad lies INSIDE the shape (same frame as the vertices; irad <= 0: none).
+  // Two shapes whose inner capsules overlap are certainly in contact -- no narrow phase needed.
+  T ia[3], ib[3], irad;
 };
-static_assert(sizeof(Shape<float>) == 192, "Shape<float> must stay a multiple of 16 bytes (cp.async.bulk granularity)");
+static_assert(sizeof(Shape<float>) == 208, "Shape<float> must stay a multiple of 16 bytes (cp.async.bulk granularity)");
 
 struct Pair {
   uint16_t sa, sb;  // shape indices (sa: plane if any; else the one with more vertices first)
@@ -774,35 +776,76 @@ struct GroupPair {
   uint16_t ga;      // moving group (index into the moving-group table = row of the centre array)
   uint16_t gb;      // GK_SPHERE: moving group; GK_CAPSULE / GK_PLANE: index into the static table
   uint16_t first;   // its shape pairs: member[first .. first + n)
-  uint16_t n;
+  uint8_t n, kind;
   float lim;        // radii + largest margin of the member pairs + slack (GK_PLANE: radius + margin + slack)
-  uint32_t kind;
+  float lim_in;     // > 0: the two groups' INNER radii around the same centres (a ball around a moving group's
+                    // centre that lies inside one of its shapes; the tube inside a world-fixed shape around its
+                    // segment).  Centres closer than this: the two shapes intersect, the row is certainly in contact.
 };
 static_assert(sizeof(GroupPair) == 16, "GroupPair is loaded as one 16-byte word");
 struct StaticGroup {   // world frame
   float a[3];          // GK_CAPSULE: segment start;   GK_PLANE: a point of the plane
   float inv_len2;      // GK_CAPSULE: 1 / |ab|^2 (0 for a point)
   float ab[3];         // GK_CAPSULE: segment vector;  GK_PLANE: unit normal
-  float pad;
+  float th;            // GK_CAPSULE: the shape's inner tube runs along the parameters |t - 0.5| <= th of the segment (< 0: none)
 };
 static_assert(sizeof(StaticGroup) == 32, "StaticGroup is loaded as two 16-byte words");
 constexpr int MAX_GROUP = MAX_BODY;
 
-// level-0 test of one group pair: false => no shape pair between the two groups can be in contact.
+// level-0 test of one group pair.  Returns 0: no shape pair between the two groups can be in contact;
+// 1: near (expand the group pair); 2: CERTAIN contact (the inner ball / tube of the two groups overlap).
 // cA: world centre of moving group ga; cB: world centre of moving group gb (GK_SPHERE only);
 // S: the static group (GK_CAPSULE / GK_PLANE).
-VK_HD bool group_pair_near(const GroupPair &g, V3<float> cA, V3<float> cB, const StaticGroup *S) {
+VK_HD int group_pair_test(const GroupPair &g, V3<float> cA, V3<float> cB, const StaticGroup *S) {
+  float d2;
   if (g.kind == GK_SPHERE) {
     const V3<float> d = cA - cB;
-    return dot(d, d) <= g.lim * g.lim;
+    d2 = dot(d, d);
+  } else {
+    const V3<float> e = cA - mk<float>(S->a[0], S->a[1], S->a[2]);
+    const V3<float> ab = mk<float>(S->ab[0], S->ab[1], S->ab[2]);
+    if (g.kind == GK_PLANE) {
+      const float h = dot(e, ab);
+      return h < g.lim_in ? 2 : (h <= g.lim ? 1 : 0);   // lim_in = inner radius of the moving group (-1e30: none)
+    }
+    float t = dot(e, ab) * S->inv_len2;
+    t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+    const V3<float> f = e - ab * t;
+    d2 = dot(f, f);
+    if (!(fabsf(t - 0.5f) <= S->th)) return d2 <= g.lim * g.lim ? 1 : 0;
   }
-  const V3<float> e = cA - mk<float>(S->a[0], S->a[1], S->a[2]);
-  const V3<float> ab = mk<float>(S->ab[0], S->ab[1], S->ab[2]);
-  if (g.kind == GK_PLANE) return dot(e, ab) <= g.lim;
-  float t = dot(e, ab) * S->inv_len2;
-  t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
-  const V3<float> f = e - ab * t;
-  return dot(f, f) <= g.lim * g.lim;
+  return d2 < g.lim_in * g.lim_in ? 2 : (d2 <= g.lim * g.lim ? 1 : 0);
+}
+VK_HD bool group_pair_near(const GroupPair &g, V3<float> cA, V3<float> cB, const StaticGroup *S) { return group_pair_test(g, cA, cB, S) != 0; }
+
+// certain contact of one shape pair from the inner capsules: true => the shapes intersect (distance < 0 <= margin)
+template <typename T>
+VK_HD bool inner_contact(const Pair &pr, const Shape<T> &A, const Shape<T> &B, const Pose<T> &PA, const Pose<T> &PB) {
+  if (!(B.irad > T(0))) return false;
+  const bool bmov = B.slot >= 0;
+  V3<T> b0 = mk<T>(B.ia[0], B.ia[1], B.ia[2]), b1 = mk<T>(B.ib[0], B.ib[1], B.ib[2]);
+  const bool bseg = !(b0.x == b1.x && b0.y == b1.y && b0.z == b1.z);
+  if (bmov) { b0 = PB.p + qrot(PB.q, b0); b1 = bseg ? PB.p + qrot(PB.q, b1) : b0; }
+  const T safety = sizeof(T) == 4 ? T(1e-5) : T(0);   // fp32 forward kinematics and end points: a few 1e-6 at arm's length
+  if (pr.kind == PK_PLANE) {
+    const V3<T> n = mk<T>(A.ax[0], A.ax[1], A.ax[2]), c = mk<T>(A.c[0], A.c[1], A.c[2]);
+    return vk_min(dot(n, b0 - c), dot(n, b1 - c)) < B.irad - safety;
+  }
+  if (!(A.irad > T(0))) return false;
+  const bool amov = A.slot >= 0;
+  V3<T> a0 = mk<T>(A.ia[0], A.ia[1], A.ia[2]), a1 = mk<T>(A.ib[0], A.ib[1], A.ib[2]);
+  const bool aseg = !(a0.x == a1.x && a0.y == a1.y && a0.z == a1.z);
+  if (amov) { a0 = PA.p + qrot(PA.q, a0); a1 = aseg ? PA.p + qrot(PA.q, a1) : a0; }
+  const T r = A.irad + B.irad - safety;
+  if (!(r > T(0))) return false;
+  T d2;
+  if (!aseg && !bseg) { const V3<T> d = a0 - b0; d2 = dot(d, d); }
+  else {
+    const V3<T> da = a1 - a0, db = b1 - b0;
+    const T la = dot(da, da), lb = dot(db, db);
+    d2 = segseg_dist2(a0, a1, aseg ? T(1) / la : T(0), b0, b1, bseg ? T(1) / lb : T(0));
+  }
+  return d2 < r * r;
 }
 
 // ------------------------------------------------------------------------------ narrow phase of one item (scalar)

@@ -616,6 +616,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
           const int i = b_pos + lane;
           bool keep = false;
           uint32_t it = 0;
+          unsigned certain = 0;
           if (i < n1) {
             it = q1[i];
             const int r = it & 0xffff;
@@ -627,8 +628,11 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
               Pose<float> PA = load_pose(pose, A.slot, wrow0 + r, TILE);
               Pose<float> PB = load_pose(pose, B.slot, wrow0 + r, TILE);
               keep = !midphase_cull(pr, A, B, PA, PB, pr.rsum - swept_radius(A) - swept_radius(B), slack);
+              // inner capsules overlap: a certain contact, the row is settled without a narrow phase
+              if (keep && pr.kind != PK_SEGSEG && inner_contact(pr, A, B, PA, PB)) { certain = 1u << r; keep = false; }
             }
           }
+          hit_mask |= __reduce_or_sync(0xffffffffu, certain);
           warp_push(keep, it, q2, n2, Q2CAP, lane);
         }
         __syncwarp();

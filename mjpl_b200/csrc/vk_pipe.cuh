@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(PIPE_FK_THREADS, 4) fk_cull_kernel(const __gri
       }
     }
     const bool do_coll = active && lim_ok && (a.flags & F_COLLISION);
-    if (__ballot_sync(0xffffffffu, do_coll) == 0) continue;
+    const unsigned coll_lanes = __ballot_sync(0xffffffffu, do_coll);
+    if (coll_lanes == 0) continue;
     if (do_coll) {
       Pose<float> prev;
       prev.p = mk<float>(0, 0, 0); prev.q.w = 1; prev.q.x = prev.q.y = prev.q.z = 0;
@@ -200,15 +201,35 @@ __global__ void __launch_bounds__(PIPE_FK_THREADS, 4) fk_cull_kernel(const __gri
 
     // ---- level 0: group pairs, lane = row; survivors -> per-warp queue -> global list --------------
     int n0 = 0;   // warp-uniform queue fill
+    // A group pair whose INNER balls / tube overlap settles the row on the spot (certain contact, see
+    // GroupPair::lim_in): the row is marked, stops queueing, and what it queued so far is dropped at the
+    // next flush (entries that left earlier are dropped by mid_kernel, which looks at the row's mask byte).
+    bool alive = do_coll;
     auto flush = [&]() {
+      const unsigned live = __ballot_sync(0xffffffffu, alive);
+      int cnt = n0;
+      if (live != coll_lanes) {   // some row of the tile has been settled: its entries stay behind
+        cnt = 0;
+        for (int i0 = 0; i0 < n0; i0 += 32) {
+          const int i = i0 + lane;
+          cnt += __popc(__ballot_sync(0xffffffffu, i < n0 && ((live >> (q0[i < n0 ? i : 0] & 31u)) & 1u)));
+        }
+      }
       unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(&a.counters[C_L0], (unsigned long long)n0);
+      if (lane == 0 && cnt) base = atomicAdd(&a.counters[C_L0], (unsigned long long)cnt);
       base = __shfl_sync(0xffffffffu, base, 0);
-      for (int i = lane; i < n0; i += 32) {
-        const uint32_t e = q0[i];
-        const unsigned long long r = (unsigned long long)(row_base + (e & 31u));
-        if (base + i < a.l0_cap) a.l0_items[base + i] = r | ((unsigned long long)(e >> 5) << 40);
-        else pipe_row_overflow(a, (long long)r);
+      for (int i0 = 0; i0 < n0; i0 += 32) {
+        const int i = i0 + lane;
+        const uint32_t e = q0[i < n0 ? i : 0];
+        const bool k = i < n0 && ((live >> (e & 31u)) & 1u);
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (k) {
+          const unsigned long long pos = base + __popc(m & below);
+          const unsigned long long r = (unsigned long long)(row_base + (e & 31u));
+          if (pos < a.l0_cap) a.l0_items[pos] = r | ((unsigned long long)(e >> 5) << 40);
+          else pipe_row_overflow(a, (long long)r);
+        }
+        base += __popc(m);
       }
       n0 = 0;
       __syncwarp();
@@ -231,7 +252,9 @@ __global__ void __launch_bounds__(PIPE_FK_THREADS, 4) fk_cull_kernel(const __gri
         const GroupPair g = s_gp[p];
         if ((int)g.ga != cached) { cached = g.ga; cA = centre(g.ga); }
         const V3<float> d = cA - centre(g.gb);
-        push(do_coll && dot(d, d) <= g.lim * g.lim, p);
+        const float d2 = dot(d, d);
+        if (d2 < g.lim_in * g.lim_in) alive = false;
+        push(alive && d2 <= g.lim * g.lim, p);
       }
     }
     {  // moving sphere against a world-fixed capsule
@@ -247,14 +270,22 @@ __global__ void __launch_bounds__(PIPE_FK_THREADS, 4) fk_cull_kernel(const __gri
         float t = dot(e, ab) * S.inv_len2;
         t = fminf(fmaxf(t, 0.f), 1.f);
         const V3<float> f = e - ab * t;
-        push(do_coll && dot(f, f) <= g.lim * g.lim, p);
+        const float d2 = dot(f, f);
+        if (d2 < g.lim_in * g.lim_in && fabsf(t - 0.5f) <= S.th) alive = false;
+        push(alive && d2 <= g.lim * g.lim, p);
       }
     }
     for (; p < a.gp_kind_end[2]; p++) {  // moving sphere against a plane
       const GroupPair g = s_gp[p];
       const StaticGroup S = s_sg[g.gb];
       const V3<float> e = centre(g.ga) - mk<float>(S.a[0], S.a[1], S.a[2]);
-      push(do_coll && dot(e, mk<float>(S.ab[0], S.ab[1], S.ab[2])) <= g.lim, p);
+      const float h = dot(e, mk<float>(S.ab[0], S.ab[1], S.ab[2]));
+      if (h < g.lim_in) alive = false;
+      push(alive && h <= g.lim, p);
+    }
+    if (do_coll && !alive) {
+      if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) atomicMin(&a.first_bad[e_idx], e_k);
+      else a.valid[row] = 0;
     }
     __syncwarp();
     if (n0) flush();
@@ -401,12 +432,20 @@ __global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid
     if (lane == 0) chunk = atomicAdd(&a.counters[C_L0TICKET], 1ull);
     return __shfl_sync(0xffffffffu, chunk, 0) * chunk_size;
   };
+  // the row's byte of the output mask doubles as its "already decided" flag (dense batches): entries of rows
+  // that level 0 or another warp of this kernel found in certain contact are dropped.  The byte is loaded
+  // with the entry, one batch ahead, and looked at when the entry's turn comes.
+  const bool by_row = !(a.mode == MODE_EDGES || a.mode == MODE_CHAINS);
+  uint8_t live_next = 1;
   auto load_entry = [&](unsigned long long pos) {   // entry of this lane in the batch starting at pos (or ~0)
     const unsigned long long ei = pos + lane;
     unsigned long long e = ~0ull;
+    live_next = 1;
     if (pos < total && ei < total) {
       e = a.l0_items[ei];
-      const char *pb = reinterpret_cast<const char *>(a.pose8) + (size_t)(e & ((1ull << 40) - 1ull)) * pose_row_bytes;
+      const size_t r = (size_t)(e & ((1ull << 40) - 1ull));
+      if (by_row) live_next = *reinterpret_cast<volatile const uint8_t *>(a.valid + r);
+      const char *pb = reinterpret_cast<const char *>(a.pose8) + r * pose_row_bytes;
       for (size_t o = 0; o < pose_row_bytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + o));
     }
     return e;
@@ -414,7 +453,7 @@ __global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid
   unsigned long long pos = claim(), chunk_end = pos + chunk_size;
   unsigned long long e_next = load_entry(pos);
   while (pos < total) {
-    const unsigned long long e_cur = e_next;
+    const unsigned long long e_cur = live_next ? e_next : ~0ull;
     // the batch after this one: same chunk, or the first batch of a freshly claimed chunk
     unsigned long long pos_next = pos + 32;
     if (pos_next >= chunk_end || pos_next >= total) { pos_next = claim(); chunk_end = pos_next + chunk_size; }
@@ -460,6 +499,7 @@ __global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid
             const Pose<float> PA = load_pose8(a.pose8, a.nslot, irow, A.slot);
             const Pose<float> PB = load_pose8(a.pose8, a.nslot, irow, B.slot);
             keep = !capsule_cull(pr, A, B, PA, PB, pr.rsum - swept_radius(A) - swept_radius(B) + slack);
+            if (keep && inner_contact(pr, A, B, PA, PB)) { mark_contact(a, irow); keep = false; }   // inner capsules overlap: certain contact
           }
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);

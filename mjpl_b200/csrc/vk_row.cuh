@@ -174,20 +174,23 @@ __global__ void __launch_bounds__(ROWK_THREADS, 2) row_kernel(const __grid_const
         return P;
       };
       // ---- level 0: lanes over the group pairs -> list0 (group pair ids) ---------------------------------
+      // (a group pair whose inner balls / tube overlap is a certain contact: the row is settled, see GroupPair::lim_in)
       int n0 = 0;
-      for (int p0 = 0; p0 < a.ngpair; p0 += 32) {
+      for (int p0 = 0; p0 < a.ngpair && !hit; p0 += 32) {
         const int p = p0 + lane;
-        bool near = false;
+        int near = 0;
         if (p < a.ngpair) {
           const GroupPair g = s_gp[p];
           const V3<float> cA = mk<float>(wcen[g.ga * 4], wcen[g.ga * 4 + 1], wcen[g.ga * 4 + 2]);
           const V3<float> cB = g.kind == GK_SPHERE ? mk<float>(wcen[g.gb * 4], wcen[g.gb * 4 + 1], wcen[g.gb * 4 + 2]) : cA;
-          near = group_pair_near(g, cA, cB, g.kind == GK_SPHERE ? nullptr : &s_sg[g.gb]);
+          near = group_pair_test(g, cA, cB, g.kind == GK_SPHERE ? nullptr : &s_sg[g.gb]);
         }
-        const unsigned m = __ballot_sync(0xffffffffu, near);
+        const unsigned m = __ballot_sync(0xffffffffu, near != 0);
         if (near) list0[n0 + __popc(m & below)] = (uint16_t)p;
         n0 += __popc(m);
+        hit = __any_sync(0xffffffffu, near == 2);
       }
+      if (hit) n0 = 0;
       __syncwarp();
       // ---- expansion: the shape pairs of the surviving group pairs -> list1 -------------------------------
       int T = 0;
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(ROWK_THREADS, 2) row_kernel(const __grid_const
       int ni = 0;
       for (int i0 = 0; i0 < T; i0 += 32) {
         const int i = i0 + lane;
-        bool keep = false;
+        bool keep = false, certain = false;
         int ip = 0;
         if (i < T) {
           ip = list1[i];
@@ -223,15 +226,19 @@ __global__ void __launch_bounds__(ROWK_THREADS, 2) row_kernel(const __grid_const
           if (use_obb) {
             const Shape<float> &A = s_shapes[pr.sa];
             const Shape<float> &B = s_shapes[pr.sb];
-            keep = !midphase_cull(pr, A, B, pose_of(A.slot), pose_of(B.slot), pr.rsum - swept_radius(A) - swept_radius(B), slack);
+            const Pose<float> PA = pose_of(A.slot), PB = pose_of(B.slot);
+            keep = !midphase_cull(pr, A, B, PA, PB, pr.rsum - swept_radius(A) - swept_radius(B), slack);
+            if (keep && pr.kind != PK_SEGSEG && inner_contact(pr, A, B, PA, PB)) certain = true;   // inner capsules overlap
           }
         }
+        if (__any_sync(0xffffffffu, certain)) { hit = true; break; }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
         __syncwarp();
         if (keep) list0[ni + __popc(m & below)] = (uint16_t)ip;   // ni <= i0: never ahead of the entries still to be read from list1
         ni += __popc(m);
       }
       __syncwarp();
+      if (hit) ni = 0;
       items_total += ni;
       // ---- narrow phase ---------------------------------------------------------------------------------------
       // closed forms and plane items: lane = item

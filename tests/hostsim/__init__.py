@@ -61,6 +61,8 @@ def lib():
         L.hs_smap_check.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p]
         L.hs_bounds_check.argtypes = [C.c_void_p]
         L.hs_bounds_check.restype = C.c_double
+        L.hs_inner_check.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
+        L.hs_inner_check.restype = C.c_double
         L.hs_segseg_check.argtypes = [C.c_int, C.c_uint64]
         L.hs_segseg_check.restype = C.c_double
         _lib = L
@@ -116,9 +118,15 @@ class HostSim:
         early exit -> (valid, {level0, expanded, capsule, items, contacts})"""
         q = np.ascontiguousarray(q, dtype=np.float32).reshape(-1, self.model.nq)
         valid = np.zeros(len(q), np.uint8)
-        stats = np.zeros(8, np.int64)
+        stats = np.zeros(48, np.int64)
         lib().hs_check_pipe(self._h, q.ctypes.data, len(q), flags, valid.ctypes.data, stats.ctypes.data)
-        return valid, dict(zip("level0 expanded capsule items contacts".split(), stats[:5].tolist()))
+        d = dict(zip("level0 expanded capsule items contacts closed_form_items".split(), stats[:6].tolist()))
+        d["gjk_iter_hist"] = stats[8:24].tolist()
+        d["gjk_verdicts_sep_pen_unc"] = stats[24:27].tolist()
+        d["gjk_one_iteration_sep_pen_unc"] = stats[27:30].tolist()
+        d["inner"] = dict(zip("invalid_rows caught_level0 caught_any level0_of_caught0 expanded_of_caught0 items_of_caught0 items_of_caught false_positives".split(),
+                              stats[32:40].tolist()))
+        return valid, d
 
     def min_distance(self, q, far_cap=0.01):
         """signed distance to contact per row through the fp64 core -> (dist, pair index)"""
@@ -136,6 +144,13 @@ class HostSim:
     def bounds_check(self):
         """largest distance by which a vertex sticks out of its bounding capsule / group sphere (<= 0: contained)"""
         return lib().hs_bounds_check(self._h)
+
+    def inner_check(self, nsample=400, seed=5):
+        """inner capsules against their shapes -> (shapes with an inner capsule, largest distance by which a
+        sampled surface point of an inner capsule sticks out of its shape; <= 0: none does)"""
+        n = C.c_int(0)
+        worst = lib().hs_inner_check(self._h, nsample, seed, C.byref(n))
+        return n.value, worst
 
     def pair_verdict(self, q, g1, g2, fp64=False):
         """(verdict, iterations) of one geom pair: 0 separated, 1 contact, 2 uncertain."""

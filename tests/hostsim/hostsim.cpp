@@ -332,10 +332,14 @@ extern "C" void hs_check_pipe(Sim *s, const float *q, int64_t n, uint32_t flags,
           cen[g] = P[k].p + qrot(P[k].q, mk<float>((float)H.group_c[g][0], (float)H.group_c[g][1], (float)H.group_c[g][2]));
       }
       bool pen = false, unc = false;
+      bool cert0 = false, cert1 = false;   // certain contact from the inner balls (level 0) / inner capsules (shape pairs)
+      int64_t row_l0 = 0, row_items = 0, row_exp = 0;
       for (const GroupPair &g : H.group_pairs) {
-        if (!group_pair_near(g, cen[g.ga], g.kind == GK_SPHERE ? cen[g.gb] : cen[g.ga],
-                             g.kind == GK_SPHERE ? nullptr : &H.static_groups[g.gb])) continue;
-        stats[0]++;
+        const int t0 = group_pair_test(g, cen[g.ga], g.kind == GK_SPHERE ? cen[g.gb] : cen[g.ga],
+                                       g.kind == GK_SPHERE ? nullptr : &H.static_groups[g.gb]);
+        if (t0 == 0) continue;
+        if (t0 == 2) cert0 = true;
+        stats[0]++; row_l0++; row_exp += g.n;
         for (int i = 0; i < g.n; i++) {
           const int p = H.gp_member[g.first + i];
           const Pair pr = H.pairs[p];
@@ -346,9 +350,20 @@ extern "C" void hs_check_pipe(Sim *s, const float *q, int64_t n, uint32_t flags,
           const float margin = pr.rsum - swept_radius(A) - swept_radius(B);
           if (capsule_cull(pr, A, B, PA, PB, margin + slack)) continue;
           stats[2]++;
+          if (pr.kind != PK_SEGSEG && inner_contact(pr, A, B, PA, PB)) cert1 = true;
           if (midphase_cull(pr, A, B, PA, PB, margin, slack)) continue;
-          stats[3]++;
-          int v = narrow_item<float>(pr.kind, A, B, s->v32.data(), PA, PB, pr.rsum);
+          stats[3]++; row_items++;
+          int v;
+          if (pr.kind == PK_GJK) {
+            int iters = 0;
+            v = gjk_classify(A, B, s->v32.data(), relative_pose(PA, PB), pr.rsum, &iters);
+            stats[8 + (iters < 15 ? iters : 15)]++;          // [8..23] GJK iteration histogram
+            stats[24 + v]++;                                 // [24..26] GJK verdicts SEP / PEN / UNC
+            if (iters == 1) stats[27 + v]++;                 // [27..29] verdicts of the items that end in one iteration
+          } else {
+            v = narrow_item<float>(pr.kind, A, B, s->v32.data(), PA, PB, pr.rsum);
+            stats[5]++;                                      // closed-form / plane items
+          }
           if (v == V_PEN) { pen = true; stats[4]++; }
           if (v == V_UNC) unc = true;
         }
@@ -356,6 +371,11 @@ extern "C" void hs_check_pipe(Sim *s, const float *q, int64_t n, uint32_t flags,
       int v = pen ? 1 : (unc ? 2 : 0);
       if (v == 2) v = row_verdict<double>(H, H.fk, H.shapes.data(), H.verts.data(), qr, false, nullptr) != 0 ? 1 : 0;
       out = v == 0 ? 1 : 0;
+      // [32..] the certain-contact shortcut: rows it catches, what they carry, and its false positives (must be 0)
+      if (out == 0) stats[32]++;
+      if (cert0) { stats[33]++; stats[35] += row_l0; stats[36] += row_exp; stats[37] += row_items; }
+      if (cert0 || cert1) { stats[34]++; stats[38] += row_items; if (out) stats[39]++; }
+      if (cert0 || cert1) out = 0;   // as on the device: the shortcut's word is final
     }
     valid[r] = (uint8_t)out;
   }
@@ -499,4 +519,54 @@ extern "C" int hs_group_census(Sim *s, const float *q, int64_t n, int64_t *out, 
     }
   }
   return (int)H.group_pairs.size();
+}
+
+// The inner capsules (fp32 tables, as the device sees them) against the shapes they must lie in: points on
+// the capsule's surface are tested against the support function of the shape in many directions (a point
+// p is inside hull (+) ball(r) iff d.p <= h(d) + r for every unit d).  Returns the largest violation found
+// (<= 0: no sample sticks out); *nshape = shapes that have an inner capsule.
+extern "C" double hs_inner_check(Sim *s, int nsample, uint64_t seed, int *nshape) {
+  double worst = -1e300;
+  int cnt = 0;
+  for (size_t k = 0; k < s->s32.size(); k++) {
+    const Shape<float> &sh = s->s32[k];
+    if (!(sh.irad > 0.f)) continue;
+    cnt++;
+    const double a[3] = {sh.ia[0], sh.ia[1], sh.ia[2]}, b[3] = {sh.ib[0], sh.ib[1], sh.ib[2]};
+    for (int i = 0; i < nsample; i++) {
+      double n[3], nn = 0;
+      for (int c = 0; c < 3; c++) { n[c] = sweep_value(seed, (uint64_t)(k * 1000003 + i), (uint32_t)c, -1.f, 1.f); nn += n[c] * n[c]; }
+      if (nn < 1e-6) continue;
+      nn = sqrt(nn);
+      const double t = 0.5 + 0.5 * sweep_value(seed, (uint64_t)(k * 1000003 + i), 3u, -1.f, 1.f);
+      double p[3];
+      for (int c = 0; c < 3; c++) { n[c] /= nn; p[c] = a[c] + t * (b[c] - a[c]) + (double)sh.irad * n[c]; }
+      if (sh.kind == SK_CYL) {
+        double e[3] = {p[0] - sh.c[0], p[1] - sh.c[1], p[2] - sh.c[2]};
+        const double h = e[0] * sh.ax[0] + e[1] * sh.ax[1] + e[2] * sh.ax[2];
+        double pr2 = 0;
+        for (int c = 0; c < 3; c++) { const double w = e[c] - h * sh.ax[c]; pr2 += w * w; }
+        worst = std::max(worst, std::max(sqrt(pr2) - (double)sh.radius, fabs(h) - (double)sh.halflen));
+        continue;
+      }
+      // directions: the capsule's normal at p, and perturbations of it
+      for (int j = 0; j < 24; j++) {
+        double d[3], dn = 0;
+        for (int c = 0; c < 3; c++) {
+          d[c] = n[c] + (j ? (j < 12 ? 0.3 : 1.5) * sweep_value(seed + 7, (uint64_t)(k * 1000003 + i), (uint32_t)(4 + 3 * j + c), -1.f, 1.f) : 0.0);
+          dn += d[c] * d[c];
+        }
+        dn = sqrt(dn);
+        if (dn < 1e-6) continue;
+        double h = -1e300;
+        for (int v = 0; v < sh.nvert; v++) {
+          const Vtx<float> &V = s->v32[sh.vadr + v];
+          h = std::max(h, (d[0] * V.x + d[1] * V.y + d[2] * V.z) / dn);
+        }
+        worst = std::max(worst, (d[0] * p[0] + d[1] * p[1] + d[2] * p[2]) / dn - h - (double)sh.radius);
+      }
+    }
+  }
+  if (nshape) *nshape = cnt;
+  return worst;
 }

@@ -469,6 +469,31 @@ def test_bounding_capsules_and_cull_groups_are_conservative():
         np.testing.assert_array_equal(got, hs.check(Q)[0])   # same answer as the per-pair sphere + mid-phase order
 
 
+def test_inner_shapes_only_certify_real_contacts():
+    """The certain-contact shortcut (inner capsule per shape, inner ball / tube per cull group): every inner
+    capsule lies inside its shape (surface samples against the shape's support function), the shortcut
+    fires on a good share of the colliding rows, and NEVER on a row the full evaluation finds free."""
+    from mjpl_b200 import mjcf, models
+    from tests import toy_models as toys
+    from tests.hostsim import HostSim
+
+    zoo = mjcf.from_xml_string(toys.PRIMITIVE_ARM)
+    zoo.geom_margin = np.where(np.arange(zoo.ngeom) % 2 == 0, 0.015, 0.004)
+    cases = [(models.load("franka_scene_with_obstacles"), [("left_finger", "right_finger")], 20000, 0.6),
+             (models.load("franka_scene"), [], 8000, 0.4), (models.load("ur5e_scene"), [], 8000, 0.4),
+             (mjcf.from_xml_string(toys.PRIMITIVE_ARM), [], 8000, 0.5), (zoo, [], 8000, 0.1)]
+    for m, allowed, n, share in cases:
+        hs = HostSim(m, allowed)
+        nshape, worst = hs.inner_check(600)
+        assert nshape > 0 and worst <= 1e-7, (nshape, worst)
+        rng = np.random.default_rng(11)
+        Q = rng.uniform(m.jnt_range[:, 0], m.jnt_range[:, 1], size=(n, m.nq)).astype(np.float32)
+        inner = hs.check_pipe(Q)[1]["inner"]
+        assert inner["false_positives"] == 0
+        assert inner["caught_any"] >= inner["caught_level0"] > 0
+        assert inner["caught_any"] >= share * inner["invalid_rows"], inner
+
+
 def test_support_maps_return_the_full_scan_maximum():
     """The cube-map support tables of the larger hulls (narrow_kernel) list, per cell, a rigorous superset of
     the vertices that can be a support for a direction of the cell: on random, near-axis and cell-border
