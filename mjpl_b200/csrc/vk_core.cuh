@@ -818,6 +818,25 @@ VK_HD int group_pair_test(const GroupPair &g, V3<float> cA, V3<float> cB, const 
 }
 VK_HD bool group_pair_near(const GroupPair &g, V3<float> cA, V3<float> cB, const StaticGroup *S) { return group_pair_test(g, cA, cB, S) != 0; }
 
+// Distance^2 between two points of the segments near their closest pair, all in the caller's precision.  The
+// parameters are feasible (clamped to [0, 1]), so the value is the distance of two actual points of the
+// segments: never BELOW the true minimum by more than rounding -- the safe side for a certain-contact test
+// (the bounding-capsule cull needs the opposite guarantee and uses the fp64 routine above).
+template <typename T>
+VK_HD T segseg_upper2(V3<T> p1, V3<T> q1, T inv_a, V3<T> p2, V3<T> q2, T inv_e) {
+  const V3<T> d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+  const T a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), c = dot(d1, r), b = dot(d1, d2);
+  const T den = a * e - b * b;
+  T s = den > T(1e-6) * a * e ? (b * f - c * e) / den : T(0);
+  s = s < T(0) ? T(0) : (s > T(1) ? T(1) : s);
+  T t = (b * s + f) * inv_e;
+  t = t < T(0) ? T(0) : (t > T(1) ? T(1) : t);
+  s = (b * t - c) * inv_a;
+  s = s < T(0) ? T(0) : (s > T(1) ? T(1) : s);
+  const V3<T> dd = r + d1 * s - d2 * t;
+  return dot(dd, dd);
+}
+
 // certain contact of one shape pair from the inner capsules: true => the shapes intersect (distance < 0 <= margin)
 template <typename T>
 VK_HD bool inner_contact(const Pair &pr, const Shape<T> &A, const Shape<T> &B, const Pose<T> &PA, const Pose<T> &PB) {
@@ -843,7 +862,11 @@ VK_HD bool inner_contact(const Pair &pr, const Shape<T> &A, const Shape<T> &B, c
   else {
     const V3<T> da = a1 - a0, db = b1 - b0;
     const T la = dot(da, da), lb = dot(db, db);
+#ifdef VK_INNER_FP64
     d2 = segseg_dist2(a0, a1, aseg ? T(1) / la : T(0), b0, b1, bseg ? T(1) / lb : T(0));
+#else
+    d2 = segseg_upper2(a0, a1, aseg ? T(1) / la : T(0), b0, b1, bseg ? T(1) / lb : T(0));
+#endif
   }
   return d2 < r * r;
 }

@@ -25,7 +25,10 @@
 
 namespace vk {
 
-constexpr int L0_QCAP = 256;          // per-warp staging queue of level-0 survivors (entries)
+#ifndef VK_L0_QCAP
+#define VK_L0_QCAP 256
+#endif
+constexpr int L0_QCAP = VK_L0_QCAP;   // per-warp staging queue of level-0 survivors (entries)
 constexpr int PIPE_FK_THREADS = 256;  // fk_cull_kernel: 8 warps per CTA, 4 CTAs per SM
 constexpr int MID_THREADS = 256;
 #ifndef VK_MID_CTAS
@@ -345,13 +348,15 @@ __device__ __noinline__ int mid_drain(const KArgs &a, const Shape<float> *s_shap
     const Shape<float> &A = s_shapes[pr.sa];
     const Shape<float> &B = s_shapes[pr.sb];
     bool keep = true;
-    if (use_obb && (pr.flags & PF_OBB)) {
+    if (use_obb && pr.kind != PK_SEGSEG) {
       const Pose<float> PB = load_pose8(a.pose8, a.nslot, irow, B.slot);
-      if (pr.kind == PK_PLANE) {
-        keep = !obb_above_plane(A, B, PB, pr.rsum - swept_radius(B) + slack);
-      } else {
-        const Pose<float> PA = load_pose8(a.pose8, a.nslot, irow, A.slot);
-        keep = !obb_disjoint(A, B, relative_pose(PA, PB), pr.rsum - swept_radius(A) - swept_radius(B) + slack);
+      const Pose<float> PA = load_pose8(a.pose8, a.nslot, irow, A.slot);   // identity for a world-fixed shape (planes)
+      // inner capsules overlap: a certain contact, the row is settled without a narrow phase (here, with
+      // full lanes, not right after the capsule cull where half of them have already dropped out)
+      if (inner_contact(pr, A, B, PA, PB)) { mark_contact(a, irow); keep = false; }
+      else if (pr.flags & PF_OBB) {
+        if (pr.kind == PK_PLANE) keep = !obb_above_plane(A, B, PB, pr.rsum - swept_radius(B) + slack);
+        else keep = !obb_disjoint(A, B, relative_pose(PA, PB), pr.rsum - swept_radius(A) - swept_radius(B) + slack);
       }
     }
     if (keep) bin = item_bin(pr, A, B);
@@ -427,25 +432,25 @@ __global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid
   // be shared out among a handful of warps (small batches run as long as their busiest warp)
   unsigned long long chunk_size = total / ((unsigned long long)gridDim.x * (MID_THREADS / 32)) / 32 * 32;
   chunk_size = chunk_size < 32 ? 32 : (chunk_size > MID_CHUNK ? MID_CHUNK : chunk_size);
-  auto claim = [&]() {
-    unsigned long long chunk = 0;
-    if (lane == 0) chunk = atomicAdd(&a.counters[C_L0TICKET], 1ull);
-    return __shfl_sync(0xffffffffu, chunk, 0) * chunk_size;
+  // The ticket of the next chunk is claimed one batch before it is needed and only read (the shuffle) when
+  // it is: every warp of the grid hits the same word, the answer takes a microsecond to come back.
+  unsigned long long ticket = 0;   // lane 0: the ticket claimed ahead
+  bool ticket_out = false;
+  auto claim_ahead = [&]() {
+    if (lane == 0) ticket = atomicAdd(&a.counters[C_L0TICKET], 1ull);
+    ticket_out = true;
   };
-  // the row's byte of the output mask doubles as its "already decided" flag (dense batches): entries of rows
-  // that level 0 or another warp of this kernel found in certain contact are dropped.  The byte is loaded
-  // with the entry, one batch ahead, and looked at when the entry's turn comes.
-  const bool by_row = !(a.mode == MODE_EDGES || a.mode == MODE_CHAINS);
-  uint8_t live_next = 1;
+  auto claim = [&]() {
+    if (!ticket_out) claim_ahead();
+    ticket_out = false;
+    return __shfl_sync(0xffffffffu, ticket, 0) * chunk_size;
+  };
   auto load_entry = [&](unsigned long long pos) {   // entry of this lane in the batch starting at pos (or ~0)
     const unsigned long long ei = pos + lane;
     unsigned long long e = ~0ull;
-    live_next = 1;
     if (pos < total && ei < total) {
       e = a.l0_items[ei];
-      const size_t r = (size_t)(e & ((1ull << 40) - 1ull));
-      if (by_row) live_next = *reinterpret_cast<volatile const uint8_t *>(a.valid + r);
-      const char *pb = reinterpret_cast<const char *>(a.pose8) + r * pose_row_bytes;
+      const char *pb = reinterpret_cast<const char *>(a.pose8) + (size_t)(e & ((1ull << 40) - 1ull)) * pose_row_bytes;
       for (size_t o = 0; o < pose_row_bytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + o));
     }
     return e;
@@ -453,11 +458,12 @@ __global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid
   unsigned long long pos = claim(), chunk_end = pos + chunk_size;
   unsigned long long e_next = load_entry(pos);
   while (pos < total) {
-    const unsigned long long e_cur = live_next ? e_next : ~0ull;
+    const unsigned long long e_cur = e_next;
     // the batch after this one: same chunk, or the first batch of a freshly claimed chunk
     unsigned long long pos_next = pos + 32;
     if (pos_next >= chunk_end || pos_next >= total) { pos_next = claim(); chunk_end = pos_next + chunk_size; }
     e_next = load_entry(pos_next);
+    if (!ticket_out && pos_next < total && (pos_next + 32 >= chunk_end || pos_next + 32 >= total)) claim_ahead();
     {
       // ---- expand: every entry (row, group pair) -> its shape pairs ----------------------------------
       long long row = 0;
@@ -499,7 +505,6 @@ __global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid
             const Pose<float> PA = load_pose8(a.pose8, a.nslot, irow, A.slot);
             const Pose<float> PB = load_pose8(a.pose8, a.nslot, irow, B.slot);
             keep = !capsule_cull(pr, A, B, PA, PB, pr.rsum - swept_radius(A) - swept_radius(B) + slack);
-            if (keep && inner_contact(pr, A, B, PA, PB)) { mark_contact(a, irow); keep = false; }   // inner capsules overlap: certain contact
           }
         }
         const unsigned m = __ballot_sync(0xffffffffu, keep);
