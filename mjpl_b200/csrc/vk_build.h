@@ -531,12 +531,13 @@ inline bool build_groups(HostModel &H) {
     Shape<double> &sh = H.shapes[k];
     StaticGroup sg; memset(&sg, 0, sizeof sg);
     if (sh.kind == SK_PLANE) {
-      for (int a = 0; a < 3; a++) { sg.a[a] = (float)sh.c[a]; sg.ab[a] = (float)sh.ax[a]; }
+      for (int a = 0; a < 3; a++) { sg.a[a] = (float)sh.c[a]; sg.u[a] = (float)sh.ax[a]; }
     } else {
       double l2 = 0;
-      for (int a = 0; a < 3; a++) { sg.a[a] = (float)sh.ca[a]; sg.ab[a] = (float)(sh.cb[a] - sh.ca[a]); l2 += (double)sg.ab[a] * sg.ab[a]; }
-      sg.inv_len2 = l2 > 1e-12 ? (float)(1.0 / l2) : 0.f;
-      if (!(l2 > 1e-12)) sg.ab[0] = sg.ab[1] = sg.ab[2] = 0.f;
+      for (int a = 0; a < 3; a++) l2 += (sh.cb[a] - sh.ca[a]) * (sh.cb[a] - sh.ca[a]);
+      const double len = sqrt(l2);
+      for (int a = 0; a < 3; a++) { sg.a[a] = (float)sh.ca[a]; sg.u[a] = len > 1e-6 ? (float)((sh.cb[a] - sh.ca[a]) / len) : 0.f; }
+      sg.len = len > 1e-6 ? (float)len : 0.f;
     }
     // inner tube: a piece of the bounding capsule's segment, symmetric about its mid-point, and a radius such
     // that the swept piece lies inside the shape
@@ -549,7 +550,7 @@ inline bool build_groups(HostModel &H) {
       const V3<double> m = (ca + cb) * 0.5;
       const double rm = ball(m);
       if (rm > 0) {
-        if (!(sh.caplen > 1e-9)) { sg.th = 1.f; tube_r[k] = rm; }
+        if (!(sh.caplen > 1e-6)) { sg.th = 0.f; tube_r[k] = rm; }
         else {
           const V3<double> u = (cb - ca) * (1.0 / sh.caplen);
           double best = -1;
@@ -557,7 +558,7 @@ inline bool build_groups(HostModel &H) {
           for (double f : fac) {
             const double t = inner_extent(ball, m, u, 0.5 * sh.caplen, f * rm, true, 0);
             const double vol = M_PI * f * rm * f * rm * 2 * t + 4.0 / 3.0 * M_PI * f * rm * f * rm * f * rm;
-            if (vol > best) { best = vol; tube_r[k] = f * rm; sg.th = (float)(t / sh.caplen * (1 - 1e-6)); }
+            if (vol > best) { best = vol; tube_r[k] = f * rm; sg.th = (float)(t * (1 - 1e-6)); }
           }
         }
       }
@@ -581,7 +582,7 @@ inline bool build_groups(HostModel &H) {
   std::vector<Key> keys;
   std::vector<std::vector<uint16_t>> members;
   std::vector<double> lims, lims_in;
-  const double inner_safety = 1e-5;   // fp32 forward kinematics and centres: a few 1e-6 at arm's length
+  const double inner_safety = 1e-4;   // fp32 forward kinematics, centres and the expanded squares of level 0: a few 1e-6
   for (size_t p = 0; p < H.pairs.size(); p++) {
     const Pair &pr = H.pairs[p];
     const Shape<double> &A = H.shapes[pr.sa], &B = H.shapes[pr.sb];
@@ -624,10 +625,11 @@ inline bool build_groups(HostModel &H) {
     if (H.gp_member.size() + members[i].size() > 65535) { H.err = "too many geom pairs"; return false; }
     if (members[i].size() > 255) { H.err = "too many geom pairs between two bodies"; return false; }
     g.first = (uint16_t)H.gp_member.size(); g.n = (uint8_t)members[i].size();
-    g.lim = (float)(lims[i] * (1 + 2e-7));
+    const bool squared = keys[i].kind != GK_PLANE;
+    g.lim = (float)((squared ? lims[i] * lims[i] + 2e-6 : lims[i]) * (1 + 4e-7));   // + the cancellation in point_segment_d2
     // sphere / capsule kinds compare squares: "none" is 0 there; the plane kind compares the signed height
-    const bool none = !(lims_in[i] > 0) || getenv("MJB_NO_INNER0");
-    g.lim_in = none ? (keys[i].kind == GK_PLANE ? -1e30f : 0.f) : (float)(lims_in[i] * (1 - 2e-7));
+    const bool none = !(lims_in[i] > 0.005) || getenv("MJB_NO_INNER0");   // (a smaller sum leaves no room for the rounding of the squares)
+    g.lim_in = none ? (squared ? 0.f : -1e30f) : (float)((squared ? lims_in[i] * lims_in[i] : lims_in[i]) * (1 - 4e-7));
     for (uint16_t p : members[i]) H.gp_member.push_back(p);
     H.group_pairs.push_back(g);
     for (int k = keys[i].kind; k < 3; k++) H.gp_kind_end[k]++;

@@ -54,7 +54,10 @@ template <> struct Num<float> {
   static constexpr float tol = 4e-6f;        // certification slack (FK + GJK rounding)
   static constexpr float conv_rel = 1e-6f;   // GJK relative convergence on |v|^2 - v.w
   static constexpr float tiny = 1e-30f;
-  static constexpr int maxit = 24;
+#ifndef VK_MAXIT32
+#define VK_MAXIT32 12   // B200, 1M Franka rows: 24 -> narrow 0.330 ms + fp64 0.048, 12 -> 0.302 + 0.054, 9 -> 0.301 + 0.055 (the kernel ends with its slowest item)
+#endif
+  static constexpr int maxit = VK_MAXIT32;   // an item that has not been certified by then is handed to the fp64 pass
 };
 template <> struct Num<double> {
   static constexpr double tol = 0.0;
@@ -777,17 +780,19 @@ struct GroupPair {
   uint16_t gb;      // GK_SPHERE: moving group; GK_CAPSULE / GK_PLANE: index into the static table
   uint16_t first;   // its shape pairs: member[first .. first + n)
   uint8_t n, kind;
-  float lim;        // radii + largest margin of the member pairs + slack (GK_PLANE: radius + margin + slack)
-  float lim_in;     // > 0: the two groups' INNER radii around the same centres (a ball around a moving group's
-                    // centre that lies inside one of its shapes; the tube inside a world-fixed shape around its
-                    // segment).  Centres closer than this: the two shapes intersect, the row is certainly in contact.
+  float lim;        // GK_SPHERE / GK_CAPSULE: (radii + largest margin of the member pairs + slack)^2, compared with a
+                    // squared distance; GK_PLANE: radius + margin + slack, compared with the signed height
+  float lim_in;     // the same for the two groups' INNER radii around the same centres (a ball around a moving
+                    // group's centre that lies inside one of its shapes; the tube inside a world-fixed shape around
+                    // its segment).  Centres closer than this: the two shapes intersect, the row is certainly in
+                    // contact.  No inner shapes: 0 (squared kinds) / -1e30 (plane) -- the test never fires.
 };
 static_assert(sizeof(GroupPair) == 16, "GroupPair is loaded as one 16-byte word");
 struct StaticGroup {   // world frame
   float a[3];          // GK_CAPSULE: segment start;   GK_PLANE: a point of the plane
-  float inv_len2;      // GK_CAPSULE: 1 / |ab|^2 (0 for a point)
-  float ab[3];         // GK_CAPSULE: segment vector;  GK_PLANE: unit normal
-  float th;            // GK_CAPSULE: the shape's inner tube runs along the parameters |t - 0.5| <= th of the segment (< 0: none)
+  float len;           // GK_CAPSULE: segment length (0 for a point)
+  float u[3];          // GK_CAPSULE: unit vector along the segment (0 for a point);  GK_PLANE: unit normal
+  float th;            // GK_CAPSULE: the shape's inner tube runs along |s - len / 2| <= th of the segment (< 0: none)
 };
 static_assert(sizeof(StaticGroup) == 32, "StaticGroup is loaded as two 16-byte words");
 constexpr int MAX_GROUP = MAX_BODY;
@@ -796,6 +801,15 @@ constexpr int MAX_GROUP = MAX_BODY;
 // 1: near (expand the group pair); 2: CERTAIN contact (the inner ball / tube of the two groups overlap).
 // cA: world centre of moving group ga; cB: world centre of moving group gb (GK_SPHERE only);
 // S: the static group (GK_CAPSULE / GK_PLANE).
+// squared distance from e (relative to the segment's start) to the segment of unit direction u and length len;
+// *s_out = parameter of the closest point.  |e - s u|^2 expanded: 14 flops; the cancellation costs a few ulps
+// of |e|^2 (< 1e-6 m^2 at arm's length), far inside the slack / safety of the two limits it is compared with.
+VK_HD float point_segment_d2(V3<float> e, V3<float> u, float len, float *s_out) {
+  const float ee = dot(e, e), s = dot(e, u);
+  const float sc = s < 0.f ? 0.f : (s > len ? len : s);
+  *s_out = sc;
+  return ee - sc * (2.f * s - sc);
+}
 VK_HD int group_pair_test(const GroupPair &g, V3<float> cA, V3<float> cB, const StaticGroup *S) {
   float d2;
   if (g.kind == GK_SPHERE) {
@@ -803,18 +817,16 @@ VK_HD int group_pair_test(const GroupPair &g, V3<float> cA, V3<float> cB, const 
     d2 = dot(d, d);
   } else {
     const V3<float> e = cA - mk<float>(S->a[0], S->a[1], S->a[2]);
-    const V3<float> ab = mk<float>(S->ab[0], S->ab[1], S->ab[2]);
+    const V3<float> u = mk<float>(S->u[0], S->u[1], S->u[2]);
     if (g.kind == GK_PLANE) {
-      const float h = dot(e, ab);
-      return h < g.lim_in ? 2 : (h <= g.lim ? 1 : 0);   // lim_in = inner radius of the moving group (-1e30: none)
+      const float h = dot(e, u);
+      return h < g.lim_in ? 2 : (h <= g.lim ? 1 : 0);
     }
-    float t = dot(e, ab) * S->inv_len2;
-    t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
-    const V3<float> f = e - ab * t;
-    d2 = dot(f, f);
-    if (!(fabsf(t - 0.5f) <= S->th)) return d2 <= g.lim * g.lim ? 1 : 0;
+    float sc;
+    d2 = point_segment_d2(e, u, S->len, &sc);
+    if (!(fabsf(sc - 0.5f * S->len) <= S->th)) return d2 <= g.lim ? 1 : 0;
   }
-  return d2 < g.lim_in * g.lim_in ? 2 : (d2 <= g.lim * g.lim ? 1 : 0);
+  return d2 < g.lim_in ? 2 : (d2 <= g.lim ? 1 : 0);
 }
 VK_HD bool group_pair_near(const GroupPair &g, V3<float> cA, V3<float> cB, const StaticGroup *S) { return group_pair_test(g, cA, cB, S) != 0; }
 

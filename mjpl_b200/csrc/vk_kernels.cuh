@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(TILE) validity_kernel(const __grid_constant__ 
         // warp only ever waits for the chunk that holds its own rows.  Bounded: a copy that never
         // lands traps instead of hanging the GPU.
         if (lane == 0) {
-          const unsigned long long need = (unsigned long long)(row_base + rows_here);
+          const unsigned long long need = (unsigned long long)(a.row0 + row_base + rows_here);   // row0: this launch's first row within the host batch
           const long long t0 = clock64();
           while (ld_acquire_sys(a.rows_ready) < need) {
             __nanosleep(256);

@@ -69,7 +69,53 @@ __device__ __forceinline__ void pipe_row_overflow(const KArgs &a, long long row)
   }
 }
 
-__global__ void __launch_bounds__(PIPE_FK_THREADS, 4) fk_cull_kernel(const __grid_constant__ KArgs a) {
+// One warp's queued level-0 entries -> the global list (one atomic).  Entries of rows that were settled
+// after they queued (`live` bit clear) stay behind.  Out of line: it runs once per ~200 entries and would
+// otherwise be inlined into every push site of the level-0 loops.
+__device__ __noinline__ void l0_flush(const KArgs &a, const uint32_t *q0, int n0, unsigned live, unsigned coll_lanes, long long row_base) {
+  const int lane = threadIdx.x & 31;
+  const unsigned below = (1u << lane) - 1u;
+  int cnt = n0;
+  if (live != coll_lanes) {   // some row of the tile has been settled: its entries stay behind
+    cnt = 0;
+    for (int i0 = 0; i0 < n0; i0 += 32) {
+      const int i = i0 + lane;
+      cnt += __popc(__ballot_sync(0xffffffffu, i < n0 && ((live >> (q0[i < n0 ? i : 0] & 31u)) & 1u)));
+    }
+  }
+  unsigned long long base = 0;
+  if (lane == 0 && cnt) base = atomicAdd(&a.counters[C_L0], (unsigned long long)cnt);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  for (int i0 = 0; i0 < n0; i0 += 32) {
+    const int i = i0 + lane;
+    const uint32_t e = q0[i < n0 ? i : 0];
+    const bool k = i < n0 && ((live >> (e & 31u)) & 1u);
+    const unsigned m = __ballot_sync(0xffffffffu, k);
+    if (k) {
+      const unsigned long long pos = base + __popc(m & below);
+      const unsigned long long r = (unsigned long long)(row_base + (e & 31u));
+      if (pos < a.l0_cap) a.l0_items[pos] = r | ((unsigned long long)(e >> 5) << 40);
+      else pipe_row_overflow(a, (long long)r);
+    }
+    base += __popc(m);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+#ifndef VK_FK_CTAS
+#define VK_FK_CTAS 4
+#endif
+#ifndef VK_L0_UNROLL
+#define VK_L0_UNROLL 2   // B200, 1M Franka rows: 1 -> 0.381 ms, 2 -> 0.361, 3 -> 0.380, 4 -> 0.374, 8 -> 0.409
+                         // (the tables as a kernel parameter, read with indexed LDC instead of LDS: 0.428)
+#endif
+__global__ void __launch_bounds__(PIPE_FK_THREADS, VK_FK_CTAS) fk_cull_kernel(const __grid_constant__ KArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int nq = a.fk.nq;
   const PipeFkLayout L = pipe_fk_layout(a.ngpair, a.nsgroup, a.ngroup_moving, nq);
@@ -125,7 +171,7 @@ __global__ void __launch_bounds__(PIPE_FK_THREADS, 4) fk_cull_kernel(const __gri
     if (a.mode == MODE_DENSE) {
       if (a.rows_ready) {   // host -> device copy still in flight (mjb_check_configs_host)
         if (lane == 0) {
-          const unsigned long long need = (unsigned long long)(row_base + rows_here);
+          const unsigned long long need = (unsigned long long)(a.row0 + row_base + rows_here);   // row0: this launch's first row within the host batch
           const long long t0 = clock64();
           while (ld_acquire_sys(a.rows_ready) < need) {
             __nanosleep(256);
@@ -206,92 +252,73 @@ __global__ void __launch_bounds__(PIPE_FK_THREADS, 4) fk_cull_kernel(const __gri
     int n0 = 0;   // warp-uniform queue fill
     // A group pair whose INNER balls / tube overlap settles the row on the spot (certain contact, see
     // GroupPair::lim_in): the row is marked, stops queueing, and what it queued so far is dropped at the
-    // next flush (entries that left earlier are dropped by mid_kernel, which looks at the row's mask byte).
+    // next flush.
     bool alive = do_coll;
-    auto flush = [&]() {
-      const unsigned live = __ballot_sync(0xffffffffu, alive);
-      int cnt = n0;
-      if (live != coll_lanes) {   // some row of the tile has been settled: its entries stay behind
-        cnt = 0;
-        for (int i0 = 0; i0 < n0; i0 += 32) {
-          const int i = i0 + lane;
-          cnt += __popc(__ballot_sync(0xffffffffu, i < n0 && ((live >> (q0[i < n0 ? i : 0] & 31u)) & 1u)));
-        }
-      }
-      unsigned long long base = 0;
-      if (lane == 0 && cnt) base = atomicAdd(&a.counters[C_L0], (unsigned long long)cnt);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      for (int i0 = 0; i0 < n0; i0 += 32) {
-        const int i = i0 + lane;
-        const uint32_t e = q0[i < n0 ? i : 0];
-        const bool k = i < n0 && ((live >> (e & 31u)) & 1u);
-        const unsigned m = __ballot_sync(0xffffffffu, k);
-        if (k) {
-          const unsigned long long pos = base + __popc(m & below);
-          const unsigned long long r = (unsigned long long)(row_base + (e & 31u));
-          if (pos < a.l0_cap) a.l0_items[pos] = r | ((unsigned long long)(e >> 5) << 40);
-          else pipe_row_overflow(a, (long long)r);
-        }
-        base += __popc(m);
-      }
-      n0 = 0;
-      __syncwarp();
-    };
-    auto push = [&](bool s, int p) {
+    // (the certain-contact test is only looked at when some lane of the warp queues the pair: a certain pair is
+    // a near pair, and most trips of the loops below end at the vote)
+    auto push = [&](bool s, int p, auto certain) {
       const unsigned m = __ballot_sync(0xffffffffu, s);
       if (m) {
-        if (s) q0[n0 + __popc(m & below)] = (uint32_t)lane | ((uint32_t)p << 5);
+        if (s) {
+          q0[n0 + __popc(m & below)] = (uint32_t)lane | ((uint32_t)p << 5);
+          if (certain()) alive = false;   // the entry just queued is dropped with the row's others at the flush
+        }
         n0 += __popc(m);
-        if (n0 + 32 > L0_QCAP) { __syncwarp(); flush(); }
+        if (n0 + 32 > L0_QCAP) {
+          __syncwarp();
+          l0_flush(a, q0, n0, __ballot_sync(0xffffffffu, alive), coll_lanes, row_base);
+          n0 = 0;
+        }
       }
     };
-    auto centre = [&](int g) { const float *cc = cen + g * 96 + lane; return mk<float>(cc[0], cc[32], cc[64]); };
+    // the tables are read through explicit shared-window addresses held in registers (the generic pointers
+    // were rebuilt from %cluster_ctaid in every trip of the loops below: three instructions and a stall per pair)
+    const uint32_t gp_sh = (uint32_t)__cvta_generic_to_shared(s_gp), sg_sh = (uint32_t)__cvta_generic_to_shared(s_sg);
+    const float *cl = cen + lane;
+    auto centre = [&](int g) { const float *cc = cl + g * 96; return mk<float>(cc[0], cc[32], cc[64]); };
     int p = 0;
     {  // moving sphere against moving sphere (pairs sorted by ga: its centre is fetched once per run)
       int cached = -1;
       V3<float> cA = mk<float>(0.f, 0.f, 0.f);
-#pragma unroll 2
+VK_UNROLL(VK_L0_UNROLL)
       for (; p < a.gp_kind_end[0]; p++) {
-        const GroupPair g = s_gp[p];
-        if ((int)g.ga != cached) { cached = g.ga; cA = centre(g.ga); }
-        const V3<float> d = cA - centre(g.gb);
+        const uint4 g = lds128(gp_sh + p * 16);   // GroupPair: ga | gb << 16, first | n << 16 | kind << 24, lim, lim_in
+        const int ga = (int)(g.x & 0xffffu), gb = (int)(g.x >> 16);
+        if (ga != cached) { cached = ga; cA = centre(ga); }
+        const V3<float> d = cA - centre(gb);
         const float d2 = dot(d, d);
-        if (d2 < g.lim_in * g.lim_in) alive = false;
-        push(alive && d2 <= g.lim * g.lim, p);
+        push(alive && d2 <= __uint_as_float(g.z), p, [&]() { return d2 < __uint_as_float(g.w); });
       }
     }
     {  // moving sphere against a world-fixed capsule
       int cached = -1;
       V3<float> cA = mk<float>(0.f, 0.f, 0.f);
-#pragma unroll 2
+VK_UNROLL(VK_L0_UNROLL)
       for (; p < a.gp_kind_end[1]; p++) {
-        const GroupPair g = s_gp[p];
-        if ((int)g.ga != cached) { cached = g.ga; cA = centre(g.ga); }
-        const StaticGroup S = s_sg[g.gb];
-        const V3<float> e = cA - mk<float>(S.a[0], S.a[1], S.a[2]);
-        const V3<float> ab = mk<float>(S.ab[0], S.ab[1], S.ab[2]);
-        float t = dot(e, ab) * S.inv_len2;
-        t = fminf(fmaxf(t, 0.f), 1.f);
-        const V3<float> f = e - ab * t;
-        const float d2 = dot(f, f);
-        if (d2 < g.lim_in * g.lim_in && fabsf(t - 0.5f) <= S.th) alive = false;
-        push(alive && d2 <= g.lim * g.lim, p);
+        const uint4 g = lds128(gp_sh + p * 16);
+        const int ga = (int)(g.x & 0xffffu), gb = (int)(g.x >> 16);
+        if (ga != cached) { cached = ga; cA = centre(ga); }
+        const uint4 s0 = lds128(sg_sh + gb * 32), s1 = lds128(sg_sh + gb * 32 + 16);   // StaticGroup: a, len | u, th
+        const V3<float> e = cA - mk<float>(__uint_as_float(s0.x), __uint_as_float(s0.y), __uint_as_float(s0.z));
+        const float len = __uint_as_float(s0.w);
+        float sc;
+        const float d2 = point_segment_d2(e, mk<float>(__uint_as_float(s1.x), __uint_as_float(s1.y), __uint_as_float(s1.z)), len, &sc);
+        push(alive && d2 <= __uint_as_float(g.z), p, [&]() { return d2 < __uint_as_float(g.w) && fabsf(sc - 0.5f * len) <= __uint_as_float(s1.w); });
       }
     }
     for (; p < a.gp_kind_end[2]; p++) {  // moving sphere against a plane
       const GroupPair g = s_gp[p];
       const StaticGroup S = s_sg[g.gb];
       const V3<float> e = centre(g.ga) - mk<float>(S.a[0], S.a[1], S.a[2]);
-      const float h = dot(e, mk<float>(S.ab[0], S.ab[1], S.ab[2]));
-      if (h < g.lim_in) alive = false;
-      push(alive && h <= g.lim, p);
+      const float h = dot(e, mk<float>(S.u[0], S.u[1], S.u[2]));
+      push(alive && h <= g.lim, p, [&]() { return h < g.lim_in; });
     }
+    __syncwarp();
+    if (n0) l0_flush(a, q0, n0, __ballot_sync(0xffffffffu, alive), coll_lanes, row_base);
     if (do_coll && !alive) {
       if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) atomicMin(&a.first_bad[e_idx], e_k);
       else a.valid[row] = 0;
     }
-    __syncwarp();
-    if (n0) flush();
   }
   if (lane == 0 && rows_total) atomicAdd(&a.counters[C_ROWS], (unsigned long long)rows_total);
 }

@@ -7,7 +7,9 @@ import mjpl_b200 as mj
 from mjpl_b200 import models
 from bench import make_rows, MODEL, ALLOWED
 model = models.load(MODEL); eng = mj.get_engine(model, ALLOWED)
-q = torch.from_numpy(make_rows(model, 1_000_000)).cuda()
+import os
+NROWS = int(os.environ.get('AB_ROWS', '1000000'))
+q = torch.from_numpy(make_rows(model, NROWS)).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for _ in range(5): eng.valid_configs(q)
 torch.cuda.synchronize()
