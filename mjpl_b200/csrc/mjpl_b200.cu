@@ -548,15 +548,14 @@ extern "C" int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n,
     CU(cudaMemcpyAsync(m->d_rows_ready, &m->h_progress[c], sizeof(unsigned long long), cudaMemcpyHostToDevice, m->copy_stream));
   }
   // Only the first kernel of a launch can work on rows as they arrive (it polls the progress word); the
-  // pipeline's later kernels start when ALL rows of their launch are on the device.  A large batch is
-  // therefore cut into a few launches: slice s is culled and decided while slices s+1.. are still on the bus.
-  // (B200, 1M Franka rows from pinned memory: 36 MB take 0.7 ms, the kernels 1.1 ms.)
+  // pipeline's later kernels start when ALL rows of their launch are on the device.  Cutting the batch into a
+  // few launches lets slice s be culled and decided while slices s+1.. are still on the bus.
+  // (Measured on B200, 1M Franka rows, 36 MB from pinned memory in 0.82 ms, kernels 1.05 ms: 1 launch 1.73 ms,
+  // 2 launches 1.74 ms, 4 launches 2.07 ms -- every launch of the pipeline costs 0.25 ms of ramp and tail, which
+  // eats what the overlap gives.  The default is therefore ONE launch; MJB_HOST_SLICES cuts the batch for A/B runs.)
   int64_t nslice = 1;
-  if (m->split && m->split_min > 0 && !(getenv("MJB_HOST_SLICES") && atoi(getenv("MJB_HOST_SLICES")) <= 1)) {
-    const int64_t per = std::max<int64_t>((int64_t)m->split_min, 250000);
-    nslice = std::min<int64_t>(std::max<int64_t>(n / per, 1), 8);
-    if (getenv("MJB_HOST_SLICES")) nslice = std::min<int64_t>(std::max<int64_t>(atoi(getenv("MJB_HOST_SLICES")), 1), std::max<int64_t>(n / (int64_t)m->split_min, 1));
-  }
+  if (m->split && m->split_min > 0 && getenv("MJB_HOST_SLICES"))
+    nslice = std::min<int64_t>(std::max<int64_t>(atoi(getenv("MJB_HOST_SLICES")), 1), std::max<int64_t>(n / (int64_t)m->split_min, 1));
   const int64_t chunks_per_slice = (nchunk + nslice - 1) / nslice;
   m->rows_total += n;
   const bool trace = getenv("MJB_HOST_TRACE") != nullptr;

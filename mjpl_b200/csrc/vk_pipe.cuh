@@ -37,7 +37,14 @@ constexpr int MID_THREADS = 256;
 constexpr int MID_CTAS = VK_MID_CTAS;      // resident CTAs per SM the register budget is set for
 constexpr int MID_Q1CAP = 1024;       // per-warp queue of expanded shape pairs
 constexpr int MID_Q2CAP = 96;         // per-warp queue of capsule survivors waiting for the OBB test
-constexpr int MID_CHUNK = 256;        // level-0 entries a warp claims per ticket
+#ifndef VK_MID_CHUNK
+#define VK_MID_CHUNK 256
+#endif
+constexpr int MID_CHUNK = VK_MID_CHUNK;        // level-0 entries a warp claims per ticket
+#ifndef VK_MID_AHEAD
+#define VK_MID_AHEAD 1
+#endif
+constexpr int MID_AHEAD = VK_MID_AHEAD;        // batches before the end of its chunk at which a warp claims the next ticket
 #ifndef VK_MID_STAGE
 #define VK_MID_STAGE 32
 #endif
@@ -475,22 +482,28 @@ __global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid
   auto load_entry = [&](unsigned long long pos) {   // entry of this lane in the batch starting at pos (or ~0)
     const unsigned long long ei = pos + lane;
     unsigned long long e = ~0ull;
-    if (pos < total && ei < total) {
-      e = a.l0_items[ei];
+    if (pos < total && ei < total) e = a.l0_items[ei];
+    return e;
+  };
+  // the pose block of an entry's row -> L1.  Issued for the NEXT batch's entries once the current batch has been
+  // expanded: by then their load has landed (issued right behind the load, the prefetch made the warp wait for
+  // it: 7 % of the stall samples), and the capsule cull of the current batch still lies ahead of their use.
+  auto prefetch_poses = [&](unsigned long long e) {
+    if (e != ~0ull) {
       const char *pb = reinterpret_cast<const char *>(a.pose8) + (size_t)(e & ((1ull << 40) - 1ull)) * pose_row_bytes;
       for (size_t o = 0; o < pose_row_bytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(pb + o));
     }
-    return e;
   };
   unsigned long long pos = claim(), chunk_end = pos + chunk_size;
   unsigned long long e_next = load_entry(pos);
+  prefetch_poses(e_next);
   while (pos < total) {
     const unsigned long long e_cur = e_next;
     // the batch after this one: same chunk, or the first batch of a freshly claimed chunk
     unsigned long long pos_next = pos + 32;
     if (pos_next >= chunk_end || pos_next >= total) { pos_next = claim(); chunk_end = pos_next + chunk_size; }
     e_next = load_entry(pos_next);
-    if (!ticket_out && pos_next < total && (pos_next + 32 >= chunk_end || pos_next + 32 >= total)) claim_ahead();
+    if (!ticket_out && pos_next < total && (pos_next + 32 * MID_AHEAD >= chunk_end || pos_next + 32 * MID_AHEAD >= total)) claim_ahead();
     {
       // ---- expand: every entry (row, group pair) -> its shape pairs ----------------------------------
       long long row = 0;
@@ -515,6 +528,7 @@ __global__ void __launch_bounds__(MID_THREADS, MID_CTAS) mid_kernel(const __grid
       // entries whose shape pairs did not fit (T > MID_Q1CAP: never with the shipped models, whose group
       // pairs have <= 18 members; 32 x 32 = 1024) fall back to whole-row fp64 re-evaluation
       if (T > MID_Q1CAP && off + n > MID_Q1CAP && n > 0) pipe_row_overflow(a, row);
+      prefetch_poses(e_next);
       // ---- capsule cull, lane = shape pair of some entry -------------------------------------------------
 #pragma unroll 1
       for (int s0 = 0; s0 < Tq; s0 += 32) {
