@@ -106,7 +106,7 @@ constexpr bool NARROW_HILL = VK_NARROW_HILL != 0;
 #endif
 constexpr int NARROW_CLAIM = VK_NARROW_CLAIM;   // items a warp claims per ticket
 #ifndef VK_NARROW_CTAS
-#define VK_NARROW_CTAS 3   // resident CTAs per SM the register budget is set for (B200, 1M Franka rows: 2 -> 2.91 ms, 3 -> 2.77, 4 -> 2.92)
+#define VK_NARROW_CTAS 2   // resident CTAs per SM the register budget is set for (B200, 1M Franka rows, narrow_kernel alone: 1 -> 0.274 ms, 2 -> 0.273, 3 -> 0.303, 4 -> 0.356; 128 registers, no spills)
 #endif
 
 __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(const __grid_constant__ KArgs a) {
