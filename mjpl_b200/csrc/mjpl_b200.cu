@@ -362,6 +362,9 @@ static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st, bool may_s
   return MJB_OK;
 }
 
+#ifndef VK_RECHECK_GRID
+#define VK_RECHECK_GRID 4
+#endif
 static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
   CU(cudaMemsetAsync(m->d_counters, 0, C_PER_LAUNCH * sizeof(unsigned long long), st));
   k.recheck_rows = m->d_recheck;
@@ -423,7 +426,7 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
     m->launches++;
   }
   if ((k.flags & F_COLLISION) && !(k.flags & F_NO_RECHECK)) {
-    recheck_kernel<<<m->num_sms * 4, 128, 0, st>>>(r);
+    recheck_kernel<<<m->num_sms * VK_RECHECK_GRID, 128, 0, st>>>(r);
     CU(cudaGetLastError());
     m->launches++;
   }

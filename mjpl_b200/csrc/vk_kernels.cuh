@@ -819,7 +819,10 @@ __device__ __forceinline__ void recheck_row(const RArgs &a, const FkTables<doubl
 //     distance <= margin, so it counts as one.
 //  2. whole ROWS (only when the item list overflowed): the 32 lanes split the static pair list.
 // Both only ever turn a tentatively valid row invalid.
-__global__ void __launch_bounds__(128) recheck_kernel(const RArgs a) {
+#ifndef VK_RECHECK_CTAS
+#define VK_RECHECK_CTAS 2
+#endif
+__global__ void __launch_bounds__(128, VK_RECHECK_CTAS) recheck_kernel(const RArgs a) {
   const FkTables<double> &fk = *a.fk;
   const int lane = threadIdx.x & 31;
   Pose<double> P[MAX_BODY];

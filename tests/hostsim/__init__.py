@@ -124,6 +124,7 @@ class HostSim:
         d["gjk_iter_hist"] = stats[8:24].tolist()
         d["gjk_verdicts_sep_pen_unc"] = stats[24:27].tolist()
         d["gjk_one_iteration_sep_pen_unc"] = stats[27:30].tolist()
+        d["fp64_iters_of_uncertain_le_4_8_12_16_24_32_48_more"] = stats[40:48].tolist()
         d["inner"] = dict(zip("invalid_rows caught_level0 caught_any level0_of_caught0 expanded_of_caught0 items_of_caught0 items_of_caught false_positives".split(),
                               stats[32:40].tolist()))
         return valid, d

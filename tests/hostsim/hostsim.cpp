@@ -360,6 +360,18 @@ extern "C" void hs_check_pipe(Sim *s, const float *q, int64_t n, uint32_t flags,
             stats[8 + (iters < 15 ? iters : 15)]++;          // [8..23] GJK iteration histogram
             stats[24 + v]++;                                 // [24..26] GJK verdicts SEP / PEN / UNC
             if (iters == 1) stats[27 + v]++;                 // [27..29] verdicts of the items that end in one iteration
+            if (v == V_UNC) {                                // [40..47] fp64 iterations of the items fp32 could not certify: <=4, <=8, <=12, <=16, <=24, <=32, <=48, more
+              Pose<double> P64[MAX_BODY], id64;
+              id64.p = mk<double>(0, 0, 0); id64.q.w = 1; id64.q.x = id64.q.y = id64.q.z = 0;
+              for (int k = 0; k < H.nslot; k++) { int ps = H.fk.body_parent[k]; P64[k] = fk_body(H.fk, k, ps < 0 ? id64 : P64[ps], qr); }
+              const Shape<double> &A64 = H.shapes[pr.sa], &B64 = H.shapes[pr.sb];
+              int it64 = 0;
+              gjk_classify(A64, B64, H.verts.data(), relative_pose(A64.slot < 0 ? id64 : P64[A64.slot], B64.slot < 0 ? id64 : P64[B64.slot]), H.pair_rsum64[p], &it64);
+              const int edges[7] = {4, 8, 12, 16, 24, 32, 48};
+              int b = 0;
+              while (b < 7 && it64 > edges[b]) b++;
+              stats[40 + b]++;
+            }
           } else {
             v = narrow_item<float>(pr.kind, A, B, s->v32.data(), PA, PB, pr.rsum);
             stats[5]++;                                      // closed-form / plane items
