@@ -405,8 +405,12 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
     // small launches: one warp per row.  Dense / sweep launches know their size here; for edges and chains
     // only the device does: both kernels are enqueued and the one out of its regime returns at once.
     const bool device_count = k.mode == MODE_EDGES || k.mode == MODE_CHAINS;
-    const bool rowk_only = m->rowk && !device_count && (long long)m->cur_rows <= m->rowk_rows;
-    k.rowk_max = (m->rowk && device_count) ? m->rowk_rows : -1;
+    // For chains cur_rows is a worst case and cur_rows_hint the expected count: when the expectation is small only
+    // row_kernel is enqueued, without a cap -- it is correct for any number of rows, merely slower than the
+    // throughput kernel if the chains turn out much longer than expected (an empty launch of that kernel's
+    // persistent grid costs 8 us, a quarter of a small extension).
+    const bool rowk_only = m->rowk && (long long)(device_count ? m->cur_rows_hint : m->cur_rows) <= m->rowk_rows;
+    k.rowk_max = (m->rowk && device_count && !rowk_only) ? m->rowk_rows : -1;
     if (rowk_only || (m->rowk && device_count)) {
       const long long want = device_count ? (long long)m->rowk_grid : std::min<long long>(m->rowk_grid, ((long long)m->cur_rows + 7) / 8);
       row_kernel<<<(unsigned)std::max<long long>(want, 1), ROWK_THREADS, m->rowk_smem, st>>>(k);
@@ -426,7 +430,9 @@ static int launch_validity(mjb_model *m, KArgs &k, RArgs &r, cudaStream_t st) {
     m->launches++;
   }
   if ((k.flags & F_COLLISION) && !(k.flags & F_NO_RECHECK)) {
-    recheck_kernel<<<m->num_sms * VK_RECHECK_GRID, 128, 0, st>>>(r);
+    // one warp per fp64 item, tickets for the rest: a small launch does not need the full grid
+    const long long rgrid = std::min<long long>((long long)m->num_sms * VK_RECHECK_GRID, std::max<long long>(((long long)m->cur_rows_hint + 3) / 4, 16));
+    recheck_kernel<<<(unsigned)rgrid, 128, 0, st>>>(r);
     CU(cudaGetLastError());
     m->launches++;
   }
@@ -761,11 +767,11 @@ extern "C" int mjb_reset_stats(mjb_model *m) {
 
 extern "C" int mjb_nearest_batch(const double *d_nodes, int64_t cap, int32_t nq, const int64_t *d_count, const int64_t *d_rows,
                                  const double *d_targets, int64_t n, int64_t *d_out, void *stream) {
-  if (n < 0 || cap < 1 || nq < 1) return fail(MJB_ERR_ARG, "bad n / cap / nq");
+  if (n < 0 || cap < 1 || nq < 1 || nq > MAX_JNT) return fail(MJB_ERR_ARG, "bad n / cap / nq");
   if (n == 0) return MJB_OK;
   if (!d_nodes || !d_count || !d_targets || !d_out) return fail(MJB_ERR_ARG, "null device pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  nearest_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_count,
+  nearest_kernel<<<(unsigned)n, NEAREST_THREADS, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_count,
                                                                   (const long long *)d_rows, d_targets, (long long)n,
                                                                   (long long *)d_out);
   CU(cudaGetLastError());
@@ -824,7 +830,7 @@ extern "C" int mjb_rrt_extend_masked(mjb_model *m, double *d_nodes, int64_t *d_p
   // (expected rows: ~24 chain steps per query on the Franka scenes; only picks the kernel instance)
   if ((rc = ensure_recheck(m, (size_t)n * (size_t)kcap, st, false, (size_t)n * 24))) return rc;
   // 1. nearest node of every query's tree   2. chain lengths + prefix sums
-  nearest_kernel<<<(unsigned)((n * 32 + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_count,
+  nearest_kernel<<<(unsigned)n, NEAREST_THREADS, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_count,
                                                                   (const long long *)d_slots, d_targets, (long long)n, m->d_chain_nn, d_active);
   chain_setup_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_slots, m->d_chain_nn,
                                                                  d_targets, (long long)n, eps, kcap, m->d_chain_near, m->d_edge_count,

@@ -1145,33 +1145,46 @@ __global__ void chain_append_kernel(double *nodes, long long *parent, long long 
 // trees are rows of a padded (B, cap, nq) fp64 array; one warp scans one tree and keeps the
 // arg-min of the squared distance (lowest index wins ties).  Nodes with non-finite entries (the
 // +inf sink root of the reference's goal tree) can never win.
-__global__ void __launch_bounds__(128) nearest_kernel(const double *nodes, long long cap, int nq, const long long *count,
-                                                      const long long *rows, const double *targets, long long n,
-                                                      long long *out, const uint8_t *active = nullptr) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// One CTA of 128 threads per tree (a warp per tree ran as long as its 19 dependent trips through a 600-node
+// tree took: 33 us per call in the planner's loop, as much as the validity check of the extension itself).
+constexpr int NEAREST_THREADS = 128;
+__global__ void __launch_bounds__(NEAREST_THREADS) nearest_kernel(const double *nodes, long long cap, int nq, const long long *count,
+                                                                  const long long *rows, const double *targets, long long n,
+                                                                  long long *out, const uint8_t *active = nullptr) {
+  const long long w = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (w >= n) return;
-  if (active && !active[w]) { if (lane == 0) out[w] = 0; return; }   // masked query: no scan (its chain is empty anyway)
+  if (active && !active[w]) { if (tid == 0) out[w] = 0; return; }   // masked query: no scan (its chain is empty anyway)
+  __shared__ double s_t[MAX_JNT];
+  __shared__ double s_best[NEAREST_THREADS / 32];
+  __shared__ long long s_bi[NEAREST_THREADS / 32];
   const long long tree = rows ? rows[w] : w;
   const double *base = nodes + tree * cap * nq;
-  const double *t = targets + w * nq;
+  if (tid < nq) s_t[tid] = targets[w * nq + tid];
+  __syncthreads();
   const long long cnt = count[tree];
   double best = 1.0e300;
   long long bi = 0;
-  for (long long i = lane; i < cnt; i += 32) {
+  for (long long i = tid; i < cnt; i += NEAREST_THREADS) {
     double d2 = 0;
     for (int j = 0; j < nq; j++) {
-      double d = base[i * nq + j] - t[j];
+      double d = base[i * nq + j] - s_t[j];
       d2 += d * d;
     }
-    if (d2 < best) { best = d2; bi = i; }   // NaN / inf never pass
+    if (d2 < best) { best = d2; bi = i; }   // NaN / inf never pass; within a thread the indices ascend: the first minimum stays
   }
   for (int o = 16; o > 0; o >>= 1) {
     double ob = __shfl_xor_sync(0xffffffffu, best, o);
     long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
   }
-  if (lane == 0) out[w] = bi;
+  if (lane == 0) { s_best[warp] = best; s_bi[warp] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int k = 1; k < NEAREST_THREADS / 32; k++)
+      if (s_best[k] < best || (s_best[k] == best && s_bi[k] < bi)) { best = s_best[k]; bi = s_bi[k]; }
+    out[w] = bi;
+  }
 }
 
 // ---------------------------------------------------------------------------- signed distance per row (band accounting)
