@@ -56,6 +56,8 @@ struct mjb_model {
   // multi-kernel pipeline (vk_pipe.cuh, large batches): poses / level-0 list / item bins / row flags of one batch
   bool split = false; size_t fk_smem = 0, mid_smem = 0, narrow_smem = 0; int fk_grid = 0, mid_grid = 0, narrow_grid = 0;
   float *d_pose8 = nullptr; unsigned long long *d_bins = nullptr; uint32_t *d_row_flags = nullptr; size_t split_cap = 0;
+  uint8_t *d_rowmask = nullptr;   // edges through the pipeline: one byte per waypoint (F_ROWMASK)
+  bool light_narrow = false;      // no hull of more than 8 vertices: edge batches stay in the single kernel
   unsigned long long *d_l0 = nullptr; size_t l0_cap = 0;
   bool rowk = false; size_t rowk_smem = 0; int rowk_grid = 0; long long rowk_rows = 0;   // one-warp-per-row kernel for small launches
   GroupPair *d_gpairs = nullptr; StaticGroup *d_sgroups = nullptr; uint16_t *d_gp_member = nullptr;
@@ -200,6 +202,8 @@ extern "C" int mjb_model_create(const mjb_model_desc *desc, mjb_model **out) {
     const char *smin = getenv("MJB_SPLIT_MIN");
     const int mode = sp ? atoi(sp) : -1;
     m->split_min = mode == 1 ? 0 : (smin ? (size_t)atoll(smin) : (size_t)200000);
+    m->light_narrow = mode != 1;
+    for (const auto &sh : H.shapes) if (sh.kind == SK_VERTS && sh.nvert > 8) m->light_narrow = false;
     const char *bc = getenv("MJB_BIN_CAP");   // testing: tiny bins force the on-the-spot path of full bins
     m->bin_cap_override = bc ? (size_t)atoll(bc) : 0;
     // launches of at most this many rows use the GRP_SMALL-lanes-per-item instance of validity_kernel.  B200, Franka rows, raw
@@ -303,7 +307,7 @@ extern "C" void mjb_model_destroy(mjb_model *m) {
   cudaFree(m->d_verts64); cudaFree(m->d_fk64); cudaFree(m->d_rsum64); cudaFree(m->d_bsum64);
   cudaFree(m->d_body_slot); cudaFree(m->d_static_pose); cudaFree(m->d_adj_start); cudaFree(m->d_adj); cudaFree(m->d_pose); cudaFree(m->d_counters);
   cudaFree(m->d_pose8); cudaFree(m->d_bins); cudaFree(m->d_row_flags); cudaFree(m->d_l0);
-  cudaFree(m->d_gpairs); cudaFree(m->d_sgroups); cudaFree(m->d_gp_member); cudaFree(m->d_smap_cells); cudaFree(m->d_smap_ids);
+  cudaFree(m->d_rowmask); cudaFree(m->d_gpairs); cudaFree(m->d_sgroups); cudaFree(m->d_gp_member); cudaFree(m->d_smap_cells); cudaFree(m->d_smap_ids);
   cudaFree(m->d_recheck); cudaFree(m->d_edge_count); cudaFree(m->d_edge_prefix); cudaFree(m->d_first_bad);
   cudaFree(m->d_cub); cudaFree(m->d_stage_q); cudaFree(m->d_stage_v); cudaFree(m->d_chain_near); cudaFree(m->d_chain_nn);
   if (m->h_pin_q) cudaFreeHost(m->h_pin_q);
@@ -340,8 +344,8 @@ static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st, bool may_s
   m->use_split = may_split && m->split && rows >= m->split_min;
   if (m->use_split && rows > m->split_cap) {
     CU(cudaStreamSynchronize(st));
-    cudaFree(m->d_pose8); cudaFree(m->d_bins); cudaFree(m->d_row_flags); cudaFree(m->d_l0);
-    m->d_pose8 = nullptr; m->d_bins = nullptr; m->d_row_flags = nullptr; m->d_l0 = nullptr;
+    cudaFree(m->d_pose8); cudaFree(m->d_bins); cudaFree(m->d_row_flags); cudaFree(m->d_l0); cudaFree(m->d_rowmask);
+    m->d_pose8 = nullptr; m->d_bins = nullptr; m->d_row_flags = nullptr; m->d_l0 = nullptr; m->d_rowmask = nullptr;
     size_t cap = std::max<size_t>(rows, 1 << 16);
     // level-0 list: 3x the calibrated survivors per row + 4 (uniform rows are what the calibration saw;
     // rows whose entries do not fit are re-evaluated whole in fp64, so a full list costs speed only)
@@ -352,6 +356,7 @@ static int ensure_recheck(mjb_model *m, size_t rows, cudaStream_t st, bool may_s
     for (int b = 0; b < NBIN; b++) tot += bin_capacity(m->H, b, cap);
     CU(cudaMalloc((void **)&m->d_bins, tot * sizeof(unsigned long long)));
     CU(cudaMalloc((void **)&m->d_row_flags, align_up(cap, 4)));
+    CU(cudaMalloc((void **)&m->d_rowmask, align_up(cap, 256)));
     m->split_cap = cap;
   }
   if (rows <= m->recheck_cap) return MJB_OK;
@@ -655,7 +660,12 @@ extern "C" int mjb_check_edges(mjb_model *m, const float *d_q0, const float *d_q
   long long total = 0;
   CU(cudaMemcpyAsync(&total, m->d_edge_prefix + ne, sizeof total, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  if ((rc = ensure_recheck(m, (size_t)std::max<long long>(total, 1), st))) return rc;
+  // Waypoints of one edge are neighbours in configuration space: the lanes of a warp agree on which pairs are near,
+  // and the single kernel skips a pair no lane of the warp needs, while the pipeline's level 0 tests every group
+  // pair for every row.  For models whose narrow phase is cheap (primitives and boxes only) that wins: UR5e, 100k
+  // edges / 12.1M waypoints 4.4 ms in the single kernel, 7.0 ms in the pipeline; with hulls to scan it is the other
+  // way round (Franka obstacle scene 23.4 vs 6.8 ms).
+  if ((rc = ensure_recheck(m, (size_t)std::max<long long>(total, 1), st, /*may_split=*/!m->light_narrow))) return rc;
   m->rows_total += total;
   KArgs k = m->kargs;
   k.mode = MODE_EDGES; k.q0 = d_q0; k.q1 = d_q1; k.ldq = ldq; k.edge_prefix = m->d_edge_prefix; k.nedge = ne;
@@ -664,7 +674,14 @@ extern "C" int mjb_check_edges(mjb_model *m, const float *d_q0, const float *d_q
   r.mode = MODE_EDGES; r.q0 = d_q0; r.q1 = d_q1; r.ldq = ldq; r.edge_prefix = m->d_edge_prefix; r.nedge = ne;
   r.step = step; r.first_bad = m->d_first_bad;
   m->launches += 2;
+  const bool rowmask = m->use_split && (flags & F_COLLISION);   // the pipeline keeps a byte per waypoint, see F_ROWMASK
+  if (rowmask) { k.valid = m->d_rowmask; k.flags |= F_ROWMASK; }
   if ((rc = launch_validity(m, k, r, st))) return rc;
+  if (rowmask) {
+    edge_rowmask_kernel<<<(unsigned)((ne * 32 + 255) / 256), 256, 0, st>>>(ne, m->d_edge_prefix, m->d_rowmask, m->d_first_bad);
+    CU(cudaGetLastError());
+    m->launches++;
+  }
   edge_finalize_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(ne, m->d_first_bad, d_valid, d_first_bad);
   CU(cudaGetLastError());
   m->launches++;

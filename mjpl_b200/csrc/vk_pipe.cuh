@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(PIPE_FK_THREADS, VK_FK_CTAS) fk_cull_kernel(co
       }
       if ((a.flags & F_LIMITS) && a.mode != MODE_CHAINS)
         lim_ok = limits_ok(q, a.fk.njnt, a.jnt_lo, a.jnt_hi, a.flags & F_LIMITS_OUTWARD);
-      if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) {
+      if ((a.mode == MODE_EDGES || a.mode == MODE_CHAINS) && !(a.flags & F_ROWMASK)) {
         if (!lim_ok) atomicMin(&a.first_bad[e_idx], e_k);
       } else {
         a.valid[row] = lim_ok ? 1 : 0;   // the later kernels can only turn it to 0
@@ -323,7 +323,7 @@ VK_UNROLL(VK_L0_UNROLL)
     __syncwarp();
     if (n0) l0_flush(a, q0, n0, __ballot_sync(0xffffffffu, alive), coll_lanes, row_base);
     if (do_coll && !alive) {
-      if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) atomicMin(&a.first_bad[e_idx], e_k);
+      if ((a.mode == MODE_EDGES || a.mode == MODE_CHAINS) && !(a.flags & F_ROWMASK)) atomicMin(&a.first_bad[e_idx], e_k);
       else a.valid[row] = 0;
     }
   }

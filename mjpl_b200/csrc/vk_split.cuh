@@ -31,7 +31,7 @@ __device__ __forceinline__ Pose<float> load_pose8(const float *pose8, int nslot,
 
 // a certain contact of `row`: the reference's answer for the row is "invalid"
 __device__ __forceinline__ void mark_contact(const KArgs &a, long long row) {
-  if (a.mode == MODE_EDGES || a.mode == MODE_CHAINS) {
+  if ((a.mode == MODE_EDGES || a.mode == MODE_CHAINS) && !(a.flags & F_ROWMASK)) {
     long long e;
     int k;
     edge_lookup(a.edge_prefix, a.nedge, row, e, k);
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(NARROW_THREADS, VK_NARROW_CTAS) narrow_kernel(
   mbar_wait(&s_bar[0], 0);
   __syncthreads();
 
-  const bool by_row = !(a.mode == MODE_EDGES || a.mode == MODE_CHAINS);  // the output mask doubles as the early-exit flag
+  const bool by_row = !(a.mode == MODE_EDGES || a.mode == MODE_CHAINS) || (a.flags & F_ROWMASK);  // the output mask doubles as the early-exit flag
   const int gl = 0;
   const unsigned gmask = 1u << lane;
   GjkState<float> gs;
