@@ -584,22 +584,37 @@ extern "C" int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n,
   // Only the first kernel of a launch can work on rows as they arrive (it polls the progress word); the
   // pipeline's later kernels start when ALL rows of their launch are on the device.  Cutting the batch into a
   // few launches lets slice s be culled and decided while slices s+1.. are still on the bus.
-  // (Measured on B200, 1M Franka rows, 36 MB from pinned memory in 0.82 ms, kernels 1.05 ms: 1 launch 1.73 ms,
-  // 2 launches 1.74 ms, 4 launches 2.07 ms -- every launch of the pipeline costs 0.25 ms of ramp and tail, which
-  // eats what the overlap gives.  The default is therefore ONE launch; MJB_HOST_SLICES cuts the batch for A/B runs.)
-  // From 4M rows on two launches do pay (4M rows: 6.38 -> 5.62 ms).
+  // (Measured on B200, 1M Franka rows, 36 MB from pinned memory in 0.77 ms, kernels 1.02 ms: 1 launch 1.73 ms,
+  // 2 equal launches 1.74 ms, 4 launches 2.07 ms -- every launch of the pipeline costs 0.25 ms of ramp and tail,
+  // which eats what the overlap gives.  What does pay is a SHORT first launch, see MJB_HOST_FIRST below; from 4M
+  // rows on equal launches of about 2M rows do too (4M rows: 6.38 -> 5.62 ms).  MJB_HOST_SLICES forces a count.)
   int64_t nslice = (m->split && m->split_min > 0) ? std::min<int64_t>(std::max<int64_t>(n / 2000000, 1), 4) : 1;
   if (m->split && m->split_min > 0 && getenv("MJB_HOST_SLICES"))
     nslice = std::min<int64_t>(std::max<int64_t>(atoi(getenv("MJB_HOST_SLICES")), 1), std::max<int64_t>(n / (int64_t)m->split_min, 1));
-  const int64_t chunks_per_slice = (nchunk + nslice - 1) / nslice;
+  // slice boundaries (multiples of the chunk size).  MJB_HOST_FIRST=f: two launches, the first with the fraction f
+  // of the rows -- a short first launch is done before the copy is, and the second starts on rows that have
+  // mostly landed (an equal split finishes its first half just AFTER the copy and gains nothing).
+  std::vector<int64_t> cuts;
+  const char *hf = getenv("MJB_HOST_FIRST");
+  const double first = hf ? atof(hf) : 0.25;   // B200, 1M Franka rows: mask on the host after 1.55 ms (one launch), 1.41 (0.25), 1.46 (0.3-0.4), 1.62 (0.5)
+  if (m->split && m->split_min > 0 && first > 0.0 && first < 1.0 && nslice == 1 && n >= 2 * (int64_t)m->split_min) {
+    int64_t c0 = std::max<int64_t>((int64_t)(first * (double)nchunk + 0.5), 1) * HOST_CHUNK_ROWS;
+    c0 = std::max<int64_t>(c0, (int64_t)align_up(m->split_min, (size_t)HOST_CHUNK_ROWS));
+    if (n - c0 >= (int64_t)m->split_min) cuts.push_back(c0);
+  } else {
+    const int64_t chunks_per_slice = (nchunk + nslice - 1) / nslice;
+    for (int64_t r = chunks_per_slice * HOST_CHUNK_ROWS; r < n; r += chunks_per_slice * HOST_CHUNK_ROWS) cuts.push_back(r);
+  }
+  cuts.push_back(n);
   m->rows_total += n;
   const bool trace = getenv("MJB_HOST_TRACE") != nullptr;
   std::vector<cudaEvent_t> tev;
   auto mark = [&](cudaStream_t s) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s); tev.push_back(e); } };
   mark(st);
   mark(m->copy_stream);
-  for (int64_t r0 = 0; r0 < n; r0 += chunks_per_slice * HOST_CHUNK_ROWS) {
-    const int64_t r1 = std::min<int64_t>(n, r0 + chunks_per_slice * HOST_CHUNK_ROWS);
+  int64_t r0 = 0;
+  for (size_t ci = 0; ci < cuts.size(); r0 = cuts[ci], ci++) {
+    const int64_t r1 = cuts[ci];
     KArgs k = m->kargs;
     k.mode = MODE_DENSE; k.q = m->d_stage_q + (size_t)r0 * nq; k.ldq = nq; k.n = r1 - r0; k.valid = m->d_stage_v + r0; k.flags = flags;
     k.rows_ready = m->d_rows_ready; k.row0 = r0;
@@ -614,7 +629,7 @@ extern "C" int mjb_check_configs_host(mjb_model *m, const float *h_q, int64_t n,
   CU(cudaStreamSynchronize(st));
   CU(cudaStreamSynchronize(m->copy_stream));
   if (trace) {
-    fprintf(stderr, "[mjb] host batch %lld rows, %lld slices:", (long long)n, (long long)nslice);
+    fprintf(stderr, "[mjb] host batch %lld rows, %lld slices:", (long long)n, (long long)cuts.size());
     for (size_t i = 1; i < tev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, tev[0], tev[i]); fprintf(stderr, " %.3f", ms); }
     fprintf(stderr, " ms (copies done, each slice done, mask on host)\n");
     for (auto e : tev) cudaEventDestroy(e);
