@@ -830,13 +830,10 @@ __device__ __forceinline__ void recheck_row(const RArgs &a, const FkTables<doubl
 __global__ void __launch_bounds__(128, VK_RECHECK_CTAS) recheck_kernel(const RArgs a) {
   const FkTables<double> &fk = *a.fk;
   const int lane = threadIdx.x & 31;
-  // The row and its poses live in SHARED memory, one copy per warp (every lane computes and stores the same
-  // values).  As per-thread arrays they sat in local memory: the kernel's length is the latency of one item, and
-  // that was a chain of ~100 dependent local loads and stores (2.3 KB of stack per thread).
-  __shared__ double s_q[4][MAX_JNT];
-  __shared__ Pose<double> s_P[4][MAX_BODY];
-  double *q = s_q[threadIdx.x >> 5];
-  Pose<double> *P = s_P[threadIdx.x >> 5];
+  // (q and P as per-warp shared arrays instead of per-thread local ones: the fp64 pass of a 1M-row launch is as
+  // long either way, 0.053 ms, and the planner's iterations got slower and jittery -- measured, dropped)
+  double q[MAX_JNT];
+  Pose<double> P[MAX_BODY];
   Pose<double> ident; ident.p = mk<double>(0, 0, 0); ident.q.w = 1; ident.q.x = ident.q.y = ident.q.z = 0;
   long long e_idx;
   int e_k;
