@@ -159,6 +159,15 @@ int mjb_nearest_batch(const double *d_nodes, int64_t cap, int32_t nq, const int6
                       void *stream);
 
 /*
+ * Tree.get_path (src/mjpl/planning/tree.py:68-81) for n trees at once: from node d_first[i] of tree d_rows[i]
+ * (NULL: tree i) follow the parent links (d_parent: (ntrees, cap) int64, -1 at the root) to the root.
+ * d_steps: (n, max_depth) int64, row i = the node indices first .. root, padded with -1; d_len[i] = their
+ * number (a chain longer than max_depth is cut there and reported with d_len[i] = -1).
+ */
+int mjb_tree_paths(const int64_t *d_parent, int64_t cap, const int64_t *d_rows, const int64_t *d_first, int64_t n,
+                   int64_t max_depth, int64_t *d_steps, int64_t *d_len, void *stream);
+
+/*
  * One _constrained_extend (src/mjpl/planning/utils.py:105-164) for n trees at once, for
  * non-projecting constraints, entirely on the device: nearest node, the chain
  * near + k*eps*(target-near)/|target-near| (k = 1..min(ceil(dist/eps), kcap); the step that covers

@@ -797,6 +797,18 @@ extern "C" int mjb_reset_stats(mjb_model *m) {
   return MJB_OK;
 }
 
+extern "C" int mjb_tree_paths(const int64_t *d_parent, int64_t cap, const int64_t *d_rows, const int64_t *d_first, int64_t n,
+                              int64_t max_depth, int64_t *d_steps, int64_t *d_len, void *stream) {
+  if (n < 0 || cap < 1 || max_depth < 1) return fail(MJB_ERR_ARG, "bad n / cap / max_depth");
+  if (n == 0) return MJB_OK;
+  if (!d_parent || !d_first || !d_steps || !d_len) return fail(MJB_ERR_ARG, "null device pointer");
+  tree_paths_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      (const long long *)d_parent, (long long)cap, (const long long *)d_rows, (const long long *)d_first, (long long)n,
+      (long long)max_depth, (long long *)d_steps, (long long *)d_len);
+  CU(cudaGetLastError());
+  return MJB_OK;
+}
+
 extern "C" int mjb_nearest_batch(const double *d_nodes, int64_t cap, int32_t nq, const int64_t *d_count, const int64_t *d_rows,
                                  const double *d_targets, int64_t n, int64_t *d_out, void *stream) {
   if (n < 0 || cap < 1 || nq < 1 || nq > MAX_JNT) return fail(MJB_ERR_ARG, "bad n / cap / nq");

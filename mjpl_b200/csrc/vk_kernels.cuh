@@ -1210,6 +1210,22 @@ __global__ void __launch_bounds__(NEAREST_THREADS) nearest_kernel(const double *
   }
 }
 
+// ---------------------------------------------------------------------------- parent chains of many trees
+// Tree.get_path (reference: src/mjpl/planning/tree.py:68-81): one thread per tree follows the parent links from
+// `first` to the root (a few hundred dependent loads: microseconds; the host-side loop it replaces launched four
+// kernels per level).
+__global__ void tree_paths_kernel(const long long *parent, long long cap, const long long *rows, const long long *first, long long n,
+                                  long long max_depth, long long *steps, long long *len) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long *par = parent + (rows ? rows[i] : i) * cap;
+  long long *out = steps + i * max_depth;
+  long long idx = first[i], d = 0;
+  while (idx >= 0 && idx < cap && d < max_depth) { out[d++] = idx; idx = par[idx]; }
+  len[i] = (idx >= 0) ? -1 : d;
+  for (long long k = d; k < max_depth; k++) out[k] = -1;
+}
+
 // ---------------------------------------------------------------------------- signed distance per row (band accounting)
 struct MArgs {
   const FkTables<double> *fk;

@@ -25,6 +25,7 @@ Two drivers share the algorithm:
 
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -330,6 +331,7 @@ class BatchedRRT:
         L = _abi.lib()
         dev, f64, i64 = eng.torch_device, torch.float64, torch.int64
         S, nq = QI.shape
+        t_wave0 = time.perf_counter()
         eps, kcap = float(self.epsilon), int(self.max_chain)
         q_idx = qpos_idx(self.model, self.planning_joints)
         plan_mask = torch.zeros(nq, dtype=torch.uint8, device=dev)
@@ -420,8 +422,13 @@ class BatchedRRT:
             except Exception:      # capture not possible (e.g. a profiler that forbids it): enqueue eagerly
                 graph = None
             t0 = time.time()
+            trace = [] if os.environ.get("MJPL_PLAN_TRACE") else None
             while True:
+                if trace is not None:
+                    trace.append(time.perf_counter())
                 it, n_active, hs, hg = look()
+                if trace is not None:
+                    trace.append(time.perf_counter())
                 if n_active == 0 or it >= self.max_iterations or time.time() - t0 >= time_left:
                     break
                 need = max(hs, hg) + headroom
@@ -438,6 +445,14 @@ class BatchedRRT:
                         for _ in range(pairs_per_sync):
                             pair()
                     side.synchronize()
+            t_loop1 = time.perf_counter()
+            if trace is not None and len(trace) > 4:
+                print(f"[plan trace] setup {1e3 * (trace[0] - t_wave0):.1f} ms, loop {1e3 * (t_loop1 - trace[0]):.1f} ms")
+                tr = np.array(trace)
+                look_ms = (tr[1::2] - tr[0::2]) * 1e3          # enqueue of the status reads + wait for the GPU to get there
+                enq_ms = (tr[2::2] - tr[1:-1:2]) * 1e3         # growth / re-capture + enqueue of the replays
+                print(f"[plan trace] syncs {len(look_ms)}: waits sum {look_ms.sum():.1f} ms max {look_ms.max():.1f}; "
+                      f"enqueue sum {enq_ms.sum():.1f} ms max {enq_ms.max():.1f}, over 5 ms: {np.round(enq_ms[enq_ms > 5], 1).tolist()}")
             torch.cuda.current_stream().wait_stream(side)
             it, n_active, hs, hg = look()
             self.stats["iterations"] = max(self.stats["iterations"], it)
@@ -446,39 +461,39 @@ class BatchedRRT:
             out: list[list[np.ndarray]] = [[] for _ in range(S)]
             solved = (res_s >= 0).nonzero(as_tuple=True)[0]
             if len(solved):
-                def walk(F, first):
-                    """-> (depth, n) node indices from `first` towards the root, -1 past the root"""
-                    idx, cols = first.clone(), []
-                    while True:
-                        cols.append(idx)
-                        nxt = torch.where(idx >= 0, F.parent[solved, idx.clamp(min=0)], idx)
-                        if len(cols) % 32 == 0 and not bool((nxt >= 0).any()):
-                            break
-                        if len(cols) > F.cap:
-                            break
-                        idx = nxt
-                    return torch.stack(cols)
+                # Tree.get_path for every solved slot in one launch per tree (mjb_tree_paths), rows gathered on the
+                # device in query-major order, one D2H copy per tree, one split per tree
+                n_solved = len(solved)
+                max_depth = max(int(hs), int(hg), 1)     # a chain cannot be longer than its tree has nodes
 
-                def rows_of(F, steps):
+                def chains(F, first):
+                    steps = torch.empty((n_solved, max_depth), dtype=i64, device=dev)
+                    length = torch.empty(n_solved, dtype=i64, device=dev)
+                    _abi.check(L.mjb_tree_paths(F.parent.data_ptr(), F.cap, solved.data_ptr(), first.data_ptr(), n_solved,
+                                                max_depth, steps.data_ptr(), length.data_ptr(), stream()))
+                    counts = length.cpu().numpy()
+                    if (counts < 0).any():
+                        raise RuntimeError("a parent chain is longer than its tree")
+                    steps = steps[:, :max(int(counts.max()), 1)]
                     valid = steps >= 0
-                    sl = solved[None, :].expand_as(steps)[valid]
-                    return F.q[sl, steps[valid]].cpu().numpy(), valid.cpu().numpy()
+                    sl = solved[:, None].expand_as(steps)[valid]
+                    rows = F.q[sl, steps[valid]].cpu().numpy()          # query by query, first node .. root
+                    return rows, counts
 
-                ws, wg = walk(start, res_s[solved]), walk(goal, res_g[solved])
-                rs, vs = rows_of(start, ws)
-                rg, vg = rows_of(goal, wg)
-                # rows come depth-major: split them back per query
-                def per_query(rows, valid):
-                    order = np.argsort(np.nonzero(valid)[1], kind="stable")   # group by query, depth order kept
-                    counts = valid.sum(axis=0)
-                    return np.split(rows[order], np.cumsum(counts)[:-1])
-
-                for k, ps, pg in zip(solved.cpu().numpy(), per_query(rs, vs), per_query(rg, vg)):
-                    a = list(ps[::-1])          # root of the start tree -> connecting node
-                    g = list(pg)                # connecting node -> root of the goal tree
-                    if np.array_equal(a[-1], g[0]):
-                        a.pop()
-                    out[int(k)] = a + g
+                tp = [time.perf_counter()]
+                rs, cs = chains(start, res_s[solved].contiguous())
+                tp.append(time.perf_counter())
+                rg, cg = chains(goal, res_g[solved].contiguous())
+                tp.append(time.perf_counter())
+                os_, og = np.concatenate(([0], np.cumsum(cs))), np.concatenate(([0], np.cumsum(cg)))
+                same = (rs[os_[:-1]] == rg[og[:-1]]).all(axis=1)       # the two extends met in one configuration
+                tp.append(time.perf_counter())
+                for i, k in enumerate(solved.cpu().numpy()):
+                    a = rs[os_[i] + (1 if same[i] else 0):os_[i + 1]][::-1]   # root of the start tree -> connecting node
+                    out[int(k)] = list(a) + list(rg[og[i]:og[i + 1]])        # connecting node -> root of the goal tree
+            if trace is not None:
+                tp.append(time.perf_counter())
+                print(f"[plan trace] paths to the host {1e3 * (time.perf_counter() - t_loop1):.1f} ms: start tree, goal tree, offsets, lists =", np.round(np.diff(tp) * 1e3, 1).tolist(), "nodes", len(rs) + len(rg))
             return out
 
     # ------------------------------------------------------------------ device driver, projecting constraint

@@ -294,3 +294,49 @@ def test_rrt_extend_matches_the_reference_extend_call_by_call():
     print(f"rrt_extend: {B} calls, mean appended {appended.mean():.2f}, reached the target {int((n_ok == K).sum())}, "
           f"chains with a row in the band {int(in_band.sum())}")
     assert (same <= (appended == 0)).all() and appended.mean() > 1.0
+
+
+@pytest.mark.gpu
+def test_tree_paths_follow_the_parent_links():
+    """``mjb_tree_paths`` (Tree.get_path, reference tree.py:68-81, for many trees at once) against a host walk:
+    random forests, chains from random nodes to the root, tree selection through ``d_rows``, padding, and a chain
+    that does not fit ``max_depth`` reported as such."""
+    import torch
+
+    from mjpl_b200 import _abi
+
+    L = _abi.lib()
+    rng = np.random.default_rng(5)
+    ntrees, cap = 37, 300
+    parent = np.full((ntrees, cap), -1, dtype=np.int64)
+    counts = rng.integers(1, cap, size=ntrees)
+    for t in range(ntrees):
+        for i in range(1, counts[t]):
+            parent[t, i] = rng.integers(max(0, i - 4), i)       # deep, thin trees
+    rows = rng.integers(0, ntrees, size=64).astype(np.int64)
+    first = np.array([rng.integers(0, counts[t]) for t in rows], dtype=np.int64)
+    want = []
+    for t, f in zip(rows, first):
+        chain, i = [], int(f)
+        while i >= 0:
+            chain.append(i)
+            i = int(parent[t, i])
+        want.append(chain)
+    depth = max(len(c) for c in want)
+    dev = torch.device("cuda")
+    P, R, F = (torch.from_numpy(a).to(dev) for a in (parent, rows, first))
+    for max_depth in (depth, depth + 7):
+        steps = torch.empty((len(rows), max_depth), dtype=torch.int64, device=dev)
+        length = torch.empty(len(rows), dtype=torch.int64, device=dev)
+        _abi.check(L.mjb_tree_paths(P.data_ptr(), cap, R.data_ptr(), F.data_ptr(), len(rows), max_depth,
+                                    steps.data_ptr(), length.data_ptr(), None))
+        steps, length = steps.cpu().numpy(), length.cpu().numpy()
+        for i, chain in enumerate(want):
+            assert length[i] == len(chain)
+            assert steps[i, :len(chain)].tolist() == chain and (steps[i, len(chain):] == -1).all()
+    short = depth - 1
+    steps = torch.empty((len(rows), short), dtype=torch.int64, device=dev)
+    length = torch.empty(len(rows), dtype=torch.int64, device=dev)
+    _abi.check(L.mjb_tree_paths(P.data_ptr(), cap, R.data_ptr(), F.data_ptr(), len(rows), short, steps.data_ptr(), length.data_ptr(), None))
+    length = length.cpu().numpy()
+    assert all((length[i] == -1) == (len(c) > short) for i, c in enumerate(want))
