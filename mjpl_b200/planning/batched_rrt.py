@@ -407,9 +407,17 @@ class BatchedRRT:
         graph = None
 
         def capture():
+            # capture_begin / capture_end directly: the torch.cuda.graph context manager first runs gc.collect() and
+            # empty_cache() (40 ms per capture on this workload, more with the previous batch's paths still alive)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
-                pair()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g.capture_begin()
+                try:
+                    pair()
+                finally:
+                    g.capture_end()
+            torch.cuda.current_stream().wait_stream(side)
             return g
 
         with eng._call_lock:
@@ -597,11 +605,17 @@ class BatchedRRT:
                 tick()             # eager once: the library grows its scratch here, never inside a capture
             side.synchronize()
 
-            def capture():
+            def capture():      # (capture_begin / capture_end directly, see _run_wave)
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    for _ in range(ticks_per_sync):
-                        tick()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    g.capture_begin()
+                    try:
+                        for _ in range(ticks_per_sync):
+                            tick()
+                    finally:
+                        g.capture_end()
+                torch.cuda.current_stream().wait_stream(side)
                 return g
 
             try:
