@@ -182,6 +182,11 @@ int mjb_rrt_extend(mjb_model *m, double *d_nodes, int64_t *d_parent, int64_t *d_
                    const int64_t *d_slots, const double *d_targets, int64_t n, double eps,
                    int32_t kcap, uint32_t flags, double *d_reached, int64_t *d_last, void *stream);
 
+/* How many chain rows the following mjb_rrt_extend / mjb_rrt_extend_masked calls on this handle are expected to
+ * check per call (0: the default, 24 per query).  A planner whose queries have mostly finished tells the library
+ * so, and the calls take the small-launch path (results do not depend on the hint, only launch choices do). */
+int mjb_set_chain_hint(mjb_model *m, int64_t expected_rows);
+
 /* Same, with a per-query mask: queries with d_active[i] == 0 (or with NaN targets) build no chain and
  * append nothing (their d_reached is the nearest node).  d_active may be NULL (all active). */
 int mjb_rrt_extend_masked(mjb_model *m, double *d_nodes, int64_t *d_parent, int64_t *d_count, int64_t cap,

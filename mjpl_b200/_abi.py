@@ -134,7 +134,7 @@ EXPORTS = (
     "mjb_last_error mjb_device_count mjb_model_create mjb_model_destroy mjb_model_npair "
     "mjb_model_pairs mjb_check_configs mjb_check_configs_host mjb_fk mjb_check_edges "
     "mjb_check_sweep mjb_sweep_rows mjb_get_stats mjb_reset_stats mjb_nearest_batch mjb_rrt_extend mjb_pose_valid mjb_pose_project mjb_site_pose "
-    "mjb_ik_solve mjb_kernel_timing mjb_fma_peak mjb_rrt_extend_masked mjb_rrt_sample mjb_rrt_meet mjb_cbirrt_tick mjb_min_distance mjb_tree_paths"
+    "mjb_ik_solve mjb_kernel_timing mjb_fma_peak mjb_rrt_extend_masked mjb_rrt_sample mjb_rrt_meet mjb_cbirrt_tick mjb_min_distance mjb_tree_paths mjb_set_chain_hint"
 ).split()
 
 
@@ -169,6 +169,7 @@ def lib():
     L.mjb_rrt_extend.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, C.c_int64, C.c_double, C.c_int32, C.c_uint32, vp, vp, vp]
     L.mjb_rrt_extend_masked.argtypes = [vp, vp, vp, vp, C.c_int64, vp, vp, vp, C.c_int64, C.c_double, C.c_int32, C.c_uint32, vp, vp, vp]
     L.mjb_rrt_sample.argtypes = [C.c_uint64, vp, C.c_int64, C.c_int32, vp, vp, vp, vp, vp, C.c_double, vp, vp, vp]
+    L.mjb_set_chain_hint.argtypes = [vp, C.c_int64]
     L.mjb_tree_paths.argtypes = [vp, C.c_int64, vp, vp, C.c_int64, C.c_int64, vp, vp, vp]
     L.mjb_rrt_meet.argtypes = [C.c_int64, C.c_int32, vp, vp, vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp]
     L.mjb_cbirrt_tick.argtypes = [vp, C.POINTER(CbirrtState), C.POINTER(PoseSpec), C.c_int32, C.c_uint32, vp]

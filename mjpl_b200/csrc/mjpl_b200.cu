@@ -57,6 +57,7 @@ struct mjb_model {
   bool split = false; size_t fk_smem = 0, mid_smem = 0, narrow_smem = 0; int fk_grid = 0, mid_grid = 0, narrow_grid = 0;
   float *d_pose8 = nullptr; unsigned long long *d_bins = nullptr; uint32_t *d_row_flags = nullptr; size_t split_cap = 0;
   uint8_t *d_rowmask = nullptr;   // edges through the pipeline: one byte per waypoint (F_ROWMASK)
+  size_t chain_hint = 0;          // mjb_set_chain_hint
   bool light_narrow = false;      // no hull of more than 8 vertices: edge batches stay in the single kernel
   unsigned long long *d_l0 = nullptr; size_t l0_cap = 0;
   bool rowk = false; size_t rowk_smem = 0; int rowk_grid = 0; long long rowk_rows = 0;   // one-warp-per-row kernel for small launches
@@ -797,6 +798,12 @@ extern "C" int mjb_reset_stats(mjb_model *m) {
   return MJB_OK;
 }
 
+extern "C" int mjb_set_chain_hint(mjb_model *m, int64_t expected_rows) {
+  if (!m || expected_rows < 0) return fail(MJB_ERR_ARG, "null model / negative hint");
+  m->chain_hint = (size_t)expected_rows;
+  return MJB_OK;
+}
+
 extern "C" int mjb_tree_paths(const int64_t *d_parent, int64_t cap, const int64_t *d_rows, const int64_t *d_first, int64_t n,
                               int64_t max_depth, int64_t *d_steps, int64_t *d_len, void *stream) {
   if (n < 0 || cap < 1 || max_depth < 1) return fail(MJB_ERR_ARG, "bad n / cap / max_depth");
@@ -872,7 +879,7 @@ extern "C" int mjb_rrt_extend_masked(mjb_model *m, double *d_nodes, int64_t *d_p
   }
   // worst case, no host read-back; the actual chains are short, so always the single kernel
   // (expected rows: ~24 chain steps per query on the Franka scenes; only picks the kernel instance)
-  if ((rc = ensure_recheck(m, (size_t)n * (size_t)kcap, st, false, (size_t)n * 24))) return rc;
+  if ((rc = ensure_recheck(m, (size_t)n * (size_t)kcap, st, false, m->chain_hint ? m->chain_hint : (size_t)n * 24))) return rc;
   // 1. nearest node of every query's tree   2. chain lengths + prefix sums
   nearest_kernel<<<(unsigned)n, NEAREST_THREADS, 0, st>>>(d_nodes, (long long)cap, nq, (const long long *)d_count,
                                                                   (const long long *)d_slots, d_targets, (long long)n, m->d_chain_nn, d_active);

@@ -430,6 +430,8 @@ class BatchedRRT:
             except Exception:      # capture not possible (e.g. a profiler that forbids it): enqueue eagerly
                 graph = None
             t0 = time.time()
+            small_tail = False
+            _abi.check(L.mjb_set_chain_hint(eng._h, 0))
             trace = [] if os.environ.get("MJPL_PLAN_TRACE") else None
             while True:
                 if trace is not None:
@@ -443,6 +445,12 @@ class BatchedRRT:
                 if need > start.cap:
                     new_cap = 1 << int(np.ceil(np.log2(need + headroom)))
                     start.grow(new_cap); goal.grow(new_cap)
+                    graph = capture() if (graph is not None) else None
+                # the tail: a few hard queries are left and an extend checks a few hundred rows.  Tell the library
+                # (launch choices only: the one-warp-per-row kernel alone, a small fp64 grid) and capture again.
+                if not small_tail and n_active * 24 <= 4096:
+                    small_tail = True
+                    _abi.check(L.mjb_set_chain_hint(eng._h, max(1, n_active * 24)))
                     graph = capture() if (graph is not None) else None
                 if graph is not None:
                     for _ in range(pairs_per_sync):
@@ -463,6 +471,8 @@ class BatchedRRT:
                       f"enqueue sum {enq_ms.sum():.1f} ms max {enq_ms.max():.1f}, over 5 ms: {np.round(enq_ms[enq_ms > 5], 1).tolist()}")
             torch.cuda.current_stream().wait_stream(side)
             it, n_active, hs, hg = look()
+            if small_tail:
+                _abi.check(L.mjb_set_chain_hint(eng._h, 0))
             self.stats["iterations"] = max(self.stats["iterations"], it)
             self.stats["gave_up"] += int(counters[2])
             # ---- paths of the solved slots: walk the parent links of both trees on the device ----------
