@@ -106,6 +106,43 @@ class _Forest:
         return out
 
 
+def _paths_of_solved(L, stream, solved, nodes_s, parent_s, first_s, nodes_g, parent_g, first_g, max_depth):
+    """Tree.get_path for every solved slot: one ``mjb_tree_paths`` launch per tree, the rows gathered on the device
+    in query-major order, one D2H copy per tree.  -> per solved slot the list of waypoints root of the start tree
+    .. connecting node .. root of the goal tree (the connecting configuration once if both trees hold it)."""
+    import torch
+
+    from .. import _abi
+
+    n = len(solved)
+    dev = solved.device
+    cap = parent_s.shape[1]
+
+    def chains(nodes, parent, first):
+        steps = torch.empty((n, max_depth), dtype=torch.int64, device=dev)
+        length = torch.empty(n, dtype=torch.int64, device=dev)
+        _abi.check(L.mjb_tree_paths(parent.data_ptr(), cap, solved.data_ptr(), first.data_ptr(), n, max_depth,
+                                    steps.data_ptr(), length.data_ptr(), stream()))
+        counts = length.cpu().numpy()
+        if (counts < 0).any():
+            raise RuntimeError("a parent chain is longer than its tree")
+        steps = steps[:, :max(int(counts.max()), 1)]
+        valid = steps >= 0
+        sl = solved[:, None].expand_as(steps)[valid]
+        return nodes[sl, steps[valid]].cpu().numpy(), counts          # query by query, first node .. root
+
+    assert parent_s.is_contiguous() and parent_g.is_contiguous() and parent_g.shape[1] == cap
+    rs, cs = chains(nodes_s, parent_s, first_s.contiguous())
+    rg, cg = chains(nodes_g, parent_g, first_g.contiguous())
+    os_, og = np.concatenate(([0], np.cumsum(cs))), np.concatenate(([0], np.cumsum(cg)))
+    same = (rs[os_[:-1]] == rg[og[:-1]]).all(axis=1)                   # the two extends met in one configuration
+    out = []
+    for i in range(n):
+        a = rs[os_[i] + (1 if same[i] else 0):os_[i + 1]][::-1]        # root of the start tree -> connecting node
+        out.append(list(a) + list(rg[og[i]:og[i + 1]]))               # connecting node -> root of the goal tree
+    return out
+
+
 class BatchedRRT:
     """Lock-step bi-RRT over many (q_init, q_goal) queries.
 
@@ -479,39 +516,14 @@ class BatchedRRT:
             out: list[list[np.ndarray]] = [[] for _ in range(S)]
             solved = (res_s >= 0).nonzero(as_tuple=True)[0]
             if len(solved):
-                # Tree.get_path for every solved slot in one launch per tree (mjb_tree_paths), rows gathered on the
-                # device in query-major order, one D2H copy per tree, one split per tree
-                n_solved = len(solved)
-                max_depth = max(int(hs), int(hg), 1)     # a chain cannot be longer than its tree has nodes
-
-                def chains(F, first):
-                    steps = torch.empty((n_solved, max_depth), dtype=i64, device=dev)
-                    length = torch.empty(n_solved, dtype=i64, device=dev)
-                    _abi.check(L.mjb_tree_paths(F.parent.data_ptr(), F.cap, solved.data_ptr(), first.data_ptr(), n_solved,
-                                                max_depth, steps.data_ptr(), length.data_ptr(), stream()))
-                    counts = length.cpu().numpy()
-                    if (counts < 0).any():
-                        raise RuntimeError("a parent chain is longer than its tree")
-                    steps = steps[:, :max(int(counts.max()), 1)]
-                    valid = steps >= 0
-                    sl = solved[:, None].expand_as(steps)[valid]
-                    rows = F.q[sl, steps[valid]].cpu().numpy()          # query by query, first node .. root
-                    return rows, counts
-
                 tp = [time.perf_counter()]
-                rs, cs = chains(start, res_s[solved].contiguous())
-                tp.append(time.perf_counter())
-                rg, cg = chains(goal, res_g[solved].contiguous())
-                tp.append(time.perf_counter())
-                os_, og = np.concatenate(([0], np.cumsum(cs))), np.concatenate(([0], np.cumsum(cg)))
-                same = (rs[os_[:-1]] == rg[og[:-1]]).all(axis=1)       # the two extends met in one configuration
-                tp.append(time.perf_counter())
-                for i, k in enumerate(solved.cpu().numpy()):
-                    a = rs[os_[i] + (1 if same[i] else 0):os_[i + 1]][::-1]   # root of the start tree -> connecting node
-                    out[int(k)] = list(a) + list(rg[og[i]:og[i + 1]])        # connecting node -> root of the goal tree
+                found = _paths_of_solved(L, stream, solved, start.q, start.parent, res_s[solved], goal.q, goal.parent, res_g[solved],
+                                         max(int(hs), int(hg), 1))     # a chain cannot be longer than its tree has nodes
+                for k, path in zip(solved.cpu().numpy(), found):
+                    out[int(k)] = path
             if trace is not None:
                 tp.append(time.perf_counter())
-                print(f"[plan trace] paths to the host {1e3 * (time.perf_counter() - t_loop1):.1f} ms: start tree, goal tree, offsets, lists =", np.round(np.diff(tp) * 1e3, 1).tolist(), "nodes", len(rs) + len(rg))
+                print(f"[plan trace] paths to the host {1e3 * (time.perf_counter() - t_loop1):.1f} ms, of which extraction {1e3 * (tp[-1] - tp[0]):.1f} ms")
             return out
 
     # ------------------------------------------------------------------ device driver, projecting constraint
@@ -659,32 +671,11 @@ class BatchedRRT:
             res_s, res_g = bufs["res_start"], bufs["res_goal"]
             solved = (res_s >= 0).nonzero(as_tuple=True)[0]
             if len(solved):
-                par0 = T["parent0"][solved, : int(T["count0"].max())].cpu().numpy()
-                par1 = T["parent1"][solved, : int(T["count1"].max())].cpu().numpy()
-                rs, rg, sl = res_s[solved].cpu().numpy(), res_g[solved].cpu().numpy(), solved.cpu().numpy()
-                want = []
-                for k in range(len(sl)):
-                    a, i = [], int(rs[k])
-                    while i >= 0:
-                        a.append(i)
-                        i = int(par0[k, i])
-                    g, i = [], int(rg[k])
-                    while i >= 0:
-                        g.append(i)
-                        i = int(par1[k, i])
-                    want.append((a[::-1], g))
-                rows_s = torch.from_numpy(np.concatenate([np.full(len(a), s_) for s_, (a, _) in zip(sl, want)])).to(dev)
-                idx_s = torch.from_numpy(np.concatenate([np.asarray(a) for a, _ in want])).to(dev)
-                rows_g = torch.from_numpy(np.concatenate([np.full(len(g), s_) for s_, (_, g) in zip(sl, want)])).to(dev)
-                idx_g = torch.from_numpy(np.concatenate([np.asarray(g) for _, g in want])).to(dev)
-                Ps, Pg = T["nodes0"][rows_s, idx_s].cpu().numpy(), T["nodes1"][rows_g, idx_g].cpu().numpy()
-                o_s = o_g = 0
-                for s_, (a, g) in zip(sl, want):
-                    ps, pg = list(Ps[o_s:o_s + len(a)]), list(Pg[o_g:o_g + len(g)])
-                    o_s += len(a); o_g += len(g)
-                    if np.array_equal(ps[-1], pg[0]):
-                        ps.pop()
-                    paths[int(ids[s_])] = ps + pg
+                depth = max(int(T["count0"].max()), int(T["count1"].max()), 1)
+                found = _paths_of_solved(L, lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream), solved,
+                                         T["nodes0"], T["parent0"], res_s[solved], T["nodes1"], T["parent1"], res_g[solved], depth)
+                for s_, path in zip(solved.cpu().numpy(), found):
+                    paths[int(ids[s_])] = path
         self.stats["solved"] = int(sum(1 for p in paths if p))
         self.stats["seconds"] = time.time() - t0
         est = eng.stats()
