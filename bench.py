@@ -66,6 +66,17 @@ def host_cores():
     return sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
 
 
+def any_rank(flag, dist, device):
+    """True on every rank iff `flag` is true on at least one (all-reduce MAX; `dist` None: single process)."""
+    if dist is None:
+        return bool(flag)
+    import torch
+
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return bool(int(t.item()))
+
+
 def bind_to_gpu_numa(local_rank):
     """Pin this rank to the CPU cores of its GPU's NUMA node (pinned-memory copies from the far node
     halve the host-side rate when 8 ranks all sit on node 0).  Best effort; returns a description."""
@@ -520,7 +531,10 @@ def main():
     while True:
         mask, step_ms, ktime, clocks, st = timed_pass()
         kernels_ms = sum(ktime[k] for k in ("first_ms", "mid_ms", "narrow_ms", "fp64_ms"))
-        if sum(step_ms) <= 1.04 * kernels_ms or retakes >= 3:
+        # the decision to take the pass again is COLLECTIVE: a pass contains barriers, so every rank has to take
+        # the same number of passes (a rank deciding on its own numbers leaves the others waiting in a barrier)
+        again = any_rank(sum(step_ms) > 1.04 * kernels_ms, dist if world > 1 else None, torch.device("cuda", local))
+        if not again or retakes >= 3:
             break
         retakes += 1
     total_ms = float(sum(step_ms))

@@ -462,10 +462,13 @@ class BatchedRRT:
             with torch.cuda.stream(side):
                 pair()             # eager once: the library grows its scratch here, never inside a capture
             side.synchronize()
-            try:
-                graph = capture() if self.use_cuda_graph else None
-            except Exception:      # capture not possible (e.g. a profiler that forbids it): enqueue eagerly
-                graph = None
+            def try_capture():     # capture not possible (e.g. a profiler that forbids it): enqueue eagerly
+                try:
+                    return capture()
+                except Exception:
+                    return None
+
+            graph = try_capture() if self.use_cuda_graph else None
             t0 = time.time()
             small_tail = False
             _abi.check(L.mjb_set_chain_hint(eng._h, 0))
@@ -482,13 +485,13 @@ class BatchedRRT:
                 if need > start.cap:
                     new_cap = 1 << int(np.ceil(np.log2(need + headroom)))
                     start.grow(new_cap); goal.grow(new_cap)
-                    graph = capture() if (graph is not None) else None
+                    graph = try_capture() if (graph is not None) else None
                 # the tail: a few hard queries are left and an extend checks a few hundred rows.  Tell the library
                 # (launch choices only: the one-warp-per-row kernel alone, a small fp64 grid) and capture again.
                 if not small_tail and n_active * 24 <= 4096:
                     small_tail = True
                     _abi.check(L.mjb_set_chain_hint(eng._h, max(1, n_active * 24)))
-                    graph = capture() if (graph is not None) else None
+                    graph = try_capture() if (graph is not None) else None
                 if graph is not None:
                     for _ in range(pairs_per_sync):
                         graph.replay()
@@ -640,10 +643,13 @@ class BatchedRRT:
                 torch.cuda.current_stream().wait_stream(side)
                 return g
 
-            try:
-                graph = capture() if self.use_cuda_graph else None
-            except Exception:
-                graph = None
+            def try_capture():
+                try:
+                    return capture()
+                except Exception:
+                    return None
+
+            graph = try_capture() if self.use_cuda_graph else None
             status = torch.empty(4, dtype=i64, device=dev)
             while True:
                 status[0], status[1] = bufs["counters"][0], bufs["counters"][3]
@@ -656,7 +662,7 @@ class BatchedRRT:
                     cap *= 2
                     alloc(cap)
                     state = make_state(cap)
-                    graph = capture() if graph is not None else None
+                    graph = try_capture() if graph is not None else None
                 if graph is not None:
                     graph.replay()
                 else:

@@ -84,3 +84,37 @@ def test_sweep_rows_host_is_deterministic_and_in_range():
     assert (big >= lo).all() and (big <= hi).all()
     assert abs(((big - lo) / (hi - lo)).mean() - 0.5) < 0.01
     assert not np.array_equal(sweep_rows_host(m, 3, 0, 10), sweep_rows_host(m, 4, 0, 10))
+
+
+def _retake_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench
+
+        # rank 1 alone wants the first pass again, nobody the second: every rank must see (True, False) --
+        # bench.py's timed pass contains barriers, so the ranks have to agree on how many passes they take
+        seen = [bench.any_rank(rank == 1 and k == 0, dist, torch.device("cpu")) for k in range(2)]
+        q.put((rank, seen))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_retaking_a_timed_pass_is_a_collective_decision():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_retake_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert got == {0: [True, False], 1: [True, False]}
+    import bench
+
+    assert bench.any_rank(True, None, None) is True and bench.any_rank(False, None, None) is False
