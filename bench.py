@@ -630,7 +630,9 @@ def main():
             out["plans"] = plans
         if sweep is not None:
             out["sweep"] = sweep
-        if not args.no_cpu_baseline:
+        # the CPU legs run at N = 1 only (task contract): at N > 1 the other ranks would sit in the final barrier for
+        # the half minute they take, and the host cores are shared with N - 1 busy rank processes anyway
+        if not args.no_cpu_baseline and world == 1:
             rate, cpu_valid, n_cpu, kind, desc = cpu_validity(model, rows, 12.0)
             out["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": len(host_cores()), "kind": kind, "sample": desc}
             out["stats"]["agreement_with_cpu_checker_on_sample"] = float((cpu_valid == host_mask[:n_cpu].numpy()).mean())
