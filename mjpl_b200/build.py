@@ -38,5 +38,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         print(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed")
-    (OUT.parent / "ptxas.log").write_text(r.stdout + r.stderr)
+    # registers / spills / stack per kernel for the record; compile times left out so that the file only changes
+    # when the code does
+    log = "\n".join(ln for ln in (r.stdout + r.stderr).splitlines() if "Compile time" not in ln)
+    (OUT.parent / "ptxas.log").write_text(log + "\n")
     return OUT
