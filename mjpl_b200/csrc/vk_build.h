@@ -63,6 +63,7 @@ struct HostModel {
   std::vector<GroupPair> group_pairs;    // sorted by kind, then by moving group
   std::vector<uint16_t> gp_member;       // pair indices (into `pairs`), grouped by group pair
   int gp_kind_end[3] = {0, 0, 0};        // group_pairs[0 .. end[0]) spheres, [end[0] .. end[1]) capsules, then planes
+  double l0_sq_err = 0;                  // what level 0's squared limits carry for fp32 rounding (build_groups)
   double calib_l0_per_row = 0, calib_sub_per_row = 0;   // calibrated level-0 survivors / expanded shape pairs per row
   double bin_expect[NBIN] = {0};   // calibrated narrow-phase items per row that land in each bin (vk_split.cuh)
   int nrounds = 0;
@@ -610,6 +611,32 @@ inline bool build_groups(HostModel &H) {
     lims[idx] = std::max(lims[idx], lim);
     lims_in[idx] = std::max(lims_in[idx], lim_in);
   }
+  // Rounding of level 0's squared distances: |e - s u|^2 is evaluated as |e|^2 - s (2 e.u - s) in fp32
+  // (point_segment_d2), which costs a few ulps of |e|^2 -- measured 2.1 eps32 |e|^2 (hs_point_segment_check).  |e| is
+  // bounded by the reach of the kinematic tree (link offsets, hinge anchors, slide ranges: rotations keep lengths)
+  // plus the far end of the world-fixed segments; the squared limits carry 8 eps32 x that bound squared.
+  double reach = 0;
+  {
+    std::vector<double> r(std::max(H.nslot, 1), 0.0);
+    for (int sl = 0; sl < H.nslot; sl++) {
+      const int ps = H.fk.body_parent[sl];
+      double a = ps >= 0 ? r[ps] : 0.0;
+      a += sqrt(H.fk.body_pos[sl][0] * H.fk.body_pos[sl][0] + H.fk.body_pos[sl][1] * H.fk.body_pos[sl][1] + H.fk.body_pos[sl][2] * H.fk.body_pos[sl][2]);
+      for (int j = H.fk.body_jntadr[sl]; j < H.fk.body_jntadr[sl] + H.fk.body_jntnum[sl]; j++) {
+        if (H.fk.jnt_type[j] == JK_SLIDE) a += std::max(fabs(H.fk.jnt_lo[j] - H.fk.qpos0[H.fk.jnt_qadr[j]]), fabs(H.fk.jnt_hi[j] - H.fk.qpos0[H.fk.jnt_qadr[j]]));   // (rows within the joint range)
+        else a += 2.0 * sqrt(H.fk.jnt_pos[j][0] * H.fk.jnt_pos[j][0] + H.fk.jnt_pos[j][1] * H.fk.jnt_pos[j][1] + H.fk.jnt_pos[j][2] * H.fk.jnt_pos[j][2]);
+      }
+      r[sl] = a;
+      for (int g = H.slot_group_adr[sl]; g < H.slot_group_adr[sl] + H.slot_group_num[sl]; g++)
+        reach = std::max(reach, a + sqrt(H.group_c[g][0] * H.group_c[g][0] + H.group_c[g][1] * H.group_c[g][1] + H.group_c[g][2] * H.group_c[g][2]));
+    }
+  }
+  double far_static = 0;
+  for (const StaticGroup &sg : H.static_groups)
+    far_static = std::max(far_static, sqrt((double)sg.a[0] * sg.a[0] + (double)sg.a[1] * sg.a[1] + (double)sg.a[2] * sg.a[2]) + (double)sg.len);
+  const double e_max = reach + far_static;
+  const double sq_err = 8.0 * 5.97e-8 * e_max * e_max + 1e-9;
+  H.l0_sq_err = sq_err;
   std::vector<int> ord(keys.size());
   for (size_t i = 0; i < ord.size(); i++) ord[i] = (int)i;
   std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
@@ -626,10 +653,11 @@ inline bool build_groups(HostModel &H) {
     if (members[i].size() > 255) { H.err = "too many geom pairs between two bodies"; return false; }
     g.first = (uint16_t)H.gp_member.size(); g.n = (uint8_t)members[i].size();
     const bool squared = keys[i].kind != GK_PLANE;
-    g.lim = (float)((squared ? lims[i] * lims[i] + 2e-6 : lims[i]) * (1 + 4e-7));   // + the cancellation in point_segment_d2
+    g.lim = (float)((squared ? lims[i] * lims[i] + sq_err : lims[i]) * (1 + 4e-7));
     // sphere / capsule kinds compare squares: "none" is 0 there; the plane kind compares the signed height
-    const bool none = !(lims_in[i] > 0.005) || getenv("MJB_NO_INNER0");   // (a smaller sum leaves no room for the rounding of the squares)
-    g.lim_in = none ? (squared ? 0.f : -1e30f) : (float)((squared ? lims_in[i] * lims_in[i] : lims_in[i]) * (1 - 4e-7));
+    // (the inner limit gives the same amount up; a sum that leaves nothing means: no certain-contact test)
+    const bool none = !(lims_in[i] > 0) || (squared && !(lims_in[i] * lims_in[i] > 2.0 * sq_err)) || getenv("MJB_NO_INNER0");
+    g.lim_in = none ? (squared ? 0.f : -1e30f) : (float)((squared ? lims_in[i] * lims_in[i] - sq_err : lims_in[i]) * (1 - 4e-7));
     for (uint16_t p : members[i]) H.gp_member.push_back(p);
     H.group_pairs.push_back(g);
     for (int k = keys[i].kind; k < 3; k++) H.gp_kind_end[k]++;

@@ -63,6 +63,10 @@ def lib():
         L.hs_bounds_check.restype = C.c_double
         L.hs_inner_check.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
         L.hs_inner_check.restype = C.c_double
+        L.hs_l0_sq_err.argtypes = [C.c_void_p]
+        L.hs_l0_sq_err.restype = C.c_double
+        L.hs_point_segment_check.argtypes = [C.c_int, C.c_uint64]
+        L.hs_point_segment_check.restype = C.c_double
         L.hs_segseg_check.argtypes = [C.c_int, C.c_uint64]
         L.hs_segseg_check.restype = C.c_double
         _lib = L
@@ -146,6 +150,10 @@ class HostSim:
         """largest distance by which a vertex sticks out of its bounding capsule / group sphere (<= 0: contained)"""
         return lib().hs_bounds_check(self._h)
 
+    def l0_sq_err(self):
+        """what the squared limits of level 0 carry for fp32 rounding (m^2)"""
+        return lib().hs_l0_sq_err(self._h)
+
     def inner_check(self, nsample=400, seed=5):
         """inner capsules against their shapes -> (shapes with an inner capsule, largest distance by which a
         sampled surface point of an inner capsule sticks out of its shape; <= 0: none does)"""
@@ -214,6 +222,11 @@ class HostSim:
         pb = np.zeros(lib().hs_npair(self._h), np.int32)
         lib().hs_bins(self._h, be.ctypes.data, C.byref(tot), pb.ctypes.data)
         return be, tot.value, pb
+
+
+def point_segment_check(ncase=200000, seed=4):
+    """largest error of level 0's expanded squared point-segment distance (fp32) against fp64, relative to |e|_max^2"""
+    return lib().hs_point_segment_check(ncase, seed)
 
 
 def segseg_check(ncase=20000, seed=3):

@@ -582,3 +582,30 @@ extern "C" double hs_inner_check(Sim *s, int nsample, uint64_t seed, int *nshape
   if (nshape) *nshape = cnt;
   return worst;
 }
+
+// point_segment_d2 (the expanded square level 0 compares with its squared limits) against the exact value in
+// fp64: returns the largest |error| / |e|_max^2 of the squared distance over random points up to |e|_max = 3 sqrt(3) m
+// from the segment's start and segments up to 2 m long (build_groups allows 8 eps32 |e|_max^2 in the squared limits)
+extern "C" double hs_point_segment_check(int ncase, uint64_t seed) {
+  double worst = 0;
+  for (int c = 0; c < ncase; c++) {
+    float x[7];
+    for (int k = 0; k < 7; k++) x[k] = sweep_value(seed, c, k, -1.f, 1.f);
+    const V3<float> e = mk<float>(3.f * x[0], 3.f * x[1], 3.f * x[2]);
+    double un = sqrt((double)x[3] * x[3] + (double)x[4] * x[4] + (double)x[5] * x[5]);
+    if (un < 1e-3) continue;
+    const V3<float> u = mk<float>((float)(x[3] / un), (float)(x[4] / un), (float)(x[5] / un));
+    const float len = (c % 5 == 0) ? 0.f : 1.f + x[6];
+    float sc;
+    const double got = (double)point_segment_d2(e, u, len, &sc);
+    // exact: the segment the fp32 tables describe (start 0, direction u as stored, length len)
+    const double ul = sqrt((double)u.x * u.x + (double)u.y * u.y + (double)u.z * u.z);
+    const double s = ((double)e.x * u.x + (double)e.y * u.y + (double)e.z * u.z) / ul;
+    const double t = s < 0 ? 0 : (s > len ? len : s);
+    const double dx = e.x - t * u.x / ul, dy = e.y - t * u.y / ul, dz = e.z - t * u.z / ul;
+    worst = std::max(worst, fabs(got - (dx * dx + dy * dy + dz * dz)));
+  }
+  return worst / 27.0;
+}
+
+extern "C" double hs_l0_sq_err(Sim *s) { return s->H.l0_sq_err; }

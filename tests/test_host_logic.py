@@ -450,6 +450,8 @@ def test_bounding_capsules_and_cull_groups_are_conservative():
     from tests.hostsim import HostSim
 
     assert hostsim.segseg_check(30000) < 1e-6
+    # level 0's squared limits carry 8 eps32 |e|_max^2 for the expanded square; measured: about 2 eps32 |e|_max^2
+    assert hostsim.point_segment_check(200000) < 4 * 5.97e-8
     zoo = mjcf.from_xml_string(toys.PRIMITIVE_ARM)
     zoo.geom_margin = np.where(np.arange(zoo.ngeom) % 2 == 0, 0.015, 0.004)   # margins widen the culls too
     cases = [(models.load("franka_scene_with_obstacles"), [("left_finger", "right_finger")], 6000),
@@ -458,6 +460,7 @@ def test_bounding_capsules_and_cull_groups_are_conservative():
     for m, allowed, n in cases:
         hs = HostSim(m, allowed)
         assert hs.bounds_check() <= 0.0
+        assert 1e-9 < hs.l0_sq_err() < 1e-4      # Franka obstacle scene: reach 2.6 m + segments to 1.5 m -> 8e-6 m^2
         rng = np.random.default_rng(8)
         Q = rng.uniform(m.jnt_range[:, 0], m.jnt_range[:, 1], size=(n, m.nq)).astype(np.float32)
         got, st = hs.check_pipe(Q)
