@@ -497,6 +497,36 @@ def test_inner_shapes_only_certify_real_contacts():
         assert inner["caught_any"] >= share * inner["invalid_rows"], inner
 
 
+def test_inner_shapes_on_rows_at_the_contact_boundary():
+    """Where a too generous inner shape would show: rows bisected between a free and a colliding configuration
+    until the two are 1e-4 rad apart (distances to contact down to 1e-8 m).  The shortcut must not fire on any free
+    one, and the culled evaluation must still agree with the oracle outside the 1e-5 band."""
+    import oracle
+    from mjpl_b200 import models
+    from tests.hostsim import HostSim
+
+    for name, allowed in (("franka_scene_with_obstacles", [("left_finger", "right_finger")]), ("ur5e_scene", [])):
+        m = models.load(name)
+        hs, orc = HostSim(m, allowed), oracle.Oracle(m, allowed)
+        rng = np.random.default_rng(3)
+        Q = rng.uniform(m.jnt_range[:, 0], m.jnt_range[:, 1], size=(4000, m.nq))
+        ok = orc.check(Q, 2)
+        n = min(int(ok.sum()), int((~ok).sum()), 600)
+        A, B = Q[ok][:n].copy(), Q[~ok][:n].copy()
+        mids = []
+        for _ in range(14):
+            M = 0.5 * (A + B)
+            v = orc.check(M, 2)
+            A[v], B[~v] = M[v], M[~v]
+            mids.append(M.copy())
+        R = np.concatenate([A, B] + mids[-4:]).astype(np.float32)
+        got, st = hs.check_pipe(R)
+        want, dist, _ = orc.check(R.astype(np.float64), 2, want_dist=True)
+        assert np.abs(dist).min() < 1e-6 and 0.3 < want.mean() < 0.7
+        assert st["inner"]["false_positives"] == 0
+        assert not ((got.astype(bool) != want) & (np.abs(dist) >= 1e-5)).any()
+
+
 def test_support_maps_return_the_full_scan_maximum():
     """The cube-map support tables of the larger hulls (narrow_kernel) list, per cell, a rigorous superset of
     the vertices that can be a support for a direction of the cell: on random, near-axis and cell-border
